@@ -1,0 +1,469 @@
+// loclinear.cu — kernel 3: Epanechnikov-weighted local-linear adjustment on the accepted rows,
+// plus the postpr model counts and the column statistics used by summary()/region checks.
+//
+// Reference semantics: third-party R `abc` 2.2.1 abc(method="loclinear") as reached from
+// src/Classes/ABC.py:1950-1953 / 2806-2809:
+//     w   <- 1 - (dist[wt1]/ds)^2
+//     fit1 <- lsfit(scaled.ss[wt1,], param[wt1,], wt = w);  pred <- [1,t] %*% coef
+//     res <- param[wt1,] - [1, scaled.ss[wt1,]] %*% coef;  the_m <- colMeans(res); res <- res - the_m
+//     fit2 <- lsfit(scaled.ss[wt1,], log(res^2), wt = w) ; adj <- pred + the_m + pred.sd * res / pred.si
+// Design choice: the design matrix is centred on the scaled target, so the intercept IS the
+// prediction at the target and X'WX is well conditioned; normal equations in fp64, fixed reduction tree.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxD = 64;
+constexpr int kMaxP = 64;
+
+struct GatherScale {
+    double div[kMaxD], rcp[kMaxD], tgt[kMaxD];
+};
+
+// accepted rows -> compact column-major blocks (leading dimension `cap`)
+__global__ void __launch_bounds__(256) k_gather(const double* __restrict__ ss, long long ld_ss,
+                                                const double* __restrict__ param, long long ld_param,
+                                                const double* __restrict__ dist, const long long* __restrict__ idx,
+                                                const long long* __restrict__ n_acc_ptr, long long row_offset,
+                                                long long cap, int d, int P, const double* __restrict__ mad,
+                                                const double* __restrict__ target, const double* __restrict__ ds_ptr,
+                                                double* __restrict__ xs, double* __restrict__ y,
+                                                double* __restrict__ ss_out, double* __restrict__ w,
+                                                double* __restrict__ dist_out) {
+    __shared__ GatherScale S;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) {
+        double m = mad[j];
+        double dv = (m == 0.0) ? 1.0 : m;
+        S.div[j] = dv;
+        S.tgt[j] = (m == 0.0) ? target[j] : target[j] / dv;
+    }
+    __syncthreads();
+    long long n_acc = *n_acc_ptr;
+    if (n_acc > cap) n_acc = cap;
+    const double ds = *ds_ptr;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_acc; r += stride) {
+        const long long i = idx[r] - row_offset;
+        for (int j = 0; j < d; ++j) {
+            double x = ss[(size_t)j * ld_ss + i];
+            ss_out[(size_t)j * cap + r] = x;
+            double sc = (S.div[j] == 1.0) ? x : x / S.div[j];  // IEEE division == R's x/mad
+            xs[(size_t)j * cap + r] = __dsub_rn(sc, S.tgt[j]);
+        }
+        for (int p = 0; p < P; ++p) y[(size_t)p * cap + r] = param[(size_t)p * ld_param + i];
+        double di = dist[i];
+        dist_out[r] = di;
+        double q = di / ds;
+        w[r] = __dsub_rn(1.0, __dmul_rn(q, q));
+    }
+}
+
+// ---- weighted normal equations ------------------------------------------------------------------
+// T_r = [1, xs_r (d), rhs_r (P)];  out = sum_r w_r * T_r[a] * T_r[b]  for (a,b) in
+// gram (M x M, a,b < M) and cross (M x P: a < M, b = M + p).
+constexpr int kNormThreads = 256;
+constexpr int kNormRows = 32;
+constexpr int kMaxSlots = 20;  // entries per thread: E <= 5120
+
+__global__ void __launch_bounds__(kNormThreads) k_normal_partial(const double* __restrict__ xs,
+                                                                 const double* __restrict__ rhs,
+                                                                 const double* __restrict__ w,
+                                                                 const long long* __restrict__ n_acc_ptr,
+                                                                 long long cap, int d, int P, int with_gram,
+                                                                 double* __restrict__ partials) {
+    extern __shared__ double sm[];
+    const int M = d + 1;
+    const int W = M + P;          // row width
+    const int Wp = W | 1;         // odd pitch: fewer bank conflicts
+    double* T = sm;               // [kNormRows][Wp]
+    double* wr = sm + kNormRows * Wp;
+    const int E = (with_gram ? M * M : 0) + M * P;
+    long long n_acc = *n_acc_ptr;
+    if (n_acc > cap) n_acc = cap;
+
+    int ea[kMaxSlots], eb[kMaxSlots];
+    double acc[kMaxSlots];
+    int nslots = 0;
+    for (int e = threadIdx.x; e < E && nslots < kMaxSlots; e += kNormThreads, ++nslots) {
+        int a, b;
+        if (with_gram && e < M * M) {
+            a = e / M;
+            b = e % M;
+        } else {
+            int e2 = e - (with_gram ? M * M : 0);
+            a = e2 / P;
+            b = M + e2 % P;
+        }
+        ea[nslots] = a;
+        eb[nslots] = b;
+        acc[nslots] = 0.0;
+    }
+
+    const long long ntile = (n_acc + kNormRows - 1) / kNormRows;
+    for (long long tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+        const long long r0 = tile * kNormRows;
+        __syncthreads();
+        for (int t = threadIdx.x; t < kNormRows * W; t += kNormThreads) {
+            int c = t / kNormRows, rr = t % kNormRows;  // consecutive threads -> consecutive rows (coalesced)
+            long long r = r0 + rr;
+            double v = 0.0;
+            if (r < n_acc) {
+                if (c == 0) v = 1.0;
+                else if (c < M) v = xs[(size_t)(c - 1) * cap + r];
+                else v = rhs[(size_t)(c - M) * cap + r];
+            }
+            T[rr * Wp + c] = v;
+        }
+        if (threadIdx.x < kNormRows) {
+            long long r = r0 + threadIdx.x;
+            wr[threadIdx.x] = r < n_acc ? w[r] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int rr = 0; rr < kNormRows; ++rr) {
+            const double wv = wr[rr];
+            const double* row = T + rr * Wp;
+#pragma unroll
+            for (int s = 0; s < kMaxSlots; ++s)
+                if (s < nslots) acc[s] = fma(wv * row[ea[s]], row[eb[s]], acc[s]);
+        }
+    }
+    double* out = partials + (size_t)blockIdx.x * E;
+    int s = 0;
+    for (int e = threadIdx.x; e < E && s < kMaxSlots; e += kNormThreads, ++s) out[e] = acc[s];
+}
+
+__global__ void k_reduce_partials(const double* __restrict__ partials, int nparts, int E, double* __restrict__ out) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    double a = 0.0;
+    for (int p = 0; p < nparts; ++p) a += partials[(size_t)p * E + e];  // fixed order: deterministic
+    out[e] = a;
+}
+
+// Cholesky solve of the (M x M) SPD gram against P right-hand sides. beta[a*P + p].
+__global__ void __launch_bounds__(64) k_solve(const double* __restrict__ gram, const double* __restrict__ rhs, int M,
+                                              int P, double* __restrict__ beta, int* status) {
+    extern __shared__ double sm[];
+    double* L = sm;  // M*M
+    __shared__ int bad;
+    for (int t = threadIdx.x; t < M * M; t += blockDim.x) L[t] = gram[t];
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double dmax = 0.0;
+        for (int a = 0; a < M; ++a) dmax = fmax(dmax, fabs(L[a * M + a]));
+        for (int c = 0; c < M; ++c) {
+            double s = L[c * M + c];
+            for (int k = 0; k < c; ++k) s -= L[c * M + k] * L[c * M + k];
+            if (!(s > 1e-13 * L[c * M + c]) || !(s > 0.0) || !(dmax > 0.0)) {
+                bad = 1;
+                s = 1.0;
+            }
+            double lcc = sqrt(s);
+            L[c * M + c] = lcc;
+            for (int r = c + 1; r < M; ++r) {
+                double t = L[r * M + c];
+                for (int k = 0; k < c; ++k) t -= L[r * M + k] * L[c * M + k];
+                L[r * M + c] = t / lcc;
+            }
+        }
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+        double z[kMaxD + 1];
+        for (int a = 0; a < M; ++a) {
+            double t = rhs[a * P + p];
+            for (int k = 0; k < a; ++k) t -= L[a * M + k] * z[k];
+            z[a] = t / L[a * M + a];
+        }
+        for (int a = M - 1; a >= 0; --a) {
+            double t = z[a];
+            for (int k = a + 1; k < M; ++k) t -= L[k * M + a] * z[k];
+            z[a] = t / L[a * M + a];
+        }
+        for (int a = 0; a < M; ++a) beta[a * P + p] = bad ? __longlong_as_double(0x7ff8000000000000ll) : z[a];
+    }
+    if (threadIdx.x == 0 && bad) atomicOr(status, ABCDLS_S_SINGULAR);
+}
+
+// res[r,p] = y[r,p] - (beta[0,p] + sum_j xs[r,j] * beta[j+1,p])
+__global__ void __launch_bounds__(256) k_residual(const double* __restrict__ xs, const double* __restrict__ y,
+                                                  const double* __restrict__ beta,
+                                                  const long long* __restrict__ n_acc_ptr, long long cap, int d,
+                                                  int P, double* __restrict__ res) {
+    extern __shared__ double sb[];  // (d+1)*P
+    for (int t = threadIdx.x; t < (d + 1) * P; t += blockDim.x) sb[t] = beta[t];
+    __syncthreads();
+    long long n_acc = *n_acc_ptr;
+    if (n_acc > cap) n_acc = cap;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_acc; r += stride) {
+        for (int p0 = 0; p0 < P; p0 += 8) {
+            double f[8];
+            const int pe = min(8, P - p0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[q] = q < pe ? sb[p0 + q] : 0.0;
+            for (int j = 0; j < d; ++j) {
+                double x = xs[(size_t)j * cap + r];
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (q < pe) f[q] = fma(x, sb[(j + 1) * P + p0 + q], f[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (q < pe) res[(size_t)(p0 + q) * cap + r] = y[(size_t)(p0 + q) * cap + r] - f[q];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_recentre_log(double* __restrict__ res, const double* __restrict__ the_m,
+                                                      const long long* __restrict__ n_acc_ptr, long long cap, int P,
+                                                      double* __restrict__ logres2) {
+    long long n_acc = *n_acc_ptr;
+    if (n_acc > cap) n_acc = cap;
+    const int p = blockIdx.y;
+    const double m = the_m[p];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_acc; r += stride) {
+        double v = res[(size_t)p * cap + r] - m;
+        res[(size_t)p * cap + r] = v;
+        if (logres2) logres2[(size_t)p * cap + r] = log(v * v);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_adjust(const double* __restrict__ xs, double* __restrict__ res,
+                                                const double* __restrict__ beta, const double* __restrict__ the_m,
+                                                const double* __restrict__ gamma,
+                                                const long long* __restrict__ n_acc_ptr, long long cap, int d, int P,
+                                                int hcorr, double* __restrict__ adj) {
+    extern __shared__ double sg[];  // (d+1)*P gamma
+    if (hcorr)
+        for (int t = threadIdx.x; t < (d + 1) * P; t += blockDim.x) sg[t] = gamma[t];
+    __syncthreads();
+    long long n_acc = *n_acc_ptr;
+    if (n_acc > cap) n_acc = cap;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_acc; r += stride) {
+        for (int p = 0; p < P; ++p) {
+            double rv = res[(size_t)p * cap + r];
+            if (hcorr) {
+                double g0 = sg[p];
+                double lin = g0;
+                for (int j = 0; j < d; ++j) lin = fma(xs[(size_t)j * cap + r], sg[(j + 1) * P + p], lin);
+                double sd = sqrt(exp(g0));
+                double si = sqrt(exp(lin));
+                rv = (sd * rv) / si;
+                res[(size_t)p * cap + r] = rv;
+            }
+            adj[(size_t)p * cap + r] = (beta[p] + the_m[p]) + rv;
+        }
+    }
+}
+
+// per-column statistics over the first n_acc rows: out[c*6 + {0:min,1:max,2:sum,3:sum w*x,4:sum w*x*x,5:sum w}]
+// one block per column, fixed traversal order => deterministic
+__global__ void __launch_bounds__(1024) k_col_stats(const double* __restrict__ v, const double* __restrict__ w,
+                                                    const long long* __restrict__ n_acc_ptr, long long cap,
+                                                    double* __restrict__ out) {
+    long long n_acc = *n_acc_ptr;
+    if (n_acc > cap) n_acc = cap;
+    const int c = blockIdx.x;
+    const double* col = v + (size_t)c * cap;
+    double mn = __longlong_as_double(0x7ff0000000000000ll), mx = -mn, s = 0, swx = 0, swx2 = 0, sw = 0;
+    for (long long r = threadIdx.x; r < n_acc; r += blockDim.x) {
+        double x = col[r];
+        double ww = w ? w[r] : 1.0;
+        mn = fmin(mn, x);
+        mx = fmax(mx, x);
+        s += x;
+        swx = fma(ww, x, swx);
+        swx2 = fma(ww * x, x, swx2);
+        sw += ww;
+    }
+    __shared__ double sh[6][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        swx += __shfl_xor_sync(0xffffffffu, swx, o);
+        swx2 += __shfl_xor_sync(0xffffffffu, swx2, o);
+        sw += __shfl_xor_sync(0xffffffffu, sw, o);
+    }
+    if (lane == 0) {
+        sh[0][wid] = mn; sh[1][wid] = mx; sh[2][wid] = s; sh[3][wid] = swx; sh[4][wid] = swx2; sh[5][wid] = sw;
+    }
+    __syncthreads();
+    if (wid == 0) {
+        const int nw = blockDim.x >> 5;
+        mn = lane < nw ? sh[0][lane] : __longlong_as_double(0x7ff0000000000000ll);
+        mx = lane < nw ? sh[1][lane] : __longlong_as_double(0xfff0000000000000ll);
+        s = lane < nw ? sh[2][lane] : 0.0;
+        swx = lane < nw ? sh[3][lane] : 0.0;
+        swx2 = lane < nw ? sh[4][lane] : 0.0;
+        sw = lane < nw ? sh[5][lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            swx += __shfl_xor_sync(0xffffffffu, swx, o);
+            swx2 += __shfl_xor_sync(0xffffffffu, swx2, o);
+            sw += __shfl_xor_sync(0xffffffffu, sw, o);
+        }
+        if (lane == 0) {
+            double* o6 = out + (size_t)c * 6;
+            o6[0] = mn; o6[1] = mx; o6[2] = s; o6[3] = swx; o6[4] = swx2; o6[5] = sw;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_postpr_counts(const int* __restrict__ model_id,
+                                                       const long long* __restrict__ idx,
+                                                       const long long* __restrict__ n_acc_ptr, long long row_offset,
+                                                       long long cap, int K, unsigned long long* __restrict__ counts) {
+    extern __shared__ unsigned int shc[];
+    for (int t = threadIdx.x; t < K; t += blockDim.x) shc[t] = 0u;
+    __syncthreads();
+    long long n_acc = *n_acc_ptr;
+    if (n_acc > cap) n_acc = cap;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_acc; r += stride) {
+        int m = model_id[idx[r] - row_offset];
+        if (m >= 0 && m < K) atomicAdd(&shc[m], 1u);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < K; t += blockDim.x)
+        if (shc[t]) atomicAdd(&counts[t], (unsigned long long)shc[t]);
+}
+
+inline unsigned grid_for(abcdls_handle_t h, long long n, int threads, int per_sm) {
+    long long b = (n + threads - 1) / threads;
+    long long mx = (long long)h->sm_count * per_sm;
+    if (b > mx) b = mx;
+    if (b < 1) b = 1;
+    return (unsigned)b;
+}
+
+inline int normal_grid(abcdls_handle_t h, long long cap) {
+    long long b = (cap + kNormRows - 1) / kNormRows;
+    long long mx = (long long)h->sm_count * 2;
+    if (b > mx) b = mx;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+}  // namespace
+
+extern "C" {
+
+int abcdls_gather(abcdls_handle_t h, const double* ss, int64_t ld_ss, const double* param, int64_t ld_param,
+                  const double* dist, const int64_t* idx, const int64_t* n_acc, int64_t row_offset, int64_t cap,
+                  int d, int P, const double* mad, const double* target, const double* ds, double* xs, double* y,
+                  double* ss_out, double* w, double* dist_out, void* stream) {
+    ABCDLS_CHECK_ARG(h, h && ss && param && dist && idx && n_acc && mad && target && ds && xs && y && ss_out && w &&
+                            dist_out,
+                     "gather: null pointer");
+    ABCDLS_CHECK_ARG(h, d >= 1 && d <= kMaxD && P >= 1 && P <= kMaxP && cap >= 1, "gather: shape");
+    k_gather<<<grid_for(h, cap, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        ss, ld_ss, param, ld_param, dist, (const long long*)idx, (const long long*)n_acc, row_offset, cap, d, P, mad,
+        target, ds, xs, y, ss_out, w, dist_out);
+    ABCDLS_LAUNCH_CHECK(h);
+    return ABCDLS_OK;
+}
+
+size_t abcdls_normal_workspace_bytes(int d, int P) {
+    int M = d + 1;
+    size_t E = (size_t)M * M + (size_t)M * P;
+    return align_up((size_t)148 * 2 * 2 * E * sizeof(double), 256);  // up to 592 partial blocks
+}
+
+int abcdls_normal(abcdls_handle_t h, const double* xs, const double* rhs, const double* w, const int64_t* n_acc,
+                  int64_t cap, int d, int P, int with_gram, double* partial, void* ws, size_t ws_bytes,
+                  void* stream) {
+    ABCDLS_CHECK_ARG(h, h && xs && rhs && w && n_acc && partial && ws, "normal: null pointer");
+    ABCDLS_CHECK_ARG(h, d >= 1 && d <= kMaxD && P >= 1 && P <= kMaxP && cap >= 1, "normal: shape");
+    const int M = d + 1;
+    const int E = (with_gram ? M * M : 0) + M * P;
+    ABCDLS_CHECK_ARG(h, E <= kMaxSlots * kNormThreads, "normal: (d+1)*(d+1+P) too large");
+    const int grid = normal_grid(h, cap);
+    if (ws_bytes < (size_t)grid * E * sizeof(double)) {
+        h->err = "normal workspace too small";
+        return ABCDLS_E_WORKSPACE;
+    }
+    const int Wp = (M + P) | 1;
+    size_t smem = (size_t)(kNormRows * Wp + kNormRows) * sizeof(double);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (smem > 48 * 1024)
+        ABCDLS_CUDA(h, cudaFuncSetAttribute(k_normal_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_normal_partial<<<grid, kNormThreads, smem, st>>>(xs, rhs, w, (const long long*)n_acc, cap, d, P, with_gram,
+                                                       reinterpret_cast<double*>(ws));
+    ABCDLS_LAUNCH_CHECK(h);
+    k_reduce_partials<<<(E + 127) / 128, 128, 0, st>>>(reinterpret_cast<const double*>(ws), grid, E, partial);
+    ABCDLS_LAUNCH_CHECK(h);
+    return ABCDLS_OK;
+}
+
+int abcdls_solve(abcdls_handle_t h, const double* gram, const double* rhs, int d, int P, double* beta,
+                 int* status_dev, void* stream) {
+    ABCDLS_CHECK_ARG(h, h && gram && rhs && beta && status_dev, "solve: null pointer");
+    ABCDLS_CHECK_ARG(h, d >= 1 && d <= kMaxD && P >= 1 && P <= kMaxP, "solve: shape");
+    const int M = d + 1;
+    k_solve<<<1, 64, (size_t)M * M * sizeof(double), (cudaStream_t)stream>>>(gram, rhs, M, P, beta, status_dev);
+    ABCDLS_LAUNCH_CHECK(h);
+    return ABCDLS_OK;
+}
+
+int abcdls_residual(abcdls_handle_t h, const double* xs, const double* y, const double* beta, const int64_t* n_acc,
+                    int64_t cap, int d, int P, double* res, void* stream) {
+    ABCDLS_CHECK_ARG(h, h && xs && y && beta && n_acc && res, "residual: null pointer");
+    ABCDLS_CHECK_ARG(h, d >= 1 && d <= kMaxD && P >= 1 && P <= kMaxP && cap >= 1, "residual: shape");
+    k_residual<<<grid_for(h, cap, 256, 8), 256, (size_t)(d + 1) * P * sizeof(double), (cudaStream_t)stream>>>(
+        xs, y, beta, (const long long*)n_acc, cap, d, P, res);
+    ABCDLS_LAUNCH_CHECK(h);
+    return ABCDLS_OK;
+}
+
+int abcdls_recentre_log(abcdls_handle_t h, double* res, const double* the_m, const int64_t* n_acc, int64_t cap,
+                        int P, double* logres2, void* stream) {
+    ABCDLS_CHECK_ARG(h, h && res && the_m && n_acc, "recentre_log: null pointer");
+    ABCDLS_CHECK_ARG(h, P >= 1 && P <= kMaxP && cap >= 1, "recentre_log: shape");
+    dim3 grid(grid_for(h, cap, 256, 4), (unsigned)P);
+    k_recentre_log<<<grid, 256, 0, (cudaStream_t)stream>>>(res, the_m, (const long long*)n_acc, cap, P, logres2);
+    ABCDLS_LAUNCH_CHECK(h);
+    return ABCDLS_OK;
+}
+
+int abcdls_adjust(abcdls_handle_t h, const double* xs, double* res, const double* beta, const double* the_m,
+                  const double* gamma, const int64_t* n_acc, int64_t cap, int d, int P, int hcorr, double* adj,
+                  void* stream) {
+    ABCDLS_CHECK_ARG(h, h && xs && res && beta && the_m && n_acc && adj && (!hcorr || gamma), "adjust: null pointer");
+    ABCDLS_CHECK_ARG(h, d >= 1 && d <= kMaxD && P >= 1 && P <= kMaxP && cap >= 1, "adjust: shape");
+    k_adjust<<<grid_for(h, cap, 256, 8), 256, (size_t)(d + 1) * P * sizeof(double), (cudaStream_t)stream>>>(
+        xs, res, beta, the_m, gamma, (const long long*)n_acc, cap, d, P, hcorr, adj);
+    ABCDLS_LAUNCH_CHECK(h);
+    return ABCDLS_OK;
+}
+
+int abcdls_col_stats(abcdls_handle_t h, const double* values, const double* w, const int64_t* n_acc, int64_t cap,
+                     int ncols, double* out, void* stream) {
+    ABCDLS_CHECK_ARG(h, h && values && n_acc && out && ncols >= 1 && cap >= 1, "col_stats");
+    k_col_stats<<<ncols, 1024, 0, (cudaStream_t)stream>>>(values, w, (const long long*)n_acc, cap, out);
+    ABCDLS_LAUNCH_CHECK(h);
+    return ABCDLS_OK;
+}
+
+int abcdls_postpr_counts(abcdls_handle_t h, const int32_t* model_id, const int64_t* idx, const int64_t* n_acc,
+                         int64_t row_offset, int64_t cap, int K, int64_t* counts, void* stream) {
+    ABCDLS_CHECK_ARG(h, h && model_id && idx && n_acc && counts && K >= 1 && K <= 4096 && cap >= 1, "postpr_counts");
+    cudaStream_t st = (cudaStream_t)stream;
+    ABCDLS_CUDA(h, cudaMemsetAsync(counts, 0, (size_t)K * sizeof(int64_t), st));
+    k_postpr_counts<<<grid_for(h, cap, 256, 4), 256, (size_t)K * sizeof(unsigned), st>>>(
+        model_id, (const long long*)idx, (const long long*)n_acc, row_offset, cap, K, (unsigned long long*)counts);
+    ABCDLS_LAUNCH_CHECK(h);
+    return ABCDLS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,381 @@
+"""Host-side sequencing of the ABC acceptance-and-adjustment path on B200.
+
+One process per GPU.  Rows are sharded in contiguous rank-major blocks (global row = row_offset +
+local row), tables live in HBM column-major (``(cols, n_local)`` torch tensors with unit stride along
+rows — R's ``as.matrix`` layout).  Every arithmetic step is a CUDA kernel behind the C ABI
+(``stages.py``); this file only orders the stages and puts the small collectives between them:
+
+    column median/MAD  : radix-select passes, histogram all-reduce per pass when world > 1
+    distance           : local
+    threshold ds       : radix-select on dist (same all-reduce)
+    cap rule           : all-gather of one int64 per rank -> exclusive scan -> local quota
+    normal equations   : all-reduce of the (d+1) x (d+1+P) fp64 partial
+    the_m / sigma2     : all-reduce of P(+1) sums
+    summary            : all-reduce min / max / sums
+
+Reference boundary: src/Classes/ABC.py:1950-1953, 1964 (abc.abc), 919 (abc.postpr), 2806-2840 (SMC
+min/max), with the arithmetic of CRAN abc 2.2.1.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import torch
+
+from . import _capi
+from .comm import Comm
+
+
+class AbcError(RuntimeError):
+    """Mirrors an R ``stop()`` inside abc()/postpr() (surfaced by rpy2 as RRuntimeError)."""
+
+
+@dataclass
+class AbcResult:
+    method: str
+    tol: float
+    nacc: int                      # ceiling(N * tol), global
+    n_global: int
+    ds: float
+    mad: torch.Tensor              # (d,)  R mad() of every column (0 => column left unscaled)
+    idx: torch.Tensor              # (n_local_acc,) ascending GLOBAL row numbers held by this rank
+    unadj_values: torch.Tensor     # (n_local_acc, P)
+    ss: torch.Tensor               # (n_local_acc, d)  unscaled accepted summary statistics
+    weights: torch.Tensor          # (n_local_acc,)    1 for rejection, Epanechnikov otherwise
+    dist_accepted: torch.Tensor    # (n_local_acc,)
+    adj_values: Optional[torch.Tensor] = None
+    residuals: Optional[torch.Tensor] = None
+    coef: Optional[torch.Tensor] = None      # (d+1, P) fit1, R convention (uncentred design [1, scaled ss])
+    coef_h: Optional[torch.Tensor] = None    # (d+1, P) fit2, R convention
+    pred: Optional[torch.Tensor] = None      # (P,) prediction at the target incl. the_m
+    sigma2: Optional[torch.Tensor] = None
+    aic: Optional[float] = None
+    bic: Optional[float] = None
+    stats: Optional[torch.Tensor] = None     # (P, 6) global {min,max,sum,sum wx,sum wx^2,sum w} of the posterior sample
+    dist: Optional[torch.Tensor] = None      # (n_local,) full local distance vector when requested
+    warnings: List[str] = field(default_factory=list)
+    numparam: int = 0
+    numstat: int = 0
+
+    @property
+    def values(self) -> torch.Tensor:
+        """The posterior sample summary() works on: adj.values if present else unadj.values."""
+        return self.adj_values if self.adj_values is not None else self.unadj_values
+
+    def minmax(self):
+        """(min, max) per parameter over the global posterior sample — what ABC-DLS's SMC reads as
+        summary(res)[0] and summary(res)[6] (ABC.py:2833, 2837)."""
+        return self.stats[:, 0].clone(), self.stats[:, 1].clone()
+
+
+@dataclass
+class PostprResult:
+    models: List[str]
+    counts: torch.Tensor           # (K,) int64 accepted simulations per model (global)
+    pred: torch.Tensor             # (K,) proportions
+    nacc: int
+    n_global: int
+    ds: float
+    mad: torch.Tensor
+    idx: torch.Tensor
+    ss: torch.Tensor
+    values: torch.Tensor           # (n_local_acc,) int32 model ids of accepted rows, row order
+    dist: Optional[torch.Tensor] = None
+
+    def bayes_factors(self) -> torch.Tensor:
+        return self.pred[:, None] / self.pred[None, :]
+
+
+def _as_table(t: torch.Tensor) -> torch.Tensor:
+    if t.dim() == 1:
+        t = t[None, :]
+    if t.dtype != torch.float64:
+        t = t.to(torch.float64)
+    if t.stride(1) != 1:
+        t = t.contiguous()
+    return t
+
+
+class AbcEngine:
+    """Drop-in compute engine for abc()/postpr() on device tables.  See ``rabc.py`` for the facade that
+    keeps rpy2's call surface."""
+
+    def __init__(self, device=None, group=None, stages=None):
+        if stages is None:
+            from .stages import CudaStages
+            if device is None:
+                device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
+            if device is None:
+                raise RuntimeError("abc_dls_b200: no CUDA device — the engine has no CPU path")
+            stages = CudaStages(torch.device(device))
+        self.k = stages
+        self.device = stages.device
+        self.comm = Comm(group, self.device)
+
+    # ---- small helpers ----------------------------------------------------------------------------
+    def _shard_info(self, n_local: int):
+        counts = self.comm.allgather_ints([n_local])  # list per rank
+        ns = [c[0] for c in counts]
+        return sum(ns), sum(ns[: self.comm.rank]), ns
+
+    def _select(self, table: torch.Tensor, n_local: int, center, k0, k1) -> torch.Tensor:
+        """Exact global order statistics k0,k1 (0-based) of every row of ``table`` (njobs, n_local)."""
+        k = self.k
+        njobs, ld = table.shape[0], table.stride(0)
+        ws = k.select_workspace(njobs)
+        k.select_begin(ws, njobs, table, n_local, ld, None, center, k0, k1)
+        hist = k.select_hist_tensor(ws, njobs) if self.comm.world > 1 else None
+        for p in range(_capi.SELECT_PASSES):
+            k.select_hist(ws, njobs, n_local, p)
+            if hist is not None:
+                self.comm.allreduce_sum(hist)
+            k.select_pick(ws, njobs, p)
+        out = k.new(njobs, 2)
+        k.select_end(ws, njobs, out)
+        return out
+
+    def column_mad(self, ss: torch.Tensor, n_global: int):
+        """R median() and mad() of every column, exactly (even N: mean of the two middle values)."""
+        k = self.k
+        d, n_local = ss.shape
+        k0, k1 = (n_global - 1) // 2, n_global // 2
+        med, mad = k.new(d), k.new(d)
+        r = self._select(ss, n_local, None, k0, k1)
+        k.median_from_ranks(r, d, 1.0, med)
+        r = self._select(ss, n_local, med, k0, k1)
+        k.median_from_ranks(r, d, 1.4826, mad)
+        return med, mad
+
+    # ---- shared front half: scaling, distance, tolerance cut ----------------------------------
+    def _front(self, target, ss, tol, status):
+        k = self.k
+        d, n_local = ss.shape
+        n_global, row_offset, _ = self._shard_info(n_local)
+        nacc = int(math.ceil(n_global * tol))
+        if not (1 <= nacc <= n_global):
+            raise AbcError("'tol' must give 1 <= ceiling(N * tol) <= N")
+        _, mad = self.column_mad(ss, n_global)
+        dist = k.new(n_local)
+        k.scale_dist(ss, n_local, d, ss.stride(0), mad, target, dist, status)
+        ds = self._select(dist[None, :], n_local, None, nacc - 1, nacc - 1)[0, :1]  # (1,) device
+        ws = k.accept_workspace(n_local)
+        le = torch.zeros(1, dtype=torch.int64, device=self.device)
+        k.count_le(dist, n_local, ds, le, ws)
+        if self.comm.world > 1:
+            allc = self.comm.allgather(le).view(-1)
+            below = allc[: self.comm.rank].sum()
+            quota = (nacc - below).clamp(min=0).view(1)
+        else:
+            quota = torch.full((1,), nacc, dtype=torch.int64, device=self.device)
+        cap = min(nacc, n_local)
+        idx = k.new(cap, dtype=torch.int64)
+        n_acc = torch.zeros(1, dtype=torch.int64, device=self.device)
+        k.accept(dist, n_local, ds, quota, row_offset, cap, idx, n_acc, ws, status)
+        return dict(n_global=n_global, row_offset=row_offset, nacc=nacc, mad=mad, dist=dist, ds=ds, cap=cap, idx=idx,
+                    n_acc=n_acc)
+
+    def _zero_variance(self, ss) -> bool:
+        """R: stop if every column of sumstat has a single unique value."""
+        k = self.k
+        d, n_local = ss.shape
+        mm = k.new(2 * d)
+        k.smc_oldrange(ss, n_local, d, ss.stride(0), mm)
+        mn, mx = mm[:d].clone(), mm[d:].clone()
+        self.comm.allreduce_min(mn)
+        self.comm.allreduce_max(mx)
+        return bool((mn == mx).all().item())
+
+    # ---- abc() ----------------------------------------------------------------------------------
+    def abc(self, target: torch.Tensor, param: torch.Tensor, sumstat: torch.Tensor, tol: float, method: str,
+            hcorr: bool = True, kernel: str = "epanechnikov", keep_dist: bool = False) -> AbcResult:
+        """``abc::abc`` for method in {rejection, loclinear} on this rank's shard.
+
+        target (d,), param (P, n_local), sumstat (d, n_local): float64 CUDA tensors, column-major tables.
+        """
+        if method not in ("rejection", "loclinear"):
+            raise AbcError("Method must be rejection or loclinear (neuralnet / ridge stay with R's nnet)")
+        if kernel != "epanechnikov":
+            raise AbcError("only kernel='epanechnikov' (the R default ABC-DLS uses) is implemented")
+        k = self.k
+        ss, par = _as_table(sumstat), _as_table(param)
+        target = target.to(device=self.device, dtype=torch.float64).reshape(-1).contiguous()
+        d, n_local = ss.shape
+        P = par.shape[0]
+        if target.numel() != d:
+            raise AbcError("Number of summary statistics in 'target' has to be the same as in 'sumstat'.")
+        if par.shape[1] != n_local:
+            raise AbcError("'param' and 'sumstat' must have the same number of rows")
+        status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        f = self._front(target, ss, tol, status)
+        cap, idx, n_acc, ds, mad = f["cap"], f["idx"], f["n_acc"], f["ds"], f["mad"]
+
+        xs, y, ss_out = k.new(d, cap), k.new(P, cap), k.new(d, cap)
+        w, dacc = k.new(cap), k.new(cap)
+        k.gather(ss, ss.stride(0), par, par.stride(0), f["dist"], idx, n_acc, f["row_offset"], cap, d, P, mad, target,
+                 ds, xs, y, ss_out, w, dacc)
+        # zero variance inside the accepted region (R cond2)
+        reg = k.new(d, 6)
+        k.col_stats(ss_out, None, n_acc, cap, d, reg)
+        rmin, rmax = reg[:, 0].clone(), reg[:, 1].clone()
+        self.comm.allreduce_min(rmin)
+        self.comm.allreduce_max(rmax)
+        region_const = (rmin == rmax).all()
+        all_mad_zero = (mad == 0).all()
+
+        beta = gamma = the_m = res = adj = sig = None
+        stats = k.new(P, 6)
+        if method == "loclinear":
+            M = d + 1
+            part = k.new(M * M + M * P)
+            k.normal(xs, y, w, n_acc, cap, d, P, True, part)
+            self.comm.allreduce_sum(part)
+            gram, rhs = part[: M * M], part[M * M:]
+            beta = k.new(M, P)
+            k.solve(gram, rhs, d, P, beta, status)
+            res = k.new(P, cap)
+            k.residual(xs, y, beta, n_acc, cap, d, P, res)
+            rs = k.new(P, 6)
+            k.col_stats(res, None, n_acc, cap, P, rs)
+            sums = torch.cat([rs[:, 2], n_acc.to(torch.float64)])
+            self.comm.allreduce_sum(sums)
+            the_m = (sums[:P] / sums[P]).contiguous()
+            logres2 = k.new(P, cap) if hcorr else None
+            k.recentre_log(res, the_m, n_acc, cap, P, logres2)
+            k.col_stats(res, w, n_acc, cap, P, rs)
+            sg = torch.cat([rs[:, 4], rs[:1, 5]])
+            self.comm.allreduce_sum(sg)
+            sig = sg[:P] / sg[P]
+            if hcorr:
+                part2 = k.new(M * P)
+                k.normal(xs, logres2, w, n_acc, cap, d, P, False, part2)
+                self.comm.allreduce_sum(part2)
+                gamma = k.new(M, P)
+                k.solve(gram, part2, d, P, gamma, status)
+            adj = k.new(P, cap)
+            k.adjust(xs, res, beta, the_m, gamma, n_acc, cap, d, P, hcorr, adj)
+            k.col_stats(adj, w, n_acc, cap, P, stats)
+        else:
+            k.col_stats(y, None, n_acc, cap, P, stats)
+        if self.comm.world > 1:
+            mn, mx, sm = stats[:, 0].contiguous(), stats[:, 1].contiguous(), stats[:, 2:].contiguous()
+            self.comm.allreduce_min(mn)
+            self.comm.allreduce_max(mx)
+            self.comm.allreduce_sum(sm)
+            stats = torch.cat([mn[:, None], mx[:, None], sm], dim=1)
+
+        # one host read for everything data dependent
+        host = torch.cat([status.to(torch.float64), n_acc.to(torch.float64), ds,
+                          region_const.to(torch.float64).view(1), all_mad_zero.to(torch.float64).view(1)]).cpu()
+        st, n_loc, ds_h = int(host[0]), int(host[1]), float(host[2])
+        st = self.comm.allreduce_or_int(st)
+        warnings: List[str] = []
+        if st & _capi.S_NONFINITE:
+            raise AbcError("non-finite values in 'sumstat'/'target' (R's NA-row handling is not implemented)")
+        if host[4] != 0 and self._zero_variance(ss):
+            raise AbcError("Zero variance in the summary statistics.")
+        if host[3] != 0:
+            msg = "Zero variance in the summary statistics in the selected region."
+            if method != "rejection":
+                raise AbcError(msg + " Try: checking summary statistics, choosing larger tolerance, or rejection method.")
+            warnings.append(msg + " Check summary statistics, consider larger tolerance.")
+        if st & _capi.S_SINGULAR:
+            raise AbcError("lsfit: X matrix deemed to be singular (collinear summary statistics in the accepted region)")
+        if st & _capi.S_CAPACITY:
+            raise AbcError("internal: accepted-row buffer overflow")
+
+        r = AbcResult(method=method, tol=tol, nacc=f["nacc"], n_global=f["n_global"], ds=ds_h, mad=mad,
+                      idx=idx[:n_loc], unadj_values=y.t()[:n_loc], ss=ss_out.t()[:n_loc],
+                      weights=(w[:n_loc] if method != "rejection" else torch.ones(n_loc, dtype=torch.float64,
+                                                                                 device=self.device)),
+                      dist_accepted=dacc[:n_loc], stats=stats, warnings=warnings, numparam=P, numstat=d,
+                      dist=f["dist"] if keep_dist else None)
+        if method == "loclinear":
+            tsc = torch.where(mad == 0, target, target / torch.where(mad == 0, torch.ones_like(mad), mad))
+            r.adj_values, r.residuals = adj.t()[:n_loc], res.t()[:n_loc]
+            r.pred = beta[0] + the_m
+            r.sigma2 = sig
+            r.coef = self._uncentre(beta, tsc)
+            if hcorr:
+                r.coef_h = self._uncentre(gamma, tsc)
+            ls = torch.log(sig).sum().item()
+            r.aic = f["nacc"] * ls + 2 * (d + 1) * P
+            r.bic = f["nacc"] * ls + math.log(f["nacc"]) * (d + 1) * P
+        return r
+
+    @staticmethod
+    def _uncentre(b: torch.Tensor, t_scaled: torch.Tensor) -> torch.Tensor:
+        """coefficients of the design centred on the target -> R's [1, scaled ss] convention."""
+        out = b.clone()
+        out[0] = b[0] - (t_scaled[:, None] * b[1:]).sum(dim=0)
+        return out
+
+    def abc_columns(self, target, param, sumstat, tol, method, hcorr: bool = True) -> List[AbcResult]:
+        """ABC-DLS's per-column mode (ABC.py:1949-1953, 2805-2809): P separate 1-D abc() problems,
+        column c of ``sumstat`` against column c of ``param``."""
+        ss, par = _as_table(sumstat), _as_table(param)
+        target = target.reshape(-1)
+        return [self.abc(target[c:c + 1], par[c:c + 1], ss[c:c + 1], tol, method, hcorr) for c in range(par.shape[0])]
+
+    # ---- postpr() -------------------------------------------------------------------------------
+    def postpr(self, target: torch.Tensor, model_id: torch.Tensor, models: List[str], sumstat: torch.Tensor,
+               tol: float, method: str = "rejection", keep_dist: bool = False) -> PostprResult:
+        """``abc::postpr(method='rejection')``: model_id int32 (n_local,) indexes ``models`` (sorted levels)."""
+        if method != "rejection":
+            raise AbcError("postpr: only method='rejection' is implemented (mnlogistic / neuralnet stay with R's nnet)")
+        k = self.k
+        ss = _as_table(sumstat)
+        target = target.to(device=self.device, dtype=torch.float64).reshape(-1).contiguous()
+        d, n_local = ss.shape
+        K = len(models)
+        if K < 2:
+            raise AbcError("At least two different models must be given.")
+        if target.numel() != d:
+            raise AbcError("Number of summary statistics in 'target' has to be the same as in 'sumstat'.")
+        if model_id.numel() != n_local:
+            raise AbcError("'index' must be the same length as the number of rows in 'sumstat'.")
+        model_id = model_id.to(device=self.device, dtype=torch.int32).contiguous()
+        status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        f = self._front(target, ss, tol, status)
+        cap, idx, n_acc = f["cap"], f["idx"], f["n_acc"]
+        counts = torch.zeros(K, dtype=torch.int64, device=self.device)
+        k.postpr_counts(model_id, idx, n_acc, f["row_offset"], cap, K, counts)
+        self.comm.allreduce_sum(counts)
+        all_mad_zero = (f["mad"] == 0).all()
+        host = torch.cat([status.to(torch.float64), n_acc.to(torch.float64), f["ds"],
+                          all_mad_zero.to(torch.float64).view(1)]).cpu()
+        st, n_loc, ds_h = self.comm.allreduce_or_int(int(host[0])), int(host[1]), float(host[2])
+        if st & _capi.S_NONFINITE:
+            raise AbcError("non-finite values in 'sumstat'/'target' (R's NA-row handling is not implemented)")
+        if host[3] != 0 and self._zero_variance(ss):
+            raise AbcError("Zero variance in the summary statistics.")
+        loc = idx[:n_loc] - f["row_offset"]
+        return PostprResult(models=list(models), counts=counts, pred=counts.to(torch.float64) / counts.sum(),
+                            nacc=f["nacc"], n_global=f["n_global"], ds=ds_h, mad=f["mad"], idx=idx[:n_loc],
+                            ss=ss[:, loc].t(), values=model_id[loc], dist=f["dist"] if keep_dist else None)
+
+    # ---- SMC table passes -------------------------------------------------------------------------
+    def oldrange(self, param_all: torch.Tensor):
+        """Per-column (min, max) over all simulated parameter rows, all ranks (ABC.py:2714-2716)."""
+        tab = _as_table(param_all)
+        P, n = tab.shape
+        mm = self.k.new(2 * P)
+        self.k.smc_oldrange(tab, n, P, tab.stride(0), mm)
+        mn, mx = mm[:P].clone(), mm[P:].clone()
+        self.comm.allreduce_min(mn)
+        self.comm.allreduce_max(mx)
+        return mn, mx
+
+    def box_filter(self, param_all: torch.Tensor, lo: torch.Tensor, hi: torch.Tensor) -> torch.Tensor:
+        """Ascending GLOBAL row numbers of this rank's rows with every parameter in [lo, hi] (ABC.py:2974-2990)."""
+        tab = _as_table(param_all)
+        P, n = tab.shape
+        _, row_offset, _ = self._shard_info(n)
+        lo = lo.to(device=self.device, dtype=torch.float64).contiguous()
+        hi = hi.to(device=self.device, dtype=torch.float64).contiguous()
+        idx = self.k.new(n, dtype=torch.int64)
+        n_out = torch.zeros(1, dtype=torch.int64, device=self.device)
+        status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.k.smc_box_filter(tab, n, P, tab.stride(0), lo, hi, row_offset, n, idx, n_out, status)
+        return idx[: int(n_out.item())]

@@ -1,0 +1,185 @@
+"""Drop-in for the rpy2 handle ABC-DLS binds as the module global ``abc`` (src/Classes/ABC.py:36).
+
+Same attribute names and keyword arguments as the reference's call sites:
+
+    abc.abc(target=, param=, sumstat=, method=, tol=)            ABC.py:1950-1953, 1964, 2806-2809, 2817
+    abc.postpr(target=, index=, sumstat=, tol=, method=)         ABC.py:919
+
+Inputs may be pandas DataFrame/Series, numpy arrays or torch tensors (host or CUDA).  Host inputs are
+copied to HBM once per call; the arithmetic runs in the CUDA engine (``engine.py``) — there is no CPU
+path.  R's defaults that matter are kept: ``hcorr=True``, ``kernel='epanechnikov'``, ``transf='none'``.
+Errors R raises with ``stop()`` surface as :class:`AbcError` with R's message.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from .engine import AbcEngine, AbcError, AbcResult, PostprResult
+from . import summary as _summary
+
+_engine: Optional[AbcEngine] = None
+
+
+def engine() -> AbcEngine:
+    """Process-wide engine on the current CUDA device (created on first use)."""
+    global _engine
+    if _engine is None:
+        _engine = AbcEngine()
+    return _engine
+
+
+def set_engine(e: Optional[AbcEngine]) -> None:
+    global _engine
+    _engine = e
+
+
+def _names(x, n: int, prefix: str) -> List[str]:
+    cols = getattr(x, "columns", None)
+    if cols is not None:
+        return [str(c) for c in cols]
+    name = getattr(x, "name", None)
+    if name is not None and n == 1:
+        return [str(name)]
+    return [f"{prefix}{i + 1}" for i in range(n)]
+
+
+def to_table(x, device) -> torch.Tensor:
+    """(rows, cols) host/device data -> (cols, rows) float64 CUDA table with unit stride along rows.
+    A column-major host array (pandas' usual block layout, R's layout) is copied without a transpose."""
+    if torch.is_tensor(x):
+        t = x
+        if t.dim() == 1:
+            t = t[:, None]
+        t = t.to(device=device, dtype=torch.float64, non_blocking=True)
+        tt = t.t()
+        return tt if tt.stride(1) == 1 else tt.contiguous()
+    if hasattr(x, "to_numpy"):
+        x = x.to_numpy()
+    a = np.asarray(x)
+    if a.dtype != np.float64:
+        a = a.astype(np.float64)
+    if a.ndim == 1:
+        a = a[:, None]
+    if a.flags.f_contiguous:
+        return torch.from_numpy(a.T).to(device)                # already (cols, rows) C-order: one H2D copy
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device).t().contiguous()  # H2D + on-device transpose
+
+
+def _to_vec(x, device) -> torch.Tensor:
+    if torch.is_tensor(x):
+        return x.to(device=device, dtype=torch.float64).reshape(-1)
+    if hasattr(x, "to_numpy"):
+        x = x.to_numpy()
+    return torch.from_numpy(np.asarray(x, dtype=np.float64).reshape(-1).copy()).to(device)
+
+
+class AbcFit:
+    """What ``abc.abc`` returns: the fields of R's S3 class ``abc`` as CUDA tensors (accepted rows in
+    ascending row order) plus ``summary()``."""
+
+    def __init__(self, res: AbcResult, eng: AbcEngine, parnames: List[str], statnames: List[str]):
+        self.res, self._eng = res, eng
+        self.names = {"parameter.names": parnames, "statistics.names": statnames}
+        self.method, self.numparam, self.numstat = res.method, res.numparam, res.numstat
+        self.adj_values, self.unadj_values = res.adj_values, res.unadj_values
+        self.ss, self.weights, self.residuals = res.ss, res.weights, res.residuals
+        self.dist, self.region_idx = res.dist, res.idx
+        self.aic, self.bic = res.aic, res.bic
+
+    def _global_sample(self):
+        r, c = self.res, self._eng.comm
+        vals, w = r.values, r.weights
+        if c.world > 1:
+            n_loc = torch.tensor([vals.shape[0]], dtype=torch.int64, device=vals.device)
+            ns = c.allgather(n_loc).view(-1).cpu().tolist()
+            cap = max(max(ns), 1)
+            pv = torch.zeros((cap, vals.shape[1]), dtype=torch.float64, device=vals.device)
+            pw = torch.zeros(cap, dtype=torch.float64, device=vals.device)
+            pv[: vals.shape[0]], pw[: vals.shape[0]] = vals, w
+            gv, gw = c.allgather(pv), c.allgather(pw)
+            vals = torch.cat([gv[i, : ns[i]] for i in range(c.world)])
+            w = torch.cat([gw[i, : ns[i]] for i in range(c.world)])
+        return vals, w
+
+    def summary(self, intvl: float = 0.95, print_: bool = True) -> _summary.SummaryTable:
+        vals, w = self._global_sample()
+        weighted = self.res.adj_values is not None
+        tab = _summary.summary_table(vals, w, self.res.stats, weighted, intvl, self.names["parameter.names"])
+        if print_:
+            print(_summary.summary_text(tab, vals.shape[0], weighted))
+        return tab
+
+    def summary_text(self, intvl: float = 0.95) -> str:
+        vals, _ = self._global_sample()
+        return _summary.summary_text(self.summary(intvl, print_=False), vals.shape[0], self.res.adj_values is not None)
+
+
+class PostprFit:
+    def __init__(self, res: PostprResult):
+        self.res = res
+        self.models, self.values, self.ss = res.models, res.values, res.ss
+        self.pred = res.pred
+        self.method = "rejection"
+
+    def _tables(self):
+        pred = self.res.pred.cpu().numpy()
+        with np.errstate(divide="ignore", invalid="ignore"):
+            bf = pred[:, None] / pred[None, :]
+        return pred, bf
+
+    def summary(self, print_: bool = True):
+        pred, bf = self._tables()
+        if print_:
+            print(self.summary_text())
+        return {"Prob": dict(zip(self.models, pred.tolist())), "BayesF": bf}
+
+    def summary_text(self) -> str:
+        pred, bf = self._tables()
+        w = max(max(len(m) for m in self.models), 8)
+        lines = ["Data:", f" postpr.out$values ({int(self.res.counts.sum())} posterior samples)", "Models a priori:",
+                 " " + ", ".join(self.models), "Models a posteriori:", " " + ", ".join(self.models), "",
+                 "Proportion of accepted simulations (rejection):",
+                 " ".join(m.rjust(w) for m in self.models), " ".join(f"{p:.4f}".rjust(w) for p in pred), "",
+                 "Bayes factors:", " " * w + " " + " ".join(m.rjust(w) for m in self.models)]
+        for i, m in enumerate(self.models):
+            lines.append(m.ljust(w) + " " + " ".join(f"{v:.4f}".rjust(w) for v in bf[i]))
+        return "\n".join(lines)
+
+
+def abc(target, param, sumstat, tol, method, hcorr: bool = True, transf: str = "none", subset=None,
+        kernel: str = "epanechnikov", **_ignored) -> AbcFit:
+    if transf != "none" and not (isinstance(transf, (list, tuple)) and all(t == "none" for t in transf)):
+        raise AbcError("only transf='none' is implemented (ABC-DLS never passes transf)")
+    if subset is not None:
+        raise AbcError("'subset' is not implemented")
+    eng = engine()
+    ss = to_table(sumstat, eng.device)
+    par = to_table(param, eng.device)
+    tgt = _to_vec(target, eng.device)
+    res = eng.abc(tgt, par, ss, float(tol), method, hcorr=hcorr, kernel=kernel)
+    for wmsg in res.warnings:
+        print("Warning message:\n" + wmsg)
+    return AbcFit(res, eng, _names(param, par.shape[0], "P"), _names(sumstat, ss.shape[0], "S"))
+
+
+def postpr(target, index, sumstat, tol, method="rejection", subset=None, **_ignored) -> PostprFit:
+    if subset is not None:
+        raise AbcError("'subset' is not implemented")
+    eng = engine()
+    ss = to_table(sumstat, eng.device)
+    tgt = _to_vec(target, eng.device)
+    if torch.is_tensor(index) and index.dtype in (torch.int32, torch.int64):
+        ids = index
+        models = [str(m) for m in range(int(index.max().item()) + 1)]
+    else:
+        if eng.comm.world > 1:
+            raise AbcError("postpr over several ranks needs integer model ids shared by all ranks")
+        labels = np.asarray(index.to_numpy() if hasattr(index, "to_numpy") else index).astype(str)
+        models, inv = np.unique(labels, return_inverse=True)   # sorted levels, like factor()
+        models = models.tolist()
+        ids = torch.from_numpy(inv.astype(np.int32))
+    res = eng.postpr(tgt, ids, models, ss, float(tol), method)
+    return PostprFit(res)

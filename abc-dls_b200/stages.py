@@ -1,0 +1,151 @@
+"""CUDA stage layer: one method per C-ABI entry point, taking torch CUDA tensors.
+
+This is the only place that marshals tensors into ``libabcdls.so`` (pointers + sizes + the current
+CUDA stream).  ``engine.py`` sequences these stages and puts the NCCL collectives between them.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _capi
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class CudaStages:
+    """Thin, stateless-but-for-workspaces wrapper over the C ABI on one device."""
+
+    def __init__(self, device: torch.device):
+        if not torch.cuda.is_available():
+            raise RuntimeError("abc_dls_b200 needs a CUDA (sm_100a / B200) device; there is no CPU path")
+        self.device = torch.device(device)
+        self.handle = _capi.Handle(self.device.index if self.device.index is not None else torch.cuda.current_device())
+        self.lib = self.handle.lib
+        self._ws = {}
+        self.launches = 0  # kernels enqueued through this object (bench.py reports it)
+
+    # ---- helpers ----------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def workspace(self, key: str, nbytes: int) -> torch.Tensor:
+        t = self._ws.get(key)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+            self._ws[key] = t
+        return t
+
+    def new(self, *shape, dtype=torch.float64):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    # ---- selection ----------------------------------------------------------------------------
+    def select_workspace(self, njobs: int) -> torch.Tensor:
+        return self.workspace(f"select{njobs}", self.lib.abcdls_select_workspace_bytes(njobs))
+
+    def select_begin(self, ws, njobs, base, n, ld, counts, center, k0, k1):
+        k0d = k0 if torch.is_tensor(k0) else None
+        k1d = k1 if torch.is_tensor(k1) else None
+        self.handle.call("abcdls_select_begin", _p(ws), ws.numel(), njobs, _p(base), n, ld, _p(counts), _p(center),
+                         _p(k0d), _p(k1d), 0 if k0d is not None else int(k0), 0 if k1d is not None else int(k1),
+                         self._stream())
+        self.launches += 2
+
+    def select_hist(self, ws, njobs, n_max, p):
+        self.handle.call("abcdls_select_hist", _p(ws), njobs, n_max, p, self._stream())
+        self.launches += 1
+
+    def select_pick(self, ws, njobs, p):
+        self.handle.call("abcdls_select_pick", _p(ws), njobs, p, self._stream())
+        self.launches += 1
+
+    def select_hist_tensor(self, ws, njobs) -> torch.Tensor:
+        buf, cnt = C.c_void_p(), C.c_size_t()
+        self.handle.call("abcdls_select_hist_buffer", _p(ws), njobs, C.byref(buf), C.byref(cnt))
+        off = buf.value - ws.data_ptr()
+        return ws[off: off + cnt.value * 8].view(torch.int64)
+
+    def select_end(self, ws, njobs, out):
+        self.handle.call("abcdls_select_end", _p(ws), njobs, _p(out), self._stream())
+        self.launches += 1
+
+    def median_from_ranks(self, ranks2, ncols, scale, out):
+        self.handle.call("abcdls_median_from_ranks", _p(ranks2), ncols, float(scale), _p(out), self._stream())
+        self.launches += 1
+
+    # ---- kernel 1 -------------------------------------------------------------------------------
+    def scale_dist(self, ss, n, d, ld, mad, target, dist, status):
+        self.handle.call("abcdls_scale_dist", _p(ss), n, d, ld, _p(mad), _p(target), _p(dist), _p(status),
+                         self._stream())
+        self.launches += 1
+
+    # ---- kernel 2 -------------------------------------------------------------------------------
+    def accept_workspace(self, n):
+        return self.workspace("accept", self.lib.abcdls_accept_workspace_bytes(n))
+
+    def count_le(self, dist, n, ds, le_count, ws):
+        self.handle.call("abcdls_count_le", _p(dist), n, _p(ds), _p(le_count), _p(ws), ws.numel(), self._stream())
+        self.launches += 4
+
+    def accept(self, dist, n, ds, quota, row_offset, cap, idx, n_out, ws, status):
+        self.handle.call("abcdls_accept", _p(dist), n, _p(ds), _p(quota), row_offset, cap, _p(idx), _p(n_out), _p(ws),
+                         ws.numel(), _p(status), self._stream())
+        self.launches += 1
+
+    # ---- kernel 3 -------------------------------------------------------------------------------
+    def gather(self, ss, ld_ss, param, ld_param, dist, idx, n_acc, row_offset, cap, d, P, mad, target, ds, xs, y,
+               ss_out, w, dist_out):
+        self.handle.call("abcdls_gather", _p(ss), ld_ss, _p(param), ld_param, _p(dist), _p(idx), _p(n_acc),
+                         row_offset, cap, d, P, _p(mad), _p(target), _p(ds), _p(xs), _p(y), _p(ss_out), _p(w),
+                         _p(dist_out), self._stream())
+        self.launches += 1
+
+    def normal(self, xs, rhs, w, n_acc, cap, d, P, with_gram, partial):
+        ws = self.workspace("normal", self.lib.abcdls_normal_workspace_bytes(d, P))
+        self.handle.call("abcdls_normal", _p(xs), _p(rhs), _p(w), _p(n_acc), cap, d, P, int(with_gram), _p(partial),
+                         _p(ws), ws.numel(), self._stream())
+        self.launches += 2
+
+    def solve(self, gram, rhs, d, P, beta, status):
+        self.handle.call("abcdls_solve", _p(gram), _p(rhs), d, P, _p(beta), _p(status), self._stream())
+        self.launches += 1
+
+    def residual(self, xs, y, beta, n_acc, cap, d, P, res):
+        self.handle.call("abcdls_residual", _p(xs), _p(y), _p(beta), _p(n_acc), cap, d, P, _p(res), self._stream())
+        self.launches += 1
+
+    def recentre_log(self, res, the_m, n_acc, cap, P, logres2):
+        self.handle.call("abcdls_recentre_log", _p(res), _p(the_m), _p(n_acc), cap, P, _p(logres2), self._stream())
+        self.launches += 1
+
+    def adjust(self, xs, res, beta, the_m, gamma, n_acc, cap, d, P, hcorr, adj):
+        self.handle.call("abcdls_adjust", _p(xs), _p(res), _p(beta), _p(the_m), _p(gamma), _p(n_acc), cap, d, P,
+                         int(hcorr), _p(adj), self._stream())
+        self.launches += 1
+
+    def col_stats(self, values, w, n_acc, cap, ncols, out):
+        self.handle.call("abcdls_col_stats", _p(values), _p(w), _p(n_acc), cap, ncols, _p(out), self._stream())
+        self.launches += 1
+
+    def postpr_counts(self, model_id, idx, n_acc, row_offset, cap, K, counts):
+        self.handle.call("abcdls_postpr_counts", _p(model_id), _p(idx), _p(n_acc), row_offset, cap, K, _p(counts),
+                         self._stream())
+        self.launches += 2
+
+    # ---- kernel 4 -------------------------------------------------------------------------------
+    def smc_workspace(self, n, P):
+        return self.workspace("smc", self.lib.abcdls_smc_workspace_bytes(n, P))
+
+    def smc_oldrange(self, table, n, P, ld, minmax):
+        ws = self.smc_workspace(n, P)
+        self.handle.call("abcdls_smc_oldrange", _p(table), n, P, ld, _p(minmax), _p(ws), ws.numel(), self._stream())
+        self.launches += 3
+
+    def smc_box_filter(self, table, n, P, ld, lo, hi, row_offset, cap, idx, n_out, status):
+        ws = self.smc_workspace(n, P)
+        self.handle.call("abcdls_smc_box_filter", _p(table), n, P, ld, _p(lo), _p(hi), row_offset, cap, _p(idx),
+                         _p(n_out), _p(ws), ws.numel(), _p(status), self._stream())
+        self.launches += 4

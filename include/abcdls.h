@@ -1,0 +1,183 @@
+/*
+ * abcdls.h — C ABI of the B200-native ABC acceptance-and-adjustment engine.
+ *
+ * This is the drop-in boundary for the step ABC-DLS delegates to R's `abc` package through rpy2
+ * (reference: src/Classes/ABC.py:36 binds the package; call sites ABC.py:919, 1950-1953, 1964,
+ * 2806-2809, 2817).  The rpy2 FFI for that path is "copy three data frames into R, call
+ * abc::abc / abc::postpr, read summary()".  The entry points below are what a native binding for the
+ * same path binds instead: plain pointers and sizes, no torch / Python types.
+ *
+ * Conventions
+ *   - every `const double*` / `double*` / `int64_t*` argument is a DEVICE pointer unless its name
+ *     ends in `_host`;
+ *   - tables are column-major (R `as.matrix` layout): element (i, j) at base[j * ld + i];
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), borrows its inputs
+ *     for the duration of the stream work and never modifies them;
+ *   - scratch memory is owned by the caller: query the size, allocate, pass it in;
+ *   - return value: 0 = ok, otherwise one of ABCDLS_E_*; abcdls_last_error() gives text.
+ *     Data-dependent conditions that R reports with stop() (zero variance, ...) cannot be known at
+ *     enqueue time; they are OR-ed into the device word `status_dev` (ABCDLS_S_* bits) which the
+ *     caller reads back together with the results.
+ *   - multi-GPU: rows are sharded in contiguous rank-major blocks.  Stages that need a global
+ *     exchange are split so the host can run an NCCL collective between them on the same stream
+ *     (the buffers to reduce / gather are returned by the *_buffers calls).
+ */
+#ifndef ABCDLS_H
+#define ABCDLS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABCDLS_VERSION_MAJOR 0
+#define ABCDLS_VERSION_MINOR 1
+
+/* return codes */
+#define ABCDLS_OK 0
+#define ABCDLS_E_INVALID 1   /* bad argument (shape, NULL, tol) */
+#define ABCDLS_E_WORKSPACE 2 /* workspace too small */
+#define ABCDLS_E_CUDA 3      /* CUDA runtime error */
+#define ABCDLS_E_NODEVICE 4  /* no sm_100 device */
+
+/* status_dev bits (data-dependent conditions, set by kernels) */
+#define ABCDLS_S_NONFINITE 0x1       /* NaN/Inf in sumstat (R: NA rows — not supported) */
+#define ABCDLS_S_FASTPATH_MISS 0x2   /* sampled bracket missed / overflowed: rerun with mode EXACT */
+#define ABCDLS_S_SINGULAR 0x4        /* normal equations not positive definite (R: lsfit singular) */
+#define ABCDLS_S_ZERO_VAR 0x8        /* every sumstat column constant (R stop: Zero variance ...) */
+#define ABCDLS_S_ZERO_VAR_REGION 0x10 /* no sumstat column varies inside the accepted region */
+#define ABCDLS_S_CAPACITY 0x20       /* an output buffer was too small */
+
+/* selection modes */
+#define ABCDLS_MODE_AUTO 0  /* sampled-bracket fast path, verified; sets FASTPATH_MISS on failure */
+#define ABCDLS_MODE_EXACT 1 /* distribution-independent 6-pass radix select */
+
+typedef struct abcdls_handle_s* abcdls_handle_t;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+int abcdls_create(abcdls_handle_t* out, int device);
+int abcdls_destroy(abcdls_handle_t h);
+const char* abcdls_last_error(abcdls_handle_t h); /* host string, valid until the next call on h */
+int abcdls_version(void);                         /* major * 100 + minor */
+int abcdls_sm_count(abcdls_handle_t h);
+
+/* ---- generic exact selection (order statistics) --------------------------------------------
+ * Used for column medians / MADs (replaces R stats::median / stats::mad inside abc:::normalise)
+ * and for the tolerance threshold `ds <- sort(dist)[nacc]`.
+ *
+ * A "selection set" is `njobs` independent problems; job j selects up to two global ranks
+ * k0[j] <= k1[j] (0-based) of the values of column j of a column-major table (optionally of
+ * |x - center[j]|).  The 64-bit order-preserving key is resolved in ABCDLS_SELECT_PASSES MSB
+ * digits; each pass is  hist -> [allreduce of the histogram buffer across ranks] -> pick.
+ */
+#define ABCDLS_SELECT_PASSES 6
+#define ABCDLS_SELECT_BINS 2048
+
+size_t abcdls_select_workspace_bytes(int njobs);
+/* job j works on column j of `base` (column-major, leading dimension ld, n rows; counts[j] (device,
+ * may be NULL) lets job j use fewer rows).  center (device, may be NULL): select on |x - center[j]|.
+ * Ranks: k0_dev/k1_dev (device, per job) or, when NULL, the host scalars k0_host/k1_host for all. */
+int abcdls_select_begin(abcdls_handle_t h, void* ws, size_t ws_bytes, int njobs, const double* base,
+                        int64_t n, int64_t ld, const int64_t* counts, const double* center,
+                        const int64_t* k0_dev, const int64_t* k1_dev, int64_t k0_host, int64_t k1_host,
+                        void* stream);
+int abcdls_select_hist(abcdls_handle_t h, void* ws, int njobs, int64_t n_max, int pass, void* stream);
+int abcdls_select_pick(abcdls_handle_t h, void* ws, int njobs, int pass, void* stream);
+/* buffer a multi-GPU caller all-reduces (sum, int64) between hist and pick */
+int abcdls_select_hist_buffer(abcdls_handle_t h, void* ws, int njobs, int64_t** buf, size_t* count);
+/* results: out[2*j + q] = value of rank kq[j] (the transformed value when center != NULL) */
+int abcdls_select_end(abcdls_handle_t h, void* ws, int njobs, double* out, void* stream);
+/* R median of an even-length vector = mean of the two middle order statistics:
+ * out[j] = scale * (0.5*ranks2[2j] + 0.5*ranks2[2j+1])   (scale 1 -> median, 1.4826 -> mad) */
+int abcdls_median_from_ranks(abcdls_handle_t h, const double* ranks2, int n_cols, double scale,
+                             double* out, void* stream);
+
+/* ---- kernel 1: MAD scaling + Euclidean distance -------------------------------------------
+ * R abc(): normalise() -> sum1 <- sum1 + (scaled[,j]-target[j])^2 -> sqrt   
+ */
+/* med[j], mad[j] of each column (single-GPU convenience: begin + 6x(hist,pick) + end, twice) */
+size_t abcdls_column_mad_workspace_bytes(int d);
+int abcdls_column_mad(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, double* med,
+                      double* mad, void* ws, size_t ws_bytes, int* status_dev, void* stream);
+/* dist[i] = sqrt(sum_j (ss[i,j]/mad[j] - target[j]/mad[j])^2), mad[j]==0 => unscaled.
+ * `target` holds the UNSCALED target (device, d doubles).  Sets NONFINITE / ZERO_VAR bits. */
+int abcdls_scale_dist(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld,
+                      const double* mad, const double* target, double* dist, int* status_dev,
+                      void* stream);
+
+/* ---- kernel 2: tolerance cut ---------------------------------------------------------------
+ * R: wt1 <- dist <= ds; wt1 <- wt1 & cumsum(wt1) <= nacc    (first nacc rows in row order)
+ * `quota` = how many rows this rank may still accept after the lower ranks took theirs
+ * (single GPU: nacc).  idx_out gets ascending global row numbers (row_offset + local row).
+ */
+size_t abcdls_accept_workspace_bytes(int64_t n);
+/* count of local rows with dist <= ds -> le_count (device int64); feeds the cross-rank scan */
+int abcdls_count_le(abcdls_handle_t h, const double* dist, int64_t n, const double* ds,
+                    int64_t* le_count, void* ws, size_t ws_bytes, void* stream);
+/* must follow abcdls_count_le on the same ws; quota is a device int64 */
+int abcdls_accept(abcdls_handle_t h, const double* dist, int64_t n, const double* ds,
+                  const int64_t* quota, int64_t row_offset, int64_t cap, int64_t* idx_out,
+                  int64_t* n_out, void* ws, size_t ws_bytes, int* status_dev, void* stream);
+
+/* ---- kernel 3: local-linear adjustment -----------------------------------------------------
+ * R: weights (epanechnikov) -> lsfit -> residual recentring -> hcorr -> adj.values.
+ * Design is centred on the scaled target; normal equations are accumulated in fp64 with a fixed
+ * reduction tree.  M = d + 1.
+ *   gather      : accepted rows -> xs (scaled & centred on the target), y, ss, w, dist   [ld = cap]
+ *   normal      : partial[ M*M + M*P ] = [X'WX | X'WY] (row-major)      -> all-reduce(sum) across ranks
+ *   solve       : beta (M x P, row-major; row 0 = intercept = prediction at the target)
+ *   residual    : res = y - X beta
+ *   col_stats   : per-column {min,max,sum,sum w x,sum w x^2,sum w}    -> sums feed the_m (all-reduce)
+ *   recentre_log: res -= the_m ; logres2 = log(res^2)
+ *   normal(with_gram=0, rhs=logres2) -> all-reduce -> solve -> gamma
+ *   adjust      : res <- pred.sd*res/pred.si (hcorr) ; adj = beta[0,] + the_m + res
+ * n_acc is a device int64 (number of valid rows, <= cap).
+ */
+int abcdls_gather(abcdls_handle_t h, const double* ss, int64_t ld_ss, const double* param,
+                  int64_t ld_param, const double* dist, const int64_t* idx, const int64_t* n_acc,
+                  int64_t row_offset, int64_t cap, int d, int P, const double* mad,
+                  const double* target, const double* ds, double* xs, double* y, double* ss_out,
+                  double* w, double* dist_out, void* stream);
+size_t abcdls_normal_workspace_bytes(int d, int P);
+int abcdls_normal(abcdls_handle_t h, const double* xs, const double* rhs, const double* w,
+                  const int64_t* n_acc, int64_t cap, int d, int P, int with_gram, double* partial,
+                  void* ws, size_t ws_bytes, void* stream);
+int abcdls_solve(abcdls_handle_t h, const double* gram, const double* rhs, int d, int P, double* beta,
+                 int* status_dev, void* stream);
+int abcdls_residual(abcdls_handle_t h, const double* xs, const double* y, const double* beta,
+                    const int64_t* n_acc, int64_t cap, int d, int P, double* res, void* stream);
+int abcdls_recentre_log(abcdls_handle_t h, double* res, const double* the_m, const int64_t* n_acc,
+                        int64_t cap, int P, double* logres2 /* may be NULL */, void* stream);
+int abcdls_adjust(abcdls_handle_t h, const double* xs, double* res, const double* beta,
+                  const double* the_m, const double* gamma, const int64_t* n_acc, int64_t cap, int d,
+                  int P, int hcorr, double* adj, void* stream);
+/* out[c*6 + {0:min, 1:max, 2:sum, 3:sum w*x, 4:sum w*x*x, 5:sum w}] over the first n_acc rows of each
+ * column (ld = cap); w may be NULL (=1).  Serves summary() min/max/weighted mean (ABC.py:2833,2837),
+ * the_m, sigma2 and the zero-variance-in-region check. */
+int abcdls_col_stats(abcdls_handle_t h, const double* values, const double* w, const int64_t* n_acc,
+                     int64_t cap, int ncols, double* out, void* stream);
+
+/* ---- postpr (rejection): accepted simulations per model ------------------------ */
+int abcdls_postpr_counts(abcdls_handle_t h, const int32_t* model_id, const int64_t* idx,
+                         const int64_t* n_acc, int64_t row_offset, int64_t cap, int K, int64_t* counts,
+                         void* stream);
+
+/* ---- kernel 4: SMC ------------------------------------------------------------------------
+ * oldrange  = per-column min/max over ALL simulated parameter rows   (ABC.py:2714-2716)
+ * box filter = rows with every parameter in [lo, hi] inclusive        (ABC.py:2974-2990)
+ */
+size_t abcdls_smc_workspace_bytes(int64_t n, int P);
+int abcdls_smc_oldrange(abcdls_handle_t h, const double* param_all, int64_t n, int P, int64_t ld,
+                        double* minmax /* [2*P]: mins then maxes */, void* ws, size_t ws_bytes,
+                        void* stream);
+int abcdls_smc_box_filter(abcdls_handle_t h, const double* param_all, int64_t n, int P, int64_t ld,
+                          const double* lo, const double* hi, int64_t row_offset, int64_t cap,
+                          int64_t* idx_out, int64_t* n_out, void* ws, size_t ws_bytes, int* status_dev,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABCDLS_H */

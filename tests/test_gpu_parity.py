@@ -1,0 +1,185 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bar (north_star): accepted index set bit-exact; dist / ds / weights / MAD bit-exact (fp64, no FMA
+contraction, R's operation order); adjusted posterior within 1e-9 relative, where "relative" is against
+max(|value|, scale of the parameter) because adjusted values may cross zero.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import abc_oracle as O
+from abc_dls_b200 import synth
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-9
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _rel(a, b):
+    scale = np.maximum(np.abs(b).max(axis=0, keepdims=True), 1e-300)
+    return float(np.max(np.abs(a - b) / scale))
+
+
+def _check_abc(engine, par, ss, tgt, tol, method, hcorr=True):
+    r = engine.abc(tgt, par, ss, tol, method, hcorr=hcorr, keep_dist=True)
+    o = O.abc(_np(tgt), _np(par).T, _np(ss).T, tol, method, hcorr=hcorr)
+    np.testing.assert_array_equal(_np(r.mad), o.mad)
+    np.testing.assert_array_equal(_np(r.dist), o.dist)
+    assert r.ds == o.ds and r.nacc == o.nacc
+    np.testing.assert_array_equal(_np(r.idx), o.idx)            # bit-exact accepted set, row order
+    np.testing.assert_array_equal(_np(r.unadj_values), o.unadj_values)
+    np.testing.assert_array_equal(_np(r.ss), o.ss)
+    if method == "loclinear":
+        np.testing.assert_array_equal(_np(r.weights), o.weights)
+        assert _rel(_np(r.adj_values), o.adj_values) < REL_TOL
+        assert _rel(_np(r.pred)[None, :], o.pred[None, :]) < REL_TOL
+        assert _rel(_np(r.coef), o.coef) < 1e-7
+        assert _rel(_np(r.sigma2)[None, :], o.sigma2[None, :]) < 1e-9
+        mn, mx = r.minmax()
+        assert _rel(_np(mn)[None, :], o.adj_values.min(axis=0)[None, :]) < REL_TOL
+        assert _rel(_np(mx)[None, :], o.adj_values.max(axis=0)[None, :]) < REL_TOL
+    else:
+        mn, mx = r.minmax()
+        np.testing.assert_array_equal(_np(mn), o.unadj_values.min(axis=0))
+        np.testing.assert_array_equal(_np(mx), o.unadj_values.max(axis=0))
+    return r, o
+
+
+@pytest.mark.parametrize("n", [2, 7, 1000, 100003, 1 << 20])
+@pytest.mark.parametrize("d,P", [(1, 1), (3, 2), (16, 16)])
+def test_rejection_parity(engine, n, d, P):
+    par, ss, tgt = synth.abc_tables(n, d, P, engine.device)
+    _check_abc(engine, par, ss, tgt, 0.3 if n < 100 else 0.01, "rejection")
+
+
+@pytest.mark.parametrize("n,tol", [(1000, 0.1), (100003, 0.01), (1 << 20, 0.01)])
+@pytest.mark.parametrize("d,P", [(1, 1), (3, 2), (10, 10), (16, 16)])
+@pytest.mark.parametrize("hcorr", [True, False])
+def test_loclinear_parity(engine, n, tol, d, P, hcorr):
+    if n * tol < 4 * (d + 1):
+        pytest.skip("fewer accepted rows than a well-posed regression needs")
+    par, ss, tgt = synth.abc_tables(n, d, P, engine.device)
+    _check_abc(engine, par, ss, tgt, tol, "loclinear", hcorr)
+
+
+def test_odd_leading_dimension_and_unaligned_columns(engine):
+    par, ss, tgt = synth.abc_tables(4097, 3, 3, engine.device)
+    big = torch.zeros((3, 4099), dtype=torch.float64, device=engine.device)
+    big[:, 1:4098] = ss
+    _check_abc(engine, par, big[:, 1:4098], tgt, 0.05, "loclinear")
+
+
+def test_ties_and_cap_rule(engine):
+    """Heavily tied distances: integer-valued statistics -> many rows exactly at ds; R keeps the first
+    nacc rows in row order among dist <= ds."""
+    g = torch.Generator(device="cpu").manual_seed(3)
+    n = 50000
+    ss = torch.randint(0, 7, (2, n), generator=g).to(torch.float64).to(engine.device)
+    par = torch.rand((2, n), generator=g, dtype=torch.float64).to(engine.device)
+    tgt = torch.tensor([3.0, 3.0], dtype=torch.float64, device=engine.device)
+    for tol in (0.001, 0.03, 0.5):
+        r, o = _check_abc(engine, par, ss, tgt, tol, "rejection")
+        assert (o.dist <= o.ds).sum() > o.nacc          # the cap rule actually bites
+        assert r.idx.numel() == o.nacc
+
+
+def test_zero_mad_column_is_left_unscaled(engine):
+    g = torch.Generator(device="cpu").manual_seed(4)
+    n = 20000
+    ss = torch.rand((2, n), generator=g, dtype=torch.float64)
+    ss[1] = torch.where(torch.rand(n, generator=g) < 0.7, torch.tensor(1.0, dtype=torch.float64), ss[1])
+    par = torch.rand((1, n), generator=g, dtype=torch.float64)
+    r, o = _check_abc(engine, par.to(engine.device), ss.to(engine.device),
+                      torch.tensor([0.5, 0.9], dtype=torch.float64, device=engine.device), 0.02, "rejection")
+    assert o.mad[1] == 0.0
+
+
+def test_nacc_edges(engine):
+    par, ss, tgt = synth.abc_tables(999, 2, 2, engine.device)
+    r, o = _check_abc(engine, par, ss, tgt, 1.0, "rejection")       # everything accepted
+    assert r.idx.numel() == 999
+    r, o = _check_abc(engine, par, ss, tgt, 0.0005, "rejection")    # nacc == 1
+    assert r.idx.numel() == 1
+
+
+def test_per_column_mode_matches_p_separate_calls(engine):
+    """ABC-DLS's rejection/loclinear path: P separate 1-D problems (ABC.py:1949-1953)."""
+    par, ss, tgt = synth.abc_tables(10000, 19, 19, engine.device)      # cfg 1: SNDX schema, test_size rows
+    out = engine.abc_columns(tgt, par, ss, 0.01, "loclinear")
+    for c, r in enumerate(out):
+        o = O.abc(_np(tgt)[c:c + 1], _np(par)[c], _np(ss)[c], 0.01, "loclinear")
+        np.testing.assert_array_equal(_np(r.idx), o.idx)
+        assert _rel(_np(r.adj_values), o.adj_values) < REL_TOL
+
+
+def test_postpr_parity(engine):
+    ids, ss, tgt = synth.postpr_tables(300000, engine.device)
+    models = ["BNDX", "MNDX", "SNDX"]
+    r = engine.postpr(tgt, ids, models, ss, 0.05, keep_dist=True)
+    o = O.postpr(_np(tgt), np.array(models)[_np(ids)], _np(ss).T, 0.05)
+    np.testing.assert_array_equal(_np(r.dist), o.dist)
+    np.testing.assert_array_equal(_np(r.idx), o.idx)
+    np.testing.assert_array_equal(_np(r.counts), o.counts)
+    assert r.ds == o.ds and (o.dist <= o.ds).sum() >= o.nacc
+    np.testing.assert_allclose(_np(r.pred), o.pred, rtol=0, atol=0)
+
+
+def test_errors_follow_r(engine):
+    from abc_dls_b200.engine import AbcError
+    par, ss, tgt = synth.abc_tables(500, 2, 2, engine.device)
+    with pytest.raises(AbcError, match="Zero variance in the summary statistics\\."):
+        engine.abc(tgt, par, torch.ones_like(ss), 0.1, "rejection")
+    with pytest.raises(AbcError, match="Number of summary statistics"):
+        engine.abc(tgt[:1], par, ss, 0.1, "rejection")
+    bad = ss.clone()
+    bad[0, 17] = float("nan")
+    with pytest.raises(AbcError, match="non-finite"):
+        engine.abc(tgt, par, bad, 0.1, "rejection")
+    with pytest.raises(AbcError, match="neuralnet"):
+        engine.abc(tgt, par, ss, 0.1, "neuralnet")
+
+
+def test_smc_table_passes(engine):
+    par, _, _ = synth.abc_tables(200001, 1, 12, engine.device)
+    mn, mx = engine.oldrange(par)
+    np.testing.assert_array_equal(_np(mn), _np(par).min(axis=1))
+    np.testing.assert_array_equal(_np(mx), _np(par).max(axis=1))
+    lo = mn + 0.1 * (mx - mn)
+    hi = mx - 0.05 * (mx - mn)
+    lo[3], hi[3] = mn[3], mx[3]
+    idx = engine.box_filter(par, lo, hi)
+    np.testing.assert_array_equal(_np(idx) + 2, O.narrowing_params(_np(par).T, _np(lo), _np(hi)))
+
+
+def test_facade_accepts_pandas_like_the_reference_call_sites(engine):
+    import pandas as pd
+    from abc_dls_b200 import rabc
+    rabc.set_engine(engine)
+    par, ss, tgt = synth.abc_tables(10000, 3, 3, "cpu")
+    names = ["N_A", "N_AF", "T_B"]
+    dfp, dfs = pd.DataFrame(par.T.numpy(), columns=names), pd.DataFrame(ss.T.numpy(), columns=names)
+    dft = pd.DataFrame(tgt.numpy()[None, :], columns=names)
+    c = 1
+    res = rabc.abc(target=pd.DataFrame(dft.iloc[:, c]), param=pd.DataFrame(dfp.iloc[:, c]),
+                   sumstat=pd.DataFrame(dfs.iloc[:, c]), method="loclinear", tol=0.01)
+    o = O.abc(tgt.numpy()[c:c + 1], par.numpy()[c], ss.numpy()[c], 0.01, "loclinear")
+    tab = res.summary(print_=False)
+    ot = O.summary_abc(o)
+    assert abs(tab[0] - ot[0, 0]) <= REL_TOL * abs(ot[0, 0]) and abs(tab[6] - ot[6, 0]) <= REL_TOL * abs(ot[6, 0])
+    np.testing.assert_allclose(np.array(tab)[[1, 2, 3, 5], 0], ot[[1, 2, 3, 5], 0], rtol=1e-9)
+    assert res.summary_text().startswith("Data:")
+    joint = rabc.abc(target=dft, param=dfp, sumstat=dfs, method="rejection", tol=0.01)
+    oj = O.abc(tgt.numpy(), par.numpy().T, ss.numpy().T, 0.01, "rejection")
+    np.testing.assert_array_equal(_np(joint.region_idx), oj.idx)
+    np.testing.assert_allclose(np.array(joint.summary(print_=False)), O.summary_abc(oj), rtol=1e-12, equal_nan=True)
+    index = pd.Series(np.array(["BNDX", "MNDX", "SNDX"])[np.arange(30000) % 3])
+    ids, ssp, tg = synth.postpr_tables(30000, "cpu")
+    pp = rabc.postpr(target=pd.Series(tg.numpy()), index=index, sumstat=pd.DataFrame(ssp.T.numpy()), tol=0.05,
+                     method="rejection")
+    op = O.postpr(tg.numpy(), index.to_numpy(), ssp.T.numpy(), 0.05)
+    np.testing.assert_array_equal(_np(pp.res.counts), op.counts)
+    assert "Proportion of accepted simulations (rejection):" in pp.summary_text()

@@ -1,0 +1,228 @@
+"""Known-answer and self-consistency tests of the CPU oracle (oracle/abc_oracle.py).
+
+The reference pins nothing on this path (tests/test_ABCDLS.py only checks that files exist) and R is not
+available, so the oracle is checked against hand-computed cases, against a second independent
+formulation of each step, and against invariances of the algorithm.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import abc_oracle as O
+
+
+def test_median_and_mad_known_answers():
+    assert O.r_median(np.array([3.0, 1.0, 2.0])) == 2.0
+    assert O.r_median(np.array([4.0, 1.0, 3.0, 2.0])) == 2.5
+    assert O.r_median(np.array([5.0])) == 5.0
+    # R: mad(c(1,2,3,4,100)) = 1.4826 * median(|x-3|) = 1.4826 * 1
+    assert O.r_mad(np.array([1.0, 2.0, 3.0, 4.0, 100.0])) == 1.4826
+    # R: mad(c(1,2,3,4)) -> median 2.5, |x-2.5| = 1.5,.5,.5,1.5 -> median 1.0
+    assert O.r_mad(np.array([1.0, 2.0, 3.0, 4.0])) == 1.4826
+    assert O.r_mad(np.array([7.0, 7.0, 7.0, 9.0])) == 0.0
+
+
+def test_median_matches_numpy_on_random_columns():
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 3, 10, 11, 1000, 1001):
+        x = rng.normal(size=n) * 10.0 ** rng.integers(-3, 4)
+        assert O.r_median(x) == np.median(x)
+
+
+def test_quantile_type7_known():
+    x = np.arange(1, 11, dtype=float)
+    np.testing.assert_allclose(O.r_quantile7(x, [0.025, 0.5, 0.975]), [1.225, 5.5, 9.775], rtol=0, atol=1e-12)
+    np.testing.assert_array_equal(O.r_quantile7(x, [0.0, 1.0]), [1.0, 10.0])
+
+
+def test_nacc_is_ceiling_of_double_product():
+    d = np.arange(100, dtype=float)
+    assert O.tolerance_cut(d, 0.01)[0] == 1
+    assert O.tolerance_cut(d, 0.011)[0] == 2
+    assert O.tolerance_cut(np.arange(10_000_000, dtype=float), 0.001)[0] == 10000
+    assert O.tolerance_cut(np.arange(3_000_000, dtype=float), 0.05)[0] == 150000
+
+
+def test_cap_rule_first_nacc_rows_in_row_order():
+    # 10 rows, tol .3 -> nacc 3; sorted dist = 0,1,1,1,... -> ds = 1; four rows have dist <= ds;
+    # R keeps the first three IN ROW ORDER, dropping row 7 (dist 0 < ds!) because it comes last.
+    dist = np.array([1.0, 5.0, 1.0, 9.0, 1.0, 8.0, 7.0, 0.0, 6.0, 4.0])
+    nacc, ds, wt1 = O.tolerance_cut(dist, 0.3)
+    assert (nacc, ds) == (3, 1.0)
+    assert np.flatnonzero(wt1).tolist() == [0, 2, 4]
+    _, _, wt_nocap = O.tolerance_cut(dist, 0.3, cap_rule="none")
+    assert np.flatnonzero(wt_nocap).tolist() == [0, 2, 4, 7]
+
+
+def test_distance_hand_case_and_zero_mad_column():
+    ss = np.array([[1.0, 5.0], [2.0, 5.0], [3.0, 5.0], [4.0, 6.0], [100.0, 5.0]])
+    tgt = np.array([2.0, 5.5])
+    scaled, t, mad, dist = O.scale_and_distance(tgt, ss)
+    assert mad[0] == 1.4826 and mad[1] == 0.0        # second column: mad 0 -> left unscaled
+    np.testing.assert_array_equal(scaled[:, 1], ss[:, 1])
+    assert t[1] == 5.5
+    exp = np.sqrt((ss[:, 0] / 1.4826 - 2.0 / 1.4826) ** 2 + (ss[:, 1] - 5.5) ** 2)
+    np.testing.assert_array_equal(dist, exp)
+
+
+def _tables(n, d, P, seed):
+    rng = np.random.default_rng(seed)
+    lo, hi = rng.uniform(0, 10, P), rng.uniform(20, 1000, P)
+    theta = (lo + (hi - lo) * rng.uniform(size=(n, P))).astype(np.float32).astype(np.float64)
+    ss = (theta[:, np.arange(d) % P] + 0.1 * (hi - lo)[np.arange(d) % P] * rng.normal(size=(n, d))).astype(
+        np.float32).astype(np.float64)
+    target = (lo + 0.37 * (hi - lo))[np.arange(d) % P]
+    return theta, ss, target
+
+
+def test_rejection_is_sort_based_selection():
+    theta, ss, tgt = _tables(5000, 4, 3, 1)
+    r = O.abc(tgt, theta, ss, 0.02, "rejection")
+    order = np.argsort(r.dist, kind="stable")
+    assert r.nacc == 100 and r.idx.size == 100
+    assert set(r.idx.tolist()) == set(order[:100].tolist())   # continuous data: no ties
+    assert np.all(np.diff(r.idx) > 0)
+    np.testing.assert_array_equal(r.unadj_values, theta[r.idx])
+    assert r.ds == np.sort(r.dist)[99]
+
+
+@pytest.mark.parametrize("d,P", [(1, 1), (3, 2), (10, 10)])
+def test_loclinear_matches_centred_normal_equations(d, P):
+    """Second formulation: weighted normal equations centred on the target, solved by Cholesky.  The
+    intercept of the centred fit is the prediction at the target."""
+    theta, ss, tgt = _tables(20000, d, P, 2 + d)
+    r = O.abc(tgt, theta, ss, 0.05, "loclinear")
+    X = (r.ss / r.mad) - (tgt / r.mad)
+    A = np.column_stack([np.ones(len(X)), X])
+    G = (A * r.weights[:, None]).T @ A
+    beta = np.linalg.solve(G, (A * r.weights[:, None]).T @ r.unadj_values)
+    res = r.unadj_values - A @ beta
+    mu = res.mean(axis=0)
+    res = res - mu
+    gam = np.linalg.solve(G, (A * r.weights[:, None]).T @ np.log(res ** 2))
+    adj = (beta[0] + mu) + np.sqrt(np.exp(gam[0])) * res / np.sqrt(np.exp(A @ gam))
+    scale = np.abs(r.adj_values).max(axis=0)
+    assert np.max(np.abs(adj - r.adj_values) / scale) < 1e-10
+    # farthest accepted row has weight exactly 0 (bandwidth = ds)
+    assert r.weights.min() == 0.0 and r.weights.max() <= 1.0
+
+
+def test_invariances():
+    theta, ss, tgt = _tables(4000, 3, 3, 7)
+    base = O.abc(tgt, theta, ss, 0.05, "loclinear")
+    # scaling a summary-statistic column (and its target) by a power of two changes nothing
+    ss2, tgt2 = ss.copy(), tgt.copy()
+    ss2[:, 1] *= 8.0
+    tgt2[1] *= 8.0
+    r2 = O.abc(tgt2, theta, ss2, 0.05, "loclinear")
+    np.testing.assert_array_equal(base.idx, r2.idx)
+    np.testing.assert_array_equal(base.dist, r2.dist)
+    np.testing.assert_allclose(base.adj_values, r2.adj_values, rtol=1e-12)
+    # tol = 1 accepts everything
+    assert O.abc(tgt, theta, ss, 1.0, "rejection").idx.size == 4000
+    # permuting rows (no ties) permutes the accepted set
+    perm = np.random.default_rng(3).permutation(4000)
+    rp = O.abc(tgt, theta[perm], ss[perm], 0.05, "rejection")
+    assert set(perm[rp.idx].tolist()) == set(base.idx.tolist())
+
+
+def test_duplicated_table_doubles_postpr_counts():
+    rng = np.random.default_rng(5)
+    n = 3000
+    ids = np.array(["BNDX", "MNDX", "SNDX"])[np.arange(n) % 3]
+    logits = rng.normal(size=(n, 3)) + 2.0 * (np.arange(3)[None, :] == (np.arange(n) % 3)[:, None])
+    sm = np.round(np.exp(logits) / np.exp(logits).sum(1, keepdims=True), 5)
+    a = O.postpr([0.2, 0.5, 0.3], ids, sm, 0.1)
+    assert a.models == ["BNDX", "MNDX", "SNDX"] and a.counts.sum() == 300
+    b = O.postpr([0.2, 0.5, 0.3], np.concatenate([ids, ids]), np.vstack([sm, sm]), 0.1)
+    assert b.counts.sum() == 600
+
+
+def test_errors_follow_r():
+    theta, ss, tgt = _tables(100, 2, 2, 9)
+    with pytest.raises(O.AbcError, match="Zero variance in the summary statistics\\."):
+        O.abc(tgt, theta, np.ones_like(ss), 0.1, "rejection")
+    with pytest.raises(O.AbcError, match="Number of summary statistics"):
+        O.abc(tgt[:1], theta, ss, 0.1, "rejection")
+    const_region = ss.copy()
+    const_region[:, 0] = np.where(np.arange(100) < 50, 1.0, np.arange(100))
+    const_region[:, 1] = np.where(np.arange(100) < 50, 2.0, 7.0 + np.arange(100))
+    with pytest.raises(O.AbcError, match="selected region"):
+        O.abc(np.array([1.0, 2.0]), theta, const_region, 0.1, "loclinear")
+    with pytest.raises(O.AbcError, match="At least two"):
+        O.postpr([1.0, 2.0], ["a"] * 100, ss, 0.1)
+
+
+def test_summary_rows():
+    theta, ss, tgt = _tables(2000, 1, 1, 11)
+    rej = O.abc(tgt, theta, ss, 0.1, "rejection")
+    tab = O.summary_abc(rej)
+    x = rej.unadj_values[:, 0]
+    assert tab[0, 0] == x.min() and tab[6, 0] == x.max()
+    assert tab[2, 0] == np.quantile(x, 0.5) and math.isclose(tab[3, 0], x.mean(), rel_tol=1e-15)
+    ll = O.abc(tgt, theta, ss, 0.1, "loclinear")
+    tl = O.summary_abc(ll)
+    assert tl[0, 0] == ll.adj_values.min() and tl[6, 0] == ll.adj_values.max()
+    assert tl[1, 0] <= tl[2, 0] <= tl[5, 0]
+
+
+# ---- SMC range rules: the oracle (numpy) against a pandas formulation of the same rules ------------
+def _pandas_rules(pmin, pmax, omin, omax, decrease, increase, hmin, hmax):
+    import pandas as pd
+    new = pd.DataFrame({"min": pmin, "max": pmax})
+    old = pd.DataFrame({"min": omin, "max": omax})
+    new["decrease"] = (new["max"] - new["min"]) / (old["max"] - old["min"])
+    weak = (new["decrease"] > decrease) & (new["decrease"] < 1)
+    new.loc[weak, ["min", "max"]] = old[weak]
+    zero = new["decrease"] == 0
+    new.loc[zero, ["min", "max"]] = old.loc[zero]
+    new["decrease"] = (new["max"] - new["min"]) / (old["max"] - old["min"])
+    new = new.round(3)
+    if increase > 0:
+        pad = (new["max"] - new["min"]) * increase * 0.5
+        sel = new["decrease"] > decrease
+        new.loc[sel, "min"] = (new["min"] - pad)[sel]
+        new.loc[sel, "max"] = (new["max"] + pad)[sel]
+        hard = pd.DataFrame({"min": hmin, "max": hmax})
+        new["min"] = pd.concat([hard["min"], new["min"]], axis=1).max(axis=1)
+        new["max"] = pd.concat([hard["max"], new["max"]], axis=1).min(axis=1)
+        new["decrease"] = (new["max"] - new["min"]) / (old["max"] - old["min"])
+        chk = new.round(3)
+        still = chk["max"] == chk["min"]
+        new.loc[still, "min"] = new.loc[still, "min"] - 10 ** (-3)
+        new.loc[still, "decrease"] = 1.0
+        new = new.round(3)
+    return new
+
+
+@pytest.mark.parametrize("increase", [0.0, 0.01])
+def test_smc_rules_match_pandas_formulation(increase):
+    rng = np.random.default_rng(21)
+    P = 12
+    omin = rng.uniform(0, 10, P)
+    omax = omin + rng.uniform(1, 100, P)
+    frac = rng.uniform(0.3, 1.0, P)
+    pmin = omin + (omax - omin) * (1 - frac) / 2
+    pmax = pmin + (omax - omin) * frac
+    pmin[3], pmax[3] = omin[3], omax[3]                 # decrease == 1 exactly
+    pmin[5] = pmax[5] = omin[5] + 1.0                   # decrease == 0 -> revert
+    pmin[7], pmax[7] = 5.0001, 5.0002                   # collapses after round(3)
+    omin[7], omax[7] = 5.0, 5.001
+    hmin, hmax = omin - 1.0, omax + 0.5
+    nmin, nmax, dec = O.updating_newrange(pmin, pmax, omin, omax, 0.95)
+    if increase > 0:
+        nmin, nmax, dec = O.noise_injection_update(nmin, nmax, dec, omin, omax, increase, hmin, hmax, 0.95)
+    ref = _pandas_rules(pmin, pmax, omin, omax, 0.95, increase, hmin, hmax)
+    np.testing.assert_array_equal(nmin, ref["min"].to_numpy())
+    np.testing.assert_array_equal(nmax, ref["max"].to_numpy())
+    np.testing.assert_array_equal(dec, ref["decrease"].to_numpy())
+
+
+def test_narrowing_and_lmrd():
+    rng = np.random.default_rng(4)
+    par = rng.uniform(0, 1, size=(1000, 3))
+    lines = O.narrowing_params(par, [0.1, 0.2, 0.0], [0.9, 0.8, 1.0])
+    keep = (par[:, 0] >= .1) & (par[:, 0] <= .9) & (par[:, 1] >= .2) & (par[:, 1] <= .8)
+    np.testing.assert_array_equal(lines, np.flatnonzero(keep) + 2)
+    assert math.isclose(O.lmrd_calculation([0, 0], [1, 2], [0, 0], [2, 4]), math.log(0.5))
