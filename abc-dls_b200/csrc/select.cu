@@ -131,6 +131,9 @@ __global__ void __launch_bounds__(kThreads) k_select_pick(SelJob* jobs, unsigned
         return;
     }
     unsigned long long* g = ghist + ((size_t)job * 2 + q) * kBins;
+    // read the query state before any thread may update it (the writer is a single thread below)
+    const long long krem = J.krem[q];
+    const unsigned long long prefix_in = J.prefix[q];
     constexpr int per = kBins / kThreads;  // 8
     long long loc[per];
     long long s = 0;
@@ -162,19 +165,23 @@ __global__ void __launch_bounds__(kThreads) k_select_pick(SelJob* jobs, unsigned
     __syncthreads();
     const long long before = wsum[wid] + incl - s;
     const long long total = wsum[kThreads / 32];
-    const long long krem = J.krem[q];
     const int bits = pass < 5 ? 11 : 9;
     if (krem >= before && krem < before + s) {
         long long a = before;
         int b = 0;
+        bool found = false;
 #pragma unroll
         for (int t = 0; t < per; ++t) {
-            if (krem >= a + loc[t]) {
-                a += loc[t];
-                b = t + 1;
+            if (!found) {
+                if (krem >= a + loc[t]) {
+                    a += loc[t];
+                    b = t + 1;
+                } else {
+                    found = true;
+                }
             }
         }
-        J.prefix[q] = (J.prefix[q] << bits) | (unsigned long long)(threadIdx.x * per + b);
+        J.prefix[q] = (prefix_in << bits) | (unsigned long long)(threadIdx.x * per + b);
         J.krem[q] = krem - a;
     }
     if (threadIdx.x == 0 && (krem < 0 || krem >= total)) J.bad = 1;
