@@ -37,10 +37,19 @@ SIGNATURES = {
     "abcdls_column_mad": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _sz, _vp, _vp]),
     "abcdls_scale_dist": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp]),
     "abcdls_accept_workspace_bytes": (_sz, [_i64]),
-    "abcdls_count_le": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
-    "abcdls_accept": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "abcdls_count_le": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "abcdls_accept": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "abcdls_gather": (_i32, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp,
-                             _vp, _vp, _vp, _vp, _vp, _vp]),
+                             _vp, _vp, _vp, _vp, _vp]),
+    "abcdls_mad_fast_workspace_bytes": (_sz, [_i64, _i32]),
+    "abcdls_mad_fast_sample": (_i32, [_vp, _vp, _i64, _i32, _i64, _i32, _vp, _sz, C.POINTER(_vp), C.POINTER(_sz), _vp]),
+    "abcdls_mad_fast_pass": (_i32, [_vp, _vp, _i64, _i32, _i64, _i32, _vp, _sz, C.POINTER(_vp), C.POINTER(_sz), _vp]),
+    "abcdls_mad_fast_finish": (_i32, [_vp, _i64, _i64, _i32, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "abcdls_dist_fast_workspace_bytes": (_sz, [_i64, _i64]),
+    "abcdls_dist_fast_sample": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _i64, _i64, _i32, _i64, _vp, _sz,
+                                       C.POINTER(_vp), C.POINTER(_sz), _vp]),
+    "abcdls_dist_fast_pass": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _i64, _i32, _i64, _i64, _vp, _vp, _vp,
+                                     _vp, _vp, _vp, _sz, _vp, _vp]),
     "abcdls_normal_workspace_bytes": (_sz, [_i32, _i32]),
     "abcdls_normal": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "abcdls_solve": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),

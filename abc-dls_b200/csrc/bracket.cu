@@ -1,0 +1,979 @@
+// bracket.cu — the two table-streaming kernels of the fast path and their small finalisers.
+//
+// Exact order statistics without sorting the table:
+//   1. a random sample of every column (resp. of row distances) is sorted in shared memory and gives a
+//      narrow *bracket* that contains the wanted order statistic with overwhelming probability;
+//   2. ONE pass over the table counts the elements on either side of the brackets, appends the few
+//      percent that fall inside to a candidate buffer and builds a fine histogram of the bracket;
+//   3. the histogram locates the 1/1024-th of the bracket that holds the wanted rank, those few values are
+//      gathered and sorted in shared memory -> the exact order statistic;
+//   4. every step is verified from the counts; a miss only sets ABCDLS_S_FASTPATH_MISS (the caller reruns
+//      with the 6-pass radix select of select.cu).  Results are therefore always exact or flagged.
+//
+// Pass A (k_bracket_pass)  : median band M and the two MAD bands L, R of all d columns in one read.
+// Pass B (k_dist_pass)     : MAD-scaled Euclidean distance of every row fused with the tolerance bracket:
+//                            rows with dist <= hi are emitted (row, dist) tile by tile; the N-vector `dist`
+//                            is only written when the caller asks for it.
+#include "common.cuh"
+#include "compact.cuh"
+
+namespace {
+
+constexpr int kNB = 1024;          // fine histogram bins per bracket
+constexpr int kSample = 4096;      // sample size sorted per CTA
+constexpr int kSmallCap = 8192;    // values gathered for the final in-smem sort
+constexpr int kMaxD = 64;
+
+// ---------------------------------------------------------------------------------------------------
+// shared-memory bitonic sort of n = power of two doubles
+__device__ void bitonic_sort(double* s, int n) {
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    double a = s[i], b = s[ixj];
+                    bool up = ((i & k) == 0);
+                    if ((a > b) == up) {
+                        s[i] = b;
+                        s[ixj] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ unsigned hash3(unsigned a, unsigned b, unsigned c) {
+    unsigned h = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA77u ^ (c + 0x165667B1u) * 0xC2B2AE3Du;
+    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+    return h;
+}
+
+// random row in [0, n): 32-byte sectors of 4 consecutive doubles are drawn, so a 4096-sample costs 1024 sectors
+__device__ __forceinline__ long long sample_row(unsigned seed, unsigned cta, int t, long long n) {
+    unsigned h = hash3(seed, cta, (unsigned)(t >> 2));
+    long long nsec = (n + 3) >> 2;
+    long long sec = (long long)(((unsigned long long)h * (unsigned long long)nsec) >> 32);
+    long long r = sec * 4 + (t & 3);
+    return r < n ? r : n - 1;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1: per-column sample -> local estimates (m_lo, m_hi, r_lo, r_hi).  grid (G, d), 512 threads.
+__global__ void __launch_bounds__(512) k_sample_cols(const double* __restrict__ ss, long long n, long long ld,
+                                                     unsigned seed, double delta, double* __restrict__ est) {
+    extern __shared__ double sm[];
+    double* s = sm;            // kSample
+    double* a = sm + kSample;  // kSample
+    const int j = blockIdx.y;
+    const double* col = ss + (size_t)j * ld;
+    for (int t = threadIdx.x; t < kSample; t += blockDim.x) s[t] = col[sample_row(seed + 977u * j, blockIdx.x, t, n)];
+    __syncthreads();
+    bitonic_sort(s, kSample);
+    const double mhat = s[kSample / 2];
+    for (int t = threadIdx.x; t < kSample; t += blockDim.x) a[t] = fabs(s[t] - mhat);
+    __syncthreads();
+    bitonic_sort(a, kSample);
+    if (threadIdx.x == 0) {
+        int il = (int)floor((0.5 - delta) * kSample), ih = (int)ceil((0.5 + delta) * kSample);
+        il = max(0, min(kSample - 1, il));
+        ih = max(0, min(kSample - 1, ih));
+        double* o = est + ((size_t)blockIdx.x * gridDim.y + j) * 4;
+        o[0] = s[il];
+        o[1] = s[ih];
+        o[2] = a[il];
+        o[3] = a[ih];
+    }
+}
+
+struct ColBrk {
+    double b[6];     // L = [b0,b1], M = [b2,b3], R = [b4,b5]
+    double scaleM;   // kNB / (b3 - b2)   (0 when the band is a single point)
+};
+
+// K1b: average the G local estimates (already summed over ranks when world > 1) -> brackets. 1 thread/column.
+__global__ void k_make_brackets(const double* __restrict__ est, int G, int d, double inv_world, ColBrk* __restrict__ brk) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= d) return;
+    double m[4] = {0, 0, 0, 0};
+    for (int g = 0; g < G; ++g)
+        for (int q = 0; q < 4; ++q) m[q] += est[((size_t)g * d + j) * 4 + q];
+    for (int q = 0; q < 4; ++q) m[q] = m[q] / G * inv_world;
+    ColBrk B;
+    B.b[0] = m[0] - m[3];
+    B.b[1] = m[1] - m[2];
+    B.b[2] = m[0];
+    B.b[3] = m[1];
+    B.b[4] = m[0] + m[2];
+    B.b[5] = m[1] + m[3];
+    double w = B.b[3] - B.b[2];
+    B.scaleM = (w > 0.0) ? (double)kNB / w : 0.0;
+    brk[j] = B;
+}
+
+__device__ __forceinline__ int bin_of(double v, double lo, double scale) {
+    double t = (v - lo) * scale;
+    int b = (int)t;                      // v >= lo inside the band, so t >= 0
+    return b < 0 ? 0 : (b >= kNB ? kNB - 1 : b);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2: pass A.  grid (gx, d), 256 threads; a CTA streams tiles of 2048 elements of ONE column.
+// counts[j*4 + {0: x<b2, 1: x in M, 2: b1<x<b4, 3: x in L u R}], histM[j][kNB] over M,
+// candM[j][capM] (values in M), candU[j][capU] (values in L u R); cnt[j*2 + {0,1}] = entries appended.
+constexpr int kAThreads = 256;
+constexpr int kAItems = 8;
+constexpr int kATile = kAThreads * kAItems;
+
+__global__ void __launch_bounds__(kAThreads) k_bracket_pass(const double* __restrict__ ss, long long n, long long ld,
+                                                            const ColBrk* __restrict__ brk,
+                                                            unsigned long long* __restrict__ counts,
+                                                            unsigned long long* __restrict__ histM,
+                                                            double* __restrict__ candM, long long capM,
+                                                            double* __restrict__ candU, long long capU,
+                                                            unsigned long long* __restrict__ cnt) {
+    __shared__ unsigned hist[kNB];
+    __shared__ int scan_sh[33];
+    __shared__ unsigned long long base_sh[2];
+    const int j = blockIdx.y;
+    const double* __restrict__ col = ss + (size_t)j * ld;
+    const ColBrk B = brk[j];
+    const double b0 = B.b[0], b1 = B.b[1], b2 = B.b[2], b3 = B.b[3], b4 = B.b[4], b5 = B.b[5];
+    const double scaleM = B.scaleM;
+    for (int t = threadIdx.x; t < kNB; t += kAThreads) hist[t] = 0u;
+    __syncthreads();
+    // 16-byte loads need an even element offset from a 16-byte aligned address
+    const bool vec = ((reinterpret_cast<uintptr_t>(col) & 15) == 0);
+    unsigned c_lt = 0, c_m = 0, c_in = 0, c_u = 0;
+    const long long ntiles = (n + kATile - 1) / kATile;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long t0 = tile * kATile;
+        double x[kAItems];
+        if (vec && t0 + kATile <= n) {
+#pragma unroll
+            for (int u = 0; u < kAItems / 2; ++u) {
+                double2 v = ld_stream2(col + t0 + (long long)u * (2 * kAThreads) + 2 * threadIdx.x);
+                x[2 * u] = v.x;
+                x[2 * u + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < kAItems; ++u) {
+                long long i = t0 + (long long)u * kAThreads + threadIdx.x;
+                x[u] = i < n ? ld_stream(col + i) : __longlong_as_double(0x7ff8000000000000ll);  // NaN: no class
+            }
+        }
+        unsigned mM = 0, mU = 0;
+#pragma unroll
+        for (int u = 0; u < kAItems; ++u) {
+            const double v = x[u];
+            const bool ge0 = v >= b0, le1 = v <= b1, ge2 = v >= b2, le3 = v <= b3, ge4 = v >= b4, le5 = v <= b5;
+            const bool inM = ge2 && le3;
+            const bool inU = (ge0 && le1) || (ge4 && le5);
+            c_lt += (v < b2) ? 1u : 0u;
+            c_m += inM ? 1u : 0u;
+            c_in += (v > b1 && v < b4) ? 1u : 0u;
+            c_u += inU ? 1u : 0u;
+            mM |= inM ? (1u << u) : 0u;
+            mU |= inU ? (1u << u) : 0u;
+        }
+        const int nM = __popc(mM), nU = __popc(mU);
+        if (__syncthreads_or((int)(mM | mU))) {
+            int tot;
+            int ex = block_exclusive_scan(nM | (nU << 16), scan_sh, &tot);
+            if (threadIdx.x == 0) {
+                base_sh[0] = (tot & 0xffff) ? atomicAdd(&cnt[j * 2 + 0], (unsigned long long)(tot & 0xffff)) : 0ull;
+                base_sh[1] = (tot >> 16) ? atomicAdd(&cnt[j * 2 + 1], (unsigned long long)(tot >> 16)) : 0ull;
+            }
+            __syncthreads();
+            long long pM = (long long)base_sh[0] + (ex & 0xffff), pU = (long long)base_sh[1] + (ex >> 16);
+#pragma unroll
+            for (int u = 0; u < kAItems; ++u) {
+                if (mM & (1u << u)) {
+                    if (pM < capM) candM[(size_t)j * capM + pM] = x[u];
+                    ++pM;
+                    atomicAdd(&hist[bin_of(x[u], b2, scaleM)], 1u);
+                }
+                if (mU & (1u << u)) {
+                    if (pU < capU) candU[(size_t)j * capU + pU] = x[u];
+                    ++pU;
+                }
+            }
+        }
+    }
+    // block totals -> global counts (4 per column)
+    c_lt = warp_sum(c_lt); c_m = warp_sum(c_m); c_in = warp_sum(c_in); c_u = warp_sum(c_u);
+    __shared__ unsigned tot4[4];
+    if (threadIdx.x < 4) tot4[threadIdx.x] = 0u;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&tot4[0], c_lt); atomicAdd(&tot4[1], c_m); atomicAdd(&tot4[2], c_in); atomicAdd(&tot4[3], c_u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 4 && tot4[threadIdx.x]) atomicAdd(&counts[j * 4 + threadIdx.x], (unsigned long long)tot4[threadIdx.x]);
+    for (int t = threadIdx.x; t < kNB; t += kAThreads)
+        if (hist[t]) atomicAdd(&histM[(size_t)j * kNB + t], (unsigned long long)hist[t]);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// refinement of one bracket: histogram -> the few bins that hold the wanted ranks -> gather -> sort.
+struct RefJob {
+    const double* src;                    // candidate values
+    const unsigned long long* src_count;  // entries appended (may exceed src_cap => miss)
+    long long src_cap;
+    int transform;                        // 1: v = |x - center|
+    int valid;                            // 0 => the bracket missed; results are NaN and MISS is flagged
+    double center;
+    double lo, scale;                     // bin(v) = clamp(int((v - lo) * scale))
+    double vmin;                          // values below vmin are outside the bracket (not binned / gathered)
+    long long kk[2];                      // 0-based ranks inside the bracket
+    int nq;
+    int bq[2];                            // bins holding kk[0], kk[1]          (filled by k_refine_pick)
+    long long before;                     // number of bracket values in bins < bq[0]
+    unsigned long long* hist;             // [kNB]
+    double* small;                        // [kSmallCap]
+    unsigned* small_count;
+    double result[2];
+};
+
+// one block per job: locate the bins.  (after the histogram is complete / all-reduced)
+__global__ void __launch_bounds__(256) k_refine_pick(RefJob* jobs, int* status) {
+    RefJob& J = jobs[blockIdx.x];
+    __shared__ long long wsum[9];
+    __shared__ int bsel[2];
+    __shared__ long long bbefore[2];
+    const long long kk0 = J.kk[0], kk1 = J.kk[1];
+    const bool valid = J.valid != 0;
+    if (threadIdx.x < 2) { bsel[threadIdx.x] = -1; bbefore[threadIdx.x] = 0; }
+    constexpr int per = kNB / 256;
+    long long loc[per], s = 0;
+#pragma unroll
+    for (int t = 0; t < per; ++t) { loc[t] = (long long)J.hist[threadIdx.x * per + t]; s += loc[t]; }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    long long incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long a = 0;
+        for (int w = 0; w < 8; ++w) { long long t = wsum[w]; wsum[w] = a; a += t; }
+        wsum[8] = a;
+    }
+    __syncthreads();
+    const long long before = wsum[wid] + incl - s;
+    for (int q = 0; q < 2; ++q) {
+        const long long kk = q ? kk1 : kk0;
+        if (kk >= before && kk < before + s) {
+            long long a = before;
+            int b = 0;
+            bool found = false;
+#pragma unroll
+            for (int t = 0; t < per; ++t) {
+                if (!found) {
+                    if (kk >= a + loc[t]) { a += loc[t]; b = t + 1; } else found = true;
+                }
+            }
+            bsel[q] = threadIdx.x * per + b;
+            bbefore[q] = a;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        bool ok = valid && bsel[0] >= 0 && bsel[1] >= 0 && kk0 >= 0 && kk1 >= kk0;
+        J.bq[0] = ok ? bsel[0] : -1;
+        J.bq[1] = ok ? bsel[1] : -1;
+        J.before = bbefore[0];
+        if (!ok) {
+            J.valid = 0;
+            atomicOr(status, ABCDLS_S_FASTPATH_MISS);
+        }
+        *J.small_count = 0u;
+    }
+}
+
+// grid (gx, njobs): append the values that fall in bins [bq0, bq1] to J.small
+__global__ void __launch_bounds__(256) k_refine_gather(RefJob* jobs, long long n_max) {
+    RefJob& J = jobs[blockIdx.y];
+    if (!J.valid) return;
+    long long n = (long long)*J.src_count;
+    if (n > J.src_cap) n = J.src_cap;   // overflow was flagged by the plan kernel
+    if (n > n_max) n = n_max;
+    const int b0 = J.bq[0], b1 = J.bq[1];
+    const double lo = J.lo, scale = J.scale, c = J.center, vmin = J.vmin;
+    const bool tr = J.transform != 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double x = J.src[i];
+        double v = tr ? fabs(__dsub_rn(x, c)) : x;
+        if (v >= vmin) {
+            int b = bin_of(v, lo, scale);
+            if (b >= b0 && b <= b1) {
+                unsigned p = atomicAdd(J.small_count, 1u);
+                if (p < (unsigned)kSmallCap) J.small[p] = v;
+            }
+        }
+    }
+}
+
+// one block (1024 threads) per job: sort the gathered values, read the ranks.
+__global__ void __launch_bounds__(1024) k_refine_final(RefJob* jobs, int* status) {
+    extern __shared__ double sm[];
+    RefJob& J = jobs[blockIdx.x];
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    const unsigned cnt = *J.small_count;
+    bool ok = J.valid && cnt <= (unsigned)kSmallCap && cnt > 0;
+    long long r0 = J.kk[0] - J.before, r1 = J.kk[1] - J.before;
+    ok = ok && r0 >= 0 && r1 < (long long)cnt;
+    if (!ok) {
+        if (threadIdx.x == 0) {
+            J.result[0] = J.result[1] = nan;
+            atomicOr(status, ABCDLS_S_FASTPATH_MISS);
+        }
+        return;
+    }
+    int np2 = 32;
+    while (np2 < (int)cnt) np2 <<= 1;
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    for (int t = threadIdx.x; t < np2; t += blockDim.x) sm[t] = t < (int)cnt ? J.small[t] : inf;
+    __syncthreads();
+    bitonic_sort(sm, np2);
+    if (threadIdx.x == 0) {
+        J.result[0] = sm[r0];
+        J.result[1] = sm[r1];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// plans (1 thread per column).  k0/k1: global 0-based ranks of the two middle order statistics.
+__global__ void k_plan_median(RefJob* jobs, int d, const ColBrk* __restrict__ brk,
+                              const unsigned long long* __restrict__ counts, unsigned long long* histM,
+                              const double* candM, long long capM, const unsigned long long* cnt, double* small,
+                              unsigned* small_count, long long k0, long long k1, int* status) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= d) return;
+    RefJob J;
+    const long long c_lt = (long long)counts[j * 4 + 0], c_m = (long long)counts[j * 4 + 1];
+    J.src = candM + (size_t)j * capM;
+    J.src_count = cnt + j * 2 + 0;
+    J.src_cap = capM;
+    J.transform = 0;
+    J.center = 0.0;
+    J.lo = brk[j].b[2];
+    J.scale = brk[j].scaleM;
+    J.vmin = -__longlong_as_double(0x7ff0000000000000ll);
+    J.kk[0] = k0 - c_lt;
+    J.kk[1] = k1 - c_lt;
+    J.nq = 2;
+    J.bq[0] = J.bq[1] = -1;
+    J.before = 0;
+    J.hist = histM + (size_t)j * kNB;
+    J.small = small + (size_t)j * kSmallCap;
+    J.small_count = small_count + j;
+    J.result[0] = J.result[1] = 0.0;
+    // the band must contain both ranks and every band value must have been stored
+    J.valid = (J.kk[0] >= 0 && J.kk[1] < c_m && (long long)cnt[j * 2 + 0] <= capM) ? 1 : 0;
+    if (!J.valid) atomicOr(status, ABCDLS_S_FASTPATH_MISS);
+    jobs[j] = J;
+}
+
+// after the medians are exact: med[j] = 0.5*r0 + 0.5*r1; prepare the |x - med| refinement over L u R
+__global__ void k_plan_mad(RefJob* jobs, int d, const ColBrk* __restrict__ brk,
+                           const unsigned long long* __restrict__ counts, unsigned long long* histU,
+                           const double* candU, long long capU, const unsigned long long* cnt, double* small,
+                           unsigned* small_count, long long k0, long long k1, double* __restrict__ med,
+                           double* __restrict__ guard, int* status) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= d) return;
+    const RefJob& Jm = jobs[j];
+    const double m = __dadd_rn(__dmul_rn(0.5, Jm.result[0]), __dmul_rn(0.5, Jm.result[1]));
+    med[j] = m;
+    const ColBrk B = brk[j];
+    RefJob J;
+    const long long c_in = (long long)counts[j * 4 + 2], c_u = (long long)counts[j * 4 + 3];
+    J.src = candU + (size_t)j * capU;
+    J.src_count = cnt + j * 2 + 1;
+    J.src_cap = capU;
+    J.transform = 1;
+    J.center = m;
+    // |x - m| of the stored values spans [alo, ahi]
+    const bool overlap = !(B.b[1] < B.b[4]);
+    double alo = overlap ? 0.0 : fmax(0.0, fmin(m - B.b[1], B.b[4] - m));
+    double ahi = fmax(m - B.b[0], B.b[5] - m);
+    J.lo = alo;
+    J.scale = (ahi > alo) ? (double)kNB / (ahi - alo) : 0.0;
+    J.vmin = -__longlong_as_double(0x7ff0000000000000ll);
+    J.kk[0] = k0 - c_in;
+    J.kk[1] = k1 - c_in;
+    J.nq = 2;
+    J.bq[0] = J.bq[1] = -1;
+    J.before = 0;
+    J.hist = histU + (size_t)j * kNB;
+    J.small = small + (size_t)(d + j) * kSmallCap;
+    J.small_count = small_count + d + j;
+    J.result[0] = J.result[1] = 0.0;
+    J.valid = (Jm.valid && J.kk[0] >= 0 && J.kk[1] < c_u && (long long)cnt[j * 2 + 1] <= capU) ? 1 : 0;
+    if (!J.valid) atomicOr(status, ABCDLS_S_FASTPATH_MISS);
+    // guards checked once r* is known: every inner value has |x-m| <= r*, every outer value >= r*
+    guard[j * 2 + 0] = overlap ? -1.0 : fmax(fabs(__dsub_rn(B.b[1], m)), fabs(__dsub_rn(B.b[4], m)));
+    guard[j * 2 + 1] = fmin(fabs(__dsub_rn(B.b[0], m)), fabs(__dsub_rn(B.b[5], m)));
+    if (!(B.b[0] <= m && m <= B.b[5])) {
+        J.valid = 0;
+        atomicOr(status, ABCDLS_S_FASTPATH_MISS);
+    }
+    jobs[d + j] = J;
+}
+
+// histogram of v = |x - center| (or x) of the candidates of every job.  grid (gx, njobs)
+__global__ void __launch_bounds__(256) k_refine_hist(RefJob* jobs, long long n_max) {
+    __shared__ unsigned hist[kNB];
+    RefJob& J = jobs[blockIdx.y];
+    if (!J.valid) return;
+    for (int t = threadIdx.x; t < kNB; t += blockDim.x) hist[t] = 0u;
+    __syncthreads();
+    long long n = (long long)*J.src_count;
+    if (n > J.src_cap) n = J.src_cap;
+    if (n > n_max) n = n_max;
+    const double lo = J.lo, scale = J.scale, c = J.center, vmin = J.vmin;
+    const bool tr = J.transform != 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double x = J.src[i];
+        double v = tr ? fabs(__dsub_rn(x, c)) : x;
+        if (v >= vmin) atomicAdd(&hist[bin_of(v, lo, scale)], 1u);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < kNB; t += blockDim.x)
+        if (hist[t]) atomicAdd(&J.hist[t], (unsigned long long)hist[t]);
+}
+
+__global__ void k_finish_mad(const RefJob* jobs, int d, const double* __restrict__ guard, double* __restrict__ mad,
+                             int* status) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= d) return;
+    const RefJob& J = jobs[d + j];
+    const double r0 = J.result[0], r1 = J.result[1];
+    // r0 <= r1 are the two middle order statistics of |x - med|
+    const bool ok = J.valid && (guard[j * 2 + 0] <= r0) && (guard[j * 2 + 1] >= r1);
+    if (!ok) atomicOr(status, ABCDLS_S_FASTPATH_MISS);
+    mad[j] = __dmul_rn(1.4826, __dadd_rn(__dmul_rn(0.5, r0), __dmul_rn(0.5, r1)));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// distance: shared scaling constants
+struct ColScale {
+    double div[kMaxD], rcp[kMaxD], tgt[kMaxD], lo[kMaxD], hi[kMaxD];
+};
+
+__device__ __forceinline__ void load_scale(ColScale& S, const double* mad, const double* target, int d) {
+    for (int j = threadIdx.x; j < d; j += blockDim.x) {
+        double m = mad[j];
+        double dv = (m == 0.0) ? 1.0 : m;
+        S.div[j] = dv;
+        S.rcp[j] = 1.0 / dv;
+        S.tgt[j] = (m == 0.0) ? target[j] : target[j] / dv;
+        double a = fabs(dv);
+        bool sane = a > 1e-290 && a < 1e290;
+        S.lo[j] = sane ? a * 1e-280 + 1e-280 : __longlong_as_double(0x7ff0000000000000ll);
+        S.hi[j] = sane ? fmin(a * 1e280, 1e280) : 0.0;
+    }
+}
+
+__device__ __forceinline__ double scaled_value(double x, const ColScale& S, int j) {
+    double ax = fabs(x);
+    if ((ax > S.lo[j] && ax < S.hi[j]) || x == 0.0) return div_const(x, S.div[j], S.rcp[j]);
+    return x / S.div[j];
+}
+
+// K6: distances of a random sample of rows -> local estimates (lo, hi) of the nacc-th smallest distance.
+// grid G, 512 threads; est[g*2 + {0,1}]
+__global__ void __launch_bounds__(512) k_sample_dist(const double* __restrict__ ss, long long n, int d, long long ld,
+                                                     const double* __restrict__ mad, const double* __restrict__ target,
+                                                     unsigned seed, double p, double delta, double* __restrict__ est) {
+    extern __shared__ double sm[];
+    __shared__ ColScale S;
+    load_scale(S, mad, target, d);
+    __syncthreads();
+    for (int t = threadIdx.x; t < kSample; t += blockDim.x) {
+        long long r = sample_row(seed, blockIdx.x, t, n);
+        double s0 = 0.0;
+        for (int j = 0; j < d; ++j) {
+            double a = __dsub_rn(scaled_value(ss[(size_t)j * ld + r], S, j), S.tgt[j]);
+            s0 = __dadd_rn(s0, __dmul_rn(a, a));
+        }
+        sm[t] = __dsqrt_rn(s0);
+    }
+    __syncthreads();
+    bitonic_sort(sm, kSample);
+    if (threadIdx.x == 0) {
+        int il = (int)floor((p - delta) * kSample) - 1, ih = (int)ceil((p + delta) * kSample) + 1;
+        il = max(0, min(kSample - 1, il));
+        ih = max(0, min(kSample - 1, ih));
+        est[blockIdx.x * 2 + 0] = (il == 0) ? 0.0 : sm[il];
+        est[blockIdx.x * 2 + 1] = sm[ih];
+    }
+}
+
+struct DistBrk {
+    double lo, hi, scale;
+};
+
+__global__ void k_make_dist_bracket(const double* __restrict__ est, int G, double inv_world, DistBrk* brk) {
+    if (threadIdx.x || blockIdx.x) return;
+    double lo = 0, hi = 0;
+    for (int g = 0; g < G; ++g) { lo += est[g * 2]; hi += est[g * 2 + 1]; }
+    lo = lo / G * inv_world;
+    hi = hi / G * inv_world;
+    brk->lo = lo;
+    brk->hi = hi;
+    brk->scale = (hi > lo) ? (double)kNB / (hi - lo) : 0.0;
+}
+
+// K7: pass B.  Tile = 512 rows (256 threads x 2 consecutive rows); every tile appends its candidate rows
+// (dist <= hi) in row order and records (offset, count) in the tile directory.
+constexpr int kBThreads = 256;
+constexpr int kBTile = 2 * kBThreads;
+
+template <bool VEC2, bool WRITE_DIST>
+__global__ void __launch_bounds__(kBThreads) k_dist_pass(const double* __restrict__ ss, long long n, int d, long long ld,
+                                                         const double* __restrict__ mad, const double* __restrict__ target,
+                                                         const DistBrk* __restrict__ brk, double* __restrict__ dist,
+                                                         long long* __restrict__ cand_row, double* __restrict__ cand_dist,
+                                                         long long cap, unsigned long long* __restrict__ cand_cnt,
+                                                         unsigned long long* __restrict__ n_lt,
+                                                         unsigned long long* __restrict__ hist_g,
+                                                         long long* __restrict__ tile_off, int* __restrict__ tile_cnt,
+                                                         int* status) {
+    __shared__ ColScale S;
+    __shared__ unsigned hist[kNB];
+    __shared__ int scan_sh[33];
+    __shared__ unsigned long long base_sh;
+    load_scale(S, mad, target, d);
+    for (int t = threadIdx.x; t < kNB; t += kBThreads) hist[t] = 0u;
+    __syncthreads();
+    const double lo = brk->lo, hi = brk->hi, scale = brk->scale;
+    const long long ntiles = (n + kBTile - 1) / kBTile;
+    bool nonfinite = false;
+    unsigned c_lt = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long i0 = tile * kBTile + 2 * threadIdx.x;
+        double s0 = 0.0, s1 = 0.0;
+        const bool full = VEC2 && (i0 + 1 < n);
+        if (full) {
+            const double* col = ss + i0;
+#pragma unroll 8
+            for (int j = 0; j < d; ++j) {
+                double2 x = ld_stream2(col);
+                col += ld;
+                const double tj = S.tgt[j];
+                const double a = __dsub_rn(scaled_value(x.x, S, j), tj);
+                const double b = __dsub_rn(scaled_value(x.y, S, j), tj);
+                s0 = __dadd_rn(s0, __dmul_rn(a, a));
+                s1 = __dadd_rn(s1, __dmul_rn(b, b));
+            }
+        } else {
+            for (int j = 0; j < d; ++j) {
+                const double tj = S.tgt[j];
+                if (i0 < n) {
+                    const double a = __dsub_rn(scaled_value(ss[(size_t)j * ld + i0], S, j), tj);
+                    s0 = __dadd_rn(s0, __dmul_rn(a, a));
+                }
+                if (i0 + 1 < n) {
+                    const double b = __dsub_rn(scaled_value(ss[(size_t)j * ld + i0 + 1], S, j), tj);
+                    s1 = __dadd_rn(s1, __dmul_rn(b, b));
+                }
+            }
+        }
+        const double d0 = __dsqrt_rn(s0), d1 = __dsqrt_rn(s1);
+        const bool v0 = i0 < n, v1 = i0 + 1 < n;
+        nonfinite |= (v0 && !isfinite(d0)) || (v1 && !isfinite(d1));
+        if (WRITE_DIST) {
+            if (full && VEC2) *reinterpret_cast<double2*>(dist + i0) = make_double2(d0, d1);
+            else {
+                if (v0) dist[i0] = d0;
+                if (v1) dist[i0 + 1] = d1;
+            }
+        }
+        const bool c0 = v0 && d0 <= hi, c1 = v1 && d1 <= hi;
+        c_lt += (v0 && d0 < lo) ? 1u : 0u;
+        c_lt += (v1 && d1 < lo) ? 1u : 0u;
+        const int nc = (c0 ? 1 : 0) + (c1 ? 1 : 0);
+        if (__syncthreads_or(nc)) {
+            int tot;
+            int ex = block_exclusive_scan(nc, scan_sh, &tot);
+            if (threadIdx.x == 0) {
+                unsigned long long b = atomicAdd(cand_cnt, (unsigned long long)tot);
+                base_sh = b;
+                tile_off[tile] = (long long)b;
+                tile_cnt[tile] = tot;
+            }
+            __syncthreads();
+            long long pos = (long long)base_sh + ex;
+            if (c0) {
+                if (pos < cap) { cand_row[pos] = i0; cand_dist[pos] = d0; }
+                ++pos;
+                if (d0 >= lo) atomicAdd(&hist[bin_of(d0, lo, scale)], 1u);
+            }
+            if (c1) {
+                if (pos < cap) { cand_row[pos] = i0 + 1; cand_dist[pos] = d1; }
+                if (d1 >= lo) atomicAdd(&hist[bin_of(d1, lo, scale)], 1u);
+            }
+        } else if (threadIdx.x == 0) {
+            tile_off[tile] = 0;
+            tile_cnt[tile] = 0;
+        }
+    }
+    c_lt = warp_sum(c_lt);
+    if ((threadIdx.x & 31) == 0 && c_lt) atomicAdd(n_lt, (unsigned long long)c_lt);
+    if (__any_sync(0xffffffffu, nonfinite) && (threadIdx.x & 31) == 0) atomicOr(status, ABCDLS_S_NONFINITE);
+    __syncthreads();
+    for (int t = threadIdx.x; t < kNB; t += kBThreads)
+        if (hist[t]) atomicAdd(&hist_g[t], (unsigned long long)hist[t]);
+}
+
+// K8: bring the tile chunks into row order.  tile_pos = exclusive scan of tile_cnt (k_scan_tiles).
+__global__ void __launch_bounds__(256) k_order_cands(const long long* __restrict__ tile_off, const int* __restrict__ tile_cnt,
+                                                     const long long* __restrict__ tile_pos, long long ntiles,
+                                                     const long long* __restrict__ row_in, const double* __restrict__ dist_in,
+                                                     long long cap, long long row_offset, long long* __restrict__ row_out,
+                                                     double* __restrict__ dist_out) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < ntiles; t += stride) {
+        const int c = tile_cnt[t];
+        const long long src = tile_off[t], dst = tile_pos[t];
+        for (int e = 0; e < c; ++e) {
+            if (src + e < cap && dst + e < cap) {
+                row_out[dst + e] = row_in[src + e] + row_offset;
+                dist_out[dst + e] = dist_in[src + e];
+            }
+        }
+    }
+}
+
+__global__ void k_plan_ds(RefJob* job, const DistBrk* __restrict__ brk, const unsigned long long* __restrict__ n_lt,
+                          const unsigned long long* __restrict__ cand_cnt, unsigned long long* hist,
+                          const double* cand_dist, long long cap, double* small, unsigned* small_count, long long k,
+                          int* status) {
+    if (threadIdx.x || blockIdx.x) return;
+    RefJob J;
+    const long long c_lt = (long long)*n_lt, c_all = (long long)*cand_cnt;
+    J.src = cand_dist;
+    J.src_count = cand_cnt;
+    J.src_cap = cap;
+    J.transform = 0;
+    J.center = 0.0;
+    J.lo = brk->lo;
+    J.scale = brk->scale;
+    J.vmin = brk->lo;
+    J.kk[0] = J.kk[1] = k - c_lt;
+    J.nq = 1;
+    J.bq[0] = J.bq[1] = -1;
+    J.before = 0;
+    J.hist = hist;
+    J.small = small;
+    J.small_count = small_count;
+    J.result[0] = J.result[1] = 0.0;
+    J.valid = (k >= c_lt && k < c_all && c_all <= cap) ? 1 : 0;
+    if (!J.valid) atomicOr(status, ABCDLS_S_FASTPATH_MISS);
+    *job = J;
+}
+
+__global__ void k_copy_result(const RefJob* job, double* out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = job->result[0];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// workspace carving
+struct MadWs {
+    double* est;                    // [G*d*4]
+    ColBrk* brk;                    // [d]
+    unsigned long long* counts;     // [d*4]      | zeroed together
+    unsigned long long* cnt;        // [d*2]      |
+    unsigned long long* histM;      // [d*kNB]    |
+    unsigned long long* histU;      // [d*kNB]    |
+    unsigned* small_count;          // [2d]       |
+    size_t zero_bytes;
+    RefJob* jobs;                   // [2d]
+    double* guard;                  // [2d]
+    double* small;                  // [2d*kSmallCap]
+    double* candM;                  // [d*capM]
+    double* candU;                  // [d*capU]
+    size_t total;
+};
+
+inline MadWs carve_mad(void* ws, int d, int G, long long capM, long long capU) {
+    MadWs w;
+    char* p = reinterpret_cast<char*>(ws);
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t a = o; o += align_up(bytes, 256); return p ? p + a : (char*)nullptr; };
+    w.est = (double*)take((size_t)G * d * 4 * 8);
+    w.brk = (ColBrk*)take((size_t)d * sizeof(ColBrk));
+    size_t z0 = o;
+    w.counts = (unsigned long long*)take((size_t)d * 4 * 8);
+    w.cnt = (unsigned long long*)take((size_t)d * 2 * 8);
+    w.histM = (unsigned long long*)take((size_t)d * kNB * 8);
+    w.histU = (unsigned long long*)take((size_t)d * kNB * 8);
+    w.small_count = (unsigned*)take((size_t)2 * d * 4);
+    w.zero_bytes = o - z0;
+    w.jobs = (RefJob*)take((size_t)2 * d * sizeof(RefJob));
+    w.guard = (double*)take((size_t)2 * d * 8);
+    w.small = (double*)take((size_t)2 * d * kSmallCap * 8);
+    w.candM = (double*)take((size_t)d * capM * 8);
+    w.candU = (double*)take((size_t)d * capU * 8);
+    w.total = o;
+    return w;
+}
+
+struct DistWs {
+    double* est;                   // [G*2]
+    DistBrk* brk;
+    unsigned long long* cand_cnt;  // | zeroed together
+    unsigned long long* n_lt;      // |
+    unsigned long long* hist;      // | [kNB]
+    unsigned* small_count;         // |
+    size_t zero_bytes;
+    RefJob* job;
+    double* small;                 // [kSmallCap]
+    long long* tile_off;           // [ntiles]
+    int* tile_cnt;                 // [ntiles]
+    long long* tile_pos;           // [ntiles]
+    long long* row_tmp;            // [cap]
+    double* dist_tmp;              // [cap]
+    size_t total;
+};
+
+inline long long dist_tiles(long long n) { return (n + kBTile - 1) / kBTile; }
+
+inline DistWs carve_dist(void* ws, int G, long long n, long long cap) {
+    DistWs w;
+    char* p = reinterpret_cast<char*>(ws);
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t a = o; o += align_up(bytes, 256); return p ? p + a : (char*)nullptr; };
+    const long long nt = dist_tiles(n);
+    w.est = (double*)take((size_t)G * 2 * 8);
+    w.brk = (DistBrk*)take(sizeof(DistBrk));
+    size_t z0 = o;
+    w.cand_cnt = (unsigned long long*)take(8);
+    w.n_lt = (unsigned long long*)take(8);
+    w.hist = (unsigned long long*)take((size_t)kNB * 8);
+    w.small_count = (unsigned*)take(4);
+    w.zero_bytes = o - z0;
+    w.job = (RefJob*)take(sizeof(RefJob));
+    w.small = (double*)take((size_t)kSmallCap * 8);
+    w.tile_off = (long long*)take((size_t)nt * 8);
+    w.tile_cnt = (int*)take((size_t)nt * 4);
+    w.tile_pos = (long long*)take((size_t)nt * 8);
+    w.row_tmp = (long long*)take((size_t)cap * 8);
+    w.dist_tmp = (double*)take((size_t)cap * 8);
+    w.total = o;
+    return w;
+}
+
+inline int sample_ctas(long long n) {
+    // total sample ~ n/64, between 8 and 64 CTAs of 4096 per column
+    long long g = n / 64 / kSample;
+    if (g < 8) g = 8;
+    if (g > 64) g = 64;
+    return (int)g;
+}
+
+constexpr double kZ = 5.5;  // bracket half-width in standard deviations of the sample-quantile estimate
+
+inline double col_delta(long long n, int world) {
+    double s_tot = (double)sample_ctas(n) * kSample * world;
+    double delta = kZ * 0.5 / sqrt(s_tot);
+    return delta < 2.0 / kSample ? 2.0 / kSample : delta;
+}
+
+// candidate capacities: the M band holds ~2*delta of the rows, L u R ~8*delta (each widened by the M band)
+inline long long cap_for(long long n, double frac) {
+    long long c = (long long)((double)n * frac * col_delta(n, 1) / 0.0054) + 32768;
+    return c > n ? n : c;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- fast column median / MAD -------------------------------------------------------------------------
+size_t abcdls_mad_fast_workspace_bytes(int64_t n, int d) {
+    const int G = sample_ctas(n);
+    return carve_mad(nullptr, d, G, cap_for(n, 0.03), cap_for(n, 0.08)).total;
+}
+
+// Stage 1: sample every column -> local bracket estimates.  est_out/est_count describe the buffer a multi-GPU
+// caller sums across ranks (then passes world to stage 2).
+int abcdls_mad_fast_sample(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, void* ws,
+                           size_t ws_bytes, double** est_out, size_t* est_count, void* stream) {
+    ABCDLS_CHECK_ARG(h, h && ss && ws && n >= kSample && d >= 1 && d <= kMaxD && ld >= n && world >= 1, "mad_fast_sample");
+    const int G = sample_ctas(n);
+    MadWs w = carve_mad(ws, d, G, cap_for(n, 0.03), cap_for(n, 0.08));
+    if (ws_bytes < w.total) {
+        h->err = "mad_fast workspace too small";
+        return ABCDLS_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const double delta = col_delta(n, world);
+    const size_t smem = (size_t)2 * kSample * sizeof(double);
+    ABCDLS_CUDA(h, cudaFuncSetAttribute(k_sample_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ABCDLS_CUDA(h, cudaMemsetAsync(w.counts, 0, w.zero_bytes, st));
+    k_sample_cols<<<dim3(G, d), 512, smem, st>>>(ss, n, ld, 0x5EEDu, delta, w.est);
+    ABCDLS_LAUNCH_CHECK(h);
+    if (est_out) *est_out = w.est;
+    if (est_count) *est_count = (size_t)G * d * 4;
+    return ABCDLS_OK;
+}
+
+// Stage 2: brackets + the table pass.  counts_out/counts_count: buffer to sum across ranks afterwards
+// (counts[d*4], cnt[d*2], histM[d*kNB], histU[d*kNB] are contiguous).
+int abcdls_mad_fast_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, void* ws,
+                         size_t ws_bytes, int64_t** counts_out, size_t* counts_count, void* stream) {
+    ABCDLS_CHECK_ARG(h, h && ss && ws && n >= kSample && d >= 1 && d <= kMaxD && ld >= n && world >= 1, "mad_fast_pass");
+    const int G = sample_ctas(n);
+    const long long capM = cap_for(n, 0.03), capU = cap_for(n, 0.08);
+    MadWs w = carve_mad(ws, d, G, capM, capU);
+    if (ws_bytes < w.total) {
+        h->err = "mad_fast workspace too small";
+        return ABCDLS_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    k_make_brackets<<<1, 64, 0, st>>>(w.est, G, d, 1.0 / world, w.brk);
+    ABCDLS_LAUNCH_CHECK(h);
+    long long gx = ((n + kATile - 1) / kATile);
+    long long mx = (long long)h->sm_count * 8 / d;
+    if (mx < 1) mx = 1;
+    if (gx > mx) gx = mx;
+    k_bracket_pass<<<dim3((unsigned)gx, d), kAThreads, 0, st>>>(ss, n, ld, w.brk, w.counts, w.histM, w.candM, capM,
+                                                                w.candU, capU, w.cnt);
+    ABCDLS_LAUNCH_CHECK(h);
+    if (counts_out) *counts_out = reinterpret_cast<int64_t*>(w.counts);
+    if (counts_count) *counts_count = w.zero_bytes / 8;  // counts, cnt, histM, histU, small_count: one zero-padded block
+    return ABCDLS_OK;
+}
+
+// Stage 3 (single GPU): finish median and MAD from the candidates.  n_global = rows over all ranks.
+int abcdls_mad_fast_finish(abcdls_handle_t h, int64_t n, int64_t n_global, int d, void* ws, size_t ws_bytes,
+                           double* med, double* mad, int* status_dev, void* stream) {
+    ABCDLS_CHECK_ARG(h, h && ws && med && mad && status_dev && d >= 1 && d <= kMaxD, "mad_fast_finish");
+    const int G = sample_ctas(n);
+    const long long capM = cap_for(n, 0.03), capU = cap_for(n, 0.08);
+    MadWs w = carve_mad(ws, d, G, capM, capU);
+    if (ws_bytes < w.total) {
+        h->err = "mad_fast workspace too small";
+        return ABCDLS_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long k0 = (n_global - 1) / 2, k1 = n_global / 2;
+    const size_t smem = (size_t)kSmallCap * sizeof(double);
+    ABCDLS_CUDA(h, cudaFuncSetAttribute(k_refine_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto gx_for = [&](long long cap) {
+        long long g = (cap + 256 * 8 - 1) / (256 * 8);
+        long long mx = (long long)h->sm_count * 8 / d;
+        if (mx < 1) mx = 1;
+        return (unsigned)(g > mx ? mx : (g < 1 ? 1 : g));
+    };
+    // median: histogram was fused into the pass
+    k_plan_median<<<1, 64, 0, st>>>(w.jobs, d, w.brk, w.counts, w.histM, w.candM, capM, w.cnt, w.small, w.small_count,
+                                    k0, k1, status_dev);
+    k_refine_pick<<<d, 256, 0, st>>>(w.jobs, status_dev);
+    k_refine_gather<<<dim3(gx_for(capM), d), 256, 0, st>>>(w.jobs, capM);
+    k_refine_final<<<d, 1024, smem, st>>>(w.jobs, status_dev);
+    // MAD: |x - med| over the L u R candidates
+    k_plan_mad<<<1, 64, 0, st>>>(w.jobs, d, w.brk, w.counts, w.histU, w.candU, capU, w.cnt, w.small, w.small_count, k0,
+                                 k1, med, w.guard, status_dev);
+    k_refine_hist<<<dim3(gx_for(capU), d), 256, 0, st>>>(w.jobs + d, capU);
+    k_refine_pick<<<d, 256, 0, st>>>(w.jobs + d, status_dev);
+    k_refine_gather<<<dim3(gx_for(capU), d), 256, 0, st>>>(w.jobs + d, capU);
+    k_refine_final<<<d, 1024, smem, st>>>(w.jobs + d, status_dev);
+    k_finish_mad<<<1, 64, 0, st>>>(w.jobs, d, w.guard, mad, status_dev);
+    ABCDLS_LAUNCH_CHECK(h);
+    return ABCDLS_OK;
+}
+
+// ---- fused distance + tolerance bracket ----------------------------------------------------------------
+size_t abcdls_dist_fast_workspace_bytes(int64_t n, int64_t cap) {
+    return carve_dist(nullptr, 64, n, cap).total;
+}
+
+int abcdls_dist_fast_sample(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, const double* mad,
+                            const double* target, int64_t nacc, int64_t n_global, int world, int64_t cap, void* ws,
+                            size_t ws_bytes, double** est_out, size_t* est_count, void* stream) {
+    ABCDLS_CHECK_ARG(h, h && ss && mad && target && ws && n >= kSample && d >= 1 && d <= kMaxD && ld >= n,
+                     "dist_fast_sample");
+    const int G = 64;
+    DistWs w = carve_dist(ws, G, n, cap);
+    if (ws_bytes < w.total) {
+        h->err = "dist_fast workspace too small";
+        return ABCDLS_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const double p = (double)nacc / (double)n_global;
+    const double s_tot = (double)G * kSample * world;
+    double delta = kZ * sqrt(p * (1.0 - p) / s_tot);
+    const size_t smem = (size_t)kSample * sizeof(double);
+    ABCDLS_CUDA(h, cudaMemsetAsync(w.cand_cnt, 0, w.zero_bytes, st));
+    k_sample_dist<<<G, 512, smem, st>>>(ss, n, d, ld, mad, target, 0xD157u, p, delta, w.est);
+    ABCDLS_LAUNCH_CHECK(h);
+    if (est_out) *est_out = w.est;
+    if (est_count) *est_count = (size_t)G * 2;
+    return ABCDLS_OK;
+}
+
+// dist may be NULL (the N-vector is then never materialised).  Outputs (row order): cand_row (global rows),
+// cand_dist, n_cand (device u64).  ds_out (device double) = exact nacc-th smallest distance.
+int abcdls_dist_fast_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, const double* mad,
+                          const double* target, int64_t nacc, int world, int64_t row_offset, int64_t cap, double* dist,
+                          int64_t* cand_row, double* cand_dist, int64_t* n_cand, double* ds_out, void* ws,
+                          size_t ws_bytes, int* status_dev, void* stream) {
+    ABCDLS_CHECK_ARG(h, h && ss && mad && target && cand_row && cand_dist && n_cand && ds_out && ws && status_dev,
+                     "dist_fast_pass: null");
+    ABCDLS_CHECK_ARG(h, n >= kSample && d >= 1 && d <= kMaxD && ld >= n && cap >= 1, "dist_fast_pass: shape");
+    const int G = 64;
+    DistWs w = carve_dist(ws, G, n, cap);
+    if (ws_bytes < w.total) {
+        h->err = "dist_fast workspace too small";
+        return ABCDLS_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    k_make_dist_bracket<<<1, 32, 0, st>>>(w.est, G, 1.0 / world, w.brk);
+    const long long nt = dist_tiles(n);
+    long long gx = nt;
+    long long mx = (long long)h->sm_count * 8;
+    if (gx > mx) gx = mx;
+    const bool vec = ((reinterpret_cast<uintptr_t>(ss) & 15) == 0) && ((ld & 1) == 0) &&
+                     (!dist || (reinterpret_cast<uintptr_t>(dist) & 15) == 0);
+#define LAUNCH_B(V, W)                                                                                          \
+    k_dist_pass<V, W><<<(unsigned)gx, kBThreads, 0, st>>>(ss, n, d, ld, mad, target, w.brk, dist, w.row_tmp,    \
+                                                          w.dist_tmp, cap, w.cand_cnt, w.n_lt, w.hist, w.tile_off, \
+                                                          w.tile_cnt, status_dev)
+    if (vec && dist) LAUNCH_B(true, true);
+    else if (vec) LAUNCH_B(true, false);
+    else if (dist) LAUNCH_B(false, true);
+    else LAUNCH_B(false, false);
+#undef LAUNCH_B
+    ABCDLS_LAUNCH_CHECK(h);
+    k_scan_tiles<<<1, 1024, 0, st>>>(w.tile_cnt, nt, w.tile_pos);
+    k_order_cands<<<(unsigned)((nt + 255) / 256 > 1184 ? 1184 : (nt + 255) / 256), 256, 0, st>>>(
+        w.tile_off, w.tile_cnt, w.tile_pos, nt, w.row_tmp, w.dist_tmp, cap, row_offset, (long long*)cand_row, cand_dist);
+    ABCDLS_CUDA(h, cudaMemcpyAsync(n_cand, w.cand_cnt, 8, cudaMemcpyDeviceToDevice, st));
+    // exact ds among the candidates in [lo, hi]
+    const size_t smem = (size_t)kSmallCap * sizeof(double);
+    ABCDLS_CUDA(h, cudaFuncSetAttribute(k_refine_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_plan_ds<<<1, 32, 0, st>>>(w.job, w.brk, w.n_lt, w.cand_cnt, w.hist, cand_dist, cap, w.small, w.small_count,
+                                nacc - 1, status_dev);
+    k_refine_pick<<<1, 256, 0, st>>>(w.job, status_dev);
+    long long gg = (cap + 2047) / 2048;
+    if (gg > (long long)h->sm_count * 4) gg = (long long)h->sm_count * 4;
+    k_refine_gather<<<dim3((unsigned)gg, 1), 256, 0, st>>>(w.job, cap);
+    k_refine_final<<<1, 1024, smem, st>>>(w.job, status_dev);
+    k_copy_result<<<1, 32, 0, st>>>(w.job, ds_out);
+    ABCDLS_LAUNCH_CHECK(h);
+    return ABCDLS_OK;
+}
+
+}  // extern "C"

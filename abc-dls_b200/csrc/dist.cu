@@ -109,11 +109,13 @@ __global__ void __launch_bounds__(kDistThreads) k_scale_dist(const double* __res
 }
 
 __global__ void __launch_bounds__(kTileThreads) k_tile_count_le(const double* __restrict__ dist, long long n,
+                                                                const long long* __restrict__ n_dev,
                                                                 const double* __restrict__ ds_ptr,
                                                                 int* __restrict__ tile_cnt,
                                                                 unsigned long long* total) {
     __shared__ int sh[33];
     const double ds = *ds_ptr;
+    if (n_dev && *n_dev < n) n = *n_dev;
     const long long base = (long long)blockIdx.x * kTile + (long long)threadIdx.x * kItems;
     int c = 0;
 #pragma unroll
@@ -130,6 +132,9 @@ __global__ void __launch_bounds__(kTileThreads) k_tile_count_le(const double* __
 }
 
 __global__ void __launch_bounds__(kTileThreads) k_tile_write_le(const double* __restrict__ dist, long long n,
+                                                                const long long* __restrict__ n_dev,
+                                                                const long long* __restrict__ src_idx,
+                                                                double* __restrict__ dist_out,
                                                                 const double* __restrict__ ds_ptr,
                                                                 const long long* __restrict__ tile_off,
                                                                 const long long* __restrict__ quota_ptr,
@@ -141,6 +146,7 @@ __global__ void __launch_bounds__(kTileThreads) k_tile_write_le(const double* __
     const double ds = *ds_ptr;
     long long quota = *quota_ptr;
     if (quota < 0) quota = 0;
+    if (n_dev && *n_dev < n) n = *n_dev;
     const long long base = (long long)blockIdx.x * kTile + (long long)threadIdx.x * kItems;
     bool f[kItems];
     int c = 0;
@@ -156,7 +162,10 @@ __global__ void __launch_bounds__(kTileThreads) k_tile_write_le(const double* __
 #pragma unroll
     for (int t = 0; t < kItems; ++t) {
         if (f[t]) {
-            if (pos < quota && pos < cap) idx_out[pos] = row_offset + base + t;
+            if (pos < quota && pos < cap) {
+                idx_out[pos] = src_idx ? src_idx[base + t] : row_offset + base + t;
+                if (dist_out) dist_out[pos] = dist[base + t];
+            }
             ++pos;
         }
     }
@@ -204,8 +213,8 @@ size_t abcdls_accept_workspace_bytes(int64_t n) {
     return 256 + align_up((size_t)nt * sizeof(int), 256) + align_up((size_t)nt * sizeof(long long), 256);
 }
 
-int abcdls_count_le(abcdls_handle_t h, const double* dist, int64_t n, const double* ds, int64_t* le_count,
-                    void* ws, size_t ws_bytes, void* stream) {
+int abcdls_count_le(abcdls_handle_t h, const double* dist, int64_t n, const int64_t* n_dev, const double* ds,
+                    int64_t* le_count, void* ws, size_t ws_bytes, void* stream) {
     ABCDLS_CHECK_ARG(h, h && dist && ds && ws && n >= 1, "count_le");
     if (ws_bytes < abcdls_accept_workspace_bytes(n)) {
         h->err = "accept workspace too small";
@@ -218,7 +227,7 @@ int abcdls_count_le(abcdls_handle_t h, const double* dist, int64_t n, const doub
     int* tile_cnt = reinterpret_cast<int*>(p + 256);
     long long* tile_off = reinterpret_cast<long long*>(p + 256 + align_up((size_t)nt * sizeof(int), 256));
     ABCDLS_CUDA(h, cudaMemsetAsync(total, 0, 8, st));
-    k_tile_count_le<<<(unsigned)nt, kTileThreads, 0, st>>>(dist, n, ds, tile_cnt, total);
+    k_tile_count_le<<<(unsigned)nt, kTileThreads, 0, st>>>(dist, n, (const long long*)n_dev, ds, tile_cnt, total);
     ABCDLS_LAUNCH_CHECK(h);
     k_scan_tiles<<<1, 1024, 0, st>>>(tile_cnt, nt, tile_off);
     ABCDLS_LAUNCH_CHECK(h);
@@ -227,9 +236,9 @@ int abcdls_count_le(abcdls_handle_t h, const double* dist, int64_t n, const doub
     return ABCDLS_OK;
 }
 
-int abcdls_accept(abcdls_handle_t h, const double* dist, int64_t n, const double* ds, const int64_t* quota,
-                  int64_t row_offset, int64_t cap, int64_t* idx_out, int64_t* n_out, void* ws, size_t ws_bytes,
-                  int* status_dev, void* stream) {
+int abcdls_accept(abcdls_handle_t h, const double* dist, int64_t n, const int64_t* n_dev, const int64_t* src_idx,
+                  const double* ds, const int64_t* quota, int64_t row_offset, int64_t cap, int64_t* idx_out,
+                  double* dist_out, int64_t* n_out, void* ws, size_t ws_bytes, int* status_dev, void* stream) {
     ABCDLS_CHECK_ARG(h, h && dist && ds && quota && idx_out && n_out && ws && status_dev && n >= 1 && cap >= 1,
                      "accept");
     if (ws_bytes < abcdls_accept_workspace_bytes(n)) {
@@ -241,8 +250,8 @@ int abcdls_accept(abcdls_handle_t h, const double* dist, int64_t n, const double
     unsigned long long* total = reinterpret_cast<unsigned long long*>(p);
     long long* tile_off = reinterpret_cast<long long*>(p + 256 + align_up((size_t)nt * sizeof(int), 256));
     k_tile_write_le<<<(unsigned)nt, kTileThreads, 0, (cudaStream_t)stream>>>(
-        dist, n, ds, tile_off, (const long long*)quota, row_offset, cap, (long long*)idx_out, total,
-        (long long*)n_out, status_dev);
+        dist, n, (const long long*)n_dev, (const long long*)src_idx, dist_out, ds, tile_off,
+        (const long long*)quota, row_offset, cap, (long long*)idx_out, total, (long long*)n_out, status_dev);
     ABCDLS_LAUNCH_CHECK(h);
     return ABCDLS_OK;
 }

@@ -23,13 +23,12 @@ struct GatherScale {
 // accepted rows -> compact column-major blocks (leading dimension `cap`)
 __global__ void __launch_bounds__(256) k_gather(const double* __restrict__ ss, long long ld_ss,
                                                 const double* __restrict__ param, long long ld_param,
-                                                const double* __restrict__ dist, const long long* __restrict__ idx,
+                                                const double* __restrict__ dist_acc, const long long* __restrict__ idx,
                                                 const long long* __restrict__ n_acc_ptr, long long row_offset,
                                                 long long cap, int d, int P, const double* __restrict__ mad,
                                                 const double* __restrict__ target, const double* __restrict__ ds_ptr,
                                                 double* __restrict__ xs, double* __restrict__ y,
-                                                double* __restrict__ ss_out, double* __restrict__ w,
-                                                double* __restrict__ dist_out) {
+                                                double* __restrict__ ss_out, double* __restrict__ w) {
     __shared__ GatherScale S;
     for (int j = threadIdx.x; j < d; j += blockDim.x) {
         double m = mad[j];
@@ -51,9 +50,7 @@ __global__ void __launch_bounds__(256) k_gather(const double* __restrict__ ss, l
             xs[(size_t)j * cap + r] = __dsub_rn(sc, S.tgt[j]);
         }
         for (int p = 0; p < P; ++p) y[(size_t)p * cap + r] = param[(size_t)p * ld_param + i];
-        double di = dist[i];
-        dist_out[r] = di;
-        double q = di / ds;
+        double q = dist_acc[r] / ds;
         w[r] = __dsub_rn(1.0, __dmul_rn(q, q));
     }
 }
@@ -360,16 +357,15 @@ inline int normal_grid(abcdls_handle_t h, long long cap) {
 extern "C" {
 
 int abcdls_gather(abcdls_handle_t h, const double* ss, int64_t ld_ss, const double* param, int64_t ld_param,
-                  const double* dist, const int64_t* idx, const int64_t* n_acc, int64_t row_offset, int64_t cap,
+                  const double* dist_acc, const int64_t* idx, const int64_t* n_acc, int64_t row_offset, int64_t cap,
                   int d, int P, const double* mad, const double* target, const double* ds, double* xs, double* y,
-                  double* ss_out, double* w, double* dist_out, void* stream) {
-    ABCDLS_CHECK_ARG(h, h && ss && param && dist && idx && n_acc && mad && target && ds && xs && y && ss_out && w &&
-                            dist_out,
+                  double* ss_out, double* w, void* stream) {
+    ABCDLS_CHECK_ARG(h, h && ss && param && dist_acc && idx && n_acc && mad && target && ds && xs && y && ss_out && w,
                      "gather: null pointer");
     ABCDLS_CHECK_ARG(h, d >= 1 && d <= kMaxD && P >= 1 && P <= kMaxP && cap >= 1, "gather: shape");
     k_gather<<<grid_for(h, cap, 256, 8), 256, 0, (cudaStream_t)stream>>>(
-        ss, ld_ss, param, ld_param, dist, (const long long*)idx, (const long long*)n_acc, row_offset, cap, d, P, mad,
-        target, ds, xs, y, ss_out, w, dist_out);
+        ss, ld_ss, param, ld_param, dist_acc, (const long long*)idx, (const long long*)n_acc, row_offset, cap, d, P,
+        mad, target, ds, xs, y, ss_out, w);
     ABCDLS_LAUNCH_CHECK(h);
     return ABCDLS_OK;
 }

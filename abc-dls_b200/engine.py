@@ -113,6 +113,31 @@ class AbcEngine:
         self.k = stages
         self.device = stages.device
         self.comm = Comm(group, self.device)
+        self.timers = None   # set to {} to record CUDA-event pairs per named stage (bench.py)
+        self.fast_misses = 0  # how often a sampled bracket missed and the radix path had to rerun the call
+
+    class _Timed:
+        def __init__(self, eng, name):
+            self.eng, self.name = eng, name
+
+        def __enter__(self):
+            if self.eng.timers is not None:
+                self.a = torch.cuda.Event(enable_timing=True)
+                self.b = torch.cuda.Event(enable_timing=True)
+                self.a.record(torch.cuda.current_stream(self.eng.device))
+
+        def __exit__(self, *exc):
+            if self.eng.timers is not None:
+                self.b.record(torch.cuda.current_stream(self.eng.device))
+                self.eng.timers.setdefault(self.name, []).append((self.a, self.b))
+            return False
+
+    def _t(self, name):
+        return AbcEngine._Timed(self, name)
+
+    def timer_ms(self):
+        """name -> list of elapsed ms for every recorded (start, end) pair; call after a synchronize."""
+        return {k: [a.elapsed_time(b) for a, b in v] for k, v in (self.timers or {}).items()}
 
     # ---- small helpers ----------------------------------------------------------------------------
     def _shard_info(self, n_local: int):
@@ -128,7 +153,8 @@ class AbcEngine:
         k.select_begin(ws, njobs, table, n_local, ld, None, center, k0, k1)
         hist = k.select_hist_tensor(ws, njobs) if self.comm.world > 1 else None
         for p in range(_capi.SELECT_PASSES):
-            k.select_hist(ws, njobs, n_local, p)
+            with self._t(f"select_hist[{njobs}x{n_local}]"):
+                k.select_hist(ws, njobs, n_local, p)
             if hist is not None:
                 self.comm.allreduce_sum(hist)
             k.select_pick(ws, njobs, p)
@@ -149,32 +175,58 @@ class AbcEngine:
         return med, mad
 
     # ---- shared front half: scaling, distance, tolerance cut ----------------------------------
-    def _front(self, target, ss, tol, status):
+    FAST_MIN_ROWS = 1 << 20   # below this the 6-pass radix select is launch-bound anyway
+
+    def _front(self, target, ss, tol, status, keep_dist=False, exact=False):
+        """MAD scaling -> distance -> exact threshold ds -> R's cap rule.  Returns the accepted rows (ascending
+        global row numbers, their distances) of this rank.
+
+        Fast path (single rank, big tables): sampled brackets, ONE table read for all medians/MADs and ONE for
+        the distances (csrc/bracket.cu); every bracket is verified on the device and a miss raises
+        S_FASTPATH_MISS, upon which abc() reruns with ``exact=True`` (6-pass radix select, always exact)."""
         k = self.k
         d, n_local = ss.shape
         n_global, row_offset, _ = self._shard_info(n_local)
         nacc = int(math.ceil(n_global * tol))
         if not (1 <= nacc <= n_global):
             raise AbcError("'tol' must give 1 <= ceiling(N * tol) <= N")
-        _, mad = self.column_mad(ss, n_global)
-        dist = k.new(n_local)
-        k.scale_dist(ss, n_local, d, ss.stride(0), mad, target, dist, status)
-        ds = self._select(dist[None, :], n_local, None, nacc - 1, nacc - 1)[0, :1]  # (1,) device
-        ws = k.accept_workspace(n_local)
-        le = torch.zeros(1, dtype=torch.int64, device=self.device)
-        k.count_le(dist, n_local, ds, le, ws)
-        if self.comm.world > 1:
-            allc = self.comm.allgather(le).view(-1)
-            below = allc[: self.comm.rank].sum()
-            quota = (nacc - below).clamp(min=0).view(1)
-        else:
-            quota = torch.full((1,), nacc, dtype=torch.int64, device=self.device)
+        fast = (not exact) and self.comm.world == 1 and n_local >= self.FAST_MIN_ROWS
         cap = min(nacc, n_local)
         idx = k.new(cap, dtype=torch.int64)
+        dacc = k.new(cap)
         n_acc = torch.zeros(1, dtype=torch.int64, device=self.device)
-        k.accept(dist, n_local, ds, quota, row_offset, cap, idx, n_acc, ws, status)
+        le = torch.zeros(1, dtype=torch.int64, device=self.device)
+        quota = torch.full((1,), nacc, dtype=torch.int64, device=self.device)
+        if fast:
+            med, mad = k.new(d), k.new(d)
+            with self._t("mad_fast"):
+                k.mad_fast(ss, n_local, n_global, d, ss.stride(0), 1, med, mad, status)
+            ccap = min(n_local, 2 * nacc + 65536)
+            dist = k.new(n_local) if keep_dist else None
+            cand_row, cand_dist = k.new(ccap, dtype=torch.int64), k.new(ccap)
+            n_cand = torch.zeros(1, dtype=torch.int64, device=self.device)
+            ds = k.new(1)
+            with self._t("dist_fast"):
+                k.dist_fast(ss, n_local, n_global, d, ss.stride(0), mad, target, nacc, 1, row_offset, ccap, dist,
+                            cand_row, cand_dist, n_cand, ds, status)
+            ws = k.accept_workspace(ccap)
+            k.count_le(cand_dist, ccap, n_cand, ds, le, ws)
+            k.accept(cand_dist, ccap, n_cand, cand_row, ds, quota, row_offset, cap, idx, dacc, n_acc, ws, status)
+        else:
+            _, mad = self.column_mad(ss, n_global)
+            dist = k.new(n_local)
+            with self._t("scale_dist"):
+                k.scale_dist(ss, n_local, d, ss.stride(0), mad, target, dist, status)
+            ds = self._select(dist[None, :], n_local, None, nacc - 1, nacc - 1)[0, :1]  # (1,) device
+            ws = k.accept_workspace(n_local)
+            k.count_le(dist, n_local, None, ds, le, ws)
+            if self.comm.world > 1:
+                allc = self.comm.allgather(le).view(-1)
+                below = allc[: self.comm.rank].sum()
+                quota = (nacc - below).clamp(min=0).view(1)
+            k.accept(dist, n_local, None, None, ds, quota, row_offset, cap, idx, dacc, n_acc, ws, status)
         return dict(n_global=n_global, row_offset=row_offset, nacc=nacc, mad=mad, dist=dist, ds=ds, cap=cap, idx=idx,
-                    n_acc=n_acc)
+                    n_acc=n_acc, dacc=dacc, fast=fast)
 
     def _zero_variance(self, ss) -> bool:
         """R: stop if every column of sumstat has a single unique value."""
@@ -189,7 +241,8 @@ class AbcEngine:
 
     # ---- abc() ----------------------------------------------------------------------------------
     def abc(self, target: torch.Tensor, param: torch.Tensor, sumstat: torch.Tensor, tol: float, method: str,
-            hcorr: bool = True, kernel: str = "epanechnikov", keep_dist: bool = False) -> AbcResult:
+            hcorr: bool = True, kernel: str = "epanechnikov", keep_dist: bool = False,
+            _exact: bool = False) -> AbcResult:
         """``abc::abc`` for method in {rejection, loclinear} on this rank's shard.
 
         target (d,), param (P, n_local), sumstat (d, n_local): float64 CUDA tensors, column-major tables.
@@ -208,13 +261,13 @@ class AbcEngine:
         if par.shape[1] != n_local:
             raise AbcError("'param' and 'sumstat' must have the same number of rows")
         status = torch.zeros(1, dtype=torch.int32, device=self.device)
-        f = self._front(target, ss, tol, status)
-        cap, idx, n_acc, ds, mad = f["cap"], f["idx"], f["n_acc"], f["ds"], f["mad"]
+        f = self._front(target, ss, tol, status, keep_dist=keep_dist, exact=_exact)
+        cap, idx, n_acc, ds, mad, dacc = f["cap"], f["idx"], f["n_acc"], f["ds"], f["mad"], f["dacc"]
 
         xs, y, ss_out = k.new(d, cap), k.new(P, cap), k.new(d, cap)
-        w, dacc = k.new(cap), k.new(cap)
-        k.gather(ss, ss.stride(0), par, par.stride(0), f["dist"], idx, n_acc, f["row_offset"], cap, d, P, mad, target,
-                 ds, xs, y, ss_out, w, dacc)
+        w = k.new(cap)
+        k.gather(ss, ss.stride(0), par, par.stride(0), dacc, idx, n_acc, f["row_offset"], cap, d, P, mad, target,
+                 ds, xs, y, ss_out, w)
         # zero variance inside the accepted region (R cond2)
         reg = k.new(d, 6)
         k.col_stats(ss_out, None, n_acc, cap, d, reg)
@@ -271,6 +324,9 @@ class AbcEngine:
         st, n_loc, ds_h = int(host[0]), int(host[1]), float(host[2])
         st = self.comm.allreduce_or_int(st)
         warnings: List[str] = []
+        if (st & _capi.S_FASTPATH_MISS) and f["fast"]:
+            self.fast_misses += 1
+            return self.abc(target, param, sumstat, tol, method, hcorr, kernel, keep_dist, _exact=True)
         if st & _capi.S_NONFINITE:
             raise AbcError("non-finite values in 'sumstat'/'target' (R's NA-row handling is not implemented)")
         if host[4] != 0 and self._zero_variance(ss):
@@ -320,7 +376,7 @@ class AbcEngine:
 
     # ---- postpr() -------------------------------------------------------------------------------
     def postpr(self, target: torch.Tensor, model_id: torch.Tensor, models: List[str], sumstat: torch.Tensor,
-               tol: float, method: str = "rejection", keep_dist: bool = False) -> PostprResult:
+               tol: float, method: str = "rejection", keep_dist: bool = False, _exact: bool = False) -> PostprResult:
         """``abc::postpr(method='rejection')``: model_id int32 (n_local,) indexes ``models`` (sorted levels)."""
         if method != "rejection":
             raise AbcError("postpr: only method='rejection' is implemented (mnlogistic / neuralnet stay with R's nnet)")
@@ -337,7 +393,7 @@ class AbcEngine:
             raise AbcError("'index' must be the same length as the number of rows in 'sumstat'.")
         model_id = model_id.to(device=self.device, dtype=torch.int32).contiguous()
         status = torch.zeros(1, dtype=torch.int32, device=self.device)
-        f = self._front(target, ss, tol, status)
+        f = self._front(target, ss, tol, status, keep_dist=keep_dist, exact=_exact)
         cap, idx, n_acc = f["cap"], f["idx"], f["n_acc"]
         counts = torch.zeros(K, dtype=torch.int64, device=self.device)
         k.postpr_counts(model_id, idx, n_acc, f["row_offset"], cap, K, counts)
@@ -346,6 +402,9 @@ class AbcEngine:
         host = torch.cat([status.to(torch.float64), n_acc.to(torch.float64), f["ds"],
                           all_mad_zero.to(torch.float64).view(1)]).cpu()
         st, n_loc, ds_h = self.comm.allreduce_or_int(int(host[0])), int(host[1]), float(host[2])
+        if (st & _capi.S_FASTPATH_MISS) and f["fast"]:
+            self.fast_misses += 1
+            return self.postpr(target, model_id, models, sumstat, tol, method, keep_dist, _exact=True)
         if st & _capi.S_NONFINITE:
             raise AbcError("non-finite values in 'sumstat'/'target' (R's NA-row handling is not implemented)")
         if host[3] != 0 and self._zero_variance(ss):

@@ -86,21 +86,56 @@ class CudaStages:
     def accept_workspace(self, n):
         return self.workspace("accept", self.lib.abcdls_accept_workspace_bytes(n))
 
-    def count_le(self, dist, n, ds, le_count, ws):
-        self.handle.call("abcdls_count_le", _p(dist), n, _p(ds), _p(le_count), _p(ws), ws.numel(), self._stream())
+    def count_le(self, dist, n, n_dev, ds, le_count, ws):
+        self.handle.call("abcdls_count_le", _p(dist), n, _p(n_dev), _p(ds), _p(le_count), _p(ws), ws.numel(),
+                         self._stream())
         self.launches += 4
 
-    def accept(self, dist, n, ds, quota, row_offset, cap, idx, n_out, ws, status):
-        self.handle.call("abcdls_accept", _p(dist), n, _p(ds), _p(quota), row_offset, cap, _p(idx), _p(n_out), _p(ws),
-                         ws.numel(), _p(status), self._stream())
+    def accept(self, dist, n, n_dev, src_idx, ds, quota, row_offset, cap, idx, dist_out, n_out, ws, status):
+        self.handle.call("abcdls_accept", _p(dist), n, _p(n_dev), _p(src_idx), _p(ds), _p(quota), row_offset, cap,
+                         _p(idx), _p(dist_out), _p(n_out), _p(ws), ws.numel(), _p(status), self._stream())
         self.launches += 1
 
+    # ---- fast path (sampled brackets) -----------------------------------------------------------
+    def _buf(self, ws, ptr, count, dtype):
+        off = ptr.value - ws.data_ptr()
+        return ws[off: off + count.value * 8].view(dtype)
+
+    def mad_fast(self, ss, n, n_global, d, ld, world, med, mad, status, reduce_sum=None):
+        """sample -> [reduce est] -> pass -> [reduce counts] -> finish.  reduce_sum: in-place all-reduce or None."""
+        ws = self.workspace("madfast", self.lib.abcdls_mad_fast_workspace_bytes(n, d))
+        ptr, cnt = C.c_void_p(), C.c_size_t()
+        self.handle.call("abcdls_mad_fast_sample", _p(ss), n, d, ld, world, _p(ws), ws.numel(), C.byref(ptr),
+                         C.byref(cnt), self._stream())
+        if reduce_sum is not None:
+            reduce_sum(self._buf(ws, ptr, cnt, torch.float64))
+        self.handle.call("abcdls_mad_fast_pass", _p(ss), n, d, ld, world, _p(ws), ws.numel(), C.byref(ptr),
+                         C.byref(cnt), self._stream())
+        if reduce_sum is not None:
+            reduce_sum(self._buf(ws, ptr, cnt, torch.int64))
+        self.handle.call("abcdls_mad_fast_finish", n, n_global, d, _p(ws), ws.numel(), _p(med), _p(mad), _p(status),
+                         self._stream())
+        self.launches += 14
+
+    def dist_fast(self, ss, n, n_global, d, ld, mad, target, nacc, world, row_offset, cap, dist, cand_row, cand_dist,
+                  n_cand, ds, status, reduce_sum=None):
+        ws = self.workspace("distfast", self.lib.abcdls_dist_fast_workspace_bytes(n, cap))
+        ptr, cnt = C.c_void_p(), C.c_size_t()
+        self.handle.call("abcdls_dist_fast_sample", _p(ss), n, d, ld, _p(mad), _p(target), nacc, n_global, world, cap,
+                         _p(ws), ws.numel(), C.byref(ptr), C.byref(cnt), self._stream())
+        if reduce_sum is not None:
+            reduce_sum(self._buf(ws, ptr, cnt, torch.float64))
+        self.handle.call("abcdls_dist_fast_pass", _p(ss), n, d, ld, _p(mad), _p(target), nacc, world, row_offset, cap,
+                         _p(dist), _p(cand_row), _p(cand_dist), _p(n_cand), _p(ds), _p(ws), ws.numel(), _p(status),
+                         self._stream())
+        self.launches += 11
+
     # ---- kernel 3 -------------------------------------------------------------------------------
-    def gather(self, ss, ld_ss, param, ld_param, dist, idx, n_acc, row_offset, cap, d, P, mad, target, ds, xs, y,
-               ss_out, w, dist_out):
-        self.handle.call("abcdls_gather", _p(ss), ld_ss, _p(param), ld_param, _p(dist), _p(idx), _p(n_acc),
+    def gather(self, ss, ld_ss, param, ld_param, dist_acc, idx, n_acc, row_offset, cap, d, P, mad, target, ds, xs, y,
+               ss_out, w):
+        self.handle.call("abcdls_gather", _p(ss), ld_ss, _p(param), ld_param, _p(dist_acc), _p(idx), _p(n_acc),
                          row_offset, cap, d, P, _p(mad), _p(target), _p(ds), _p(xs), _p(y), _p(ss_out), _p(w),
-                         _p(dist_out), self._stream())
+                         self._stream())
         self.launches += 1
 
     def normal(self, xs, rhs, w, n_acc, cap, d, P, with_gram, partial):

@@ -1,0 +1,266 @@
+#!/usr/bin/env python
+"""Benchmark of the ABC acceptance-and-adjustment hot path (BASELINE.json metric:
+"simulations scored/sec (ABC loclinear)").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # CPU arm: the oracle port of R abc's algorithm
+
+A "step" is one full abc(method="loclinear") call (MAD scaling -> distance -> tolerance cut -> local-linear
+adjustment with hcorr -> summary reductions) over one synthetic table (SURVEY.md §8d recipe).
+Workload: BASELINE config 5 headline shape, N = 1e8 simulations x 16 summaries x 16 parameters, tol 0.01,
+sharded by rows over the ranks (strong scaling: the table is fixed, N_local = N / n_gpus).
+
+`value`  : whole-job sims/s, tables resident in HBM, CUDA events, max over ranks.
+`e2e`    : same metric through the host-buffer API (pinned host tables -> H2D -> abc -> D2H of the
+           posterior sample and summary) per step.
+`roofline`: dominant table-streaming kernel, algorithmic bytes / its measured duration vs MEASURED_PEAKS.json.
+`cpu_baseline`: the numpy oracle (port of CRAN abc 2.2.1's algorithm; R itself is absent on the box) timed on
+           the host, 1 core (R abc is single threaded), on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "simulations scored/sec (ABC loclinear)"
+UNIT = "sims/s"
+
+
+def _args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=float, default=1e8, help="global simulations N")
+    ap.add_argument("--stats", type=int, default=16)
+    ap.add_argument("--params", type=int, default=16)
+    ap.add_argument("--tol", type=float, default=0.01)
+    ap.add_argument("--method", default="loclinear")
+    ap.add_argument("--cpu-rows", type=float, default=1e6, help="bounded sample for the CPU arm")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.thread.join(timeout=5)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(int(float(r[0])) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.rows[0][1])), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_arm(args, steps, warmup):
+    """Oracle port timed on the host: bounded sample of the same workload (same d, P, tol, method)."""
+    import numpy as np
+    import torch
+    from abc_dls_b200 import synth
+    from oracle import abc_oracle as O
+    n = int(args.cpu_rows)
+    par, ss, tgt = synth.abc_tables(n, args.stats, args.params, "cpu")
+    par_np, ss_np, tgt_np = par.numpy().T.copy(order="F"), ss.numpy().T.copy(order="F"), tgt.numpy()
+    torch.set_num_threads(1)
+    for _ in range(warmup):
+        O.abc(tgt_np, par_np, ss_np, args.tol, args.method)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        r = O.abc(tgt_np, par_np, ss_np, args.tol, args.method)
+        O.summary_abc(r)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": n / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"numpy oracle (port of CRAN abc 2.2.1 abc(); R/rpy2 absent on the box), {n} rows x {args.stats} "
+                      f"stats x {args.params} params, tol {args.tol}, {args.method}, {steps} calls, {dt * 1e3:.1f} ms/call; "
+                      f"R abc is single threaded so 1 of {os.cpu_count()} cores is used"}, dt
+
+
+def main():
+    args = _args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = {"workload": f"cfg5 abc(method={args.method}, hcorr) joint: N={int(args.rows):d} sims x d={args.stats} "
+                       f"stats x P={args.params} params, tol={args.tol}, fp64 column-major tables",
+           "rows": int(args.rows), "stats": args.stats, "params": args.params, "tol": args.tol,
+           "sharding": f"rows/{world}", "l2": "tables larger than L2 (no flush needed)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        base, dt = cpu_arm(args, max(1, args.steps), max(1, min(args.warmup, 1)))
+        line = {"metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "impl": "reference",
+                "cpu_baseline": base,
+                "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from abc_dls_b200 import synth
+    from abc_dls_b200.engine import AbcEngine
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    eng = AbcEngine(dev)
+    N = int(args.rows)
+    per = (N + world - 1) // world
+    r0, r1 = min(rank * per, N), min((rank + 1) * per, N)
+    n_local = r1 - r0
+    d, P = args.stats, args.params
+    par, ss, tgt = synth.abc_tables(n_local, d, P, dev, row_start=r0)
+
+    def step():
+        return eng.abc(tgt, par, ss, args.tol, args.method)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync()
+    eng.timers = {}
+    l0 = eng.k.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        sync()
+        ev0.record()
+        for _ in range(args.steps):
+            res = step()
+        ev1.record()
+        sync()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.k.launches - l0
+    tms = eng.timer_ms()
+    eng.timers = None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_step = ms / args.steps
+    value = N / (ms_step * 1e-3)
+
+    # ---- roofline of the dominant table-streaming kernel (per launch, this rank) ----------------
+    peak, peak_src = _peaks()
+    kern = {}
+    for name, v in tms.items():
+        kern[name] = {"launches": len(v), "avg_ms": sum(v) / len(v), "total_ms_per_step": sum(v) / args.steps}
+    dom = max(kern, key=lambda k_: kern[k_]["total_ms_per_step"])
+    if dom.startswith("select_hist"):
+        alg_bytes = 8.0 * d * n_local            # one read of the N x d table per radix pass
+    else:
+        alg_bytes = (8.0 * d + 8.0) * n_local    # scale_dist: read the table once, write dist
+    achieved = alg_bytes / (kern[dom]["avg_ms"] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": kern[dom]["avg_ms"],
+                "whole_call": {"algorithmic_bytes_per_sim": 16 * d + 16,
+                               "achieved_GBps": (16 * d + 16) * N / (ms_step * 1e-3) / 1e9 / world,
+                               "frac_of_peak_per_gpu": (16 * d + 16) * N / (ms_step * 1e-3) / 1e9 / world / peak},
+                "kernels": kern}
+
+    # ---- end to end through host buffers -----------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h_par = torch.empty((P, n_local), dtype=torch.float64, pin_memory=True)
+        h_ss = torch.empty((d, n_local), dtype=torch.float64, pin_memory=True)
+        h_par.copy_(par)
+        h_ss.copy_(ss)
+        h_tgt = tgt.cpu().pin_memory()
+        h2d = h_par.numel() * 8 + h_ss.numel() * 8 + h_tgt.numel() * 8
+        d2h = [0]
+
+        def e2e_step():
+            dp = h_par.to(dev, non_blocking=True)
+            dss = h_ss.to(dev, non_blocking=True)
+            dt_ = h_tgt.to(dev, non_blocking=True)
+            r = eng.abc(dt_, dp, dss, args.tol, args.method)
+            out = (r.adj_values if r.adj_values is not None else r.unadj_values).contiguous().cpu()
+            st = r.stats.cpu()
+            d2h[0] = out.numel() * 8 + st.numel() * 8
+            return out, st
+
+        del par, ss
+        torch.cuda.empty_cache()
+        e2e_step()
+        sync()
+        nstep = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(nstep):
+            e2e_step()
+        sync()
+        dt_e = torch.tensor([(time.perf_counter() - t0) / nstep], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt_e, op=dist.ReduceOp.MAX)
+        e2e = {"value": N / float(dt_e.item()), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h[0],
+               "ms_per_step": float(dt_e.item()) * 1e3, "steps": nstep,
+               "api": "AbcEngine.abc on pinned host tables (H2D) -> posterior sample + summary (D2H)"}
+
+    if rank == 0:
+        base = None
+        if not args.no_cpu:
+            base, _ = cpu_arm(args, 2, 1)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "roofline": roofline,
+                "cpu_baseline": base, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
+                "nacc": res.nacc, "ds": res.ds}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

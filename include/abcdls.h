@@ -113,13 +113,39 @@ int abcdls_scale_dist(abcdls_handle_t h, const double* ss, int64_t n, int d, int
  * (single GPU: nacc).  idx_out gets ascending global row numbers (row_offset + local row).
  */
 size_t abcdls_accept_workspace_bytes(int64_t n);
-/* count of local rows with dist <= ds -> le_count (device int64); feeds the cross-rank scan */
-int abcdls_count_le(abcdls_handle_t h, const double* dist, int64_t n, const double* ds,
+/* count of rows with dist <= ds among the first min(n, *n_dev) entries -> le_count (device int64); feeds the
+ * cross-rank scan.  n_dev (device, may be NULL) lets the list length live on the device (candidate lists). */
+int abcdls_count_le(abcdls_handle_t h, const double* dist, int64_t n, const int64_t* n_dev, const double* ds,
                     int64_t* le_count, void* ws, size_t ws_bytes, void* stream);
-/* must follow abcdls_count_le on the same ws; quota is a device int64 */
-int abcdls_accept(abcdls_handle_t h, const double* dist, int64_t n, const double* ds,
-                  const int64_t* quota, int64_t row_offset, int64_t cap, int64_t* idx_out,
-                  int64_t* n_out, void* ws, size_t ws_bytes, int* status_dev, void* stream);
+/* must follow abcdls_count_le on the same ws; quota is a device int64.  src_idx (may be NULL): entry i of
+ * `dist` belongs to global row src_idx[i] (candidate list) instead of row_offset + i.  dist_out (may be
+ * NULL) receives the distances of the accepted rows. */
+int abcdls_accept(abcdls_handle_t h, const double* dist, int64_t n, const int64_t* n_dev, const int64_t* src_idx,
+                  const double* ds, const int64_t* quota, int64_t row_offset, int64_t cap, int64_t* idx_out,
+                  double* dist_out, int64_t* n_out, void* ws, size_t ws_bytes, int* status_dev, void* stream);
+
+/* ---- fast path: sampled brackets, one table pass each (csrc/bracket.cu) -----------------------
+ * Exact results or ABCDLS_S_FASTPATH_MISS in status_dev (then rerun with the radix select above).
+ * column median + MAD:  sample -> [all-reduce est] -> pass -> [all-reduce counts] -> finish
+ * distance + threshold: sample -> [all-reduce est] -> pass (emits the rows with dist <= bracket top in row
+ *                       order, the exact ds, and the N-vector dist only if `dist` != NULL)
+ * n must be >= 4096 (smaller tables use the radix path).
+ */
+size_t abcdls_mad_fast_workspace_bytes(int64_t n, int d);
+int abcdls_mad_fast_sample(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, void* ws,
+                           size_t ws_bytes, double** est_out, size_t* est_count, void* stream);
+int abcdls_mad_fast_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, void* ws,
+                         size_t ws_bytes, int64_t** counts_out, size_t* counts_count, void* stream);
+int abcdls_mad_fast_finish(abcdls_handle_t h, int64_t n, int64_t n_global, int d, void* ws, size_t ws_bytes,
+                           double* med, double* mad, int* status_dev, void* stream);
+size_t abcdls_dist_fast_workspace_bytes(int64_t n, int64_t cap);
+int abcdls_dist_fast_sample(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, const double* mad,
+                            const double* target, int64_t nacc, int64_t n_global, int world, int64_t cap, void* ws,
+                            size_t ws_bytes, double** est_out, size_t* est_count, void* stream);
+int abcdls_dist_fast_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, const double* mad,
+                          const double* target, int64_t nacc, int world, int64_t row_offset, int64_t cap, double* dist,
+                          int64_t* cand_row, double* cand_dist, int64_t* n_cand, double* ds_out, void* ws,
+                          size_t ws_bytes, int* status_dev, void* stream);
 
 /* ---- kernel 3: local-linear adjustment -----------------------------------------------------
  * R: weights (epanechnikov) -> lsfit -> residual recentring -> hcorr -> adj.values.
@@ -136,10 +162,10 @@ int abcdls_accept(abcdls_handle_t h, const double* dist, int64_t n, const double
  * n_acc is a device int64 (number of valid rows, <= cap).
  */
 int abcdls_gather(abcdls_handle_t h, const double* ss, int64_t ld_ss, const double* param,
-                  int64_t ld_param, const double* dist, const int64_t* idx, const int64_t* n_acc,
-                  int64_t row_offset, int64_t cap, int d, int P, const double* mad,
-                  const double* target, const double* ds, double* xs, double* y, double* ss_out,
-                  double* w, double* dist_out, void* stream);
+                  int64_t ld_param, const double* dist_acc /* distances of the accepted rows */,
+                  const int64_t* idx, const int64_t* n_acc, int64_t row_offset, int64_t cap, int d, int P,
+                  const double* mad, const double* target, const double* ds, double* xs, double* y,
+                  double* ss_out, double* w, void* stream);
 size_t abcdls_normal_workspace_bytes(int d, int P);
 int abcdls_normal(abcdls_handle_t h, const double* xs, const double* rhs, const double* w,
                   const int64_t* n_acc, int64_t cap, int d, int P, int with_gram, double* partial,
