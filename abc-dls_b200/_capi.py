@@ -56,7 +56,8 @@ SIGNATURES = {
     "abcdls_residual": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "abcdls_recentre_log": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "abcdls_adjust": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
-    "abcdls_col_stats": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "abcdls_col_stats_workspace_bytes": (_sz, [_i32]),
+    "abcdls_col_stats": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _sz, _vp]),
     "abcdls_postpr_counts": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp]),
     "abcdls_smc_workspace_bytes": (_sz, [_i64, _i32]),
     "abcdls_smc_oldrange": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _sz, _vp]),

@@ -124,9 +124,64 @@ __device__ __forceinline__ int bin_of(double v, double lo, double scale) {
 // counts[j*4 + {0: x<b2, 1: x in M, 2: b1<x<b4, 3: x in L u R}], histM[j][kNB] over M,
 // candM[j][capM] (values in M), candU[j][capU] (values in L u R); cnt[j*2 + {0,1}] = entries appended.
 constexpr int kAThreads = 256;
-constexpr int kAItems = 8;
-constexpr int kATile = kAThreads * kAItems;
+constexpr int kAItems = 8;                    // elements per lane per warp-tile
+constexpr int kAWarpTile = 32 * kAItems;      // 256 elements
+constexpr int kATile = kAThreads * kAItems;   // used for grid sizing only
+constexpr int kStageM = 64;                   // per-warp staging (doubles) for the M band
+constexpr int kStageU = 160;                  // ... and for L u R
 
+// Same-address global atomics cost ~15 ns each on B200, so candidates are staged per warp in shared memory
+// and flushed with ONE atomic + a coalesced copy when the stage is full.
+// Appends `tot` values (this lane contributes those flagged in `mask`, at exclusive offset `ex`) to the stage,
+// flushing / bypassing as needed.  Warp-uniform: tot, fill.
+__device__ __forceinline__ void stage_append(double* stage, int cap_stage, int& fill, const double (&x)[kAItems],
+                                             unsigned mask, int ex, int tot, double* __restrict__ gbuf,
+                                             long long gcap, unsigned long long* gcnt, int lane) {
+    if (tot == 0) return;
+    if (fill + tot > cap_stage && fill > 0) {   // flush what is staged
+        unsigned long long base = 0ull;
+        if (lane == 0) base = atomicAdd(gcnt, (unsigned long long)fill);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int t = lane; t < fill; t += 32)
+            if ((long long)base + t < gcap) gbuf[base + t] = stage[t];
+        fill = 0;
+        __syncwarp();
+    }
+    if (tot > cap_stage) {                       // a single warp-tile larger than the stage: straight to HBM
+        unsigned long long base = 0ull;
+        if (lane == 0) base = atomicAdd(gcnt, (unsigned long long)tot);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        long long p = (long long)base + ex;
+#pragma unroll
+        for (int u = 0; u < kAItems; ++u)
+            if (mask & (1u << u)) {
+                if (p < gcap) gbuf[p] = x[u];
+                ++p;
+            }
+        return;
+    }
+    int p = fill + ex;
+#pragma unroll
+    for (int u = 0; u < kAItems; ++u)
+        if (mask & (1u << u)) stage[p++] = x[u];
+    fill += tot;
+    __syncwarp();
+}
+
+__device__ __forceinline__ void stage_flush(double* stage, int& fill, double* __restrict__ gbuf, long long gcap,
+                                            unsigned long long* gcnt, int lane) {
+    if (fill == 0) return;
+    unsigned long long base = 0ull;
+    if (lane == 0) base = atomicAdd(gcnt, (unsigned long long)fill);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (int t = lane; t < fill; t += 32)
+        if ((long long)base + t < gcap) gbuf[base + t] = stage[t];
+    fill = 0;
+    __syncwarp();
+}
+
+// No block barriers in the streaming loop: every warp owns warp-tiles of 256 consecutive elements, classifies
+// its 8 elements per lane from registers and prefetches the next warp-tile before working.
 __global__ void __launch_bounds__(kAThreads) k_bracket_pass(const double* __restrict__ ss, long long n, long long ld,
                                                             const ColBrk* __restrict__ brk,
                                                             unsigned long long* __restrict__ counts,
@@ -135,36 +190,54 @@ __global__ void __launch_bounds__(kAThreads) k_bracket_pass(const double* __rest
                                                             double* __restrict__ candU, long long capU,
                                                             unsigned long long* __restrict__ cnt) {
     __shared__ unsigned hist[kNB];
-    __shared__ int scan_sh[33];
-    __shared__ unsigned long long base_sh[2];
+    __shared__ unsigned tot4[4];
+    __shared__ double stM[kAThreads / 32][kStageM];
+    __shared__ double stU[kAThreads / 32][kStageU];
     const int j = blockIdx.y;
     const double* __restrict__ col = ss + (size_t)j * ld;
     const ColBrk B = brk[j];
     const double b0 = B.b[0], b1 = B.b[1], b2 = B.b[2], b3 = B.b[3], b4 = B.b[4], b5 = B.b[5];
     const double scaleM = B.scaleM;
     for (int t = threadIdx.x; t < kNB; t += kAThreads) hist[t] = 0u;
+    if (threadIdx.x < 4) tot4[threadIdx.x] = 0u;
     __syncthreads();
-    // 16-byte loads need an even element offset from a 16-byte aligned address
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long warp_id = (long long)blockIdx.x * (kAThreads / 32) + wid;
+    const long long warp_stride = (long long)gridDim.x * (kAThreads / 32);
     const bool vec = ((reinterpret_cast<uintptr_t>(col) & 15) == 0);
+    const long long nfull = n / kAWarpTile;          // warp-tiles that need no bounds checks
+    const long long ntiles = (n + kAWarpTile - 1) / kAWarpTile;
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
     unsigned c_lt = 0, c_m = 0, c_in = 0, c_u = 0;
-    const long long ntiles = (n + kATile - 1) / kATile;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long t0 = tile * kATile;
-        double x[kAItems];
-        if (vec && t0 + kATile <= n) {
+    int fillM = 0, fillU = 0;
+    double* gM = candM + (size_t)j * capM;
+    double* gU = candU + (size_t)j * capU;
+
+    auto load_tile = [&](long long wt, double (&x)[kAItems]) {
+        const long long t0 = wt * kAWarpTile;
+        if (vec && wt < nfull) {
 #pragma unroll
             for (int u = 0; u < kAItems / 2; ++u) {
-                double2 v = ld_stream2(col + t0 + (long long)u * (2 * kAThreads) + 2 * threadIdx.x);
+                const double2 v = ld_stream2(col + t0 + u * 64 + 2 * lane);
                 x[2 * u] = v.x;
                 x[2 * u + 1] = v.y;
             }
         } else {
 #pragma unroll
-            for (int u = 0; u < kAItems; ++u) {
-                long long i = t0 + (long long)u * kAThreads + threadIdx.x;
-                x[u] = i < n ? ld_stream(col + i) : __longlong_as_double(0x7ff8000000000000ll);  // NaN: no class
+            for (int u = 0; u < kAItems / 2; ++u) {
+                const long long i = t0 + u * 64 + 2 * lane;
+                x[2 * u] = i < n ? ld_stream(col + i) : nan;
+                x[2 * u + 1] = i + 1 < n ? ld_stream(col + i + 1) : nan;
             }
         }
+    };
+
+    double x[kAItems], xn[kAItems];
+    long long wt = warp_id;
+    if (wt < ntiles) load_tile(wt, x);
+    for (; wt < ntiles; wt += warp_stride) {
+        const long long wnext = wt + warp_stride;
+        if (wnext < ntiles) load_tile(wnext, xn);
         unsigned mM = 0, mU = 0;
 #pragma unroll
         for (int u = 0; u < kAItems; ++u) {
@@ -179,36 +252,29 @@ __global__ void __launch_bounds__(kAThreads) k_bracket_pass(const double* __rest
             mM |= inM ? (1u << u) : 0u;
             mU |= inU ? (1u << u) : 0u;
         }
-        const int nM = __popc(mM), nU = __popc(mU);
-        if (__syncthreads_or((int)(mM | mU))) {
-            int tot;
-            int ex = block_exclusive_scan(nM | (nU << 16), scan_sh, &tot);
-            if (threadIdx.x == 0) {
-                base_sh[0] = (tot & 0xffff) ? atomicAdd(&cnt[j * 2 + 0], (unsigned long long)(tot & 0xffff)) : 0ull;
-                base_sh[1] = (tot >> 16) ? atomicAdd(&cnt[j * 2 + 1], (unsigned long long)(tot >> 16)) : 0ull;
-            }
-            __syncthreads();
-            long long pM = (long long)base_sh[0] + (ex & 0xffff), pU = (long long)base_sh[1] + (ex >> 16);
+        if (__any_sync(0xffffffffu, (mM | mU) != 0u)) {
+            const int packed = __popc(mM) | (__popc(mU) << 16);
+            int incl = packed;
 #pragma unroll
-            for (int u = 0; u < kAItems; ++u) {
-                if (mM & (1u << u)) {
-                    if (pM < capM) candM[(size_t)j * capM + pM] = x[u];
-                    ++pM;
-                    atomicAdd(&hist[bin_of(x[u], b2, scaleM)], 1u);
-                }
-                if (mU & (1u << u)) {
-                    if (pU < capU) candU[(size_t)j * capU + pU] = x[u];
-                    ++pU;
-                }
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
             }
+            const int tot = __shfl_sync(0xffffffffu, incl, 31);
+            const int ex = incl - packed;
+            stage_append(stM[wid], kStageM, fillM, x, mM, ex & 0xffff, tot & 0xffff, gM, capM, &cnt[j * 2 + 0], lane);
+            stage_append(stU[wid], kStageU, fillU, x, mU, ex >> 16, tot >> 16, gU, capU, &cnt[j * 2 + 1], lane);
+#pragma unroll
+            for (int u = 0; u < kAItems; ++u)
+                if (mM & (1u << u)) atomicAdd(&hist[bin_of(x[u], b2, scaleM)], 1u);
         }
+#pragma unroll
+        for (int u = 0; u < kAItems; ++u) x[u] = xn[u];
     }
-    // block totals -> global counts (4 per column)
+    stage_flush(stM[wid], fillM, gM, capM, &cnt[j * 2 + 0], lane);
+    stage_flush(stU[wid], fillU, gU, capU, &cnt[j * 2 + 1], lane);
     c_lt = warp_sum(c_lt); c_m = warp_sum(c_m); c_in = warp_sum(c_in); c_u = warp_sum(c_u);
-    __shared__ unsigned tot4[4];
-    if (threadIdx.x < 4) tot4[threadIdx.x] = 0u;
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
         atomicAdd(&tot4[0], c_lt); atomicAdd(&tot4[1], c_m); atomicAdd(&tot4[2], c_in); atomicAdd(&tot4[3], c_u);
     }
     __syncthreads();
@@ -534,10 +600,22 @@ __global__ void k_make_dist_bracket(const double* __restrict__ est, int G, doubl
     brk->scale = (hi > lo) ? (double)kNB / (hi - lo) : 0.0;
 }
 
-// K7: pass B.  Tile = 512 rows (256 threads x 2 consecutive rows); every tile appends its candidate rows
-// (dist <= hi) in row order and records (offset, count) in the tile directory.
+// K7: pass B.  Every warp owns one contiguous range of rows and walks it in warp-tiles of 128 rows (lane l holds
+// rows {2l, 2l+1} of each 64-row half: two 16-byte loads per column).  Candidate rows (dist <= hi) are staged
+// per warp in shared memory in row order and flushed with one atomic + coalesced copies; each flush leaves a
+// record (offset, count) so that k_order_cands can lay all chunks out in global row order.  No block barriers.
 constexpr int kBThreads = 256;
-constexpr int kBTile = 2 * kBThreads;
+constexpr int kBGrid = 148 * 8;                 // CTAs (fixed: the record directory is sized from it)
+constexpr int kBWarps = kBGrid * (kBThreads / 32);
+constexpr int kBHalf = 64;
+constexpr int kBWarpTile = 128;
+constexpr int kStageB = 96;                     // staged candidates per warp
+
+inline long long rows_per_warp(long long n) {
+    long long r = (n + kBWarps - 1) / kBWarps;
+    return (r + kBWarpTile - 1) / kBWarpTile * kBWarpTile;
+}
+inline long long recs_per_warp(long long n) { return 2 * (rows_per_warp(n) / kBWarpTile) + 2; }
 
 template <bool VEC2, bool WRITE_DIST>
 __global__ void __launch_bounds__(kBThreads) k_dist_pass(const double* __restrict__ ss, long long n, int d, long long ld,
@@ -547,111 +625,167 @@ __global__ void __launch_bounds__(kBThreads) k_dist_pass(const double* __restric
                                                          long long cap, unsigned long long* __restrict__ cand_cnt,
                                                          unsigned long long* __restrict__ n_lt,
                                                          unsigned long long* __restrict__ hist_g,
-                                                         long long* __restrict__ tile_off, int* __restrict__ tile_cnt,
-                                                         int* status) {
+                                                         long long rpw, long long rcap, long long* __restrict__ rec_off,
+                                                         int* __restrict__ rec_cnt, int* __restrict__ wtot,
+                                                         int* __restrict__ nrec, int* status) {
     __shared__ ColScale S;
     __shared__ unsigned hist[kNB];
-    __shared__ int scan_sh[33];
-    __shared__ unsigned long long base_sh;
+    __shared__ long long st_row[kBThreads / 32][kStageB];
+    __shared__ double st_dist[kBThreads / 32][kStageB];
     load_scale(S, mad, target, d);
     for (int t = threadIdx.x; t < kNB; t += kBThreads) hist[t] = 0u;
     __syncthreads();
     const double lo = brk->lo, hi = brk->hi, scale = brk->scale;
-    const long long ntiles = (n + kBTile - 1) / kBTile;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long gw = (long long)blockIdx.x * (kBThreads / 32) + wid;
+    const long long r_begin = gw * rpw, r_end = min(n, r_begin + rpw);
     bool nonfinite = false;
     unsigned c_lt = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long i0 = tile * kBTile + 2 * threadIdx.x;
-        double s0 = 0.0, s1 = 0.0;
-        const bool full = VEC2 && (i0 + 1 < n);
+    int fill = 0, seq = 0, total = 0;
+
+    auto flush = [&]() {
+        unsigned long long base = 0ull;
+        if (lane == 0) {
+            base = atomicAdd(cand_cnt, (unsigned long long)fill);
+            if (seq < rcap) {
+                rec_off[gw * rcap + seq] = (long long)base;
+                rec_cnt[gw * rcap + seq] = fill;
+            }
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int t = lane; t < fill; t += 32)
+            if ((long long)base + t < cap) {
+                cand_row[base + t] = st_row[wid][t];
+                cand_dist[base + t] = st_dist[wid][t];
+            }
+        ++seq;
+        fill = 0;
+        __syncwarp();
+    };
+
+    for (long long t0 = r_begin; t0 < r_end; t0 += kBWarpTile) {
+        const long long i0 = t0 + 2 * lane, i1 = i0 + kBHalf;
+        double s[4] = {0.0, 0.0, 0.0, 0.0};
+        const bool full = VEC2 && (t0 + kBWarpTile <= n);
         if (full) {
             const double* col = ss + i0;
-#pragma unroll 8
+#pragma unroll 4
             for (int j = 0; j < d; ++j) {
-                double2 x = ld_stream2(col);
+                const double2 xa = ld_stream2(col);
+                const double2 xb = ld_stream2(col + kBHalf);
                 col += ld;
                 const double tj = S.tgt[j];
-                const double a = __dsub_rn(scaled_value(x.x, S, j), tj);
-                const double b = __dsub_rn(scaled_value(x.y, S, j), tj);
-                s0 = __dadd_rn(s0, __dmul_rn(a, a));
-                s1 = __dadd_rn(s1, __dmul_rn(b, b));
+                const double a0 = __dsub_rn(scaled_value(xa.x, S, j), tj);
+                const double a1 = __dsub_rn(scaled_value(xa.y, S, j), tj);
+                const double a2 = __dsub_rn(scaled_value(xb.x, S, j), tj);
+                const double a3 = __dsub_rn(scaled_value(xb.y, S, j), tj);
+                s[0] = __dadd_rn(s[0], __dmul_rn(a0, a0));
+                s[1] = __dadd_rn(s[1], __dmul_rn(a1, a1));
+                s[2] = __dadd_rn(s[2], __dmul_rn(a2, a2));
+                s[3] = __dadd_rn(s[3], __dmul_rn(a3, a3));
             }
         } else {
+            const long long rows[4] = {i0, i0 + 1, i1, i1 + 1};
             for (int j = 0; j < d; ++j) {
                 const double tj = S.tgt[j];
-                if (i0 < n) {
-                    const double a = __dsub_rn(scaled_value(ss[(size_t)j * ld + i0], S, j), tj);
-                    s0 = __dadd_rn(s0, __dmul_rn(a, a));
-                }
-                if (i0 + 1 < n) {
-                    const double b = __dsub_rn(scaled_value(ss[(size_t)j * ld + i0 + 1], S, j), tj);
-                    s1 = __dadd_rn(s1, __dmul_rn(b, b));
-                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (rows[q] < n) {
+                        const double a = __dsub_rn(scaled_value(ss[(size_t)j * ld + rows[q]], S, j), tj);
+                        s[q] = __dadd_rn(s[q], __dmul_rn(a, a));
+                    }
             }
         }
-        const double d0 = __dsqrt_rn(s0), d1 = __dsqrt_rn(s1);
-        const bool v0 = i0 < n, v1 = i0 + 1 < n;
-        nonfinite |= (v0 && !isfinite(d0)) || (v1 && !isfinite(d1));
+        const long long rows[4] = {i0, i0 + 1, i1, i1 + 1};
+        double dd[4];
+        bool c[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            dd[q] = __dsqrt_rn(s[q]);
+            const bool v = rows[q] < n;
+            nonfinite |= v && !isfinite(dd[q]);
+            c[q] = v && dd[q] <= hi;
+            c_lt += (v && dd[q] < lo) ? 1u : 0u;
+        }
         if (WRITE_DIST) {
-            if (full && VEC2) *reinterpret_cast<double2*>(dist + i0) = make_double2(d0, d1);
-            else {
-                if (v0) dist[i0] = d0;
-                if (v1) dist[i0 + 1] = d1;
+            if (full) {
+                *reinterpret_cast<double2*>(dist + i0) = make_double2(dd[0], dd[1]);
+                *reinterpret_cast<double2*>(dist + i1) = make_double2(dd[2], dd[3]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (rows[q] < n) dist[rows[q]] = dd[q];
             }
         }
-        const bool c0 = v0 && d0 <= hi, c1 = v1 && d1 <= hi;
-        c_lt += (v0 && d0 < lo) ? 1u : 0u;
-        c_lt += (v1 && d1 < lo) ? 1u : 0u;
-        const int nc = (c0 ? 1 : 0) + (c1 ? 1 : 0);
-        if (__syncthreads_or(nc)) {
-            int tot;
-            int ex = block_exclusive_scan(nc, scan_sh, &tot);
-            if (threadIdx.x == 0) {
-                unsigned long long b = atomicAdd(cand_cnt, (unsigned long long)tot);
-                base_sh = b;
-                tile_off[tile] = (long long)b;
-                tile_cnt[tile] = tot;
+        const int packed = ((c[0] ? 1 : 0) + (c[1] ? 1 : 0)) | (((c[2] ? 1 : 0) + (c[3] ? 1 : 0)) << 8);
+        if (__any_sync(0xffffffffu, packed != 0)) {
+            int incl = packed;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
             }
-            __syncthreads();
-            long long pos = (long long)base_sh + ex;
-            if (c0) {
-                if (pos < cap) { cand_row[pos] = i0; cand_dist[pos] = d0; }
-                ++pos;
-                if (d0 >= lo) atomicAdd(&hist[bin_of(d0, lo, scale)], 1u);
+            const int tot = __shfl_sync(0xffffffffu, incl, 31);
+            const int tot0 = tot & 0xff, tot1 = tot >> 8;
+            const int ex = incl - packed;
+            // the two halves are appended one after the other (row order); each is at most 64 <= kStageB
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int th = half ? tot1 : tot0;
+                if (th == 0) continue;
+                if (fill + th > kStageB) flush();
+                int p = fill + (half ? (ex >> 8) : (ex & 0xff));
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int qq = 2 * half + q;
+                    if (c[qq]) {
+                        st_row[wid][p] = rows[qq];
+                        st_dist[wid][p] = dd[qq];
+                        ++p;
+                        if (dd[qq] >= lo) atomicAdd(&hist[bin_of(dd[qq], lo, scale)], 1u);
+                    }
+                }
+                fill += th;
+                total += th;
+                __syncwarp();
             }
-            if (c1) {
-                if (pos < cap) { cand_row[pos] = i0 + 1; cand_dist[pos] = d1; }
-                if (d1 >= lo) atomicAdd(&hist[bin_of(d1, lo, scale)], 1u);
-            }
-        } else if (threadIdx.x == 0) {
-            tile_off[tile] = 0;
-            tile_cnt[tile] = 0;
         }
     }
+    if (fill > 0) flush();
+    if (lane == 0) {
+        wtot[gw] = total;
+        nrec[gw] = seq < rcap ? seq : (int)rcap;
+        if (seq > rcap) atomicOr(status, ABCDLS_S_FASTPATH_MISS);
+    }
     c_lt = warp_sum(c_lt);
-    if ((threadIdx.x & 31) == 0 && c_lt) atomicAdd(n_lt, (unsigned long long)c_lt);
-    if (__any_sync(0xffffffffu, nonfinite) && (threadIdx.x & 31) == 0) atomicOr(status, ABCDLS_S_NONFINITE);
+    if (lane == 0 && c_lt) atomicAdd(n_lt, (unsigned long long)c_lt);
+    if (__any_sync(0xffffffffu, nonfinite) && lane == 0) atomicOr(status, ABCDLS_S_NONFINITE);
     __syncthreads();
     for (int t = threadIdx.x; t < kNB; t += kBThreads)
         if (hist[t]) atomicAdd(&hist_g[t], (unsigned long long)hist[t]);
 }
 
-// K8: bring the tile chunks into row order.  tile_pos = exclusive scan of tile_cnt (k_scan_tiles).
-__global__ void __launch_bounds__(256) k_order_cands(const long long* __restrict__ tile_off, const int* __restrict__ tile_cnt,
-                                                     const long long* __restrict__ tile_pos, long long ntiles,
-                                                     const long long* __restrict__ row_in, const double* __restrict__ dist_in,
-                                                     long long cap, long long row_offset, long long* __restrict__ row_out,
+// K8: lay the flushed chunks out in global row order.  One warp per producer warp; wpos = exclusive scan of wtot.
+__global__ void __launch_bounds__(256) k_order_cands(const long long* __restrict__ rec_off, const int* __restrict__ rec_cnt,
+                                                     const int* __restrict__ nrec, const long long* __restrict__ wpos,
+                                                     long long rcap, const long long* __restrict__ row_in,
+                                                     const double* __restrict__ dist_in, long long cap,
+                                                     long long row_offset, long long* __restrict__ row_out,
                                                      double* __restrict__ dist_out) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < ntiles; t += stride) {
-        const int c = tile_cnt[t];
-        const long long src = tile_off[t], dst = tile_pos[t];
-        for (int e = 0; e < c; ++e) {
+    const int lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (gw >= kBWarps) return;
+    long long dst = wpos[gw];
+    const int nr = nrec[gw];
+    for (int r = 0; r < nr; ++r) {
+        const long long src = rec_off[gw * rcap + r];
+        const int c = rec_cnt[gw * rcap + r];
+        for (int e = lane; e < c; e += 32)
             if (src + e < cap && dst + e < cap) {
                 row_out[dst + e] = row_in[src + e] + row_offset;
                 dist_out[dst + e] = dist_in[src + e];
             }
-        }
+        dst += c;
     }
 }
 
@@ -739,22 +873,22 @@ struct DistWs {
     size_t zero_bytes;
     RefJob* job;
     double* small;                 // [kSmallCap]
-    long long* tile_off;           // [ntiles]
-    int* tile_cnt;                 // [ntiles]
-    long long* tile_pos;           // [ntiles]
+    long long* rec_off;            // [kBWarps * rcap]
+    int* rec_cnt;                  // [kBWarps * rcap]
+    int* wtot;                     // [kBWarps]
+    int* nrec;                     // [kBWarps]
+    long long* wpos;               // [kBWarps]
     long long* row_tmp;            // [cap]
     double* dist_tmp;              // [cap]
     size_t total;
 };
-
-inline long long dist_tiles(long long n) { return (n + kBTile - 1) / kBTile; }
 
 inline DistWs carve_dist(void* ws, int G, long long n, long long cap) {
     DistWs w;
     char* p = reinterpret_cast<char*>(ws);
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t a = o; o += align_up(bytes, 256); return p ? p + a : (char*)nullptr; };
-    const long long nt = dist_tiles(n);
+    const long long rcap = recs_per_warp(n);
     w.est = (double*)take((size_t)G * 2 * 8);
     w.brk = (DistBrk*)take(sizeof(DistBrk));
     size_t z0 = o;
@@ -765,9 +899,11 @@ inline DistWs carve_dist(void* ws, int G, long long n, long long cap) {
     w.zero_bytes = o - z0;
     w.job = (RefJob*)take(sizeof(RefJob));
     w.small = (double*)take((size_t)kSmallCap * 8);
-    w.tile_off = (long long*)take((size_t)nt * 8);
-    w.tile_cnt = (int*)take((size_t)nt * 4);
-    w.tile_pos = (long long*)take((size_t)nt * 8);
+    w.rec_off = (long long*)take((size_t)kBWarps * rcap * 8);
+    w.rec_cnt = (int*)take((size_t)kBWarps * rcap * 4);
+    w.wtot = (int*)take((size_t)kBWarps * 4);
+    w.nrec = (int*)take((size_t)kBWarps * 4);
+    w.wpos = (long long*)take((size_t)kBWarps * 8);
     w.row_tmp = (long long*)take((size_t)cap * 8);
     w.dist_tmp = (double*)take((size_t)cap * 8);
     w.total = o;
@@ -941,25 +1077,22 @@ int abcdls_dist_fast_pass(abcdls_handle_t h, const double* ss, int64_t n, int d,
     }
     cudaStream_t st = (cudaStream_t)stream;
     k_make_dist_bracket<<<1, 32, 0, st>>>(w.est, G, 1.0 / world, w.brk);
-    const long long nt = dist_tiles(n);
-    long long gx = nt;
-    long long mx = (long long)h->sm_count * 8;
-    if (gx > mx) gx = mx;
+    const long long rpw = rows_per_warp(n), rcap = recs_per_warp(n);
     const bool vec = ((reinterpret_cast<uintptr_t>(ss) & 15) == 0) && ((ld & 1) == 0) &&
                      (!dist || (reinterpret_cast<uintptr_t>(dist) & 15) == 0);
-#define LAUNCH_B(V, W)                                                                                          \
-    k_dist_pass<V, W><<<(unsigned)gx, kBThreads, 0, st>>>(ss, n, d, ld, mad, target, w.brk, dist, w.row_tmp,    \
-                                                          w.dist_tmp, cap, w.cand_cnt, w.n_lt, w.hist, w.tile_off, \
-                                                          w.tile_cnt, status_dev)
+#define LAUNCH_B(V, W)                                                                                            \
+    k_dist_pass<V, W><<<kBGrid, kBThreads, 0, st>>>(ss, n, d, ld, mad, target, w.brk, dist, w.row_tmp, w.dist_tmp, \
+                                                    cap, w.cand_cnt, w.n_lt, w.hist, rpw, rcap, w.rec_off,         \
+                                                    w.rec_cnt, w.wtot, w.nrec, status_dev)
     if (vec && dist) LAUNCH_B(true, true);
     else if (vec) LAUNCH_B(true, false);
     else if (dist) LAUNCH_B(false, true);
     else LAUNCH_B(false, false);
 #undef LAUNCH_B
     ABCDLS_LAUNCH_CHECK(h);
-    k_scan_tiles<<<1, 1024, 0, st>>>(w.tile_cnt, nt, w.tile_pos);
-    k_order_cands<<<(unsigned)((nt + 255) / 256 > 1184 ? 1184 : (nt + 255) / 256), 256, 0, st>>>(
-        w.tile_off, w.tile_cnt, w.tile_pos, nt, w.row_tmp, w.dist_tmp, cap, row_offset, (long long*)cand_row, cand_dist);
+    k_scan_tiles<<<1, 1024, 0, st>>>(w.wtot, kBWarps, w.wpos);
+    k_order_cands<<<kBWarps / 8, 256, 0, st>>>(w.rec_off, w.rec_cnt, w.nrec, w.wpos, rcap, w.row_tmp, w.dist_tmp, cap,
+                                               row_offset, (long long*)cand_row, cand_dist);
     ABCDLS_CUDA(h, cudaMemcpyAsync(n_cand, w.cand_cnt, 8, cudaMemcpyDeviceToDevice, st));
     // exact ds among the candidates in [lo, hi]
     const size_t smem = (size_t)kSmallCap * sizeof(double);

@@ -56,11 +56,13 @@ __global__ void __launch_bounds__(256) k_gather(const double* __restrict__ ss, l
 }
 
 // ---- weighted normal equations ------------------------------------------------------------------
-// T_r = [1, xs_r (d), rhs_r (P)];  out = sum_r w_r * T_r[a] * T_r[b]  for (a,b) in
-// gram (M x M, a,b < M) and cross (M x P: a < M, b = M + p).
+// T_r = [1, xs_r (d), rhs_r (P)] (width W = M + P);  C[a][b] = sum_r w_r * T_r[a] * T_r[b] for a < M, b < W.
+// Register blocking: the (M x W) result is cut into 4x4 blocks; a thread owns one block per "slot" and keeps
+// its 16 accumulators in registers, so a row costs 8 shared-memory doubles per 16 FMAs.  The 256 threads of a
+// CTA form `groups` row-groups that take alternate rows of a staged tile; groups are summed in a fixed order.
 constexpr int kNormThreads = 256;
-constexpr int kNormRows = 32;
-constexpr int kMaxSlots = 20;  // entries per thread: E <= 5120
+constexpr int kNormRows = 64;   // rows staged per tile
+constexpr int kBlk = 4;
 
 __global__ void __launch_bounds__(kNormThreads) k_normal_partial(const double* __restrict__ xs,
                                                                  const double* __restrict__ rhs,
@@ -68,66 +70,96 @@ __global__ void __launch_bounds__(kNormThreads) k_normal_partial(const double* _
                                                                  const long long* __restrict__ n_acc_ptr,
                                                                  long long cap, int d, int P, int with_gram,
                                                                  double* __restrict__ partials) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(32) double smn[];
+    double* sm = smn;
     const int M = d + 1;
-    const int W = M + P;          // row width
-    const int Wp = W | 1;         // odd pitch: fewer bank conflicts
-    double* T = sm;               // [kNormRows][Wp]
-    double* wr = sm + kNormRows * Wp;
-    const int E = (with_gram ? M * M : 0) + M * P;
+    const int W = M + P;
+    const int Wp = (W + kBlk - 1) / kBlk * kBlk;       // row pitch, zero padded, 32-byte aligned rows
+    const int nbA = (M + kBlk - 1) / kBlk;
+    const int b_first = with_gram ? 0 : M / kBlk;      // without gram only columns >= M are needed
+    const int nbB = Wp / kBlk - b_first;
+    const int nblocks = nbA * nbB;
+    double* T = sm;                                    // [kNormRows][Wp]
+    double* wr = sm + (size_t)kNormRows * Wp;          // [kNormRows]
     long long n_acc = *n_acc_ptr;
     if (n_acc > cap) n_acc = cap;
 
-    int ea[kMaxSlots], eb[kMaxSlots];
-    double acc[kMaxSlots];
-    int nslots = 0;
-    for (int e = threadIdx.x; e < E && nslots < kMaxSlots; e += kNormThreads, ++nslots) {
-        int a, b;
-        if (with_gram && e < M * M) {
-            a = e / M;
-            b = e % M;
-        } else {
-            int e2 = e - (with_gram ? M * M : 0);
-            a = e2 / P;
-            b = M + e2 % P;
-        }
-        ea[nslots] = a;
-        eb[nslots] = b;
-        acc[nslots] = 0.0;
-    }
+    // thread -> (group, block).  groups = how many disjoint row subsets run side by side
+    const int groups = max(1, kNormThreads / nblocks);
+    const int slots = (nblocks + kNormThreads - 1) / kNormThreads;   // >1 only when nblocks > 256
+    const int grp = (slots == 1) ? threadIdx.x / nblocks : 0;
+    const int blk0 = (slots == 1) ? threadIdx.x % nblocks : threadIdx.x;
+    const bool active = (slots == 1) ? (grp < groups) : true;
 
-    const long long ntile = (n_acc + kNormRows - 1) / kNormRows;
-    for (long long tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
-        const long long r0 = tile * kNormRows;
-        __syncthreads();
-        for (int t = threadIdx.x; t < kNormRows * W; t += kNormThreads) {
-            int c = t / kNormRows, rr = t % kNormRows;  // consecutive threads -> consecutive rows (coalesced)
-            long long r = r0 + rr;
-            double v = 0.0;
-            if (r < n_acc) {
-                if (c == 0) v = 1.0;
-                else if (c < M) v = xs[(size_t)(c - 1) * cap + r];
-                else v = rhs[(size_t)(c - M) * cap + r];
-            }
-            T[rr * Wp + c] = v;
-        }
-        if (threadIdx.x < kNormRows) {
-            long long r = r0 + threadIdx.x;
-            wr[threadIdx.x] = r < n_acc ? w[r] : 0.0;
-        }
-        __syncthreads();
-#pragma unroll 4
-        for (int rr = 0; rr < kNormRows; ++rr) {
-            const double wv = wr[rr];
-            const double* row = T + rr * Wp;
-#pragma unroll
-            for (int s = 0; s < kMaxSlots; ++s)
-                if (s < nslots) acc[s] = fma(wv * row[ea[s]], row[eb[s]], acc[s]);
-        }
-    }
+    const int E = (with_gram ? M * M : 0) + M * P;
     double* out = partials + (size_t)blockIdx.x * E;
-    int s = 0;
-    for (int e = threadIdx.x; e < E && s < kMaxSlots; e += kNormThreads, ++s) out[e] = acc[s];
+    for (int e = threadIdx.x; e < E; e += kNormThreads) out[e] = 0.0;
+
+    for (int slot = 0; slot < slots; ++slot) {
+        const int blk = blk0 + slot * kNormThreads;
+        const bool on = active && blk < nblocks;
+        const int ba = on ? (blk / nbB) * kBlk : 0;
+        const int bb = on ? (blk % nbB + b_first) * kBlk : 0;
+        double acc[kBlk][kBlk];
+#pragma unroll
+        for (int i = 0; i < kBlk; ++i)
+#pragma unroll
+            for (int j = 0; j < kBlk; ++j) acc[i][j] = 0.0;
+
+        const long long ntile = (n_acc + kNormRows - 1) / kNormRows;
+        for (long long tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+            const long long r0 = tile * kNormRows;
+            __syncthreads();
+            for (int t = threadIdx.x; t < kNormRows * Wp; t += kNormThreads) {
+                const int c = t / kNormRows, rr = t % kNormRows;   // consecutive threads -> consecutive rows
+                const long long r = r0 + rr;
+                double v = 0.0;
+                if (r < n_acc && c < W) {
+                    if (c == 0) v = 1.0;
+                    else if (c < M) v = xs[(size_t)(c - 1) * cap + r];
+                    else v = rhs[(size_t)(c - M) * cap + r];
+                }
+                T[rr * Wp + c] = v;
+            }
+            if (threadIdx.x < kNormRows) {
+                const long long r = r0 + threadIdx.x;
+                wr[threadIdx.x] = r < n_acc ? w[r] : 0.0;
+            }
+            __syncthreads();
+            if (on) {
+                for (int rr = grp; rr < kNormRows; rr += groups) {
+                    const double wv = wr[rr];
+                    const double4 a4 = *reinterpret_cast<const double4*>(T + rr * Wp + ba);
+                    const double4 b4 = *reinterpret_cast<const double4*>(T + rr * Wp + bb);
+                    const double av[4] = {a4.x * wv, a4.y * wv, a4.z * wv, a4.w * wv};
+                    const double bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                    for (int i = 0; i < kBlk; ++i)
+#pragma unroll
+                        for (int j = 0; j < kBlk; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+                }
+            }
+        }
+        // combine the row-groups in a fixed order (deterministic): group g adds in turn
+        for (int g = 0; g < groups; ++g) {
+            __syncthreads();
+            if (on && grp == g) {
+#pragma unroll
+                for (int i = 0; i < kBlk; ++i)
+#pragma unroll
+                    for (int j = 0; j < kBlk; ++j) {
+                        const int a = ba + i, b = bb + j;
+                        if (a < M && b < W) {
+                            int e = -1;
+                            if (b < M) { if (with_gram) e = a * M + b; }
+                            else e = (with_gram ? M * M : 0) + a * P + (b - M);
+                            if (e >= 0) out[e] += acc[i][j];
+                        }
+                    }
+            }
+        }
+        __syncthreads();
+    }
 }
 
 __global__ void k_reduce_partials(const double* __restrict__ partials, int nparts, int E, double* __restrict__ out) {
@@ -259,61 +291,81 @@ __global__ void __launch_bounds__(256) k_adjust(const double* __restrict__ xs, d
 }
 
 // per-column statistics over the first n_acc rows: out[c*6 + {0:min,1:max,2:sum,3:sum w*x,4:sum w*x*x,5:sum w}]
-// one block per column, fixed traversal order => deterministic
-__global__ void __launch_bounds__(1024) k_col_stats(const double* __restrict__ v, const double* __restrict__ w,
-                                                    const long long* __restrict__ n_acc_ptr, long long cap,
-                                                    double* __restrict__ out) {
-    long long n_acc = *n_acc_ptr;
-    if (n_acc > cap) n_acc = cap;
-    const int c = blockIdx.x;
-    const double* col = v + (size_t)c * cap;
-    double mn = __longlong_as_double(0x7ff0000000000000ll), mx = -mn, s = 0, swx = 0, swx2 = 0, sw = 0;
-    for (long long r = threadIdx.x; r < n_acc; r += blockDim.x) {
-        double x = col[r];
-        double ww = w ? w[r] : 1.0;
-        mn = fmin(mn, x);
-        mx = fmax(mx, x);
-        s += x;
-        swx = fma(ww, x, swx);
-        swx2 = fma(ww * x, x, swx2);
-        sw += ww;
-    }
-    __shared__ double sh[6][32];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+// grid (kStatChunks, ncols): every block reduces a fixed contiguous chunk, the last block to finish a column
+// combines the chunk partials in chunk order => deterministic for a given (n_acc, cap).
+constexpr int kStatChunks = 64;
+
+__device__ __forceinline__ void stat_reduce6(double v[6], double (*sh)[32]) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-        swx += __shfl_xor_sync(0xffffffffu, swx, o);
-        swx2 += __shfl_xor_sync(0xffffffffu, swx2, o);
-        sw += __shfl_xor_sync(0xffffffffu, sw, o);
-    }
-    if (lane == 0) {
-        sh[0][wid] = mn; sh[1][wid] = mx; sh[2][wid] = s; sh[3][wid] = swx; sh[4][wid] = swx2; sh[5][wid] = sw;
+        v[0] = fmin(v[0], __shfl_xor_sync(0xffffffffu, v[0], o));
+        v[1] = fmax(v[1], __shfl_xor_sync(0xffffffffu, v[1], o));
+#pragma unroll
+        for (int q = 2; q < 6; ++q) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
     }
     __syncthreads();
+    if (lane == 0)
+        for (int q = 0; q < 6; ++q) sh[q][wid] = v[q];
+    __syncthreads();
     if (wid == 0) {
-        const int nw = blockDim.x >> 5;
-        mn = lane < nw ? sh[0][lane] : __longlong_as_double(0x7ff0000000000000ll);
-        mx = lane < nw ? sh[1][lane] : __longlong_as_double(0xfff0000000000000ll);
-        s = lane < nw ? sh[2][lane] : 0.0;
-        swx = lane < nw ? sh[3][lane] : 0.0;
-        swx2 = lane < nw ? sh[4][lane] : 0.0;
-        sw = lane < nw ? sh[5][lane] : 0.0;
+        const double inf = __longlong_as_double(0x7ff0000000000000ll);
+        v[0] = lane < nw ? sh[0][lane] : inf;
+        v[1] = lane < nw ? sh[1][lane] : -inf;
+        for (int q = 2; q < 6; ++q) v[q] = lane < nw ? sh[q][lane] : 0.0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            s += __shfl_xor_sync(0xffffffffu, s, o);
-            swx += __shfl_xor_sync(0xffffffffu, swx, o);
-            swx2 += __shfl_xor_sync(0xffffffffu, swx2, o);
-            sw += __shfl_xor_sync(0xffffffffu, sw, o);
+            v[0] = fmin(v[0], __shfl_xor_sync(0xffffffffu, v[0], o));
+            v[1] = fmax(v[1], __shfl_xor_sync(0xffffffffu, v[1], o));
+#pragma unroll
+            for (int q = 2; q < 6; ++q) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
         }
-        if (lane == 0) {
-            double* o6 = out + (size_t)c * 6;
-            o6[0] = mn; o6[1] = mx; o6[2] = s; o6[3] = swx; o6[4] = swx2; o6[5] = sw;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_col_stats(const double* __restrict__ v, const double* __restrict__ w,
+                                                   const long long* __restrict__ n_acc_ptr, long long cap,
+                                                   double* __restrict__ part, unsigned* __restrict__ done,
+                                                   double* __restrict__ out) {
+    long long n_acc = *n_acc_ptr;
+    if (n_acc > cap) n_acc = cap;
+    const int c = blockIdx.y;
+    const double* col = v + (size_t)c * cap;
+    const long long per = (n_acc + kStatChunks - 1) / kStatChunks;
+    const long long lo = (long long)blockIdx.x * per, hi = min(n_acc, lo + per);
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    double a[6] = {inf, -inf, 0, 0, 0, 0};
+    for (long long r = lo + threadIdx.x; r < hi; r += blockDim.x) {
+        const double x = col[r];
+        const double ww = w ? w[r] : 1.0;
+        a[0] = fmin(a[0], x);
+        a[1] = fmax(a[1], x);
+        a[2] += x;
+        a[3] = fma(ww, x, a[3]);
+        a[4] = fma(ww * x, x, a[4]);
+        a[5] += ww;
+    }
+    __shared__ double sh[6][32];
+    __shared__ bool last;
+    stat_reduce6(a, sh);
+    if (threadIdx.x == 0) {
+        double* p6 = part + ((size_t)c * kStatChunks + blockIdx.x) * 6;
+        for (int q = 0; q < 6; ++q) p6[q] = a[q];
+        __threadfence();
+        last = (atomicAdd(&done[c], 1u) == (unsigned)kStatChunks - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        double r6[6] = {inf, -inf, 0, 0, 0, 0};
+        for (int k = 0; k < kStatChunks; ++k) {
+            const volatile double* p6 = part + ((size_t)c * kStatChunks + k) * 6;
+            r6[0] = fmin(r6[0], p6[0]);
+            r6[1] = fmax(r6[1], p6[1]);
+            for (int q = 2; q < 6; ++q) r6[q] += p6[q];
         }
+        for (int q = 0; q < 6; ++q) out[(size_t)c * 6 + q] = r6[q];
+        done[c] = 0u;   // ready for the next call on this workspace
     }
 }
 
@@ -383,13 +435,12 @@ int abcdls_normal(abcdls_handle_t h, const double* xs, const double* rhs, const 
     ABCDLS_CHECK_ARG(h, d >= 1 && d <= kMaxD && P >= 1 && P <= kMaxP && cap >= 1, "normal: shape");
     const int M = d + 1;
     const int E = (with_gram ? M * M : 0) + M * P;
-    ABCDLS_CHECK_ARG(h, E <= kMaxSlots * kNormThreads, "normal: (d+1)*(d+1+P) too large");
     const int grid = normal_grid(h, cap);
     if (ws_bytes < (size_t)grid * E * sizeof(double)) {
         h->err = "normal workspace too small";
         return ABCDLS_E_WORKSPACE;
     }
-    const int Wp = (M + P) | 1;
+    const int Wp = (M + P + kBlk - 1) / kBlk * kBlk;
     size_t smem = (size_t)(kNormRows * Wp + kNormRows) * sizeof(double);
     cudaStream_t st = (cudaStream_t)stream;
     if (smem > 48 * 1024)
@@ -443,10 +494,23 @@ int abcdls_adjust(abcdls_handle_t h, const double* xs, double* res, const double
     return ABCDLS_OK;
 }
 
+size_t abcdls_col_stats_workspace_bytes(int ncols) {
+    return align_up((size_t)ncols * kStatChunks * 6 * sizeof(double), 256) + align_up((size_t)ncols * 4, 256);
+}
+
+// ws must be zero-initialised once by the caller (the kernel leaves it zeroed again)
 int abcdls_col_stats(abcdls_handle_t h, const double* values, const double* w, const int64_t* n_acc, int64_t cap,
-                     int ncols, double* out, void* stream) {
-    ABCDLS_CHECK_ARG(h, h && values && n_acc && out && ncols >= 1 && cap >= 1, "col_stats");
-    k_col_stats<<<ncols, 1024, 0, (cudaStream_t)stream>>>(values, w, (const long long*)n_acc, cap, out);
+                     int ncols, double* out, void* ws, size_t ws_bytes, void* stream) {
+    ABCDLS_CHECK_ARG(h, h && values && n_acc && out && ws && ncols >= 1 && cap >= 1, "col_stats");
+    if (ws_bytes < abcdls_col_stats_workspace_bytes(ncols)) {
+        h->err = "col_stats workspace too small";
+        return ABCDLS_E_WORKSPACE;
+    }
+    double* part = reinterpret_cast<double*>(ws);
+    unsigned* done = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) +
+                                                 align_up((size_t)ncols * kStatChunks * 6 * sizeof(double), 256));
+    k_col_stats<<<dim3(kStatChunks, ncols), 256, 0, (cudaStream_t)stream>>>(values, w, (const long long*)n_acc, cap,
+                                                                            part, done, out);
     ABCDLS_LAUNCH_CHECK(h);
     return ABCDLS_OK;
 }

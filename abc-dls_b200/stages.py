@@ -162,7 +162,12 @@ class CudaStages:
         self.launches += 1
 
     def col_stats(self, values, w, n_acc, cap, ncols, out):
-        self.handle.call("abcdls_col_stats", _p(values), _p(w), _p(n_acc), cap, ncols, _p(out), self._stream())
+        key = f"colstats{ncols}"
+        if key not in self._ws:
+            self.workspace(key, self.lib.abcdls_col_stats_workspace_bytes(ncols)).zero_()
+        ws = self._ws[key]
+        self.handle.call("abcdls_col_stats", _p(values), _p(w), _p(n_acc), cap, ncols, _p(out), _p(ws), ws.numel(),
+                         self._stream())
         self.launches += 1
 
     def postpr_counts(self, model_id, idx, n_acc, row_offset, cap, K, counts):

@@ -22,7 +22,6 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -59,25 +58,28 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region through NVML in-process (forking
+    nvidia-smi from a process that maps tens of GB stalls the launching thread for milliseconds)."""
 
     def __init__(self, index: int):
         self.index, self.rows, self.stop = index, [], threading.Event()
         self.thread = threading.Thread(target=self._run, daemon=True)
+        self.max_mhz = None
 
     def _run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 6:
-                    self.rows.append(f)
-            except Exception:
-                pass
-            self.stop.wait(0.2)
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            while not self.stop.is_set():
+                self.rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetCurrentClocksEventReasons(h)))
+                self.stop.wait(0.02)
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
 
     def __enter__(self):
         self.thread.start()
@@ -89,12 +91,12 @@ class ClockSampler:
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(int(float(r[0])) for r in self.rows)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.rows[0][1])), "reasons": reasons,
-                "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled: " + getattr(self, "err", "")]}
+        sm = sorted(r[0] for r in self.rows)
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                "hw_power_brake_slowdown": 0x80}
+        reasons = [n for n, b in bits.items() if any(r[1] & b for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm)}
 
 
 def cpu_arm(args, steps, warmup):

@@ -182,8 +182,10 @@ int abcdls_adjust(abcdls_handle_t h, const double* xs, double* res, const double
 /* out[c*6 + {0:min, 1:max, 2:sum, 3:sum w*x, 4:sum w*x*x, 5:sum w}] over the first n_acc rows of each
  * column (ld = cap); w may be NULL (=1).  Serves summary() min/max/weighted mean (ABC.py:2833,2837),
  * the_m, sigma2 and the zero-variance-in-region check. */
+size_t abcdls_col_stats_workspace_bytes(int ncols);
+/* ws: zero it once after allocation; every call leaves it zeroed again */
 int abcdls_col_stats(abcdls_handle_t h, const double* values, const double* w, const int64_t* n_acc,
-                     int64_t cap, int ncols, double* out, void* stream);
+                     int64_t cap, int ncols, double* out, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- postpr (rejection): accepted simulations per model ------------------------ */
 int abcdls_postpr_counts(abcdls_handle_t h, const int32_t* model_id, const int64_t* idx,
