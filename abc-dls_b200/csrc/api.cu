@@ -1,5 +1,6 @@
 // api.cu — handle lifetime and error reporting for the abcdls C ABI (include/abcdls.h).
 #include "common.cuh"
+#include <stdlib.h>
 
 extern "C" {
 
@@ -20,6 +21,8 @@ int abcdls_create(abcdls_handle_t* out, int device) {
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
     h->smem_optin = prop.sharedMemPerBlockOptin;
+    const char* e = getenv("ABCDLS_NO_TMA");
+    h->no_tma = (e && e[0] == '1') ? 1 : 0;
     *out = h;
     return ABCDLS_OK;
 }

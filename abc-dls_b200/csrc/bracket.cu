@@ -17,6 +17,16 @@
 #include "common.cuh"
 #include "compact.cuh"
 
+// function attributes are set once per process (the call is not free and must not sit in the hot path)
+#define ABCDLS_ONCE(h, call)             \
+    do {                                 \
+        static bool _done = false;       \
+        if (!_done) {                    \
+            ABCDLS_CUDA(h, call);        \
+            _done = true;                \
+        }                                \
+    } while (0)
+
 namespace {
 
 constexpr int kNB = 1024;          // fine histogram bins per bracket
@@ -88,9 +98,15 @@ __global__ void __launch_bounds__(512) k_sample_cols(const double* __restrict__ 
     }
 }
 
+// Brackets of one column in "radial" form around a centre estimate c (NOT the exact median):
+//   s = x - c,  y = |s|  (both correctly rounded; fl(x - c) is monotone in x, so every class is an interval)
+//   below  : s < -r0          (strictly below the median band)
+//   M band : y <= r0          (contains the two middle order statistics)
+//   inner  : y <  r1          (certainly closer to the median than the MAD radius)
+//   U band : r1 <= y <= r2    (contains the two middle order statistics of |x - median|)
 struct ColBrk {
-    double b[6];     // L = [b0,b1], M = [b2,b3], R = [b4,b5]
-    double scaleM;   // kNB / (b3 - b2)   (0 when the band is a single point)
+    double c, r0, r1, r2;
+    double loM, scaleM;   // fine histogram of the M band: bin((x - loM) * scaleM), loM = c - r0
 };
 
 // K1b: average the G local estimates (already summed over ranks when world > 1) -> brackets. 1 thread/column.
@@ -101,15 +117,15 @@ __global__ void k_make_brackets(const double* __restrict__ est, int G, int d, do
     for (int g = 0; g < G; ++g)
         for (int q = 0; q < 4; ++q) m[q] += est[((size_t)g * d + j) * 4 + q];
     for (int q = 0; q < 4; ++q) m[q] = m[q] / G * inv_world;
+    // m = {m_lo, m_hi, r_lo, r_hi}
     ColBrk B;
-    B.b[0] = m[0] - m[3];
-    B.b[1] = m[1] - m[2];
-    B.b[2] = m[0];
-    B.b[3] = m[1];
-    B.b[4] = m[0] + m[2];
-    B.b[5] = m[1] + m[3];
-    double w = B.b[3] - B.b[2];
-    B.scaleM = (w > 0.0) ? (double)kNB / w : 0.0;
+    B.c = 0.5 * m[0] + 0.5 * m[1];
+    const double hm = fmax(fmax(m[1] - B.c, B.c - m[0]), 0.0);
+    B.r0 = hm;
+    B.r1 = fmax(m[2] - hm, 0.0);
+    B.r2 = m[3] + hm;
+    B.loM = B.c - B.r0;
+    B.scaleM = (B.r0 > 0.0) ? (double)kNB / (2.0 * B.r0) : 0.0;
     brk[j] = B;
 }
 
@@ -127,79 +143,48 @@ constexpr int kAThreads = 256;
 constexpr int kAItems = 8;                    // elements per lane per warp-tile
 constexpr int kAWarpTile = 32 * kAItems;      // 256 elements
 constexpr int kATile = kAThreads * kAItems;   // used for grid sizing only
-constexpr int kStageM = 64;                   // per-warp staging (doubles) for the M band
-constexpr int kStageU = 160;                  // ... and for L u R
+constexpr int kStageM = 96;                   // per-warp staging (doubles) for the M band
+constexpr int kStageU = 288;                  // ... and for the U band  (>= 256: a whole warp-tile always fits)
 
 // Same-address global atomics cost ~15 ns each on B200, so candidates are staged per warp in shared memory
-// and flushed with ONE atomic + a coalesced copy when the stage is full.
-// Appends `tot` values (this lane contributes those flagged in `mask`, at exclusive offset `ex`) to the stage,
-// flushing / bypassing as needed.  Warp-uniform: tot, fill.
-__device__ __forceinline__ void stage_append(double* stage, int cap_stage, int& fill, const double (&x)[kAItems],
-                                             unsigned mask, int ex, int tot, double* __restrict__ gbuf,
-                                             long long gcap, unsigned long long* gcnt, int lane) {
-    if (tot == 0) return;
-    if (fill + tot > cap_stage && fill > 0) {   // flush what is staged
-        unsigned long long base = 0ull;
-        if (lane == 0) base = atomicAdd(gcnt, (unsigned long long)fill);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        for (int t = lane; t < fill; t += 32)
-            if ((long long)base + t < gcap) gbuf[base + t] = stage[t];
-        fill = 0;
-        __syncwarp();
-    }
-    if (tot > cap_stage) {                       // a single warp-tile larger than the stage: straight to HBM
-        unsigned long long base = 0ull;
-        if (lane == 0) base = atomicAdd(gcnt, (unsigned long long)tot);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        long long p = (long long)base + ex;
-#pragma unroll
-        for (int u = 0; u < kAItems; ++u)
-            if (mask & (1u << u)) {
-                if (p < gcap) gbuf[p] = x[u];
-                ++p;
-            }
-        return;
-    }
-    int p = fill + ex;
-#pragma unroll
-    for (int u = 0; u < kAItems; ++u)
-        if (mask & (1u << u)) stage[p++] = x[u];
-    fill += tot;
-    __syncwarp();
-}
-
+// and flushed with ONE atomic + a coalesced copy.  The fine histogram of the M band is built at flush time.
+template <bool HIST>
 __device__ __forceinline__ void stage_flush(double* stage, int& fill, double* __restrict__ gbuf, long long gcap,
-                                            unsigned long long* gcnt, int lane) {
+                                            unsigned long long* gcnt, int lane, unsigned* hist, double lo,
+                                            double scale) {
     if (fill == 0) return;
     unsigned long long base = 0ull;
     if (lane == 0) base = atomicAdd(gcnt, (unsigned long long)fill);
     base = __shfl_sync(0xffffffffu, base, 0);
-    for (int t = lane; t < fill; t += 32)
-        if ((long long)base + t < gcap) gbuf[base + t] = stage[t];
+    for (int t = lane; t < fill; t += 32) {
+        const double v = stage[t];
+        if ((long long)base + t < gcap) gbuf[base + t] = v;
+        if (HIST) atomicAdd(&hist[bin_of(v, lo, scale)], 1u);
+    }
     fill = 0;
     __syncwarp();
 }
 
-// No block barriers in the streaming loop: every warp owns warp-tiles of 256 consecutive elements, classifies
-// its 8 elements per lane from registers and prefetches the next warp-tile before working.
-__global__ void __launch_bounds__(kAThreads) k_bracket_pass(const double* __restrict__ ss, long long n, long long ld,
-                                                            const ColBrk* __restrict__ brk,
-                                                            unsigned long long* __restrict__ counts,
-                                                            unsigned long long* __restrict__ histM,
-                                                            double* __restrict__ candM, long long capM,
-                                                            double* __restrict__ candU, long long capU,
-                                                            unsigned long long* __restrict__ cnt) {
+// Streaming loop without block barriers: a warp owns warp-tiles of 256 consecutive elements (8 per lane in
+// registers), classifies them with one subtract + four compares each, and prefetches its next warp-tile into a
+// second register set (ping-pong, no copies).
+__global__ void __launch_bounds__(kAThreads, 3) k_bracket_pass(const double* __restrict__ ss, long long n, long long ld,
+                                                               const ColBrk* __restrict__ brk,
+                                                               unsigned long long* __restrict__ counts,
+                                                               unsigned long long* __restrict__ histM,
+                                                               double* __restrict__ candM, long long capM,
+                                                               double* __restrict__ candU, long long capU,
+                                                               unsigned long long* __restrict__ cnt) {
     __shared__ unsigned hist[kNB];
-    __shared__ unsigned tot4[4];
+    __shared__ unsigned tot2[2];
     __shared__ double stM[kAThreads / 32][kStageM];
     __shared__ double stU[kAThreads / 32][kStageU];
     const int j = blockIdx.y;
     const double* __restrict__ col = ss + (size_t)j * ld;
     const ColBrk B = brk[j];
-    const double b0 = B.b[0], b1 = B.b[1], b2 = B.b[2], b3 = B.b[3], b4 = B.b[4], b5 = B.b[5];
-    const double scaleM = B.scaleM;
+    const double c = B.c, r0 = B.r0, r1 = B.r1, r2 = B.r2, nr0 = -B.r0, loM = B.loM, scaleM = B.scaleM;
     for (int t = threadIdx.x; t < kNB; t += kAThreads) hist[t] = 0u;
-    if (threadIdx.x < 4) tot4[threadIdx.x] = 0u;
+    if (threadIdx.x < 2) tot2[threadIdx.x] = 0u;
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const long long warp_id = (long long)blockIdx.x * (kAThreads / 32) + wid;
@@ -208,10 +193,14 @@ __global__ void __launch_bounds__(kAThreads) k_bracket_pass(const double* __rest
     const long long nfull = n / kAWarpTile;          // warp-tiles that need no bounds checks
     const long long ntiles = (n + kAWarpTile - 1) / kAWarpTile;
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
-    unsigned c_lt = 0, c_m = 0, c_in = 0, c_u = 0;
+    unsigned c_lt = 0, c_in = 0;
     int fillM = 0, fillU = 0;
     double* gM = candM + (size_t)j * capM;
     double* gU = candU + (size_t)j * capU;
+    double* sM = stM[wid];
+    double* sU = stU[wid];
+    unsigned long long* cntM = &cnt[j * 2 + 0];
+    unsigned long long* cntU = &cnt[j * 2 + 1];
 
     auto load_tile = [&](long long wt, double (&x)[kAItems]) {
         const long long t0 = wt * kAWarpTile;
@@ -232,25 +221,17 @@ __global__ void __launch_bounds__(kAThreads) k_bracket_pass(const double* __rest
         }
     };
 
-    double x[kAItems], xn[kAItems];
-    long long wt = warp_id;
-    if (wt < ntiles) load_tile(wt, x);
-    for (; wt < ntiles; wt += warp_stride) {
-        const long long wnext = wt + warp_stride;
-        if (wnext < ntiles) load_tile(wnext, xn);
+    auto process = [&](const double (&x)[kAItems]) {
         unsigned mM = 0, mU = 0;
 #pragma unroll
         for (int u = 0; u < kAItems; ++u) {
-            const double v = x[u];
-            const bool ge0 = v >= b0, le1 = v <= b1, ge2 = v >= b2, le3 = v <= b3, ge4 = v >= b4, le5 = v <= b5;
-            const bool inM = ge2 && le3;
-            const bool inU = (ge0 && le1) || (ge4 && le5);
-            c_lt += (v < b2) ? 1u : 0u;
-            c_m += inM ? 1u : 0u;
-            c_in += (v > b1 && v < b4) ? 1u : 0u;
-            c_u += inU ? 1u : 0u;
-            mM |= inM ? (1u << u) : 0u;
-            mU |= inU ? (1u << u) : 0u;
+            const double sgn = __dsub_rn(x[u], c);
+            const double y = fabs(sgn);
+            const bool in1 = y < r1;
+            c_lt += (sgn < nr0) ? 1u : 0u;
+            c_in += in1 ? 1u : 0u;
+            mM |= (y <= r0) ? (1u << u) : 0u;
+            mU |= (!in1 && y <= r2) ? (1u << u) : 0u;
         }
         if (__any_sync(0xffffffffu, (mM | mU) != 0u)) {
             const int packed = __popc(mM) | (__popc(mU) << 16);
@@ -261,24 +242,67 @@ __global__ void __launch_bounds__(kAThreads) k_bracket_pass(const double* __rest
                 if (lane >= o) incl += t;
             }
             const int tot = __shfl_sync(0xffffffffu, incl, 31);
-            const int ex = incl - packed;
-            stage_append(stM[wid], kStageM, fillM, x, mM, ex & 0xffff, tot & 0xffff, gM, capM, &cnt[j * 2 + 0], lane);
-            stage_append(stU[wid], kStageU, fillU, x, mU, ex >> 16, tot >> 16, gU, capU, &cnt[j * 2 + 1], lane);
+            const int totM = tot & 0xffff, totU = tot >> 16;
+            // a warp-tile holds at most 256 values: after a flush it always fits the stage
+            if (fillM + totM > kStageM) stage_flush<true>(sM, fillM, gM, capM, cntM, lane, hist, loM, scaleM);
+            if (fillU + totU > kStageU) stage_flush<false>(sU, fillU, gU, capU, cntU, lane, nullptr, 0.0, 0.0);
+            int pM = fillM + ((incl - packed) & 0xffff);
+            int pU = fillU + ((incl - packed) >> 16);
+            if (totM <= kStageM) {
 #pragma unroll
-            for (int u = 0; u < kAItems; ++u)
-                if (mM & (1u << u)) atomicAdd(&hist[bin_of(x[u], b2, scaleM)], 1u);
+                for (int u = 0; u < kAItems; ++u) {
+                    if (mM & (1u << u)) sM[pM] = x[u];
+                    pM += (mM >> u) & 1u;
+                }
+                fillM += totM;
+            } else {   // > 96 of 256 values inside the median band: heavy ties; flush straight to HBM
+                unsigned long long base = 0ull;
+                if (lane == 0) base = atomicAdd(cntM, (unsigned long long)totM);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                long long p = (long long)base + ((incl - packed) & 0xffff);
+#pragma unroll
+                for (int u = 0; u < kAItems; ++u)
+                    if (mM & (1u << u)) {
+                        if (p < capM) gM[p] = x[u];
+                        ++p;
+                        atomicAdd(&hist[bin_of(x[u], loM, scaleM)], 1u);
+                    }
+            }
+#pragma unroll
+            for (int u = 0; u < kAItems; ++u) {
+                if (mU & (1u << u)) sU[pU] = x[u];
+                pU += (mU >> u) & 1u;
+            }
+            fillU += totU;
+            __syncwarp();
         }
-#pragma unroll
-        for (int u = 0; u < kAItems; ++u) x[u] = xn[u];
+    };
+
+    double xa[kAItems], xb[kAItems];
+    long long wt = warp_id;
+    if (wt < ntiles) load_tile(wt, xa);
+    while (wt < ntiles) {
+        long long wnext = wt + warp_stride;
+        if (wnext < ntiles) load_tile(wnext, xb);
+        process(xa);
+        wt = wnext;
+        if (wt >= ntiles) break;
+        wnext = wt + warp_stride;
+        if (wnext < ntiles) load_tile(wnext, xa);
+        process(xb);
+        wt = wnext;
     }
-    stage_flush(stM[wid], fillM, gM, capM, &cnt[j * 2 + 0], lane);
-    stage_flush(stU[wid], fillU, gU, capU, &cnt[j * 2 + 1], lane);
-    c_lt = warp_sum(c_lt); c_m = warp_sum(c_m); c_in = warp_sum(c_in); c_u = warp_sum(c_u);
+    stage_flush<true>(sM, fillM, gM, capM, cntM, lane, hist, loM, scaleM);
+    stage_flush<false>(sU, fillU, gU, capU, cntU, lane, nullptr, 0.0, 0.0);
+    c_lt = warp_sum(c_lt);
+    c_in = warp_sum(c_in);
     if (lane == 0) {
-        atomicAdd(&tot4[0], c_lt); atomicAdd(&tot4[1], c_m); atomicAdd(&tot4[2], c_in); atomicAdd(&tot4[3], c_u);
+        atomicAdd(&tot2[0], c_lt);
+        atomicAdd(&tot2[1], c_in);
     }
     __syncthreads();
-    if (threadIdx.x < 4 && tot4[threadIdx.x]) atomicAdd(&counts[j * 4 + threadIdx.x], (unsigned long long)tot4[threadIdx.x]);
+    if (threadIdx.x < 2 && tot2[threadIdx.x])
+        atomicAdd(&counts[j * 4 + 2 * threadIdx.x], (unsigned long long)tot2[threadIdx.x]);   // [0]=below, [2]=inner
     for (int t = threadIdx.x; t < kNB; t += kAThreads)
         if (hist[t]) atomicAdd(&histM[(size_t)j * kNB + t], (unsigned long long)hist[t]);
 }
@@ -424,13 +448,13 @@ __global__ void k_plan_median(RefJob* jobs, int d, const ColBrk* __restrict__ br
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= d) return;
     RefJob J;
-    const long long c_lt = (long long)counts[j * 4 + 0], c_m = (long long)counts[j * 4 + 1];
+    const long long c_lt = (long long)counts[j * 4 + 0], c_m = (long long)cnt[j * 2 + 0];  // every M value was appended
     J.src = candM + (size_t)j * capM;
     J.src_count = cnt + j * 2 + 0;
     J.src_cap = capM;
     J.transform = 0;
     J.center = 0.0;
-    J.lo = brk[j].b[2];
+    J.lo = brk[j].loM;
     J.scale = brk[j].scaleM;
     J.vmin = -__longlong_as_double(0x7ff0000000000000ll);
     J.kk[0] = k0 - c_lt;
@@ -461,16 +485,17 @@ __global__ void k_plan_mad(RefJob* jobs, int d, const ColBrk* __restrict__ brk,
     med[j] = m;
     const ColBrk B = brk[j];
     RefJob J;
-    const long long c_in = (long long)counts[j * 4 + 2], c_u = (long long)counts[j * 4 + 3];
+    const long long c_in = (long long)counts[j * 4 + 2], c_u = (long long)cnt[j * 2 + 1];
     J.src = candU + (size_t)j * capU;
     J.src_count = cnt + j * 2 + 1;
     J.src_cap = capU;
     J.transform = 1;
     J.center = m;
-    // |x - m| of the stored values spans [alo, ahi]
-    const bool overlap = !(B.b[1] < B.b[4]);
-    double alo = overlap ? 0.0 : fmax(0.0, fmin(m - B.b[1], B.b[4] - m));
-    double ahi = fmax(m - B.b[0], B.b[5] - m);
+    // x in U has fl|x - c| in [r1, r2]; with e = |c - m| its |x - m| lies in [r1 - e, r2 + e] up to rounding
+    const double e = fabs(__dsub_rn(B.c, m));
+    const double up = 1.0 + 0x1p-48, dn = 1.0 - 0x1p-48;
+    const double alo = fmax(0.0, (B.r1 - e) * dn);
+    const double ahi = (B.r2 + e) * up;
     J.lo = alo;
     J.scale = (ahi > alo) ? (double)kNB / (ahi - alo) : 0.0;
     J.vmin = -__longlong_as_double(0x7ff0000000000000ll);
@@ -483,15 +508,13 @@ __global__ void k_plan_mad(RefJob* jobs, int d, const ColBrk* __restrict__ brk,
     J.small = small + (size_t)(d + j) * kSmallCap;
     J.small_count = small_count + d + j;
     J.result[0] = J.result[1] = 0.0;
-    J.valid = (Jm.valid && J.kk[0] >= 0 && J.kk[1] < c_u && (long long)cnt[j * 2 + 1] <= capU) ? 1 : 0;
+    J.valid = (Jm.valid && J.kk[0] >= 0 && J.kk[1] < c_u && c_u <= capU) ? 1 : 0;
     if (!J.valid) atomicOr(status, ABCDLS_S_FASTPATH_MISS);
-    // guards checked once r* is known: every inner value has |x-m| <= r*, every outer value >= r*
-    guard[j * 2 + 0] = overlap ? -1.0 : fmax(fabs(__dsub_rn(B.b[1], m)), fabs(__dsub_rn(B.b[4], m)));
-    guard[j * 2 + 1] = fmin(fabs(__dsub_rn(B.b[0], m)), fabs(__dsub_rn(B.b[5], m)));
-    if (!(B.b[0] <= m && m <= B.b[5])) {
-        J.valid = 0;
-        atomicOr(status, ABCDLS_S_FASTPATH_MISS);
-    }
+    // guards checked once r* is known (triangle inequality + rounding slack):
+    //   inner rows (fl|x-c| < r1)  have |x - m| <= (r1 + e) * up   -> must be <= the smaller rank value
+    //   outer rows (fl|x-c| > r2)  have |x - m| >= (r2 - e) * dn   -> must be >= the larger rank value
+    guard[j * 2 + 0] = (B.r1 > 0.0) ? (B.r1 + e) * up : -1.0;
+    guard[j * 2 + 1] = (B.r2 - e) * dn;
     jobs[d + j] = J;
 }
 
@@ -533,27 +556,28 @@ __global__ void k_finish_mad(const RefJob* jobs, int d, const double* __restrict
 // ---------------------------------------------------------------------------------------------------
 // distance: shared scaling constants
 struct ColScale {
-    double div[kMaxD], rcp[kMaxD], tgt[kMaxD], lo[kMaxD], hi[kMaxD];
+    double2 dr[kMaxD];   // (divisor, RN(1/divisor)); rcp = 0 marks a column whose divisor is outside [1e-90, 1e90]
+    double tgt[kMaxD];   // target / divisor
 };
 
 __device__ __forceinline__ void load_scale(ColScale& S, const double* mad, const double* target, int d) {
     for (int j = threadIdx.x; j < d; j += blockDim.x) {
         double m = mad[j];
         double dv = (m == 0.0) ? 1.0 : m;
-        S.div[j] = dv;
-        S.rcp[j] = 1.0 / dv;
-        S.tgt[j] = (m == 0.0) ? target[j] : target[j] / dv;
         double a = fabs(dv);
-        bool sane = a > 1e-290 && a < 1e290;
-        S.lo[j] = sane ? a * 1e-280 + 1e-280 : __longlong_as_double(0x7ff0000000000000ll);
-        S.hi[j] = sane ? fmin(a * 1e280, 1e280) : 0.0;
+        bool sane = a > 1e-90 && a < 1e90;
+        S.dr[j] = make_double2(dv, sane ? 1.0 / dv : 0.0);
+        S.tgt[j] = (m == 0.0) ? target[j] : target[j] / dv;
     }
 }
 
-__device__ __forceinline__ double scaled_value(double x, const ColScale& S, int j) {
-    double ax = fabs(x);
-    if ((ax > S.lo[j] && ax < S.hi[j]) || x == 0.0) return div_const(x, S.div[j], S.rcp[j]);
-    return x / S.div[j];
+// x / div, correctly rounded.  Markstein's sequence is exact while no intermediate leaves the normal range:
+// |x| in (1e-200, 1e200) with |div| in (1e-90, 1e90) keeps q, the remainders and their products normal; x == 0 is
+// exact too.  Everything else takes the IEEE division.
+__device__ __forceinline__ double scaled_value(double x, const double2 dr) {
+    const double ax = fabs(x);
+    if ((ax > 1e-200 && ax < 1e200 && dr.y != 0.0) || x == 0.0) return div_const(x, dr.x, dr.y);
+    return x / dr.x;
 }
 
 // K6: distances of a random sample of rows -> local estimates (lo, hi) of the nacc-th smallest distance.
@@ -569,7 +593,7 @@ __global__ void __launch_bounds__(512) k_sample_dist(const double* __restrict__ 
         long long r = sample_row(seed, blockIdx.x, t, n);
         double s0 = 0.0;
         for (int j = 0; j < d; ++j) {
-            double a = __dsub_rn(scaled_value(ss[(size_t)j * ld + r], S, j), S.tgt[j]);
+            double a = __dsub_rn(scaled_value(ss[(size_t)j * ld + r], S.dr[j]), S.tgt[j]);
             s0 = __dadd_rn(s0, __dmul_rn(a, a));
         }
         sm[t] = __dsqrt_rn(s0);
@@ -625,7 +649,8 @@ __global__ void __launch_bounds__(kBThreads) k_dist_pass(const double* __restric
                                                          long long cap, unsigned long long* __restrict__ cand_cnt,
                                                          unsigned long long* __restrict__ n_lt,
                                                          unsigned long long* __restrict__ hist_g,
-                                                         long long rpw, long long rcap, long long* __restrict__ rec_off,
+                                                         long long row_lo, int prod0, long long rpw, long long rcap,
+                                                         long long* __restrict__ rec_off,
                                                          int* __restrict__ rec_cnt, int* __restrict__ wtot,
                                                          int* __restrict__ nrec, int* status) {
     __shared__ ColScale S;
@@ -637,8 +662,9 @@ __global__ void __launch_bounds__(kBThreads) k_dist_pass(const double* __restric
     __syncthreads();
     const double lo = brk->lo, hi = brk->hi, scale = brk->scale;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const long long gw = (long long)blockIdx.x * (kBThreads / 32) + wid;
-    const long long r_begin = gw * rpw, r_end = min(n, r_begin + rpw);
+    const long long gw0 = (long long)blockIdx.x * (kBThreads / 32) + wid;
+    const long long gw = prod0 + gw0;   // slot in the record directory
+    const long long r_begin = min(n, row_lo + gw0 * rpw), r_end = min(n, r_begin + rpw);
     bool nonfinite = false;
     unsigned c_lt = 0;
     int fill = 0, seq = 0, total = 0;
@@ -675,10 +701,11 @@ __global__ void __launch_bounds__(kBThreads) k_dist_pass(const double* __restric
                 const double2 xb = ld_stream2(col + kBHalf);
                 col += ld;
                 const double tj = S.tgt[j];
-                const double a0 = __dsub_rn(scaled_value(xa.x, S, j), tj);
-                const double a1 = __dsub_rn(scaled_value(xa.y, S, j), tj);
-                const double a2 = __dsub_rn(scaled_value(xb.x, S, j), tj);
-                const double a3 = __dsub_rn(scaled_value(xb.y, S, j), tj);
+                const double2 dr = S.dr[j];
+                const double a0 = __dsub_rn(scaled_value(xa.x, dr), tj);
+                const double a1 = __dsub_rn(scaled_value(xa.y, dr), tj);
+                const double a2 = __dsub_rn(scaled_value(xb.x, dr), tj);
+                const double a3 = __dsub_rn(scaled_value(xb.y, dr), tj);
                 s[0] = __dadd_rn(s[0], __dmul_rn(a0, a0));
                 s[1] = __dadd_rn(s[1], __dmul_rn(a1, a1));
                 s[2] = __dadd_rn(s[2], __dmul_rn(a2, a2));
@@ -691,7 +718,7 @@ __global__ void __launch_bounds__(kBThreads) k_dist_pass(const double* __restric
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                     if (rows[q] < n) {
-                        const double a = __dsub_rn(scaled_value(ss[(size_t)j * ld + rows[q]], S, j), tj);
+                        const double a = __dsub_rn(scaled_value(ss[(size_t)j * ld + rows[q]], S.dr[j]), tj);
                         s[q] = __dadd_rn(s[q], __dmul_rn(a, a));
                     }
             }
@@ -765,16 +792,192 @@ __global__ void __launch_bounds__(kBThreads) k_dist_pass(const double* __restric
         if (hist[t]) atomicAdd(&hist_g[t], (unsigned long long)hist[t]);
 }
 
+// K7-TMA: the same pass with the table streamed by the TMA engine.  One producer warp issues 1-D bulk copies
+// (cp.async.bulk, 2 KB per column per tile) into a 3-stage shared-memory ring guarded by mbarriers; 8 consumer
+// warps own one row each of the 256-row tile and never wait on HBM latency themselves, so the bytes in flight
+// (up to 96 KB per CTA, 2 CTAs per SM) no longer depend on registers.  Tiles are handed to CTAs in contiguous
+// ranges; per tile the 8 consumer warps meet once at a named barrier to append their candidates in row order to
+// a CTA-level stage, which is flushed with one atomic + coalesced copies and leaves a record for k_order_cands.
+constexpr int kTRows = 256;                  // rows per tile = consumer threads
+constexpr int kTCols = 16;                   // columns per ring stage
+constexpr int kTStages = 3;
+constexpr int kTConsumers = 256;
+constexpr int kTThreads = kTConsumers + 32;  // + producer warp
+constexpr int kTGrid = 148 * 2;
+constexpr int kTStageCta = 512;              // staged candidates per CTA (a tile adds at most 256)
+
+struct TmaSmem {
+    double ring[kTStages][kTCols][kTRows];   // 96 KB
+    long long st_row[kTStageCta];
+    double st_dist[kTStageCta];
+    unsigned hist[kNB];
+    ColScale S;
+    unsigned long long full[kTStages], empty[kTStages];
+    int warp_cnt[2][8];
+    unsigned long long base_sh;
+};
+
+static_assert(sizeof(TmaSmem) <= 113 * 1024, "two CTAs of the TMA distance kernel must fit one SM");
+
+inline long long tma_tiles_per_cta(long long ntiles) { return (ntiles + kTGrid - 1) / kTGrid; }
+inline long long tma_recs_per_cta(long long ntiles) { return tma_tiles_per_cta(ntiles) / 2 + 3; }
+
+template <bool WRITE_DIST>
+__global__ void __launch_bounds__(kTThreads, 2) k_dist_pass_tma(const double* __restrict__ ss, long long ntiles, int d,
+                                                                long long ld, const double* __restrict__ mad,
+                                                                const double* __restrict__ target,
+                                                                const DistBrk* __restrict__ brk, double* __restrict__ dist,
+                                                                long long* __restrict__ cand_row,
+                                                                double* __restrict__ cand_dist, long long cap,
+                                                                unsigned long long* __restrict__ cand_cnt,
+                                                                unsigned long long* __restrict__ n_lt,
+                                                                unsigned long long* __restrict__ hist_g, long long tpc,
+                                                                long long rcap, long long* __restrict__ rec_off,
+                                                                int* __restrict__ rec_cnt, int* __restrict__ wtot,
+                                                                int* __restrict__ nrec, int* status) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TmaSmem& sm = *reinterpret_cast<TmaSmem*>(smem_raw);
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    load_scale(sm.S, mad, target, d);
+    for (int t = threadIdx.x; t < kNB; t += kTThreads) sm.hist[t] = 0u;
+    if (threadIdx.x == 0) {
+        for (int s2 = 0; s2 < kTStages; ++s2) {
+            mbar_init(&sm.full[s2], 1);
+            mbar_init(&sm.empty[s2], kTConsumers / 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const long long t_begin = (long long)blockIdx.x * tpc, t_end = min(ntiles, t_begin + tpc);
+    const int nchunk = (d + kTCols - 1) / kTCols;
+
+    if (wid == kTConsumers / 32) {
+        // ===== producer warp: one elected lane feeds the ring =====
+        if (lane == 0) {
+            long long it = 0;
+            for (long long tile = t_begin; tile < t_end; ++tile) {
+                const double* src0 = ss + tile * kTRows;
+                for (int ch = 0; ch < nchunk; ++ch, ++it) {
+                    const int st = (int)(it % kTStages);
+                    const unsigned ph = (unsigned)((it / kTStages) & 1);
+                    mbar_wait(&sm.empty[st], ph ^ 1u);
+                    const int j0 = ch * kTCols, nc = min(kTCols, d - j0);
+                    mbar_expect_tx(&sm.full[st], (unsigned)(nc * kTRows * 8));
+                    for (int c = 0; c < nc; ++c)
+                        bulk_g2s(&sm.ring[st][c][0], src0 + (size_t)(j0 + c) * ld, kTRows * 8, &sm.full[st]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers: thread t owns row t of every tile =====
+    const double lo = brk->lo, hi = brk->hi, scale = brk->scale;
+    const int row_in_tile = threadIdx.x;   // 0..255
+    bool nonfinite = false;
+    unsigned c_lt = 0;
+    int fill = 0, seq = 0, total = 0;
+    long long it = 0;
+
+    auto flush = [&]() {   // all 256 consumers; every earlier append is visible (it happened before this tile's barrier)
+        if (threadIdx.x == 0) {
+            const unsigned long long b = atomicAdd(cand_cnt, (unsigned long long)fill);
+            sm.base_sh = b;
+            if (seq < rcap) {
+                rec_off[(long long)blockIdx.x * rcap + seq] = (long long)b;
+                rec_cnt[(long long)blockIdx.x * rcap + seq] = fill;
+            }
+        }
+        named_bar_sync(1, kTConsumers);
+        const long long base = (long long)sm.base_sh;
+        for (int t = threadIdx.x; t < fill; t += kTConsumers)
+            if (base + t < cap) {
+                cand_row[base + t] = sm.st_row[t];
+                cand_dist[base + t] = sm.st_dist[t];
+            }
+        named_bar_sync(1, kTConsumers);
+        ++seq;
+        fill = 0;
+    };
+
+    for (long long tile = t_begin; tile < t_end; ++tile) {
+        double s0 = 0.0;
+        for (int ch = 0; ch < nchunk; ++ch, ++it) {
+            const int st = (int)(it % kTStages);
+            const unsigned ph = (unsigned)((it / kTStages) & 1);
+            mbar_wait(&sm.full[st], ph);
+            const int j0 = ch * kTCols, nc = min(kTCols, d - j0);
+            if (nc == kTCols) {
+#pragma unroll
+                for (int c = 0; c < kTCols; ++c) {
+                    const double x = sm.ring[st][c][row_in_tile];
+                    const double a = __dsub_rn(scaled_value(x, sm.S.dr[j0 + c]), sm.S.tgt[j0 + c]);
+                    s0 = __dadd_rn(s0, __dmul_rn(a, a));
+                }
+            } else {
+                for (int c = 0; c < nc; ++c) {
+                    const double x = sm.ring[st][c][row_in_tile];
+                    const double a = __dsub_rn(scaled_value(x, sm.S.dr[j0 + c]), sm.S.tgt[j0 + c]);
+                    s0 = __dadd_rn(s0, __dmul_rn(a, a));
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty[st]);   // this warp is done with the stage
+        }
+        const long long row = tile * kTRows + row_in_tile;
+        const double dd = __dsqrt_rn(s0);
+        nonfinite |= !isfinite(dd);
+        if (WRITE_DIST) dist[row] = dd;
+        const bool cnd = dd <= hi;
+        c_lt += (dd < lo) ? 1u : 0u;
+        const unsigned bal = __ballot_sync(0xffffffffu, cnd);
+        const int par = (int)(tile & 1);
+        if (lane == 0) sm.warp_cnt[par][wid] = __popc(bal);
+        named_bar_sync(1, kTConsumers);
+        int pre = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const int t = sm.warp_cnt[par][w];
+            pre += (w < wid) ? t : 0;
+            tot += t;
+        }
+        if (tot) {
+            if (fill + tot > kTStageCta) flush();
+            if (cnd) {
+                const int p = fill + pre + __popc(bal & ((1u << lane) - 1u));
+                sm.st_row[p] = row;
+                sm.st_dist[p] = dd;
+                if (dd >= lo) atomicAdd(&sm.hist[bin_of(dd, lo, scale)], 1u);
+            }
+            fill += tot;
+            total += tot;
+        }
+    }
+    named_bar_sync(1, kTConsumers);   // appends of the last tile are visible
+    if (fill > 0) flush();
+    if (threadIdx.x == 0) {
+        wtot[blockIdx.x] = total;
+        nrec[blockIdx.x] = seq < rcap ? seq : (int)rcap;
+        if (seq > rcap) atomicOr(status, ABCDLS_S_FASTPATH_MISS);
+    }
+    c_lt = warp_sum(c_lt);
+    if (lane == 0 && c_lt) atomicAdd(n_lt, (unsigned long long)c_lt);
+    if (__any_sync(0xffffffffu, nonfinite) && lane == 0) atomicOr(status, ABCDLS_S_NONFINITE);
+    named_bar_sync(1, kTConsumers);
+    for (int t = threadIdx.x; t < kNB; t += kTConsumers)
+        if (sm.hist[t]) atomicAdd(&hist_g[t], (unsigned long long)sm.hist[t]);
+}
+
 // K8: lay the flushed chunks out in global row order.  One warp per producer warp; wpos = exclusive scan of wtot.
 __global__ void __launch_bounds__(256) k_order_cands(const long long* __restrict__ rec_off, const int* __restrict__ rec_cnt,
                                                      const int* __restrict__ nrec, const long long* __restrict__ wpos,
-                                                     long long rcap, const long long* __restrict__ row_in,
+                                                     int nprod, long long rcap, const long long* __restrict__ row_in,
                                                      const double* __restrict__ dist_in, long long cap,
                                                      long long row_offset, long long* __restrict__ row_out,
                                                      double* __restrict__ dist_out) {
     const int lane = threadIdx.x & 31;
     const long long gw = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
-    if (gw >= kBWarps) return;
+    if (gw >= nprod) return;
     long long dst = wpos[gw];
     const int nr = nrec[gw];
     for (int r = 0; r < nr; ++r) {
@@ -888,7 +1091,9 @@ inline DistWs carve_dist(void* ws, int G, long long n, long long cap) {
     char* p = reinterpret_cast<char*>(ws);
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t a = o; o += align_up(bytes, 256); return p ? p + a : (char*)nullptr; };
-    const long long rcap = recs_per_warp(n);
+    const long long dir_ldg = (long long)kBWarps * recs_per_warp(n);
+    const long long dir_tma = (long long)(kTGrid + 8) * tma_recs_per_cta(n / kTRows + 1);
+    const long long dir_entries = dir_ldg > dir_tma ? dir_ldg : dir_tma;
     w.est = (double*)take((size_t)G * 2 * 8);
     w.brk = (DistBrk*)take(sizeof(DistBrk));
     size_t z0 = o;
@@ -899,8 +1104,8 @@ inline DistWs carve_dist(void* ws, int G, long long n, long long cap) {
     w.zero_bytes = o - z0;
     w.job = (RefJob*)take(sizeof(RefJob));
     w.small = (double*)take((size_t)kSmallCap * 8);
-    w.rec_off = (long long*)take((size_t)kBWarps * rcap * 8);
-    w.rec_cnt = (int*)take((size_t)kBWarps * rcap * 4);
+    w.rec_off = (long long*)take((size_t)dir_entries * 8);
+    w.rec_cnt = (int*)take((size_t)dir_entries * 4);
     w.wtot = (int*)take((size_t)kBWarps * 4);
     w.nrec = (int*)take((size_t)kBWarps * 4);
     w.wpos = (long long*)take((size_t)kBWarps * 8);
@@ -956,7 +1161,7 @@ int abcdls_mad_fast_sample(abcdls_handle_t h, const double* ss, int64_t n, int d
     cudaStream_t st = (cudaStream_t)stream;
     const double delta = col_delta(n, world);
     const size_t smem = (size_t)2 * kSample * sizeof(double);
-    ABCDLS_CUDA(h, cudaFuncSetAttribute(k_sample_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ABCDLS_ONCE(h, cudaFuncSetAttribute(k_sample_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ABCDLS_CUDA(h, cudaMemsetAsync(w.counts, 0, w.zero_bytes, st));
     k_sample_cols<<<dim3(G, d), 512, smem, st>>>(ss, n, ld, 0x5EEDu, delta, w.est);
     ABCDLS_LAUNCH_CHECK(h);
@@ -1006,7 +1211,7 @@ int abcdls_mad_fast_finish(abcdls_handle_t h, int64_t n, int64_t n_global, int d
     cudaStream_t st = (cudaStream_t)stream;
     const long long k0 = (n_global - 1) / 2, k1 = n_global / 2;
     const size_t smem = (size_t)kSmallCap * sizeof(double);
-    ABCDLS_CUDA(h, cudaFuncSetAttribute(k_refine_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ABCDLS_ONCE(h, cudaFuncSetAttribute(k_refine_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     auto gx_for = [&](long long cap) {
         long long g = (cap + 256 * 8 - 1) / (256 * 8);
         long long mx = (long long)h->sm_count * 8 / d;
@@ -1077,26 +1282,54 @@ int abcdls_dist_fast_pass(abcdls_handle_t h, const double* ss, int64_t n, int d,
     }
     cudaStream_t st = (cudaStream_t)stream;
     k_make_dist_bracket<<<1, 32, 0, st>>>(w.est, G, 1.0 / world, w.brk);
-    const long long rpw = rows_per_warp(n), rcap = recs_per_warp(n);
     const bool vec = ((reinterpret_cast<uintptr_t>(ss) & 15) == 0) && ((ld & 1) == 0) &&
                      (!dist || (reinterpret_cast<uintptr_t>(dist) & 15) == 0);
-#define LAUNCH_B(V, W)                                                                                            \
-    k_dist_pass<V, W><<<kBGrid, kBThreads, 0, st>>>(ss, n, d, ld, mad, target, w.brk, dist, w.row_tmp, w.dist_tmp, \
-                                                    cap, w.cand_cnt, w.n_lt, w.hist, rpw, rcap, w.rec_off,         \
-                                                    w.rec_cnt, w.wtot, w.nrec, status_dev)
-    if (vec && dist) LAUNCH_B(true, true);
-    else if (vec) LAUNCH_B(true, false);
-    else if (dist) LAUNCH_B(false, true);
-    else LAUNCH_B(false, false);
-#undef LAUNCH_B
+    const long long ntiles = n / kTRows;   // full 256-row tiles go through the TMA ring
+    int nprod;
+    long long rcap;
+#define LAUNCH_LDG(V, W, GRID, ROW_LO, PROD0, RPW)                                                                 \
+    k_dist_pass<V, W><<<GRID, kBThreads, 0, st>>>(ss, n, d, ld, mad, target, w.brk, dist, w.row_tmp, w.dist_tmp,    \
+                                                  cap, w.cand_cnt, w.n_lt, w.hist, ROW_LO, PROD0, RPW, rcap,        \
+                                                  w.rec_off, w.rec_cnt, w.wtot, w.nrec, status_dev)
+    if (vec && ntiles >= kTGrid && !h->no_tma) {
+        const long long tpc = tma_tiles_per_cta(ntiles);
+        rcap = tma_recs_per_cta(ntiles);
+        if (rcap < 2 * 1 + 2) rcap = 4;
+        nprod = kTGrid + 8;
+        const size_t smem = sizeof(TmaSmem);
+        if (dist) {
+            ABCDLS_ONCE(h, cudaFuncSetAttribute(k_dist_pass_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_dist_pass_tma<true><<<kTGrid, kTThreads, smem, st>>>(ss, ntiles, d, ld, mad, target, w.brk, dist, w.row_tmp,
+                                                                  w.dist_tmp, cap, w.cand_cnt, w.n_lt, w.hist, tpc, rcap,
+                                                                  w.rec_off, w.rec_cnt, w.wtot, w.nrec, status_dev);
+        } else {
+            ABCDLS_ONCE(h, cudaFuncSetAttribute(k_dist_pass_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_dist_pass_tma<false><<<kTGrid, kTThreads, smem, st>>>(ss, ntiles, d, ld, mad, target, w.brk, dist, w.row_tmp,
+                                                                   w.dist_tmp, cap, w.cand_cnt, w.n_lt, w.hist, tpc, rcap,
+                                                                   w.rec_off, w.rec_cnt, w.wtot, w.nrec, status_dev);
+        }
+        ABCDLS_LAUNCH_CHECK(h);
+        // ragged tail (< 256 rows): one CTA of the load/store kernel, directory slots kTGrid..kTGrid+7
+        if (dist) LAUNCH_LDG(true, true, 1, ntiles * kTRows, kTGrid, (long long)kBWarpTile);
+        else LAUNCH_LDG(true, false, 1, ntiles * kTRows, kTGrid, (long long)kBWarpTile);
+    } else {
+        const long long rpw = rows_per_warp(n);
+        rcap = recs_per_warp(n);
+        nprod = kBWarps;
+        if (vec && dist) LAUNCH_LDG(true, true, kBGrid, 0ll, 0, rpw);
+        else if (vec) LAUNCH_LDG(true, false, kBGrid, 0ll, 0, rpw);
+        else if (dist) LAUNCH_LDG(false, true, kBGrid, 0ll, 0, rpw);
+        else LAUNCH_LDG(false, false, kBGrid, 0ll, 0, rpw);
+    }
+#undef LAUNCH_LDG
     ABCDLS_LAUNCH_CHECK(h);
-    k_scan_tiles<<<1, 1024, 0, st>>>(w.wtot, kBWarps, w.wpos);
-    k_order_cands<<<kBWarps / 8, 256, 0, st>>>(w.rec_off, w.rec_cnt, w.nrec, w.wpos, rcap, w.row_tmp, w.dist_tmp, cap,
-                                               row_offset, (long long*)cand_row, cand_dist);
+    k_scan_tiles<<<1, 1024, 0, st>>>(w.wtot, nprod, w.wpos);
+    k_order_cands<<<(nprod + 7) / 8, 256, 0, st>>>(w.rec_off, w.rec_cnt, w.nrec, w.wpos, nprod, rcap, w.row_tmp,
+                                                   w.dist_tmp, cap, row_offset, (long long*)cand_row, cand_dist);
     ABCDLS_CUDA(h, cudaMemcpyAsync(n_cand, w.cand_cnt, 8, cudaMemcpyDeviceToDevice, st));
     // exact ds among the candidates in [lo, hi]
     const size_t smem = (size_t)kSmallCap * sizeof(double);
-    ABCDLS_CUDA(h, cudaFuncSetAttribute(k_refine_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ABCDLS_ONCE(h, cudaFuncSetAttribute(k_refine_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_plan_ds<<<1, 32, 0, st>>>(w.job, w.brk, w.n_lt, w.cand_cnt, w.hist, cand_dist, cap, w.small, w.small_count,
                                 nacc - 1, status_dev);
     k_refine_pick<<<1, 256, 0, st>>>(w.job, status_dev);

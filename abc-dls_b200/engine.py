@@ -209,9 +209,10 @@ class AbcEngine:
             with self._t("dist_fast"):
                 k.dist_fast(ss, n_local, n_global, d, ss.stride(0), mad, target, nacc, 1, row_offset, ccap, dist,
                             cand_row, cand_dist, n_cand, ds, status)
-            ws = k.accept_workspace(ccap)
-            k.count_le(cand_dist, ccap, n_cand, ds, le, ws)
-            k.accept(cand_dist, ccap, n_cand, cand_row, ds, quota, row_offset, cap, idx, dacc, n_acc, ws, status)
+            with self._t("accept"):
+                ws = k.accept_workspace(ccap)
+                k.count_le(cand_dist, ccap, n_cand, ds, le, ws)
+                k.accept(cand_dist, ccap, n_cand, cand_row, ds, quota, row_offset, cap, idx, dacc, n_acc, ws, status)
         else:
             _, mad = self.column_mad(ss, n_global)
             dist = k.new(n_local)
@@ -266,8 +267,9 @@ class AbcEngine:
 
         xs, y, ss_out = k.new(d, cap), k.new(P, cap), k.new(d, cap)
         w = k.new(cap)
-        k.gather(ss, ss.stride(0), par, par.stride(0), dacc, idx, n_acc, f["row_offset"], cap, d, P, mad, target,
-                 ds, xs, y, ss_out, w)
+        with self._t("gather"):
+            k.gather(ss, ss.stride(0), par, par.stride(0), dacc, idx, n_acc, f["row_offset"], cap, d, P, mad, target,
+                     ds, xs, y, ss_out, w)
         # zero variance inside the accepted region (R cond2)
         reg = k.new(d, 6)
         k.col_stats(ss_out, None, n_acc, cap, d, reg)
@@ -279,6 +281,8 @@ class AbcEngine:
 
         beta = gamma = the_m = res = adj = sig = None
         stats = k.new(P, 6)
+        _tl = self._t("loclinear")
+        _tl.__enter__()
         if method == "loclinear":
             M = d + 1
             part = k.new(M * M + M * P)
@@ -311,6 +315,7 @@ class AbcEngine:
             k.col_stats(adj, w, n_acc, cap, P, stats)
         else:
             k.col_stats(y, None, n_acc, cap, P, stats)
+        _tl.__exit__()
         if self.comm.world > 1:
             mn, mx, sm = stats[:, 0].contiguous(), stats[:, 1].contiguous(), stats[:, 2:].contiguous()
             self.comm.allreduce_min(mn)

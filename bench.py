@@ -64,22 +64,30 @@ class ClockSampler:
     def __init__(self, index: int):
         self.index, self.rows, self.stop = index, [], threading.Event()
         self.thread = threading.Thread(target=self._run, daemon=True)
-        self.max_mhz = None
-
-    def _run(self):
-        try:
+        self.max_mhz, self.nv, self.h = None, None, None
+        try:  # import + nvmlInit are slow (tens of ms, GIL held): do them before the timed region
             import pynvml as nv
             nv.nvmlInit()
             visible = os.environ.get("CUDA_VISIBLE_DEVICES")
-            idx = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
-            h = nv.nvmlDeviceGetHandleByIndex(idx)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            while not self.stop.is_set():
-                self.rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
-                                  nv.nvmlDeviceGetCurrentClocksEventReasons(h)))
-                self.stop.wait(0.02)
+            idx = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self.h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            self.nv = nv
         except Exception as e:  # pragma: no cover
             self.err = repr(e)
+
+    def _run(self):
+        nv, h = self.nv, self.h
+        if nv is None:
+            return
+        while not self.stop.is_set():
+            try:
+                self.rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetCurrentClocksEventReasons(h)))
+            except Exception as e:  # pragma: no cover
+                self.err = repr(e)
+                return
+            self.stop.wait(0.01)
 
     def __enter__(self):
         self.thread.start()
@@ -175,7 +183,8 @@ def main():
     eng.timers = {}
     l0 = eng.k.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
+    sampler = ClockSampler(local_rank)
+    with sampler as clocks:
         sync()
         ev0.record()
         for _ in range(args.steps):
@@ -257,7 +266,7 @@ def main():
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "roofline": roofline,
                 "cpu_baseline": base, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
-                "nacc": res.nacc, "ds": res.ds}
+                "nacc": res.nacc, "ds": res.ds, "fast_path_misses": eng.fast_misses}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
