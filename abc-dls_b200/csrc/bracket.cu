@@ -412,13 +412,31 @@ __global__ void __launch_bounds__(256) k_refine_gather(RefJob* jobs, long long n
 }
 
 // one block (1024 threads) per job: sort the gathered values, read the ranks.
-__global__ void __launch_bounds__(1024) k_refine_final(RefJob* jobs, int* status) {
+// one block (1024 threads) per job: sort the gathered values, read the ranks.
+// gsmall == NULL: the job's own buffer.  Otherwise the all-gathered exchange block of this phase,
+// gsmall[world][nj][kSmallCap] / gcnt[world][nj], job = blockIdx.x within the phase.
+__global__ void __launch_bounds__(1024) k_refine_final(RefJob* jobs, const double* __restrict__ gsmall,
+                                                       const unsigned* __restrict__ gcnt, int world, int nj,
+                                                       int* status) {
     extern __shared__ double sm[];
+    __shared__ unsigned off[65];
     RefJob& J = jobs[blockIdx.x];
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
-    const unsigned cnt = *J.small_count;
-    bool ok = J.valid && cnt <= (unsigned)kSmallCap && cnt > 0;
-    long long r0 = J.kk[0] - J.before, r1 = J.kk[1] - J.before;
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    bool ok = J.valid != 0 && world <= 64;
+    if (threadIdx.x == 0) {
+        unsigned a = 0;
+        for (int r = 0; r < world; ++r) {
+            off[r] = a;
+            const unsigned c = gsmall ? gcnt[r * nj + blockIdx.x] : *J.small_count;
+            a += c;
+        }
+        off[world] = a;
+    }
+    __syncthreads();
+    const unsigned cnt = off[world];
+    ok = ok && cnt <= (unsigned)kSmallCap && cnt > 0;
+    const long long r0 = J.kk[0] - J.before, r1 = J.kk[1] - J.before;
     ok = ok && r0 >= 0 && r1 < (long long)cnt;
     if (!ok) {
         if (threadIdx.x == 0) {
@@ -429,8 +447,13 @@ __global__ void __launch_bounds__(1024) k_refine_final(RefJob* jobs, int* status
     }
     int np2 = 32;
     while (np2 < (int)cnt) np2 <<= 1;
-    const double inf = __longlong_as_double(0x7ff0000000000000ll);
-    for (int t = threadIdx.x; t < np2; t += blockDim.x) sm[t] = t < (int)cnt ? J.small[t] : inf;
+    for (int t = threadIdx.x; t < np2; t += blockDim.x) sm[t] = inf;
+    __syncthreads();
+    for (int r = 0; r < world; ++r) {
+        const unsigned c = off[r + 1] - off[r];
+        const double* src = gsmall ? gsmall + ((size_t)r * nj + blockIdx.x) * kSmallCap : J.small;
+        for (int t = threadIdx.x; t < (int)c; t += blockDim.x) sm[off[r] + t] = src[t];
+    }
     __syncthreads();
     bitonic_sort(sm, np2);
     if (threadIdx.x == 0) {
@@ -439,16 +462,23 @@ __global__ void __launch_bounds__(1024) k_refine_final(RefJob* jobs, int* status
     }
 }
 
+__global__ void k_copy_u64(unsigned long long* dst, const unsigned long long* src, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+
 // ---------------------------------------------------------------------------------------------------
 // plans (1 thread per column).  k0/k1: global 0-based ranks of the two middle order statistics.
 __global__ void k_plan_median(RefJob* jobs, int d, const ColBrk* __restrict__ brk,
                               const unsigned long long* __restrict__ counts, unsigned long long* histM,
-                              const double* candM, long long capM, const unsigned long long* cnt, double* small,
-                              unsigned* small_count, long long k0, long long k1, int* status) {
+                              const double* candM, long long capM, const unsigned long long* cnt,
+                              const unsigned long long* gcnt, double* small, unsigned* small_count, long long k0,
+                              long long k1, int* status) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= d) return;
     RefJob J;
-    const long long c_lt = (long long)counts[j * 4 + 0], c_m = (long long)cnt[j * 2 + 0];  // every M value was appended
+    // counts / gcnt are summed over ranks; cnt is what THIS rank appended (every band value is appended)
+    const long long c_lt = (long long)counts[j * 4 + 0], c_m = (long long)gcnt[j * 2 + 0];
     J.src = candM + (size_t)j * capM;
     J.src_count = cnt + j * 2 + 0;
     J.src_cap = capM;
@@ -475,9 +505,9 @@ __global__ void k_plan_median(RefJob* jobs, int d, const ColBrk* __restrict__ br
 // after the medians are exact: med[j] = 0.5*r0 + 0.5*r1; prepare the |x - med| refinement over L u R
 __global__ void k_plan_mad(RefJob* jobs, int d, const ColBrk* __restrict__ brk,
                            const unsigned long long* __restrict__ counts, unsigned long long* histU,
-                           const double* candU, long long capU, const unsigned long long* cnt, double* small,
-                           unsigned* small_count, long long k0, long long k1, double* __restrict__ med,
-                           double* __restrict__ guard, int* status) {
+                           const double* candU, long long capU, const unsigned long long* cnt,
+                           const unsigned long long* gcnt, double* small, unsigned* small_count, long long k0,
+                           long long k1, double* __restrict__ med, double* __restrict__ guard, int* status) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= d) return;
     const RefJob& Jm = jobs[j];
@@ -485,7 +515,7 @@ __global__ void k_plan_mad(RefJob* jobs, int d, const ColBrk* __restrict__ brk,
     med[j] = m;
     const ColBrk B = brk[j];
     RefJob J;
-    const long long c_in = (long long)counts[j * 4 + 2], c_u = (long long)cnt[j * 2 + 1];
+    const long long c_in = (long long)counts[j * 4 + 2], c_u = (long long)gcnt[j * 2 + 1];
     J.src = candU + (size_t)j * capU;
     J.src_count = cnt + j * 2 + 1;
     J.src_cap = capU;
@@ -508,7 +538,7 @@ __global__ void k_plan_mad(RefJob* jobs, int d, const ColBrk* __restrict__ brk,
     J.small = small + (size_t)(d + j) * kSmallCap;
     J.small_count = small_count + d + j;
     J.result[0] = J.result[1] = 0.0;
-    J.valid = (Jm.valid && J.kk[0] >= 0 && J.kk[1] < c_u && c_u <= capU) ? 1 : 0;
+    J.valid = (Jm.valid && J.kk[0] >= 0 && J.kk[1] < c_u && (long long)cnt[j * 2 + 1] <= capU) ? 1 : 0;
     if (!J.valid) atomicOr(status, ABCDLS_S_FASTPATH_MISS);
     // guards checked once r* is known (triangle inequality + rounding slack):
     //   inner rows (fl|x-c| < r1)  have |x - m| <= (r1 + e) * up   -> must be <= the smaller rank value
@@ -993,12 +1023,13 @@ __global__ void __launch_bounds__(256) k_order_cands(const long long* __restrict
 }
 
 __global__ void k_plan_ds(RefJob* job, const DistBrk* __restrict__ brk, const unsigned long long* __restrict__ n_lt,
-                          const unsigned long long* __restrict__ cand_cnt, unsigned long long* hist,
+                          const unsigned long long* __restrict__ cand_cnt,
+                          const unsigned long long* __restrict__ gcand_cnt, unsigned long long* hist,
                           const double* cand_dist, long long cap, double* small, unsigned* small_count, long long k,
                           int* status) {
     if (threadIdx.x || blockIdx.x) return;
     RefJob J;
-    const long long c_lt = (long long)*n_lt, c_all = (long long)*cand_cnt;
+    const long long c_lt = (long long)*n_lt, c_all = (long long)*gcand_cnt;   // summed over ranks
     J.src = cand_dist;
     J.src_count = cand_cnt;
     J.src_cap = cap;
@@ -1015,7 +1046,7 @@ __global__ void k_plan_ds(RefJob* job, const DistBrk* __restrict__ brk, const un
     J.small = small;
     J.small_count = small_count;
     J.result[0] = J.result[1] = 0.0;
-    J.valid = (k >= c_lt && k < c_all && c_all <= cap) ? 1 : 0;
+    J.valid = (k >= c_lt && k < c_all && (long long)*cand_cnt <= cap) ? 1 : 0;
     if (!J.valid) atomicOr(status, ABCDLS_S_FASTPATH_MISS);
     *job = J;
 }
@@ -1029,12 +1060,13 @@ __global__ void k_copy_result(const RefJob* job, double* out) {
 struct MadWs {
     double* est;                    // [G*d*4]
     ColBrk* brk;                    // [d]
-    unsigned long long* counts;     // [d*4]      | zeroed together
-    unsigned long long* cnt;        // [d*2]      |
-    unsigned long long* histM;      // [d*kNB]    |
-    unsigned long long* histU;      // [d*kNB]    |
-    unsigned* small_count;          // [2d]       |
-    size_t zero_bytes;
+    unsigned long long* cnt;        // [d*2]   entries appended by THIS rank   | zeroed together
+    unsigned long long* counts;     // [d*4]   } reduce block A (summed        |
+    unsigned long long* gcnt;       // [d*2]   }  over ranks after the pass)   |
+    unsigned long long* histM;      // [d*kNB] }                               |
+    unsigned long long* histU;      // [d*kNB] reduce block B                  |
+    unsigned* small_count;          // [2d]                                    |
+    size_t zero_bytes, redA_count, redB_count;
     RefJob* jobs;                   // [2d]
     double* guard;                  // [2d]
     double* small;                  // [2d*kSmallCap]
@@ -1051,12 +1083,18 @@ inline MadWs carve_mad(void* ws, int d, int G, long long capM, long long capU) {
     w.est = (double*)take((size_t)G * d * 4 * 8);
     w.brk = (ColBrk*)take((size_t)d * sizeof(ColBrk));
     size_t z0 = o;
-    w.counts = (unsigned long long*)take((size_t)d * 4 * 8);
     w.cnt = (unsigned long long*)take((size_t)d * 2 * 8);
+    size_t a0 = o;
+    w.counts = (unsigned long long*)take((size_t)d * 4 * 8);
+    w.gcnt = (unsigned long long*)take((size_t)d * 2 * 8);
     w.histM = (unsigned long long*)take((size_t)d * kNB * 8);
+    size_t b0 = o;
     w.histU = (unsigned long long*)take((size_t)d * kNB * 8);
+    size_t b1 = o;
     w.small_count = (unsigned*)take((size_t)2 * d * 4);
     w.zero_bytes = o - z0;
+    w.redA_count = (b0 - a0) / 8;
+    w.redB_count = (b1 - b0) / 8;
     w.jobs = (RefJob*)take((size_t)2 * d * sizeof(RefJob));
     w.guard = (double*)take((size_t)2 * d * 8);
     w.small = (double*)take((size_t)2 * d * kSmallCap * 8);
@@ -1069,11 +1107,12 @@ inline MadWs carve_mad(void* ws, int d, int G, long long capM, long long capU) {
 struct DistWs {
     double* est;                   // [G*2]
     DistBrk* brk;
-    unsigned long long* cand_cnt;  // | zeroed together
-    unsigned long long* n_lt;      // |
-    unsigned long long* hist;      // | [kNB]
-    unsigned* small_count;         // |
-    size_t zero_bytes;
+    unsigned long long* cand_cnt;  // candidates appended by THIS rank  | zeroed together
+    unsigned long long* gcand_cnt; // } reduce block (summed over ranks) |
+    unsigned long long* n_lt;      // }                                  |
+    unsigned long long* hist;      // } [kNB]                            |
+    unsigned* small_count;         //                                    |
+    size_t zero_bytes, red_count;
     RefJob* job;
     double* small;                 // [kSmallCap]
     long long* rec_off;            // [kBWarps * rcap]
@@ -1098,10 +1137,14 @@ inline DistWs carve_dist(void* ws, int G, long long n, long long cap) {
     w.brk = (DistBrk*)take(sizeof(DistBrk));
     size_t z0 = o;
     w.cand_cnt = (unsigned long long*)take(8);
+    size_t r0 = o;
+    w.gcand_cnt = (unsigned long long*)take(8);
     w.n_lt = (unsigned long long*)take(8);
     w.hist = (unsigned long long*)take((size_t)kNB * 8);
+    size_t r1 = o;
     w.small_count = (unsigned*)take(4);
     w.zero_bytes = o - z0;
+    w.red_count = (r1 - r0) / 8;
     w.job = (RefJob*)take(sizeof(RefJob));
     w.small = (double*)take((size_t)kSmallCap * 8);
     w.rec_off = (long long*)take((size_t)dir_entries * 8);
@@ -1162,7 +1205,7 @@ int abcdls_mad_fast_sample(abcdls_handle_t h, const double* ss, int64_t n, int d
     const double delta = col_delta(n, world);
     const size_t smem = (size_t)2 * kSample * sizeof(double);
     ABCDLS_ONCE(h, cudaFuncSetAttribute(k_sample_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ABCDLS_CUDA(h, cudaMemsetAsync(w.counts, 0, w.zero_bytes, st));
+    ABCDLS_CUDA(h, cudaMemsetAsync(w.cnt, 0, w.zero_bytes, st));
     k_sample_cols<<<dim3(G, d), 512, smem, st>>>(ss, n, ld, 0x5EEDu, delta, w.est);
     ABCDLS_LAUNCH_CHECK(h);
     if (est_out) *est_out = w.est;
@@ -1191,16 +1234,28 @@ int abcdls_mad_fast_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, 
     if (gx > mx) gx = mx;
     k_bracket_pass<<<dim3((unsigned)gx, d), kAThreads, 0, st>>>(ss, n, ld, w.brk, w.counts, w.histM, w.candM, capM,
                                                                 w.candU, capU, w.cnt);
+    k_copy_u64<<<1, 128, 0, st>>>(w.gcnt, w.cnt, 2 * d);
     ABCDLS_LAUNCH_CHECK(h);
     if (counts_out) *counts_out = reinterpret_cast<int64_t*>(w.counts);
-    if (counts_count) *counts_count = w.zero_bytes / 8;  // counts, cnt, histM, histU, small_count: one zero-padded block
+    if (counts_count) *counts_count = w.redA_count;   // counts | gcnt | histM, contiguous (zero padded)
     return ABCDLS_OK;
 }
 
-// Stage 3 (single GPU): finish median and MAD from the candidates.  n_global = rows over all ranks.
-int abcdls_mad_fast_finish(abcdls_handle_t h, int64_t n, int64_t n_global, int d, void* ws, size_t ws_bytes,
-                           double* med, double* mad, int* status_dev, void* stream) {
-    ABCDLS_CHECK_ARG(h, h && ws && med && mad && status_dev && d >= 1 && d <= kMaxD, "mad_fast_finish");
+// Stage 3: finish median and MAD from the candidates, in four phases so that a multi-rank caller can exchange
+// between them (single rank: abcdls_mad_fast_finish runs all four back to back):
+//   phase 0: plan + locate bins + gather (median)      -> exchange: all-gather x0 = small block, x1 = counts
+//   phase 1: sort the (gathered) values -> medians; plan MAD; histogram of |x - med| over the U candidates
+//                                                       -> exchange: all-reduce x0 = histU
+//   phase 2: locate bins + gather (MAD)                 -> exchange: all-gather x0 = small block, x1 = counts
+//   phase 3: sort -> MAD, guards
+// gath_small / gath_cnt: the all-gathered exchange block of the previous phase (NULL on a single rank).
+int abcdls_mad_fast_refine(abcdls_handle_t h, int64_t n, int64_t n_global, int d, int phase, int world,
+                           const double* gath_small, const int32_t* gath_cnt, void* ws, size_t ws_bytes, double* med,
+                           double* mad, int* status_dev, void** x0, size_t* x0_count, void** x1, size_t* x1_count,
+                           void* stream) {
+    ABCDLS_CHECK_ARG(h, h && ws && med && mad && status_dev && d >= 1 && d <= kMaxD && phase >= 0 && phase <= 3 &&
+                            world >= 1 && world <= 64,
+                     "mad_fast_refine");
     const int G = sample_ctas(n);
     const long long capM = cap_for(n, 0.03), capU = cap_for(n, 0.08);
     MadWs w = carve_mad(ws, d, G, capM, capU);
@@ -1218,21 +1273,47 @@ int abcdls_mad_fast_finish(abcdls_handle_t h, int64_t n, int64_t n_global, int d
         if (mx < 1) mx = 1;
         return (unsigned)(g > mx ? mx : (g < 1 ? 1 : g));
     };
-    // median: histogram was fused into the pass
-    k_plan_median<<<1, 64, 0, st>>>(w.jobs, d, w.brk, w.counts, w.histM, w.candM, capM, w.cnt, w.small, w.small_count,
-                                    k0, k1, status_dev);
-    k_refine_pick<<<d, 256, 0, st>>>(w.jobs, status_dev);
-    k_refine_gather<<<dim3(gx_for(capM), d), 256, 0, st>>>(w.jobs, capM);
-    k_refine_final<<<d, 1024, smem, st>>>(w.jobs, status_dev);
-    // MAD: |x - med| over the L u R candidates
-    k_plan_mad<<<1, 64, 0, st>>>(w.jobs, d, w.brk, w.counts, w.histU, w.candU, capU, w.cnt, w.small, w.small_count, k0,
-                                 k1, med, w.guard, status_dev);
-    k_refine_hist<<<dim3(gx_for(capU), d), 256, 0, st>>>(w.jobs + d, capU);
-    k_refine_pick<<<d, 256, 0, st>>>(w.jobs + d, status_dev);
-    k_refine_gather<<<dim3(gx_for(capU), d), 256, 0, st>>>(w.jobs + d, capU);
-    k_refine_final<<<d, 1024, smem, st>>>(w.jobs + d, status_dev);
-    k_finish_mad<<<1, 64, 0, st>>>(w.jobs, d, w.guard, mad, status_dev);
+    const unsigned* gc = reinterpret_cast<const unsigned*>(gath_cnt);
+    if (x0) *x0 = nullptr;
+    if (x1) *x1 = nullptr;
+    switch (phase) {
+        case 0:
+            k_plan_median<<<1, 64, 0, st>>>(w.jobs, d, w.brk, w.counts, w.histM, w.candM, capM, w.cnt, w.gcnt, w.small,
+                                            w.small_count, k0, k1, status_dev);
+            k_refine_pick<<<d, 256, 0, st>>>(w.jobs, status_dev);
+            k_refine_gather<<<dim3(gx_for(capM), d), 256, 0, st>>>(w.jobs, capM);
+            if (x0) { *x0 = w.small; *x0_count = (size_t)d * kSmallCap; }
+            if (x1) { *x1 = w.small_count; *x1_count = (size_t)d; }
+            break;
+        case 1:
+            k_refine_final<<<d, 1024, smem, st>>>(w.jobs, gath_small, gc, gath_small ? world : 1, d, status_dev);
+            k_plan_mad<<<1, 64, 0, st>>>(w.jobs, d, w.brk, w.counts, w.histU, w.candU, capU, w.cnt, w.gcnt, w.small,
+                                         w.small_count, k0, k1, med, w.guard, status_dev);
+            k_refine_hist<<<dim3(gx_for(capU), d), 256, 0, st>>>(w.jobs + d, capU);
+            if (x0) { *x0 = w.histU; *x0_count = w.redB_count; }
+            break;
+        case 2:
+            k_refine_pick<<<d, 256, 0, st>>>(w.jobs + d, status_dev);
+            k_refine_gather<<<dim3(gx_for(capU), d), 256, 0, st>>>(w.jobs + d, capU);
+            if (x0) { *x0 = w.small + (size_t)d * kSmallCap; *x0_count = (size_t)d * kSmallCap; }
+            if (x1) { *x1 = w.small_count + d; *x1_count = (size_t)d; }
+            break;
+        default:
+            k_refine_final<<<d, 1024, smem, st>>>(w.jobs + d, gath_small, gc, gath_small ? world : 1, d, status_dev);
+            k_finish_mad<<<1, 64, 0, st>>>(w.jobs, d, w.guard, mad, status_dev);
+            break;
+    }
     ABCDLS_LAUNCH_CHECK(h);
+    return ABCDLS_OK;
+}
+
+int abcdls_mad_fast_finish(abcdls_handle_t h, int64_t n, int64_t n_global, int d, void* ws, size_t ws_bytes,
+                           double* med, double* mad, int* status_dev, void* stream) {
+    for (int phase = 0; phase < 4; ++phase) {
+        int rc = abcdls_mad_fast_refine(h, n, n_global, d, phase, 1, nullptr, nullptr, ws, ws_bytes, med, mad,
+                                        status_dev, nullptr, nullptr, nullptr, nullptr, stream);
+        if (rc) return rc;
+    }
     return ABCDLS_OK;
 }
 
@@ -1265,12 +1346,47 @@ int abcdls_dist_fast_sample(abcdls_handle_t h, const double* ss, int64_t n, int 
     return ABCDLS_OK;
 }
 
+// exact ds among the candidates in [lo, hi].  phase 0: plan + locate bins + gather (exchange: all-gather
+// x0 = small block, x1 = count); phase 1: sort the (gathered) values -> ds_out.
+int abcdls_dist_fast_refine(abcdls_handle_t h, int64_t n, int64_t nacc, int64_t cap, int phase, int world,
+                            const double* gath_small, const int32_t* gath_cnt, const double* cand_dist, double* ds_out,
+                            void* ws, size_t ws_bytes, int* status_dev, void** x0, size_t* x0_count, void** x1,
+                            size_t* x1_count, void* stream) {
+    ABCDLS_CHECK_ARG(h, h && ws && cand_dist && ds_out && status_dev && (phase == 0 || phase == 1) && world >= 1 &&
+                            world <= 64,
+                     "dist_fast_refine");
+    DistWs w = carve_dist(ws, 64, n, cap);
+    if (ws_bytes < w.total) {
+        h->err = "dist_fast workspace too small";
+        return ABCDLS_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = (size_t)kSmallCap * sizeof(double);
+    ABCDLS_ONCE(h, cudaFuncSetAttribute(k_refine_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (phase == 0) {
+        k_plan_ds<<<1, 32, 0, st>>>(w.job, w.brk, w.n_lt, w.cand_cnt, w.gcand_cnt, w.hist, cand_dist, cap, w.small,
+                                    w.small_count, nacc - 1, status_dev);
+        k_refine_pick<<<1, 256, 0, st>>>(w.job, status_dev);
+        long long gg = (cap + 2047) / 2048;
+        if (gg > (long long)h->sm_count * 4) gg = (long long)h->sm_count * 4;
+        k_refine_gather<<<dim3((unsigned)gg, 1), 256, 0, st>>>(w.job, cap);
+        if (x0) { *x0 = w.small; *x0_count = (size_t)kSmallCap; }
+        if (x1) { *x1 = w.small_count; *x1_count = 1; }
+    } else {
+        k_refine_final<<<1, 1024, smem, st>>>(w.job, gath_small, reinterpret_cast<const unsigned*>(gath_cnt),
+                                              gath_small ? world : 1, 1, status_dev);
+        k_copy_result<<<1, 32, 0, st>>>(w.job, ds_out);
+    }
+    ABCDLS_LAUNCH_CHECK(h);
+    return ABCDLS_OK;
+}
+
 // dist may be NULL (the N-vector is then never materialised).  Outputs (row order): cand_row (global rows),
 // cand_dist, n_cand (device u64).  ds_out (device double) = exact nacc-th smallest distance.
 int abcdls_dist_fast_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, const double* mad,
                           const double* target, int64_t nacc, int world, int64_t row_offset, int64_t cap, double* dist,
                           int64_t* cand_row, double* cand_dist, int64_t* n_cand, double* ds_out, void* ws,
-                          size_t ws_bytes, int* status_dev, void* stream) {
+                          size_t ws_bytes, int* status_dev, int64_t** red_out, size_t* red_count, void* stream) {
     ABCDLS_CHECK_ARG(h, h && ss && mad && target && cand_row && cand_dist && n_cand && ds_out && ws && status_dev,
                      "dist_fast_pass: null");
     ABCDLS_CHECK_ARG(h, n >= kSample && d >= 1 && d <= kMaxD && ld >= n && cap >= 1, "dist_fast_pass: shape");
@@ -1327,18 +1443,16 @@ int abcdls_dist_fast_pass(abcdls_handle_t h, const double* ss, int64_t n, int d,
     k_order_cands<<<(nprod + 7) / 8, 256, 0, st>>>(w.rec_off, w.rec_cnt, w.nrec, w.wpos, nprod, rcap, w.row_tmp,
                                                    w.dist_tmp, cap, row_offset, (long long*)cand_row, cand_dist);
     ABCDLS_CUDA(h, cudaMemcpyAsync(n_cand, w.cand_cnt, 8, cudaMemcpyDeviceToDevice, st));
-    // exact ds among the candidates in [lo, hi]
-    const size_t smem = (size_t)kSmallCap * sizeof(double);
-    ABCDLS_ONCE(h, cudaFuncSetAttribute(k_refine_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_plan_ds<<<1, 32, 0, st>>>(w.job, w.brk, w.n_lt, w.cand_cnt, w.hist, cand_dist, cap, w.small, w.small_count,
-                                nacc - 1, status_dev);
-    k_refine_pick<<<1, 256, 0, st>>>(w.job, status_dev);
-    long long gg = (cap + 2047) / 2048;
-    if (gg > (long long)h->sm_count * 4) gg = (long long)h->sm_count * 4;
-    k_refine_gather<<<dim3((unsigned)gg, 1), 256, 0, st>>>(w.job, cap);
-    k_refine_final<<<1, 1024, smem, st>>>(w.job, status_dev);
-    k_copy_result<<<1, 32, 0, st>>>(w.job, ds_out);
-    ABCDLS_LAUNCH_CHECK(h);
+    ABCDLS_CUDA(h, cudaMemcpyAsync(w.gcand_cnt, w.cand_cnt, 8, cudaMemcpyDeviceToDevice, st));
+    if (red_out) *red_out = reinterpret_cast<int64_t*>(w.gcand_cnt);
+    if (red_count) *red_count = w.red_count;   // gcand_cnt | n_lt | hist: all-reduce(sum) across ranks
+    if (world == 1) {
+        for (int phase = 0; phase < 2; ++phase) {
+            int rc = abcdls_dist_fast_refine(h, n, nacc, cap, phase, 1, nullptr, nullptr, cand_dist, ds_out, ws, ws_bytes,
+                                             status_dev, nullptr, nullptr, nullptr, nullptr, stream);
+            if (rc) return rc;
+        }
+    }
     return ABCDLS_OK;
 }
 

@@ -186,32 +186,36 @@ class AbcEngine:
         S_FASTPATH_MISS, upon which abc() reruns with ``exact=True`` (6-pass radix select, always exact)."""
         k = self.k
         d, n_local = ss.shape
-        n_global, row_offset, _ = self._shard_info(n_local)
+        n_global, row_offset, ns = self._shard_info(n_local)
         nacc = int(math.ceil(n_global * tol))
         if not (1 <= nacc <= n_global):
             raise AbcError("'tol' must give 1 <= ceiling(N * tol) <= N")
-        fast = (not exact) and self.comm.world == 1 and n_local >= self.FAST_MIN_ROWS
+        fast = (not exact) and min(ns) >= self.FAST_MIN_ROWS   # every rank must take the same path
         cap = min(nacc, n_local)
         idx = k.new(cap, dtype=torch.int64)
         dacc = k.new(cap)
         n_acc = torch.zeros(1, dtype=torch.int64, device=self.device)
         le = torch.zeros(1, dtype=torch.int64, device=self.device)
         quota = torch.full((1,), nacc, dtype=torch.int64, device=self.device)
+        comm = self.comm if self.comm.world > 1 else None
         if fast:
             med, mad = k.new(d), k.new(d)
             with self._t("mad_fast"):
-                k.mad_fast(ss, n_local, n_global, d, ss.stride(0), 1, med, mad, status)
+                k.mad_fast(ss, n_local, n_global, d, ss.stride(0), med, mad, status, comm)
             ccap = min(n_local, 2 * nacc + 65536)
             dist = k.new(n_local) if keep_dist else None
             cand_row, cand_dist = k.new(ccap, dtype=torch.int64), k.new(ccap)
             n_cand = torch.zeros(1, dtype=torch.int64, device=self.device)
             ds = k.new(1)
             with self._t("dist_fast"):
-                k.dist_fast(ss, n_local, n_global, d, ss.stride(0), mad, target, nacc, 1, row_offset, ccap, dist,
-                            cand_row, cand_dist, n_cand, ds, status)
+                k.dist_fast(ss, n_local, n_global, d, ss.stride(0), mad, target, nacc, row_offset, ccap, dist,
+                            cand_row, cand_dist, n_cand, ds, status, comm)
             with self._t("accept"):
                 ws = k.accept_workspace(ccap)
                 k.count_le(cand_dist, ccap, n_cand, ds, le, ws)
+                if comm is not None:   # R's cap rule across ranks: lower ranks take their rows first
+                    below = comm.allgather(le).view(-1)[: comm.rank].sum()
+                    quota = (nacc - below).clamp(min=0).view(1)
                 k.accept(cand_dist, ccap, n_cand, cand_row, ds, quota, row_offset, cap, idx, dacc, n_acc, ws, status)
         else:
             _, mad = self.column_mad(ss, n_global)

@@ -101,34 +101,64 @@ class CudaStages:
         off = ptr.value - ws.data_ptr()
         return ws[off: off + count.value * 8].view(dtype)
 
-    def mad_fast(self, ss, n, n_global, d, ld, world, med, mad, status, reduce_sum=None):
-        """sample -> [reduce est] -> pass -> [reduce counts] -> finish.  reduce_sum: in-place all-reduce or None."""
-        ws = self.workspace("madfast", self.lib.abcdls_mad_fast_workspace_bytes(n, d))
-        ptr, cnt = C.c_void_p(), C.c_size_t()
-        self.handle.call("abcdls_mad_fast_sample", _p(ss), n, d, ld, world, _p(ws), ws.numel(), C.byref(ptr),
-                         C.byref(cnt), self._stream())
-        if reduce_sum is not None:
-            reduce_sum(self._buf(ws, ptr, cnt, torch.float64))
-        self.handle.call("abcdls_mad_fast_pass", _p(ss), n, d, ld, world, _p(ws), ws.numel(), C.byref(ptr),
-                         C.byref(cnt), self._stream())
-        if reduce_sum is not None:
-            reduce_sum(self._buf(ws, ptr, cnt, torch.int64))
-        self.handle.call("abcdls_mad_fast_finish", n, n_global, d, _p(ws), ws.numel(), _p(med), _p(mad), _p(status),
-                         self._stream())
-        self.launches += 14
+    def _view(self, ws, ptr, count, dtype, itemsize):
+        off = ptr.value - ws.data_ptr()
+        return ws[off: off + count.value * itemsize].view(dtype)
 
-    def dist_fast(self, ss, n, n_global, d, ld, mad, target, nacc, world, row_offset, cap, dist, cand_row, cand_dist,
-                  n_cand, ds, status, reduce_sum=None):
+    def mad_fast(self, ss, n, n_global, d, ld, med, mad, status, comm=None):
+        """Exact median + MAD of every column with ONE table read.  comm (world > 1): all-reduce / all-gather
+        between the stages (csrc/bracket.cu phase comments)."""
+        world = comm.world if comm is not None else 1
+        ws = self.workspace("madfast", self.lib.abcdls_mad_fast_workspace_bytes(n, d))
+        p0, c0, p1, c1 = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t()
+        self.handle.call("abcdls_mad_fast_sample", _p(ss), n, d, ld, world, _p(ws), ws.numel(), C.byref(p0),
+                         C.byref(c0), self._stream())
+        if world > 1:
+            comm.allreduce_sum(self._view(ws, p0, c0, torch.float64, 8))
+        self.handle.call("abcdls_mad_fast_pass", _p(ss), n, d, ld, world, _p(ws), ws.numel(), C.byref(p0),
+                         C.byref(c0), self._stream())
+        if world == 1:
+            self.handle.call("abcdls_mad_fast_finish", n, n_global, d, _p(ws), ws.numel(), _p(med), _p(mad),
+                             _p(status), self._stream())
+            self.launches += 15
+            return
+        comm.allreduce_sum(self._view(ws, p0, c0, torch.int64, 8))
+        gs = gc = None
+        for phase in range(4):
+            self.handle.call("abcdls_mad_fast_refine", n, n_global, d, phase, world, _p(gs), _p(gc), _p(ws), ws.numel(),
+                             _p(med), _p(mad), _p(status), C.byref(p0), C.byref(c0), C.byref(p1), C.byref(c1),
+                             self._stream())
+            if phase in (0, 2):
+                gs = comm.allgather(self._view(ws, p0, c0, torch.float64, 8)).contiguous()
+                gc = comm.allgather(self._view(ws, p1, c1, torch.int32, 4)).contiguous()
+            elif phase == 1:
+                comm.allreduce_sum(self._view(ws, p0, c0, torch.int64, 8))
+        self.launches += 15
+
+    def dist_fast(self, ss, n, n_global, d, ld, mad, target, nacc, row_offset, cap, dist, cand_row, cand_dist,
+                  n_cand, ds, status, comm=None):
+        """Fused distance + tolerance bracket: candidate rows in row order and the exact global threshold ds."""
+        world = comm.world if comm is not None else 1
         ws = self.workspace("distfast", self.lib.abcdls_dist_fast_workspace_bytes(n, cap))
-        ptr, cnt = C.c_void_p(), C.c_size_t()
+        p0, c0, p1, c1 = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t()
         self.handle.call("abcdls_dist_fast_sample", _p(ss), n, d, ld, _p(mad), _p(target), nacc, n_global, world, cap,
-                         _p(ws), ws.numel(), C.byref(ptr), C.byref(cnt), self._stream())
-        if reduce_sum is not None:
-            reduce_sum(self._buf(ws, ptr, cnt, torch.float64))
+                         _p(ws), ws.numel(), C.byref(p0), C.byref(c0), self._stream())
+        if world > 1:
+            comm.allreduce_sum(self._view(ws, p0, c0, torch.float64, 8))
         self.handle.call("abcdls_dist_fast_pass", _p(ss), n, d, ld, _p(mad), _p(target), nacc, world, row_offset, cap,
                          _p(dist), _p(cand_row), _p(cand_dist), _p(n_cand), _p(ds), _p(ws), ws.numel(), _p(status),
+                         C.byref(p0), C.byref(c0), self._stream())
+        self.launches += 12
+        if world == 1:
+            return
+        comm.allreduce_sum(self._view(ws, p0, c0, torch.int64, 8))
+        self.handle.call("abcdls_dist_fast_refine", n, nacc, cap, 0, world, None, None, _p(cand_dist), _p(ds), _p(ws),
+                         ws.numel(), _p(status), C.byref(p0), C.byref(c0), C.byref(p1), C.byref(c1), self._stream())
+        gs = comm.allgather(self._view(ws, p0, c0, torch.float64, 8)).contiguous()
+        gc = comm.allgather(self._view(ws, p1, c1, torch.int32, 4)).contiguous()
+        self.handle.call("abcdls_dist_fast_refine", n, nacc, cap, 1, world, _p(gs), _p(gc), _p(cand_dist), _p(ds),
+                         _p(ws), ws.numel(), _p(status), C.byref(p0), C.byref(c0), C.byref(p1), C.byref(c1),
                          self._stream())
-        self.launches += 11
 
     # ---- kernel 3 -------------------------------------------------------------------------------
     def gather(self, ss, ld_ss, param, ld_param, dist_acc, idx, n_acc, row_offset, cap, d, P, mad, target, ds, xs, y,

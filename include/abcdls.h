@@ -132,20 +132,37 @@ int abcdls_accept(abcdls_handle_t h, const double* dist, int64_t n, const int64_
  * n must be >= 4096 (smaller tables use the radix path).
  */
 size_t abcdls_mad_fast_workspace_bytes(int64_t n, int d);
+/* est_out / est_count: buffer (doubles) a multi-rank caller all-reduces (sum) before the pass */
 int abcdls_mad_fast_sample(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, void* ws,
                            size_t ws_bytes, double** est_out, size_t* est_count, void* stream);
+/* counts_out / counts_count: int64 block (counts | appended | median histogram) to all-reduce (sum) after it */
 int abcdls_mad_fast_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, void* ws,
                          size_t ws_bytes, int64_t** counts_out, size_t* counts_count, void* stream);
+/* phases 0..3, see csrc/bracket.cu: 0 -> all-gather (x0: doubles, x1: uint32 counts); 1 -> all-reduce x0 (int64);
+ * 2 -> all-gather (x0, x1); 3 -> med / mad final.  gath_small / gath_cnt: the gathered block of the previous phase
+ * ([world][d][8192] doubles, [world][d] counts), NULL on a single rank. */
+int abcdls_mad_fast_refine(abcdls_handle_t h, int64_t n, int64_t n_global, int d, int phase, int world,
+                           const double* gath_small, const int32_t* gath_cnt, void* ws, size_t ws_bytes, double* med,
+                           double* mad, int* status_dev, void** x0, size_t* x0_count, void** x1, size_t* x1_count,
+                           void* stream);
+/* single rank: the four phases back to back */
 int abcdls_mad_fast_finish(abcdls_handle_t h, int64_t n, int64_t n_global, int d, void* ws, size_t ws_bytes,
                            double* med, double* mad, int* status_dev, void* stream);
 size_t abcdls_dist_fast_workspace_bytes(int64_t n, int64_t cap);
 int abcdls_dist_fast_sample(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, const double* mad,
                             const double* target, int64_t nacc, int64_t n_global, int world, int64_t cap, void* ws,
                             size_t ws_bytes, double** est_out, size_t* est_count, void* stream);
+/* dist may be NULL.  Emits this rank's candidate rows (dist <= bracket top) in row order.  world == 1: ds_out is
+ * final on return.  world > 1: all-reduce (sum) the int64 block red_out/red_count, then run the refine phases. */
 int abcdls_dist_fast_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, const double* mad,
                           const double* target, int64_t nacc, int world, int64_t row_offset, int64_t cap, double* dist,
                           int64_t* cand_row, double* cand_dist, int64_t* n_cand, double* ds_out, void* ws,
-                          size_t ws_bytes, int* status_dev, void* stream);
+                          size_t ws_bytes, int* status_dev, int64_t** red_out, size_t* red_count, void* stream);
+/* phase 0 -> all-gather (x0: 8192 doubles, x1: one uint32 count); phase 1 -> ds_out */
+int abcdls_dist_fast_refine(abcdls_handle_t h, int64_t n, int64_t nacc, int64_t cap, int phase, int world,
+                            const double* gath_small, const int32_t* gath_cnt, const double* cand_dist, double* ds_out,
+                            void* ws, size_t ws_bytes, int* status_dev, void** x0, size_t* x0_count, void** x1,
+                            size_t* x1_count, void* stream);
 
 /* ---- kernel 3: local-linear adjustment -----------------------------------------------------
  * R: weights (epanechnikov) -> lsfit -> residual recentring -> hcorr -> adj.values.

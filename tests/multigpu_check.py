@@ -1,0 +1,76 @@
+"""Multi-GPU parity check, launched with torchrun (one process per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/multigpu_check.py [--rows N]
+
+Every rank holds a contiguous row block of the same seeded table; the sharded engine result (accepted rows,
+ds, MAD, adjusted values, summary) must equal the single-table CPU oracle: accepted set bit-exact, adjusted
+values within 1e-9.  Rank 0 prints PASS/FAIL lines; exit code 1 on failure.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from abc_dls_b200 import synth  # noqa: E402
+from abc_dls_b200.engine import AbcEngine  # noqa: E402
+from oracle import abc_oracle as O  # noqa: E402
+
+
+def gather_rows(t, world):
+    n = torch.tensor([t.shape[0]], device=t.device)
+    ns = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(ns, n)
+    cap = max(int(x) for x in ns)
+    pad = torch.zeros((cap,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[: t.shape[0]] = t
+    out = [torch.zeros_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad)
+    return torch.cat([o[: int(k)] for o, k in zip(out, ns)])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rows", type=int, default=300001)
+    ap.add_argument("--big", type=int, default=0, help="also run a fast-path sized table (rows per rank)")
+    a = ap.parse_args()
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    dist.init_process_group("nccl", device_id=dev)
+    eng = AbcEngine(dev)
+    ok = True
+    cases = [(a.rows, 3, 2, 0.01, "rejection"), (a.rows, 16, 16, 0.02, "loclinear"), (a.rows, 1, 1, 0.05, "loclinear")]
+    if a.big:
+        cases += [(a.big * world, 16, 16, 0.01, "loclinear"), (a.big * world + 77, 3, 3, 0.002, "rejection")]
+    for (N, d, P, tol, method) in cases:
+        per = (N + world - 1) // world
+        r0, r1 = min(rank * per, N), min((rank + 1) * per, N)
+        par, ss, tgt = synth.abc_tables(r1 - r0, d, P, dev, row_start=r0)
+        res = eng.abc(tgt, par, ss, tol, method)
+        idx = gather_rows(res.idx, world)
+        vals = gather_rows(res.values.contiguous(), world)
+        if rank == 0:
+            fpar, fss, ftgt = synth.abc_tables(N, d, P, dev)
+            o = O.abc(ftgt.cpu().numpy(), fpar.cpu().numpy().T, fss.cpu().numpy().T, tol, method)
+            good = np.array_equal(idx.cpu().numpy(), o.idx) and res.ds == o.ds and np.array_equal(res.mad.cpu().numpy(), o.mad)
+            ref = o.adj_values if method == "loclinear" else o.unadj_values
+            err = float(np.max(np.abs(vals.cpu().numpy() - ref) / np.abs(ref).max(axis=0)))
+            mn, mx = res.minmax()
+            e2 = float(np.max(np.abs(mn.cpu().numpy() - ref.min(axis=0)) / np.abs(ref).max(axis=0)))
+            good = good and err < 1e-9 and e2 < 1e-9
+            print(f"{'PASS' if good else 'FAIL'} world={world} N={N} d={d} P={P} tol={tol} {method}: nacc={o.nacc} "
+                  f"max rel err={err:.2e} fast_misses={eng.fast_misses} collectives={eng.comm.calls}", flush=True)
+            ok = ok and good
+    flag = torch.tensor([0 if ok else 1], device=dev)
+    dist.all_reduce(flag)
+    dist.destroy_process_group()
+    sys.exit(1 if int(flag) else 0)
+
+
+if __name__ == "__main__":
+    main()
