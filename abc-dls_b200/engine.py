@@ -115,6 +115,8 @@ class AbcEngine:
         self.comm = Comm(group, self.device)
         self.timers = None   # set to {} to record CUDA-event pairs per named stage (bench.py)
         self.fast_misses = 0  # how often a sampled bracket missed and the radix path had to rerun the call
+        if hasattr(stages, "timer"):
+            stages.timer = self._t
 
     class _Timed:
         def __init__(self, eng, name):

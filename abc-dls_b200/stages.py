@@ -27,6 +27,11 @@ class CudaStages:
         self.lib = self.handle.lib
         self._ws = {}
         self.launches = 0  # kernels enqueued through this object (bench.py reports it)
+        self.timer = None  # optional: callable(name) -> context manager recording CUDA events (engine._t)
+
+    def _timed(self, name):
+        import contextlib
+        return self.timer(name) if self.timer is not None else contextlib.nullcontext()
 
     # ---- helpers ----------------------------------------------------------------------------
     def _stream(self):
@@ -115,8 +120,9 @@ class CudaStages:
                          C.byref(c0), self._stream())
         if world > 1:
             comm.allreduce_sum(self._view(ws, p0, c0, torch.float64, 8))
-        self.handle.call("abcdls_mad_fast_pass", _p(ss), n, d, ld, world, _p(ws), ws.numel(), C.byref(p0),
-                         C.byref(c0), self._stream())
+        with self._timed("k_bracket_pass"):
+            self.handle.call("abcdls_mad_fast_pass", _p(ss), n, d, ld, world, _p(ws), ws.numel(), C.byref(p0),
+                             C.byref(c0), self._stream())
         if world == 1:
             self.handle.call("abcdls_mad_fast_finish", n, n_global, d, _p(ws), ws.numel(), _p(med), _p(mad),
                              _p(status), self._stream())
@@ -145,9 +151,10 @@ class CudaStages:
                          _p(ws), ws.numel(), C.byref(p0), C.byref(c0), self._stream())
         if world > 1:
             comm.allreduce_sum(self._view(ws, p0, c0, torch.float64, 8))
-        self.handle.call("abcdls_dist_fast_pass", _p(ss), n, d, ld, _p(mad), _p(target), nacc, world, row_offset, cap,
-                         _p(dist), _p(cand_row), _p(cand_dist), _p(n_cand), _p(ds), _p(ws), ws.numel(), _p(status),
-                         C.byref(p0), C.byref(c0), self._stream())
+        with self._timed("k_dist_pass"):
+            self.handle.call("abcdls_dist_fast_pass", _p(ss), n, d, ld, _p(mad), _p(target), nacc, world, row_offset,
+                             cap, _p(dist), _p(cand_row), _p(cand_dist), _p(n_cand), _p(ds), _p(ws), ws.numel(),
+                             _p(status), C.byref(p0), C.byref(c0), self._stream())
         self.launches += 12
         if world == 1:
             return

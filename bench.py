@@ -30,6 +30,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "simulations scored/sec (ABC loclinear)"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture at the default
+# workload (profiles/r01_ncu_full_*.csv); None until a capture of the current kernel is committed
+TRAFFIC = {"k_bracket_pass": 12.800307e9 + 0.494554e9, "k_dist_pass": None}
 UNIT = "sims/s"
 
 
@@ -203,23 +206,34 @@ def main():
     value = N / (ms_step * 1e-3)
 
     # ---- roofline of the dominant table-streaming kernel (per launch, this rank) ----------------
+    # CUDA events on the launching stream around the C-ABI call that enqueues the kernel.  "k_bracket_pass" also
+    # covers k_make_brackets + a 32-thread copy (~10 us); "k_dist_pass" also covers the candidate ordering and, on
+    # a single rank, the ds refinement (~60 us) — both are noted in the JSON.
     peak, peak_src = _peaks()
     kern = {}
     for name, v in tms.items():
         kern[name] = {"launches": len(v), "avg_ms": sum(v) / len(v), "total_ms_per_step": sum(v) / args.steps}
-    dom = max(kern, key=lambda k_: kern[k_]["total_ms_per_step"])
-    if dom.startswith("select_hist"):
-        alg_bytes = 8.0 * d * n_local            # one read of the N x d table per radix pass
-    else:
-        alg_bytes = (8.0 * d + 8.0) * n_local    # scale_dist: read the table once, write dist
+    alg = {"k_bracket_pass": 8.0 * d * n_local,      # one read of the N x d table (all medians + MADs)
+           "k_dist_pass": 8.0 * d * n_local,         # one read of the table; dist is not materialised
+           "scale_dist": (8.0 * d + 8.0) * n_local}
+    for name in list(kern):
+        if name.startswith("select_hist"):
+            alg[name] = 8.0 * float(name.split("[")[1].split("x")[0]) * n_local
+    streaming = [k_ for k_ in kern if k_ in alg]
+    dom = max(streaming, key=lambda k_: kern[k_]["total_ms_per_step"])
+    alg_bytes = alg[dom]
     achieved = alg_bytes / (kern[dom]["avg_ms"] * 1e-3) / 1e9
+    per_kernel = {k_: {"algorithmic_bytes": alg[k_], "avg_ms": kern[k_]["avg_ms"],
+                       "GBps": alg[k_] / (kern[k_]["avg_ms"] * 1e-3) / 1e9,
+                       "frac": alg[k_] / (kern[k_]["avg_ms"] * 1e-3) / 1e9 / peak} for k_ in streaming}
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": TRAFFIC.get(dom), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": kern[dom]["avg_ms"],
+                "streaming_kernels": per_kernel,
                 "whole_call": {"algorithmic_bytes_per_sim": 16 * d + 16,
                                "achieved_GBps": (16 * d + 16) * N / (ms_step * 1e-3) / 1e9 / world,
                                "frac_of_peak_per_gpu": (16 * d + 16) * N / (ms_step * 1e-3) / 1e9 / world / peak},
-                "kernels": kern}
+                "stages_ms": {k_: round(v_["avg_ms"], 4) for k_, v_ in kern.items()}}
 
     # ---- end to end through host buffers -----------------------------------------------------------
     e2e = None

@@ -1,0 +1,95 @@
+"""Host-side logic on CPU: SMC range rules, summary table semantics, and the engine's sharded sequencing of
+stages and collectives under gloo with world_size 2 (numpy test double for the CUDA stages, tests/cpu_stages.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import abc_oracle as O  # noqa: E402
+from abc_dls_b200 import smc, summary, synth  # noqa: E402
+
+
+def test_smc_rules_match_oracle():
+    rng = np.random.default_rng(21)
+    P = 24
+    omin = rng.uniform(0, 10, P)
+    omax = omin + rng.uniform(1, 100, P)
+    frac = rng.uniform(0.3, 1.0, P)
+    pmin = omin + (omax - omin) * (1 - frac) / 2
+    pmax = pmin + (omax - omin) * frac
+    pmin[3], pmax[3] = omin[3], omax[3]
+    pmin[5] = pmax[5] = omin[5] + 1.0
+    pmin[7], pmax[7], omin[7], omax[7] = 5.0001, 5.0002, 5.0, 5.001
+    hmin, hmax = omin - 1.0, omax + 0.5
+    r = smc.updating_newrange(pmin, pmax, omin, omax, 0.95)
+    o = O.updating_newrange(pmin, pmax, omin, omax, 0.95)
+    for a, b in zip((r.min, r.max, r.decrease), o):
+        np.testing.assert_array_equal(a, b)
+    r2 = smc.noise_injection_update(r, omin, omax, 0.01, hmin, hmax, 0.95)
+    o2 = O.noise_injection_update(*o, omin, omax, 0.01, hmin, hmax, 0.95)
+    for a, b in zip((r2.min, r2.max, r2.decrease), o2):
+        np.testing.assert_array_equal(a, b)
+    assert smc.lmrd_calculation(r2, hmin, hmax) == O.lmrd_calculation(o2[0], o2[1], hmin, hmax)
+
+
+def test_summary_table_indexing_follows_r():
+    tab = summary.SummaryTable(np.arange(14.0).reshape(7, 2), ["a", "b"])
+    assert tab[0] == 0.0 and tab[6] == 12.0            # column-major flat index: Min / Max of parameter 1
+    assert tab[7] == 1.0 and tab[13] == 13.0           # ... of parameter 2
+    assert np.array(tab).shape == (7, 2)
+    np.testing.assert_array_equal(np.array(tab)[0], [0.0, 1.0])     # ABC.py:2854 reads row 0 / row -1
+    txt = summary.summary_text(tab, 10, True)
+    assert txt.startswith("Data:") and "Weights:" in txt and "Min.:" in txt
+
+
+def _worker(rank, world, port, N, d, P, tol, method, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from abc_dls_b200.engine import AbcEngine
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from cpu_stages import CpuStages
+    eng = AbcEngine(stages=CpuStages())
+    per = (N + world - 1) // world
+    r0, r1 = rank * per, min(N, (rank + 1) * per)
+    par, ss, tgt = synth.abc_tables(N, d, P, "cpu")
+    res = eng.abc(tgt, par[:, r0:r1].contiguous(), ss[:, r0:r1].contiguous(), tol, method)
+    mn, mx = res.minmax()
+    q.put((rank, res.idx.numpy(), res.values.contiguous().numpy(), res.ds, res.mad.numpy(), mn.numpy(), mx.numpy(),
+           eng.comm.calls))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("method,tol", [("rejection", 0.03), ("loclinear", 0.05)])
+def test_sharded_sequencing_world2_gloo(method, tol):
+    N, d, P, world = 4001, 3, 2, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 300) + (1 if method == "rejection" else 2)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, N, d, P, tol, method, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    par, ss, tgt = synth.abc_tables(N, d, P, "cpu")
+    o = O.abc(tgt.numpy(), par.numpy().T, ss.numpy().T, tol, method)
+    idx = np.concatenate([t[1] for t in out])
+    vals = np.concatenate([t[2] for t in out])
+    np.testing.assert_array_equal(idx, o.idx)                # bit-exact accepted set, global row order across ranks
+    assert out[0][3] == o.ds and out[1][3] == o.ds
+    np.testing.assert_array_equal(out[0][4], o.mad)
+    ref = o.adj_values if method == "loclinear" else o.unadj_values
+    assert np.max(np.abs(vals - ref) / np.abs(ref).max(axis=0)) < 1e-9
+    for t in out:                                            # global summary on every rank
+        np.testing.assert_allclose(t[5], ref.min(axis=0), rtol=1e-9)
+        np.testing.assert_allclose(t[6], ref.max(axis=0), rtol=1e-9)
+        assert t[7] >= 12                                    # the radix passes alone need 18 all-reduces
