@@ -89,6 +89,8 @@ class PostprResult:
 
 
 def _as_table(t: torch.Tensor) -> torch.Tensor:
+    """(cols, rows) float64 view with unit stride along rows.  The tensor stays where it is: a PINNED host table is
+    legal for `param` (the gather kernel then reads the accepted rows zero-copy over PCIe/UVA)."""
     if t.dim() == 1:
         t = t[None, :]
     if t.dtype != torch.float64:
@@ -253,6 +255,8 @@ class AbcEngine:
         """``abc::abc`` for method in {rejection, loclinear} on this rank's shard.
 
         target (d,), param (P, n_local), sumstat (d, n_local): float64 CUDA tensors, column-major tables.
+        `param` may instead be a PINNED host tensor: only the accepted rows (tol * N) are ever read, so the table is
+        left in host memory and gathered zero-copy (saves the H2D copy of N x P doubles).
         """
         if method not in ("rejection", "loclinear"):
             raise AbcError("Method must be rejection or loclinear (neuralnet / ridge stay with R's nnet)")
@@ -267,6 +271,13 @@ class AbcEngine:
             raise AbcError("Number of summary statistics in 'target' has to be the same as in 'sumstat'.")
         if par.shape[1] != n_local:
             raise AbcError("'param' and 'sumstat' must have the same number of rows")
+        if par.device.type == "cpu":
+            if self.device.type == "cuda" and not par.is_pinned():
+                par = par.to(self.device)      # pageable host memory cannot be mapped: stage it
+        elif par.device != self.device:
+            par = par.to(self.device)
+        if ss.device != self.device:
+            ss = ss.to(self.device)
         status = torch.zeros(1, dtype=torch.int32, device=self.device)
         f = self._front(target, ss, tol, status, keep_dist=keep_dist, exact=_exact)
         cap, idx, n_acc, ds, mad, dacc = f["cap"], f["idx"], f["n_acc"], f["ds"], f["mad"], f["dacc"]

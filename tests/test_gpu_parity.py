@@ -183,3 +183,22 @@ def test_facade_accepts_pandas_like_the_reference_call_sites(engine):
     op = O.postpr(tg.numpy(), index.to_numpy(), ssp.T.numpy(), 0.05)
     np.testing.assert_array_equal(_np(pp.res.counts), op.counts)
     assert "Proportion of accepted simulations (rejection):" in pp.summary_text()
+
+
+def test_param_table_may_stay_in_pinned_host_memory(engine):
+    """Only the accepted rows of `param` are read: a pinned host table is gathered zero-copy."""
+    par, ss, tgt = synth.abc_tables(1 << 20, 4, 3, engine.device)
+    ref = engine.abc(tgt, par, ss, 0.01, "loclinear")
+    hpar = par.cpu().pin_memory()
+    r = engine.abc(tgt, hpar, ss, 0.01, "loclinear")
+    assert torch.equal(r.idx, ref.idx) and torch.equal(r.unadj_values, ref.unadj_values)
+    assert torch.equal(r.adj_values, ref.adj_values) and engine.fast_misses == 0
+
+
+def test_fast_path_is_taken_without_misses(engine):
+    before = engine.fast_misses
+    par, ss, tgt = synth.abc_tables((1 << 21) + 13, 16, 16, engine.device)
+    r, o = _check_abc(engine, par, ss, tgt, 0.005, "loclinear")
+    r2 = engine.abc(tgt, par, ss, 0.005, "loclinear")               # dist not kept: TMA kernel without the N-vector
+    assert torch.equal(r2.idx, r.idx) and r2.dist is None
+    assert engine.fast_misses == before
