@@ -143,16 +143,15 @@ constexpr int kAThreads = 256;
 constexpr int kAItems = 8;                    // elements per lane per warp-tile
 constexpr int kAWarpTile = 32 * kAItems;      // 256 elements
 constexpr int kATile = kAThreads * kAItems;   // used for grid sizing only
-constexpr int kStageM = 96;                   // per-warp staging (doubles) for the M band
-constexpr int kStageU = 288;                  // ... and for the U band  (>= 256: a whole warp-tile always fits)
+constexpr int kStageM = 288;                  // per-warp staging (doubles): a whole warp-tile (256) always fits
+constexpr int kStageU = 384;                  //   after the flush threshold (32 / 128 staged values)
 
 // Same-address global atomics cost ~15 ns each on B200, so candidates are staged per warp in shared memory
 // and flushed with ONE atomic + a coalesced copy.  The fine histogram of the M band is built at flush time.
 template <bool HIST>
-__device__ __forceinline__ void stage_flush(double* stage, int& fill, double* __restrict__ gbuf, long long gcap,
-                                            unsigned long long* gcnt, int lane, unsigned* hist, double lo,
-                                            double scale) {
-    if (fill == 0) return;
+__device__ __noinline__ void stage_flush(double* stage, int fill, double* __restrict__ gbuf, long long gcap,
+                                         unsigned long long* gcnt, unsigned* hist, double lo, double scale) {
+    const int lane = threadIdx.x & 31;
     unsigned long long base = 0ull;
     if (lane == 0) base = atomicAdd(gcnt, (unsigned long long)fill);
     base = __shfl_sync(0xffffffffu, base, 0);
@@ -161,13 +160,13 @@ __device__ __forceinline__ void stage_flush(double* stage, int& fill, double* __
         if ((long long)base + t < gcap) gbuf[base + t] = v;
         if (HIST) atomicAdd(&hist[bin_of(v, lo, scale)], 1u);
     }
-    fill = 0;
     __syncwarp();
 }
 
-// Streaming loop without block barriers: a warp owns warp-tiles of 256 consecutive elements (8 per lane in
-// registers), classifies them with one subtract + four compares each, and prefetches its next warp-tile into a
-// second register set (ping-pong, no copies).
+// Streaming loop without block barriers.  A warp owns warp-tiles of 256 consecutive elements (8 per lane in
+// registers, next tile prefetched into a second register set).  Per element: one subtract, four compares, two
+// predicated counter increments; per 32 elements two ballots.  Candidate stores only happen under warp-uniform
+// branches (positions from popc of the ballot), so the common path is ~8 instructions per element.
 __global__ void __launch_bounds__(kAThreads, 3) k_bracket_pass(const double* __restrict__ ss, long long n, long long ld,
                                                                const ColBrk* __restrict__ brk,
                                                                unsigned long long* __restrict__ counts,
@@ -187,6 +186,7 @@ __global__ void __launch_bounds__(kAThreads, 3) k_bracket_pass(const double* __r
     if (threadIdx.x < 2) tot2[threadIdx.x] = 0u;
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const long long warp_id = (long long)blockIdx.x * (kAThreads / 32) + wid;
     const long long warp_stride = (long long)gridDim.x * (kAThreads / 32);
     const bool vec = ((reinterpret_cast<uintptr_t>(col) & 15) == 0);
@@ -194,11 +194,9 @@ __global__ void __launch_bounds__(kAThreads, 3) k_bracket_pass(const double* __r
     const long long ntiles = (n + kAWarpTile - 1) / kAWarpTile;
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
     unsigned c_lt = 0, c_in = 0;
-    int fillM = 0, fillU = 0;
+    int fillM = 0, fillU = 0;                         // warp-uniform
     double* gM = candM + (size_t)j * capM;
     double* gU = candU + (size_t)j * capU;
-    double* sM = stM[wid];
-    double* sU = stU[wid];
     unsigned long long* cntM = &cnt[j * 2 + 0];
     unsigned long long* cntU = &cnt[j * 2 + 1];
 
@@ -221,62 +219,36 @@ __global__ void __launch_bounds__(kAThreads, 3) k_bracket_pass(const double* __r
         }
     };
 
-    auto process = [&](const double (&x)[kAItems]) {
-        unsigned mM = 0, mU = 0;
-#pragma unroll
-        for (int u = 0; u < kAItems; ++u) {
-            const double sgn = __dsub_rn(x[u], c);
-            const double y = fabs(sgn);
-            const bool in1 = y < r1;
-            c_lt += (sgn < nr0) ? 1u : 0u;
-            c_in += in1 ? 1u : 0u;
-            mM |= (y <= r0) ? (1u << u) : 0u;
-            mU |= (!in1 && y <= r2) ? (1u << u) : 0u;
-        }
-        if (__any_sync(0xffffffffu, (mM | mU) != 0u)) {
-            const int packed = __popc(mM) | (__popc(mU) << 16);
-            int incl = packed;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            const int tot = __shfl_sync(0xffffffffu, incl, 31);
-            const int totM = tot & 0xffff, totU = tot >> 16;
-            // a warp-tile holds at most 256 values: after a flush it always fits the stage
-            if (fillM + totM > kStageM) stage_flush<true>(sM, fillM, gM, capM, cntM, lane, hist, loM, scaleM);
-            if (fillU + totU > kStageU) stage_flush<false>(sU, fillU, gU, capU, cntU, lane, nullptr, 0.0, 0.0);
-            int pM = fillM + ((incl - packed) & 0xffff);
-            int pU = fillU + ((incl - packed) >> 16);
-            if (totM <= kStageM) {
-#pragma unroll
-                for (int u = 0; u < kAItems; ++u) {
-                    if (mM & (1u << u)) sM[pM] = x[u];
-                    pM += (mM >> u) & 1u;
-                }
-                fillM += totM;
-            } else {   // > 96 of 256 values inside the median band: heavy ties; flush straight to HBM
-                unsigned long long base = 0ull;
-                if (lane == 0) base = atomicAdd(cntM, (unsigned long long)totM);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                long long p = (long long)base + ((incl - packed) & 0xffff);
-#pragma unroll
-                for (int u = 0; u < kAItems; ++u)
-                    if (mM & (1u << u)) {
-                        if (p < capM) gM[p] = x[u];
-                        ++p;
-                        atomicAdd(&hist[bin_of(x[u], loM, scaleM)], 1u);
-                    }
-            }
-#pragma unroll
-            for (int u = 0; u < kAItems; ++u) {
-                if (mU & (1u << u)) sU[pU] = x[u];
-                pU += (mU >> u) & 1u;
-            }
-            fillU += totU;
-            __syncwarp();
-        }
-    };
+#define PROCESS_TILE(x)                                                                                       \
+    {                                                                                                         \
+        if (fillM > kStageM - kAWarpTile) {                                                                   \
+            stage_flush<true>(stM[wid], fillM, gM, capM, cntM, hist, loM, scaleM);                            \
+            fillM = 0;                                                                                        \
+        }                                                                                                     \
+        if (fillU > kStageU - kAWarpTile) {                                                                   \
+            stage_flush<false>(stU[wid], fillU, gU, capU, cntU, nullptr, 0.0, 0.0);                           \
+            fillU = 0;                                                                                        \
+        }                                                                                                     \
+        _Pragma("unroll") for (int u = 0; u < kAItems; ++u) {                                                 \
+            const double sgn = __dsub_rn(x[u], c);                                                            \
+            const double y = fabs(sgn);                                                                       \
+            const bool in1 = y < r1;                                                                          \
+            const bool inM = y <= r0;                                                                         \
+            const bool inU = !in1 && y <= r2;                                                                 \
+            if (sgn < nr0) ++c_lt;                                                                            \
+            if (in1) ++c_in;                                                                                  \
+            const unsigned bM = __ballot_sync(0xffffffffu, inM);                                              \
+            const unsigned bU = __ballot_sync(0xffffffffu, inU);                                              \
+            if (bM) {                                                                                         \
+                if (inM) stM[wid][fillM + __popc(bM & lt_mask)] = x[u];                                       \
+                fillM += __popc(bM);                                                                          \
+            }                                                                                                 \
+            if (bU) {                                                                                         \
+                if (inU) stU[wid][fillU + __popc(bU & lt_mask)] = x[u];                                       \
+                fillU += __popc(bU);                                                                          \
+            }                                                                                                 \
+        }                                                                                                     \
+    }
 
     double xa[kAItems], xb[kAItems];
     long long wt = warp_id;
@@ -284,16 +256,18 @@ __global__ void __launch_bounds__(kAThreads, 3) k_bracket_pass(const double* __r
     while (wt < ntiles) {
         long long wnext = wt + warp_stride;
         if (wnext < ntiles) load_tile(wnext, xb);
-        process(xa);
+        PROCESS_TILE(xa);
         wt = wnext;
         if (wt >= ntiles) break;
         wnext = wt + warp_stride;
         if (wnext < ntiles) load_tile(wnext, xa);
-        process(xb);
+        PROCESS_TILE(xb);
         wt = wnext;
     }
-    stage_flush<true>(sM, fillM, gM, capM, cntM, lane, hist, loM, scaleM);
-    stage_flush<false>(sU, fillU, gU, capU, cntU, lane, nullptr, 0.0, 0.0);
+#undef PROCESS_TILE
+    __syncwarp();
+    if (fillM) stage_flush<true>(stM[wid], fillM, gM, capM, cntM, hist, loM, scaleM);
+    if (fillU) stage_flush<false>(stU[wid], fillU, gU, capU, cntU, nullptr, 0.0, 0.0);
     c_lt = warp_sum(c_lt);
     c_in = warp_sum(c_in);
     if (lane == 0) {
