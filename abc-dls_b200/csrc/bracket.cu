@@ -287,6 +287,7 @@ struct RefJob {
     const double* src;                    // candidate values
     const unsigned long long* src_count;  // entries appended (may exceed src_cap => miss)
     long long src_cap;
+    const int* dir;                       // chunked source (one-pass kernel): slot i is valid iff (i & 255) < dir[i >> 8]
     int transform;                        // 1: v = |x - center|
     int valid;                            // 0 => the bracket missed; results are NaN and MISS is flagged
     double center;
@@ -372,7 +373,9 @@ __global__ void __launch_bounds__(256) k_refine_gather(RefJob* jobs, long long n
     const double lo = J.lo, scale = J.scale, c = J.center, vmin = J.vmin;
     const bool tr = J.transform != 0;
     const long long stride = (long long)gridDim.x * blockDim.x;
+    const int* __restrict__ dir = J.dir;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (dir && (int)(i & 255) >= dir[i >> 8]) continue;
         double x = J.src[i];
         double v = tr ? fabs(__dsub_rn(x, c)) : x;
         if (v >= vmin) {
@@ -447,15 +450,16 @@ __global__ void k_plan_median(RefJob* jobs, int d, const ColBrk* __restrict__ br
                               const unsigned long long* __restrict__ counts, unsigned long long* histM,
                               const double* candM, long long capM, const unsigned long long* cnt,
                               const unsigned long long* gcnt, double* small, unsigned* small_count, long long k0,
-                              long long k1, int* status) {
+                              long long k1, const int* dirM, int* status) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= d) return;
     RefJob J;
+    J.dir = dirM ? dirM + (size_t)j * (capM / 256) : nullptr;
     // counts / gcnt are summed over ranks; cnt is what THIS rank appended (every band value is appended)
     const long long c_lt = (long long)counts[j * 4 + 0], c_m = (long long)gcnt[j * 2 + 0];
     J.src = candM + (size_t)j * capM;
     J.src_count = cnt + j * 2 + 0;
-    J.src_cap = capM;
+    J.src_cap = dirM ? capM - 256 : capM;   // chunked source: the last chunk is the overflow sink
     J.transform = 0;
     J.center = 0.0;
     J.lo = brk[j].loM;
@@ -471,7 +475,7 @@ __global__ void k_plan_median(RefJob* jobs, int d, const ColBrk* __restrict__ br
     J.small_count = small_count + j;
     J.result[0] = J.result[1] = 0.0;
     // the band must contain both ranks and every band value must have been stored
-    J.valid = (J.kk[0] >= 0 && J.kk[1] < c_m && (long long)cnt[j * 2 + 0] <= capM) ? 1 : 0;
+    J.valid = (J.kk[0] >= 0 && J.kk[1] < c_m && (long long)cnt[j * 2 + 0] <= J.src_cap) ? 1 : 0;
     if (!J.valid) atomicOr(status, ABCDLS_S_FASTPATH_MISS);
     jobs[j] = J;
 }
@@ -481,7 +485,8 @@ __global__ void k_plan_mad(RefJob* jobs, int d, const ColBrk* __restrict__ brk,
                            const unsigned long long* __restrict__ counts, unsigned long long* histU,
                            const double* candU, long long capU, const unsigned long long* cnt,
                            const unsigned long long* gcnt, double* small, unsigned* small_count, long long k0,
-                           long long k1, double* __restrict__ med, double* __restrict__ guard, int* status) {
+                           long long k1, double* __restrict__ med, double* __restrict__ guard, const int* dirU,
+                           int* status) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= d) return;
     const RefJob& Jm = jobs[j];
@@ -489,10 +494,11 @@ __global__ void k_plan_mad(RefJob* jobs, int d, const ColBrk* __restrict__ brk,
     med[j] = m;
     const ColBrk B = brk[j];
     RefJob J;
+    J.dir = dirU ? dirU + (size_t)j * (capU / 256) : nullptr;
     const long long c_in = (long long)counts[j * 4 + 2], c_u = (long long)gcnt[j * 2 + 1];
     J.src = candU + (size_t)j * capU;
     J.src_count = cnt + j * 2 + 1;
-    J.src_cap = capU;
+    J.src_cap = dirU ? capU - 256 : capU;
     J.transform = 1;
     J.center = m;
     // x in U has fl|x - c| in [r1, r2]; with e = |c - m| its |x - m| lies in [r1 - e, r2 + e] up to rounding
@@ -512,7 +518,7 @@ __global__ void k_plan_mad(RefJob* jobs, int d, const ColBrk* __restrict__ brk,
     J.small = small + (size_t)(d + j) * kSmallCap;
     J.small_count = small_count + d + j;
     J.result[0] = J.result[1] = 0.0;
-    J.valid = (Jm.valid && J.kk[0] >= 0 && J.kk[1] < c_u && (long long)cnt[j * 2 + 1] <= capU) ? 1 : 0;
+    J.valid = (Jm.valid && J.kk[0] >= 0 && J.kk[1] < c_u && (long long)cnt[j * 2 + 1] <= J.src_cap) ? 1 : 0;
     if (!J.valid) atomicOr(status, ABCDLS_S_FASTPATH_MISS);
     // guards checked once r* is known (triangle inequality + rounding slack):
     //   inner rows (fl|x-c| < r1)  have |x - m| <= (r1 + e) * up   -> must be <= the smaller rank value
@@ -535,7 +541,9 @@ __global__ void __launch_bounds__(256) k_refine_hist(RefJob* jobs, long long n_m
     const double lo = J.lo, scale = J.scale, c = J.center, vmin = J.vmin;
     const bool tr = J.transform != 0;
     const long long stride = (long long)gridDim.x * blockDim.x;
+    const int* __restrict__ dir = J.dir;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (dir && (int)(i & 255) >= dir[i >> 8]) continue;
         double x = J.src[i];
         double v = tr ? fabs(__dsub_rn(x, c)) : x;
         if (v >= vmin) atomicAdd(&hist[bin_of(v, lo, scale)], 1u);
@@ -1003,6 +1011,7 @@ __global__ void k_plan_ds(RefJob* job, const DistBrk* __restrict__ brk, const un
                           int* status) {
     if (threadIdx.x || blockIdx.x) return;
     RefJob J;
+    J.dir = nullptr;
     const long long c_lt = (long long)*n_lt, c_all = (long long)*gcand_cnt;   // summed over ranks
     J.src = cand_dist;
     J.src_count = cand_cnt;
@@ -1046,6 +1055,8 @@ struct MadWs {
     double* small;                  // [2d*kSmallCap]
     double* candM;                  // [d*capM]
     double* candU;                  // [d*capU]
+    int* dirM;                      // [d*capM/256] chunk fills (one-pass kernel only)
+    int* dirU;                      // [d*capU/256]
     size_t total;
 };
 
@@ -1074,6 +1085,8 @@ inline MadWs carve_mad(void* ws, int d, int G, long long capM, long long capU) {
     w.small = (double*)take((size_t)2 * d * kSmallCap * 8);
     w.candM = (double*)take((size_t)d * capM * 8);
     w.candU = (double*)take((size_t)d * capU * 8);
+    w.dirM = (int*)take((size_t)d * (capM / 256 + 1) * 4);
+    w.dirU = (int*)take((size_t)d * (capU / 256 + 1) * 4);
     w.total = o;
     return w;
 }
@@ -1223,21 +1236,12 @@ int abcdls_mad_fast_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, 
 //   phase 2: locate bins + gather (MAD)                 -> exchange: all-gather x0 = small block, x1 = counts
 //   phase 3: sort -> MAD, guards
 // gath_small / gath_cnt: the all-gathered exchange block of the previous phase (NULL on a single rank).
-int abcdls_mad_fast_refine(abcdls_handle_t h, int64_t n, int64_t n_global, int d, int phase, int world,
-                           const double* gath_small, const int32_t* gath_cnt, void* ws, size_t ws_bytes, double* med,
-                           double* mad, int* status_dev, void** x0, size_t* x0_count, void** x1, size_t* x1_count,
-                           void* stream) {
-    ABCDLS_CHECK_ARG(h, h && ws && med && mad && status_dev && d >= 1 && d <= kMaxD && phase >= 0 && phase <= 3 &&
-                            world >= 1 && world <= 64,
-                     "mad_fast_refine");
-    const int G = sample_ctas(n);
-    const long long capM = cap_for(n, 0.03), capU = cap_for(n, 0.08);
-    MadWs w = carve_mad(ws, d, G, capM, capU);
-    if (ws_bytes < w.total) {
-        h->err = "mad_fast workspace too small";
-        return ABCDLS_E_WORKSPACE;
-    }
-    cudaStream_t st = (cudaStream_t)stream;
+// shared by the two-pass path (fused = false: histM was built by the pass) and the one-pass path (fused.cuh:
+// candidates live in 256-slot chunks described by dirM / dirU)
+static int refine_impl(abcdls_handle_t h, const MadWs& w, long long capM, long long capU, bool fused, int64_t n_global,
+                       int d, int phase, int world, const double* gath_small, const int32_t* gath_cnt, double* med,
+                       double* mad, int* status_dev, void** x0, size_t* x0_count, void** x1, size_t* x1_count,
+                       cudaStream_t st) {
     const long long k0 = (n_global - 1) / 2, k1 = n_global / 2;
     const size_t smem = (size_t)kSmallCap * sizeof(double);
     ABCDLS_ONCE(h, cudaFuncSetAttribute(k_refine_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1253,7 +1257,7 @@ int abcdls_mad_fast_refine(abcdls_handle_t h, int64_t n, int64_t n_global, int d
     switch (phase) {
         case 0:
             k_plan_median<<<1, 64, 0, st>>>(w.jobs, d, w.brk, w.counts, w.histM, w.candM, capM, w.cnt, w.gcnt, w.small,
-                                            w.small_count, k0, k1, status_dev);
+                                            w.small_count, k0, k1, fused ? w.dirM : nullptr, status_dev);
             k_refine_pick<<<d, 256, 0, st>>>(w.jobs, status_dev);
             k_refine_gather<<<dim3(gx_for(capM), d), 256, 0, st>>>(w.jobs, capM);
             if (x0) { *x0 = w.small; *x0_count = (size_t)d * kSmallCap; }
@@ -1262,7 +1266,7 @@ int abcdls_mad_fast_refine(abcdls_handle_t h, int64_t n, int64_t n_global, int d
         case 1:
             k_refine_final<<<d, 1024, smem, st>>>(w.jobs, gath_small, gc, gath_small ? world : 1, d, status_dev);
             k_plan_mad<<<1, 64, 0, st>>>(w.jobs, d, w.brk, w.counts, w.histU, w.candU, capU, w.cnt, w.gcnt, w.small,
-                                         w.small_count, k0, k1, med, w.guard, status_dev);
+                                         w.small_count, k0, k1, med, w.guard, fused ? w.dirU : nullptr, status_dev);
             k_refine_hist<<<dim3(gx_for(capU), d), 256, 0, st>>>(w.jobs + d, capU);
             if (x0) { *x0 = w.histU; *x0_count = w.redB_count; }
             break;
@@ -1279,6 +1283,24 @@ int abcdls_mad_fast_refine(abcdls_handle_t h, int64_t n, int64_t n_global, int d
     }
     ABCDLS_LAUNCH_CHECK(h);
     return ABCDLS_OK;
+}
+
+int abcdls_mad_fast_refine(abcdls_handle_t h, int64_t n, int64_t n_global, int d, int phase, int world,
+                           const double* gath_small, const int32_t* gath_cnt, void* ws, size_t ws_bytes, double* med,
+                           double* mad, int* status_dev, void** x0, size_t* x0_count, void** x1, size_t* x1_count,
+                           void* stream) {
+    ABCDLS_CHECK_ARG(h, h && ws && med && mad && status_dev && d >= 1 && d <= kMaxD && phase >= 0 && phase <= 3 &&
+                            world >= 1 && world <= 64,
+                     "mad_fast_refine");
+    const int G = sample_ctas(n);
+    const long long capM = cap_for(n, 0.03), capU = cap_for(n, 0.08);
+    MadWs w = carve_mad(ws, d, G, capM, capU);
+    if (ws_bytes < w.total) {
+        h->err = "mad_fast workspace too small";
+        return ABCDLS_E_WORKSPACE;
+    }
+    return refine_impl(h, w, capM, capU, false, n_global, d, phase, world, gath_small, gath_cnt, med, mad, status_dev, x0,
+                       x0_count, x1, x1_count, (cudaStream_t)stream);
 }
 
 int abcdls_mad_fast_finish(abcdls_handle_t h, int64_t n, int64_t n_global, int d, void* ws, size_t ws_bytes,
@@ -1431,3 +1453,5 @@ int abcdls_dist_fast_pass(abcdls_handle_t h, const double* ss, int64_t n, int d,
 }
 
 }  // extern "C"
+
+#include "fused.cuh"

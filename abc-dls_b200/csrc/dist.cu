@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(kTileThreads) k_tile_write_le(const double* __
                                                                 const long long* __restrict__ quota_ptr,
                                                                 long long row_offset, long long cap,
                                                                 long long* __restrict__ idx_out,
+                                                                long long* __restrict__ slot_out,
                                                                 const unsigned long long* __restrict__ total,
                                                                 long long* __restrict__ n_out, int* status) {
     __shared__ int sh[33];
@@ -165,6 +166,7 @@ __global__ void __launch_bounds__(kTileThreads) k_tile_write_le(const double* __
             if (pos < quota && pos < cap) {
                 idx_out[pos] = src_idx ? src_idx[base + t] : row_offset + base + t;
                 if (dist_out) dist_out[pos] = dist[base + t];
+                if (slot_out) slot_out[pos] = base + t;
             }
             ++pos;
         }
@@ -238,7 +240,8 @@ int abcdls_count_le(abcdls_handle_t h, const double* dist, int64_t n, const int6
 
 int abcdls_accept(abcdls_handle_t h, const double* dist, int64_t n, const int64_t* n_dev, const int64_t* src_idx,
                   const double* ds, const int64_t* quota, int64_t row_offset, int64_t cap, int64_t* idx_out,
-                  double* dist_out, int64_t* n_out, void* ws, size_t ws_bytes, int* status_dev, void* stream) {
+                  double* dist_out, int64_t* slot_out, int64_t* n_out, void* ws, size_t ws_bytes, int* status_dev,
+                  void* stream) {
     ABCDLS_CHECK_ARG(h, h && dist && ds && quota && idx_out && n_out && ws && status_dev && n >= 1 && cap >= 1,
                      "accept");
     if (ws_bytes < abcdls_accept_workspace_bytes(n)) {
@@ -251,7 +254,8 @@ int abcdls_accept(abcdls_handle_t h, const double* dist, int64_t n, const int64_
     long long* tile_off = reinterpret_cast<long long*>(p + 256 + align_up((size_t)nt * sizeof(int), 256));
     k_tile_write_le<<<(unsigned)nt, kTileThreads, 0, (cudaStream_t)stream>>>(
         dist, n, (const long long*)n_dev, (const long long*)src_idx, dist_out, ds, tile_off,
-        (const long long*)quota, row_offset, cap, (long long*)idx_out, total, (long long*)n_out, status_dev);
+        (const long long*)quota, row_offset, cap, (long long*)idx_out, (long long*)slot_out, total, (long long*)n_out,
+        status_dev);
     ABCDLS_LAUNCH_CHECK(h);
     return ABCDLS_OK;
 }

@@ -1,0 +1,671 @@
+// fused.cuh — the ONE-pass front half of abc()/postpr(): column medians + MADs AND the tolerance cut from a single
+// read of the N x d table (included at the end of bracket.cu; shares its brackets, refiners and workspace).
+//
+// R's data dependency (the MADs must be known before any scaled distance) is broken with interval
+// reasoning instead of a second read:
+//   1. the column samples that bracket median / MAD also give an estimate mu_j of every MAD with a relative
+//      uncertainty eps (the width of the 5.5-sigma sample band);
+//   2. a row sample evaluated with rho_j = 1/mu_j brackets the nacc-th smallest APPROXIMATE squared distance
+//      q~(x) = sum_j ((x_j - t_j) rho_j)^2  from above: Q_hi;
+//   3. the pass classifies every element against the column brackets (exactly as k_bracket_pass) and, from the same
+//      shared-memory tile, marks every row with q~ <= thr = Q_hi ((1+eps)/(1-eps))^2 in a row bitmap;
+//   4. once the exact MADs M_j are known the marked rows (~1.5 nacc) get R's exact distance, ds is selected among
+//      them, and the result is PROVEN complete on the device:  |rho_j M_j - 1| <= eps for all j and
+//      ds^2 (1+eps)^2 (1+eta) <= thr  imply that every unmarked row has dist > ds.  Otherwise FASTPATH_MISS is set
+//      and the caller reruns with the two-pass path.  Exact or flagged, never approximate.
+//
+// Table streaming: TMA bulk copies (cp.async.bulk, 2 KB per column per 256-row tile) into an up-to-8-stage
+// shared-memory ring (192 KB, one CTA per SM), 16 consumer warps.  Warp w classifies column w of the tile (8
+// elements per lane from conflict-free 16-byte shared loads) and appends band candidates straight to 256-slot
+// chunks in HBM (one global atomic per chunk, chunk fills in a directory).  For the distance each row is shared by
+// two lanes (even / odd columns) and combined with one shuffle; the 16-bit ballot of the warp is one store into
+// the row bitmap, so candidate rows come out in row order without any barrier, atomic or staging.
+
+namespace {
+
+constexpr int kFRows = 256;
+constexpr int kFMaxD = 16;
+constexpr int kFWarps = 16;
+constexpr int kFConsumers = kFWarps * 32;
+constexpr int kFThreads = kFConsumers + 32;
+constexpr int kFMaxStages = 8;
+constexpr int kFRingBytes = 96 * 1024;
+constexpr int kFChunk = 256;
+constexpr int kFHeader = 1024;   // bytes in front of the ring
+constexpr int kFQCapM = 12;      // per-lane queue slots, M band (flushed when a lane holds more than cap - 8)
+constexpr int kFQCapU = 16;      //   ... U band
+constexpr int kFQWarpBytes = (kFQCapM + kFQCapU) * 256;   // per consumer warp
+constexpr int kFQBytes = kFWarps * kFQWarpBytes;          // 112 KB
+
+struct FusedPar {
+    double rho[kFMaxD];   // 1 / (1.4826 * sampled MAD estimate)
+    double tgt[kFMaxD];   // unscaled target
+    double eps;           // relative uncertainty assumed for every rho_j * MAD_j
+    double eta;           // rounding slack
+    double qhi;           // sampled upper bracket of the nacc-th smallest q~
+    double thr;           // candidate threshold on q~   (< 0: the one-pass path is not usable)
+    int ok;
+};
+
+struct FusedSmem {
+    unsigned long long full[kFMaxStages], empty[kFMaxStages];
+    double2 sc[kFMaxD];   // (target, rho)
+};
+static_assert(sizeof(FusedSmem) <= kFHeader, "header");
+
+inline int fused_stages(int d) {
+    int s = kFRingBytes / (d * kFRows * 8);
+    return s > kFMaxStages ? kFMaxStages : s;
+}
+
+// scale estimates from the (rank-summed) column sample: est[g][j][{m_lo, m_hi, r_lo, r_hi}]
+__global__ void k_make_fused_scale(const double* __restrict__ est, int G, int d, double inv_world,
+                                   const double* __restrict__ target, FusedPar* par) {
+    const int j = threadIdx.x;   // one warp
+    double eps = 0.0;
+    bool ok = true;
+    if (j < d) {
+        double a = 0.0, b = 0.0;
+        for (int g = 0; g < G; ++g) {
+            a += est[((size_t)g * d + j) * 4 + 2];
+            b += est[((size_t)g * d + j) * 4 + 3];
+        }
+        a = a / G * inv_world;
+        b = b / G * inv_world;
+        const double mid = 0.5 * a + 0.5 * b;
+        ok = (mid > 1e-150) && (mid < 1e150) && (a > 0.0);
+        par->rho[j] = ok ? 1.0 / (1.4826 * mid) : 0.0;
+        par->tgt[j] = target[j];
+        eps = ok ? 1.25 * (b - a) / (b + a) + 1e-7 : 1.0;
+        ok = ok && isfinite(target[j]);
+    } else if (j < kFMaxD) {
+        par->rho[j] = 0.0;
+        par->tgt[j] = 0.0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) eps = fmax(eps, __shfl_xor_sync(0xffffffffu, eps, o));
+    const bool all_ok = __all_sync(0xffffffffu, ok);
+    if (j == 0) {
+        par->eps = eps;
+        par->ok = (all_ok && eps < 0.2) ? 1 : 0;
+        par->thr = -1.0;
+        par->qhi = 0.0;
+        par->eta = 1e-9;
+    }
+}
+
+// q~ of a random sample of rows -> per-CTA estimate of the (p + delta) quantile.  grid G, 512 threads
+__global__ void __launch_bounds__(512) k_sample_qdist(const double* __restrict__ ss, long long n, int d, long long ld,
+                                                      const FusedPar* __restrict__ par, unsigned seed, double p,
+                                                      double delta, double* __restrict__ est) {
+    extern __shared__ double sm[];
+    __shared__ double2 sc[kFMaxD];
+    if (threadIdx.x < kFMaxD) sc[threadIdx.x] = make_double2(par->tgt[threadIdx.x], par->rho[threadIdx.x]);
+    __syncthreads();
+    for (int t = threadIdx.x; t < kSample; t += blockDim.x) {
+        const long long r = sample_row(seed, blockIdx.x, t, n);
+        double q = 0.0;
+        for (int j = 0; j < d; ++j) {
+            const double a = (ss[(size_t)j * ld + r] - sc[j].x) * sc[j].y;
+            q = fma(a, a, q);
+        }
+        sm[t] = (q == q) ? q : __longlong_as_double(0x7ff0000000000000ll);   // NaN rows sort last
+    }
+    __syncthreads();
+    bitonic_sort(sm, kSample);
+    if (threadIdx.x == 0) {
+        int ih = (int)ceil((p + delta) * kSample) + 1;
+        ih = max(0, min(kSample - 1, ih));
+        est[blockIdx.x] = sm[ih];
+    }
+}
+
+__global__ void k_make_fused_thr(const double* __restrict__ est, int G, double inv_world, int d, FusedPar* par) {
+    if (threadIdx.x || blockIdx.x) return;
+    double hi = 0.0;
+    for (int g = 0; g < G; ++g) hi += est[g];
+    hi = hi / G * inv_world;
+    double amax = 0.0;
+    for (int j = 0; j < d; ++j) amax = fmax(amax, fabs(par->tgt[j] * par->rho[j]));
+    const double eps = par->eps;
+    // rounding of R's (x/m - t/m)^2 terms: absolute error ~ 2^-52 |t/m| per term against distances ~ sqrt(hi)
+    const double eta = 1e-9 + 1e-14 * (1.0 + amax / sqrt(fmax(hi, 1e-300)));
+    const bool ok = par->ok && hi > 0.0 && isfinite(hi) && eta < 1e-3;
+    const double f = (1.0 + eps) / (1.0 - eps);
+    par->qhi = hi;
+    par->eta = eta;
+    par->thr = ok ? hi * f * f * (1.0 + eta) * (1.0 + eta) : -1.0;
+    if (!ok) par->ok = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFThreads, 1)
+k_fused_pass(const double* __restrict__ ss, long long n, long long ntiles, int d, long long ld, int nstages,
+             const ColBrk* __restrict__ brk, const FusedPar* __restrict__ par, unsigned long long* __restrict__ counts,
+             double* __restrict__ candM, long long capM, double* __restrict__ candU, long long capU,
+             unsigned long long* __restrict__ cnt, unsigned short* __restrict__ mask16, long long tpc, int* status) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FusedSmem& sm = *reinterpret_cast<FusedSmem*>(smem_raw);
+    double* ring = reinterpret_cast<double*>(smem_raw + kFHeader);
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < kFMaxD) sm.sc[threadIdx.x] = make_double2(par->tgt[threadIdx.x], par->rho[threadIdx.x]);
+    if (threadIdx.x == 0) {
+        for (int s2 = 0; s2 < nstages; ++s2) {
+            mbar_init(&sm.full[s2], 1);
+            mbar_init(&sm.empty[s2], kFWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const long long t_begin = (long long)blockIdx.x * tpc, t_end = min(ntiles, t_begin + tpc);
+    const size_t stage_doubles = (size_t)d * kFRows;
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+
+    if (wid == kFWarps) {
+        // ===== producer warp: lane 0 feeds the ring; the ragged last tile is completed with plain stores =====
+        int st = 0;
+        unsigned ph = 0;
+        for (long long tile = t_begin; tile < t_end; ++tile) {
+            if (lane == 0) mbar_wait(&sm.empty[st], ph ^ 1u);
+            __syncwarp();
+            double* dst = ring + (size_t)st * stage_doubles;
+            const double* src0 = ss + tile * kFRows;
+            const long long left = n - tile * kFRows;
+            if (left >= kFRows) {
+                if (lane == 0) {
+                    mbar_expect_tx(&sm.full[st], (unsigned)(stage_doubles * 8));
+                    for (int c = 0; c < d; ++c)
+                        bulk_g2s(dst + c * kFRows, src0 + (size_t)c * ld, kFRows * 8, &sm.full[st]);
+                }
+            } else {
+                const int rows = (int)left, nb = rows & ~1;   // bulk copies move multiples of 16 bytes
+                for (int c = 0; c < d; ++c)
+                    for (int r = nb + lane; r < kFRows; r += 32)
+                        dst[c * kFRows + r] = r < rows ? src0[(size_t)c * ld + r] : nan;
+                __syncwarp();
+                if (lane == 0) {
+                    if (nb > 0) {
+                        mbar_expect_tx(&sm.full[st], (unsigned)(d * nb * 8));
+                        for (int c = 0; c < d; ++c) bulk_g2s(dst + c * kFRows, src0 + (size_t)c * ld, nb * 8, &sm.full[st]);
+                    } else {
+                        mbar_arrive(&sm.full[st]);
+                    }
+                }
+            }
+            if (++st == nstages) { st = 0; ph ^= 1u; }
+        }
+        return;
+    }
+
+    // ===== consumers =====
+    const int j = wid;                  // column classified by this warp
+    const bool has_col = j < d;
+    const int jc = has_col ? j : 0;
+    const ColBrk B = brk[jc];
+    const double c = B.c, r0 = B.r0, mr1 = -B.r1;
+    // U band as an integer test on the high word of u = fl(|x - c| - r1): u >= 0 and hi(u) <= hi(fl(r2 - r1)).
+    // fl(a - b) is monotone and never rounds a non-zero difference to zero, so the sign of u is exact (y < r1 <=> u < 0)
+    // and every y in [r1, r2] passes; the few values just above r2 that share the top word only widen the band.
+    const unsigned hiW = (unsigned)__double2hiint(__dsub_rn(B.r2, B.r1));
+    const double thr = par->thr;
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    // Band candidates go to per-LANE queues in shared memory ([slot][lane]: conflict free, no votes, no branches:
+    // one predicated store + one predicated pointer bump per band and element).  When some lane could overflow
+    // in the next tile the warp flushes: one scan, ONE global atomic, dense coalesced-by-runs copy.
+    unsigned char* qbase = smem_raw + kFHeader + (size_t)nstages * stage_doubles * 8 + (size_t)wid * kFQWarpBytes;
+    const unsigned qM0 = smem_u32(qbase) + lane * 8;                       // my M queue: slot s at qM0 + s * 256
+    const unsigned qU0 = qM0 + kFQCapM * 256;                              // my U queue
+    unsigned pM = qM0, pU = qU0;
+    const unsigned limM = qM0 + (kFQCapM - 8) * 256, limU = qU0 + (kFQCapU - 8) * 256;
+    double* __restrict__ gM = candM + (size_t)jc * capM;
+    double* __restrict__ gU = candU + (size_t)jc * capU;
+    unsigned long long* cntM = &cnt[jc * 2 + 0];
+    unsigned long long* cntU = &cnt[jc * 2 + 1];
+    unsigned c_neg = 0, c_in = 0;                // per lane: x < c, |x - c| < r1
+    bool bad = false;
+    const int row = (wid << 4) | (lane & 15);    // row of the tile this lane helps with
+    const int half = lane >> 4;                  // 0: even columns, 1: odd columns
+    // scaling constants of this lane's (up to 8) columns in registers: a = x * rho - t * rho as one fma
+    double rh[8], mt[8];
+#pragma unroll
+    for (int q8 = 0; q8 < 8; ++q8) {
+        const int cc = 2 * q8 + half;
+        rh[q8] = cc < d ? sm.sc[cc].y : 0.0;
+        mt[q8] = cc < d ? -sm.sc[cc].x * sm.sc[cc].y : 0.0;
+    }
+
+    auto flush = [&](unsigned& p, unsigned q0, double* __restrict__ g, long long cap, unsigned long long* cntp) {
+        const int fill = (int)((p - q0) >> 8);
+        int incl = fill;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int tot = __shfl_sync(0xffffffffu, incl, 31);
+        const int mx = __reduce_max_sync(0xffffffffu, fill);
+        unsigned long long b = 0ull;
+        if (lane == 0) b = atomicAdd(cntp, (unsigned long long)tot);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        const long long dst0 = (long long)b + (incl - fill);
+        for (int t = 0; t < mx; ++t) {
+            if (t < fill && dst0 + t < cap) {
+                double v;
+                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(q0 + t * 256));
+                g[dst0 + t] = v;
+            }
+        }
+        p = q0;
+        __syncwarp();
+    };
+
+    int st = 0;
+    unsigned ph = 0;
+    for (long long tile = t_begin; tile < t_end; ++tile) {
+        mbar_wait(&sm.full[st], ph);
+        const double* __restrict__ stage = ring + (size_t)st * stage_doubles;
+        if (has_col) {
+            if (__any_sync(0xffffffffu, pM > limM || pU > limU)) {
+                if (__any_sync(0xffffffffu, pM > limM)) flush(pM, qM0, gM, capM, cntM);
+                if (__any_sync(0xffffffffu, pU > limU)) flush(pU, qU0, gU, capU, cntU);
+            }
+            const double* __restrict__ colp = stage + j * kFRows + 2 * lane;
+            double x[8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double2 v = *reinterpret_cast<const double2*>(colp + 64 * u);
+                x[2 * u] = v.x;
+                x[2 * u + 1] = v.y;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const double sgn = __dsub_rn(x[u], c);
+                const double uu = __dadd_rn(fabs(sgn), mr1);          // |x - c| - r1
+                const unsigned hu = (unsigned)__double2hiint(uu);
+                c_neg += (unsigned)__double2hiint(sgn) >> 31;
+                c_in += hu >> 31;
+                const bool inM = fabs(sgn) <= r0;
+                const bool inU = hu <= hiW;
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred pm, pu;\n\t"
+                    "setp.ne.u32 pm, %2, 0;\n\t"
+                    "setp.ne.u32 pu, %3, 0;\n\t"
+                    "@pm st.shared.f64 [%0], %4;\n\t"
+                    "@pu st.shared.f64 [%1], %4;\n\t"
+                    "@pm add.u32 %0, %0, 256;\n\t"
+                    "@pu add.u32 %1, %1, 256;\n\t"
+                    "}"
+                    : "+r"(pM), "+r"(pU)
+                    : "r"((unsigned)inM), "r"((unsigned)inU), "d"(x[u])
+                    : "memory");
+            }
+        }
+        // approximate squared distance of row `row`: this lane sums the columns of its parity
+        double q = 0.0;
+        if (d == kFMaxD) {
+#pragma unroll
+            for (int q8 = 0; q8 < 8; ++q8) {
+                const double a = fma(stage[(2 * q8 + half) * kFRows + row], rh[q8], mt[q8]);
+                q = fma(a, a, q);
+            }
+        } else {
+#pragma unroll
+            for (int q8 = 0; q8 < 8; ++q8) {
+                const int cc = 2 * q8 + half;
+                if (cc < d) {
+                    const double a = fma(stage[cc * kFRows + row], rh[q8], mt[q8]);
+                    q = fma(a, a, q);
+                }
+            }
+        }
+        q += __shfl_xor_sync(0xffffffffu, q, 16);
+        const bool valid = (tile + 1) * kFRows <= n || tile * kFRows + row < n;
+        bad |= valid && !(q < inf);
+        const unsigned bal = __ballot_sync(0xffffffffu, q <= thr);
+        if (lane == 0) {
+            mask16[tile * kFWarps + wid] = (unsigned short)(bal & 0xffffu);
+            mbar_arrive(&sm.empty[st]);   // every lane's shared loads completed before the shuffle / ballot
+        }
+        if (++st == nstages) { st = 0; ph ^= 1u; }
+    }
+    if (has_col) {
+        flush(pM, qM0, gM, capM, cntM);
+        flush(pU, qU0, gU, capU, cntU);
+        c_neg = warp_sum(c_neg);
+        c_in = warp_sum(c_in);
+        if (lane == 0) {
+            // counts[4j]: x < c for now; k_fused_histM subtracts the M-band values below c => "strictly below the band"
+            if (c_neg) atomicAdd(&counts[j * 4 + 0], (unsigned long long)c_neg);
+            if (c_in) atomicAdd(&counts[j * 4 + 2], (unsigned long long)c_in);
+        }
+    }
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(status, ABCDLS_S_NONFINITE);
+}
+
+// Fine histogram of the M band of every column from its (dense) candidates, after the pass: the pass itself stays
+// free of the binning arithmetic and of 16M global reductions.  Also turns counts[4j] from "x < c" into "strictly
+// below the M band" by subtracting the band values below c (same predicate as the pass: sign of fl(x - c)).
+// grid (gx, d)
+__global__ void __launch_bounds__(256) k_fused_histM(const double* __restrict__ candM, long long capM,
+                                                     const unsigned long long* __restrict__ cnt,
+                                                     const ColBrk* __restrict__ brk,
+                                                     unsigned long long* __restrict__ histM,
+                                                     unsigned long long* __restrict__ counts) {
+    __shared__ unsigned hist[kNB];
+    __shared__ unsigned negs;
+    const int j = blockIdx.y;
+    for (int t = threadIdx.x; t < kNB; t += blockDim.x) hist[t] = 0u;
+    if (threadIdx.x == 0) negs = 0u;
+    __syncthreads();
+    long long nv = (long long)cnt[j * 2 + 0];
+    if (nv > capM) nv = capM;
+    const double lo = brk[j].loM, scale = brk[j].scaleM, c = brk[j].c;
+    const double* __restrict__ src = candM + (size_t)j * capM;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    unsigned neg = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        const double x = src[i];
+        atomicAdd(&hist[bin_of(x, lo, scale)], 1u);
+        neg += (unsigned)__double2hiint(__dsub_rn(x, c)) >> 31;
+    }
+    neg = warp_sum(neg);
+    if ((threadIdx.x & 31) == 0 && neg) atomicAdd(&negs, neg);
+    __syncthreads();
+    for (int t = threadIdx.x; t < kNB; t += blockDim.x)
+        if (hist[t]) atomicAdd(&histM[(size_t)j * kNB + t], (unsigned long long)hist[t]);
+    if (threadIdx.x == 0 && negs) atomicAdd(&counts[j * 4 + 0], 0ull - (unsigned long long)negs);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// row bitmap -> ascending candidate rows.  Word w covers rows 32w .. 32w+31.
+constexpr int kMWords = 8;   // words per thread
+__global__ void __launch_bounds__(256) k_mask_count(const unsigned* __restrict__ bitmap, long long nwords,
+                                                    int* __restrict__ tile_cnt, unsigned long long* total) {
+    __shared__ int sh[33];
+    const long long base = ((long long)blockIdx.x * 256 + threadIdx.x) * kMWords;
+    int c = 0;
+#pragma unroll
+    for (int t = 0; t < kMWords; ++t)
+        if (base + t < nwords) c += __popc(bitmap[base + t]);
+    int tot;
+    block_exclusive_scan(c, sh, &tot);
+    if (threadIdx.x == 0) {
+        tile_cnt[blockIdx.x] = tot;
+        if (tot) atomicAdd(total, (unsigned long long)tot);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_mask_write(const unsigned* __restrict__ bitmap, long long nwords,
+                                                    const long long* __restrict__ tile_off, long long row_offset,
+                                                    long long cap, long long* __restrict__ rows_out,
+                                                    const unsigned long long* __restrict__ total,
+                                                    long long* __restrict__ n_out, int* status) {
+    __shared__ int sh[33];
+    const long long base = ((long long)blockIdx.x * 256 + threadIdx.x) * kMWords;
+    unsigned wv[kMWords];
+    int c = 0;
+#pragma unroll
+    for (int t = 0; t < kMWords; ++t) {
+        wv[t] = (base + t < nwords) ? bitmap[base + t] : 0u;
+        c += __popc(wv[t]);
+    }
+    int tot;
+    const int ex = block_exclusive_scan(c, sh, &tot);
+    long long pos = tile_off[blockIdx.x] + ex;
+#pragma unroll
+    for (int t = 0; t < kMWords; ++t) {
+        unsigned m = wv[t];
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            if (pos < cap) rows_out[pos] = row_offset + (base + t) * 32 + b;
+            ++pos;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const long long tt = (long long)*total;
+        *n_out = tt < cap ? tt : cap;
+        if (tt > cap) atomicOr(status, ABCDLS_S_FASTPATH_MISS);
+    }
+}
+
+// R's exact distance of the candidate rows (same arithmetic as k_dist_pass) + their raw statistics, compacted
+__global__ void __launch_bounds__(256) k_cand_exact(const double* __restrict__ ss, int d, long long ld,
+                                                    const double* __restrict__ mad, const double* __restrict__ target,
+                                                    const long long* __restrict__ cand_row,
+                                                    const long long* __restrict__ n_cand, long long row_offset,
+                                                    long long cap, double* __restrict__ cand_dist,
+                                                    double* __restrict__ cand_ss, int* status) {
+    __shared__ ColScale S;
+    load_scale(S, mad, target, d);
+    __syncthreads();
+    long long nc = *n_cand;
+    if (nc > cap) nc = cap;
+    bool nonfinite = false;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += stride) {
+        const long long r = cand_row[i] - row_offset;
+        const double* p = ss + r;
+        double s0 = 0.0;
+        int jj = 0;
+        for (; jj + 4 <= d; jj += 4) {
+            double x[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) x[q] = ld_stream(p + (size_t)(jj + q) * ld);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (cand_ss) cand_ss[(size_t)(jj + q) * cap + i] = x[q];
+                const double a = __dsub_rn(scaled_value(x[q], S.dr[jj + q]), S.tgt[jj + q]);
+                s0 = __dadd_rn(s0, __dmul_rn(a, a));
+            }
+        }
+        for (; jj < d; ++jj) {
+            const double x = ld_stream(p + (size_t)jj * ld);
+            if (cand_ss) cand_ss[(size_t)jj * cap + i] = x;
+            const double a = __dsub_rn(scaled_value(x, S.dr[jj]), S.tgt[jj]);
+            s0 = __dadd_rn(s0, __dmul_rn(a, a));
+        }
+        const double dd = __dsqrt_rn(s0);
+        nonfinite |= !isfinite(dd);
+        cand_dist[i] = dd;
+    }
+    if (__any_sync(0xffffffffu, nonfinite) && (threadIdx.x & 31) == 0) atomicOr(status, ABCDLS_S_NONFINITE);
+}
+
+// the completeness proof (header comment, item 4)
+__global__ void k_fused_check(const FusedPar* __restrict__ par, const double* __restrict__ mad, int d,
+                              const double* __restrict__ ds_ptr, int* status) {
+    if (threadIdx.x || blockIdx.x) return;
+    const double eps = par->eps, eta = par->eta, thr = par->thr, ds = *ds_ptr;
+    bool ok = par->ok != 0 && thr > 0.0;
+    for (int j = 0; j < d; ++j) {
+        const double e = fabs(par->rho[j] * mad[j] - 1.0);
+        ok = ok && (e <= eps);
+    }
+    const double lim = ds * ds * (1.0 + eps) * (1.0 + eps) * (1.0 + eta);
+    ok = ok && (ds == ds) && (lim <= thr);
+    if (!ok) atomicOr(status, ABCDLS_S_FASTPATH_MISS);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+struct FusedWs {
+    MadWs m;
+    long long capM, capU;
+    FusedPar* par;
+    double* est2;                  // [G2]
+    unsigned long long* total;     // candidate rows marked (zeroed with the MAD counters)
+    unsigned short* mask16;        // [ntiles * 16]
+    int* tile_cnt;
+    long long* tile_off;
+    size_t total_bytes;
+};
+
+constexpr int kFG2 = 64;
+
+inline long long round_chunk(long long x) { return (x + kFChunk - 1) / kFChunk * kFChunk; }
+
+inline FusedWs carve_fused(void* ws, int64_t n, int d) {
+    FusedWs w;
+    const int G = sample_ctas(n);
+    w.capM = round_chunk(cap_for(n, 0.03));
+    w.capU = round_chunk(cap_for(n, 0.08));
+    w.m = carve_mad(ws, d, G, w.capM, w.capU);
+    char* p = reinterpret_cast<char*>(ws);
+    size_t o = w.m.total;
+    auto take = [&](size_t bytes) { size_t a = o; o += align_up(bytes, 256); return p ? p + a : (char*)nullptr; };
+    const long long ntiles = (n + kFRows - 1) / kFRows;
+    const long long nwords = ntiles * (kFRows / 32);
+    const long long nblk = (nwords + 256 * kMWords - 1) / (256 * kMWords);
+    w.par = (FusedPar*)take(sizeof(FusedPar));
+    w.est2 = (double*)take((size_t)kFG2 * 8);
+    w.total = (unsigned long long*)take(8);
+    w.mask16 = (unsigned short*)take((size_t)ntiles * kFWarps * 2 + 64);
+    w.tile_cnt = (int*)take((size_t)nblk * 4);
+    w.tile_off = (long long*)take((size_t)nblk * 8);
+    w.total_bytes = o;
+    return w;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t abcdls_fused_workspace_bytes(int64_t n, int d) { return carve_fused(nullptr, n, d).total_bytes; }
+
+// 1 if the one-pass path can stream this table (TMA needs 16-byte aligned columns; d <= 16 fits one ring stage)
+int abcdls_fused_supported(const double* ss, int64_t n, int d, int64_t ld) {
+    if (!(d >= 1 && d <= kFMaxD && n >= 4 * kSample && ld >= n && (ld & 1) == 0 &&
+          (reinterpret_cast<uintptr_t>(ss) & 15) == 0))
+        return 0;
+    return 1;
+}
+
+#define FUSED_PROLOGUE(name)                                                                                        \
+    ABCDLS_CHECK_ARG(h, h && ss && ws && abcdls_fused_supported(ss, n, d, ld) && world >= 1 && world <= 64, name);   \
+    FusedWs w = carve_fused(ws, n, d);                                                                              \
+    if (ws_bytes < w.total_bytes) {                                                                                 \
+        h->err = "fused workspace too small";                                                                       \
+        return ABCDLS_E_WORKSPACE;                                                                                  \
+    }                                                                                                               \
+    cudaStream_t st = (cudaStream_t)stream;                                                                         \
+    const int G = sample_ctas(n);                                                                                   \
+    (void)G
+
+// Stage 1: column samples.  est_out: doubles a multi-rank caller all-reduces (sum) before stage 2.
+int abcdls_fused_sample_cols(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, void* ws,
+                             size_t ws_bytes, double** est_out, size_t* est_count, void* stream) {
+    FUSED_PROLOGUE("fused_sample_cols");
+    const double delta = col_delta(n, world);
+    const size_t smem = (size_t)2 * kSample * sizeof(double);
+    ABCDLS_ONCE(h, cudaFuncSetAttribute(k_sample_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ABCDLS_CUDA(h, cudaMemsetAsync(w.m.cnt, 0, w.m.zero_bytes, st));
+    ABCDLS_CUDA(h, cudaMemsetAsync(w.total, 0, 8, st));
+    k_sample_cols<<<dim3(G, d), 512, smem, st>>>(ss, n, ld, 0x5EEDu, delta, w.m.est);
+    ABCDLS_LAUNCH_CHECK(h);
+    if (est_out) *est_out = w.m.est;
+    if (est_count) *est_count = (size_t)G * d * 4;
+    return ABCDLS_OK;
+}
+
+// Stage 2: brackets + scale estimates from the (reduced) column samples, then the row sample of approximate
+// distances.  est_out: doubles to all-reduce (sum) before stage 3.
+int abcdls_fused_sample_dist(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, const double* target,
+                             int64_t nacc, int64_t n_global, int world, void* ws, size_t ws_bytes, double** est_out,
+                             size_t* est_count, void* stream) {
+    FUSED_PROLOGUE("fused_sample_dist");
+    ABCDLS_CHECK_ARG(h, target && nacc >= 1 && n_global >= nacc, "fused_sample_dist: nacc");
+    k_make_brackets<<<1, 64, 0, st>>>(w.m.est, G, d, 1.0 / world, w.m.brk);
+    k_make_fused_scale<<<1, 32, 0, st>>>(w.m.est, G, d, 1.0 / world, target, w.par);
+    const double p = (double)nacc / (double)n_global;
+    const double delta = kZ * sqrt(p * (1.0 - p) / ((double)kFG2 * kSample * world));
+    k_sample_qdist<<<kFG2, 512, (size_t)kSample * sizeof(double), st>>>(ss, n, d, ld, w.par, 0xD157u, p, delta, w.est2);
+    ABCDLS_LAUNCH_CHECK(h);
+    if (est_out) *est_out = w.est2;
+    if (est_count) *est_count = (size_t)kFG2;
+    return ABCDLS_OK;
+}
+
+// Stage 3: THE table pass.  counts_out: int64 block (counts | band counts | median histogram) to all-reduce (sum).
+int abcdls_fused_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, void* ws,
+                      size_t ws_bytes, int* status_dev, int64_t** counts_out, size_t* counts_count, void* stream) {
+    FUSED_PROLOGUE("fused_pass");
+    ABCDLS_CHECK_ARG(h, status_dev, "fused_pass: status");
+    k_make_fused_thr<<<1, 32, 0, st>>>(w.est2, kFG2, 1.0 / world, d, w.par);
+    const int nstages = fused_stages(d);
+    const size_t smem = kFHeader + (size_t)nstages * d * kFRows * 8 + kFQBytes;
+    ABCDLS_ONCE(h, cudaFuncSetAttribute(k_fused_pass, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kFHeader + kFRingBytes + kFQBytes));
+    const long long ntiles = (n + kFRows - 1) / kFRows;
+    long long grid = h->sm_count;
+    if (grid > ntiles) grid = ntiles;
+    const long long tpc = (ntiles + grid - 1) / grid;
+    k_fused_pass<<<(unsigned)grid, kFThreads, smem, st>>>(ss, n, ntiles, d, ld, nstages, w.m.brk, w.par, w.m.counts,
+                                                         w.m.candM, w.capM, w.m.candU, w.capU, w.m.cnt, w.mask16, tpc,
+                                                         status_dev);
+    ABCDLS_LAUNCH_CHECK(h);
+    {
+        long long gx = (w.capM + 256 * 8 - 1) / (256 * 8);
+        long long mx = (long long)h->sm_count * 8 / d;
+        if (mx < 1) mx = 1;
+        if (gx > mx) gx = mx;
+        k_fused_histM<<<dim3((unsigned)gx, d), 256, 0, st>>>(w.m.candM, w.capM, w.m.cnt, w.m.brk, w.m.histM, w.m.counts);
+        k_copy_u64<<<1, 128, 0, st>>>(w.m.gcnt, w.m.cnt, 2 * d);
+        ABCDLS_LAUNCH_CHECK(h);
+    }
+    if (counts_out) *counts_out = reinterpret_cast<int64_t*>(w.m.counts);
+    if (counts_count) *counts_count = w.m.redA_count;
+    return ABCDLS_OK;
+}
+
+// Stage 4: median / MAD refinement, phases 0..3 with the same exchanges as abcdls_mad_fast_refine.
+int abcdls_fused_refine(abcdls_handle_t h, const double* ss, int64_t n, int64_t n_global, int d, int64_t ld, int phase,
+                        int world, const double* gath_small, const int32_t* gath_cnt, void* ws, size_t ws_bytes,
+                        double* med, double* mad, int* status_dev, void** x0, size_t* x0_count, void** x1,
+                        size_t* x1_count, void* stream) {
+    FUSED_PROLOGUE("fused_refine");
+    ABCDLS_CHECK_ARG(h, med && mad && status_dev && phase >= 0 && phase <= 3, "fused_refine: args");
+    return refine_impl(h, w.m, w.capM, w.capU, false, n_global, d, phase, world, gath_small, gath_cnt, med, mad,
+                       status_dev, x0, x0_count, x1, x1_count, st);
+}
+
+// Stage 5: marked rows -> ascending global candidate rows, R's exact distance for each, their raw statistics
+// (cand_ss: column-major, leading dimension cap; may be NULL).  n_cand: device int64.
+int abcdls_fused_candidates(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world,
+                            const double* mad, const double* target, int64_t row_offset, int64_t cap, int64_t* cand_row,
+                            double* cand_dist, double* cand_ss, int64_t* n_cand, void* ws, size_t ws_bytes,
+                            int* status_dev, void* stream) {
+    FUSED_PROLOGUE("fused_candidates");
+    ABCDLS_CHECK_ARG(h, mad && target && cand_row && cand_dist && n_cand && status_dev && cap >= 1, "fused_candidates");
+    const long long ntiles = (n + kFRows - 1) / kFRows;
+    const long long nwords = ntiles * (kFRows / 32);
+    const long long nblk = (nwords + 256 * kMWords - 1) / (256 * kMWords);
+    const unsigned* bitmap = reinterpret_cast<const unsigned*>(w.mask16);
+    k_mask_count<<<(unsigned)nblk, 256, 0, st>>>(bitmap, nwords, w.tile_cnt, w.total);
+    k_scan_tiles<<<1, 1024, 0, st>>>(w.tile_cnt, nblk, w.tile_off);
+    k_mask_write<<<(unsigned)nblk, 256, 0, st>>>(bitmap, nwords, w.tile_off, row_offset, cap, (long long*)cand_row,
+                                                 w.total, (long long*)n_cand, status_dev);
+    ABCDLS_LAUNCH_CHECK(h);
+    long long g = (cap + 255) / 256;
+    if (g > (long long)h->sm_count * 16) g = (long long)h->sm_count * 16;
+    k_cand_exact<<<(unsigned)g, 256, 0, st>>>(ss, d, ld, mad, target, (const long long*)cand_row,
+                                              (const long long*)n_cand, row_offset, cap, cand_dist, cand_ss, status_dev);
+    ABCDLS_LAUNCH_CHECK(h);
+    return ABCDLS_OK;
+}
+
+// Stage 6 (after the exact ds has been selected among the candidates of all ranks): completeness proof.
+int abcdls_fused_check(abcdls_handle_t h, int64_t n, int d, const double* mad, const double* ds, void* ws,
+                       size_t ws_bytes, int* status_dev, void* stream) {
+    ABCDLS_CHECK_ARG(h, h && ws && mad && ds && status_dev && d >= 1 && d <= kFMaxD, "fused_check");
+    FusedWs w = carve_fused(ws, n, d);
+    if (ws_bytes < w.total_bytes) {
+        h->err = "fused workspace too small";
+        return ABCDLS_E_WORKSPACE;
+    }
+    k_fused_check<<<1, 32, 0, (cudaStream_t)stream>>>(w.par, mad, d, ds, status_dev);
+    ABCDLS_LAUNCH_CHECK(h);
+    return ABCDLS_OK;
+}
+
+}  // extern "C"

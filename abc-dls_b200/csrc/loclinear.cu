@@ -55,6 +55,49 @@ __global__ void __launch_bounds__(256) k_gather(const double* __restrict__ ss, l
     }
 }
 
+// same outputs, one thread per (accepted row, column): blockIdx.y < d -> statistic column (from the compact
+// candidate block through slot[]), else parameter column (from the table, possibly pinned host memory, through idx[]).
+__global__ void __launch_bounds__(256) k_gather_cand(const double* __restrict__ cand_ss, long long ld_cand,
+                                                     const long long* __restrict__ slot,
+                                                     const double* __restrict__ param, long long ld_param,
+                                                     const double* __restrict__ dist_acc,
+                                                     const long long* __restrict__ idx,
+                                                     const long long* __restrict__ n_acc_ptr, long long row_offset,
+                                                     long long cap, int d, const double* __restrict__ mad,
+                                                     const double* __restrict__ target,
+                                                     const double* __restrict__ ds_ptr, double* __restrict__ xs,
+                                                     double* __restrict__ y, double* __restrict__ ss_out,
+                                                     double* __restrict__ w) {
+    long long n_acc = *n_acc_ptr;
+    if (n_acc > cap) n_acc = cap;
+    const int col = blockIdx.y;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long r0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col < d) {
+        const double m = mad[col];
+        const double dv = (m == 0.0) ? 1.0 : m;
+        const double tj = (m == 0.0) ? target[col] : target[col] / dv;
+        const double* __restrict__ src = cand_ss + (size_t)col * ld_cand;
+        for (long long r = r0; r < n_acc; r += stride) {
+            const double x = src[slot[r]];
+            ss_out[(size_t)col * cap + r] = x;
+            const double sc = (dv == 1.0) ? x : x / dv;   // IEEE division == R's x/mad
+            xs[(size_t)col * cap + r] = __dsub_rn(sc, tj);
+        }
+        if (col == 0) {
+            const double ds = *ds_ptr;
+            for (long long r = r0; r < n_acc; r += stride) {
+                const double q = dist_acc[r] / ds;
+                w[r] = __dsub_rn(1.0, __dmul_rn(q, q));
+            }
+        }
+    } else {
+        const int p = col - d;
+        const double* __restrict__ src = param + (size_t)p * ld_param - row_offset;
+        for (long long r = r0; r < n_acc; r += stride) y[(size_t)p * cap + r] = src[idx[r]];
+    }
+}
+
 // ---- weighted normal equations ------------------------------------------------------------------
 // T_r = [1, xs_r (d), rhs_r (P)] (width W = M + P);  C[a][b] = sum_r w_r * T_r[a] * T_r[b] for a < M, b < W.
 // Register blocking: the (M x W) result is cut into 4x4 blocks; a thread owns one block per "slot" and keeps
@@ -418,6 +461,24 @@ int abcdls_gather(abcdls_handle_t h, const double* ss, int64_t ld_ss, const doub
     k_gather<<<grid_for(h, cap, 256, 8), 256, 0, (cudaStream_t)stream>>>(
         ss, ld_ss, param, ld_param, dist_acc, (const long long*)idx, (const long long*)n_acc, row_offset, cap, d, P,
         mad, target, ds, xs, y, ss_out, w);
+    ABCDLS_LAUNCH_CHECK(h);
+    return ABCDLS_OK;
+}
+
+int abcdls_gather_cand(abcdls_handle_t h, const double* cand_ss, int64_t ld_cand, const int64_t* slot,
+                       const double* param, int64_t ld_param, const double* dist_acc, const int64_t* idx,
+                       const int64_t* n_acc, int64_t row_offset, int64_t cap, int d, int P, const double* mad,
+                       const double* target, const double* ds, double* xs, double* y, double* ss_out, double* w,
+                       void* stream) {
+    ABCDLS_CHECK_ARG(h, h && cand_ss && slot && param && dist_acc && idx && n_acc && mad && target && ds && xs && y &&
+                            ss_out && w,
+                     "gather_cand: null pointer");
+    ABCDLS_CHECK_ARG(h, d >= 1 && d <= kMaxD && P >= 1 && P <= kMaxP && cap >= 1 && ld_cand >= 1, "gather_cand: shape");
+    unsigned gx = grid_for(h, cap, 256, 16);
+    if (gx > 2048) gx = 2048;
+    k_gather_cand<<<dim3(gx, (unsigned)(d + P)), 256, 0, (cudaStream_t)stream>>>(
+        cand_ss, ld_cand, (const long long*)slot, param, ld_param, dist_acc, (const long long*)idx,
+        (const long long*)n_acc, row_offset, cap, d, mad, target, ds, xs, y, ss_out, w);
     ABCDLS_LAUNCH_CHECK(h);
     return ABCDLS_OK;
 }

@@ -19,6 +19,7 @@ min/max), with the arithmetic of CRAN abc 2.2.1.
 from __future__ import annotations
 
 import math
+import time
 from dataclasses import dataclass, field
 from typing import List, Optional
 
@@ -116,7 +117,9 @@ class AbcEngine:
         self.device = stages.device
         self.comm = Comm(group, self.device)
         self.timers = None   # set to {} to record CUDA-event pairs per named stage (bench.py)
-        self.fast_misses = 0  # how often a sampled bracket missed and the radix path had to rerun the call
+        self.fast_misses = 0  # how often a sampled bracket missed and the next path of the ladder reran the call
+        self.path_calls = {"fused": 0, "two_pass": 0, "exact": 0}   # front-half path taken, per call
+        self.host_enqueue_ms = []   # per abc() call: host time spent enqueueing before the one blocking read
         if hasattr(stages, "timer"):
             stages.timer = self._t
 
@@ -144,17 +147,19 @@ class AbcEngine:
         return {k: [a.elapsed_time(b) for a, b in v] for k, v in (self.timers or {}).items()}
 
     # ---- small helpers ----------------------------------------------------------------------------
-    def _shard_info(self, n_local: int):
-        counts = self.comm.allgather_ints([n_local])  # list per rank
+    def _shard_info(self, n_local: int, flag: int = 1):
+        """(global rows, first global row of this rank, rows per rank, AND of `flag` over ranks)."""
+        counts = self.comm.allgather_ints([n_local, flag])  # list per rank
         ns = [c[0] for c in counts]
-        return sum(ns), sum(ns[: self.comm.rank]), ns
+        return sum(ns), sum(ns[: self.comm.rank]), ns, all(c[1] for c in counts)
 
-    def _select(self, table: torch.Tensor, n_local: int, center, k0, k1) -> torch.Tensor:
-        """Exact global order statistics k0,k1 (0-based) of every row of ``table`` (njobs, n_local)."""
+    def _select(self, table: torch.Tensor, n_local: int, center, k0, k1, counts=None) -> torch.Tensor:
+        """Exact global order statistics k0,k1 (0-based) of every row of ``table`` (njobs, n_local); counts (device
+        int64 per job, optional): only the first counts[j] entries of row j exist."""
         k = self.k
         njobs, ld = table.shape[0], table.stride(0)
         ws = k.select_workspace(njobs)
-        k.select_begin(ws, njobs, table, n_local, ld, None, center, k0, k1)
+        k.select_begin(ws, njobs, table, n_local, ld, counts, center, k0, k1)
         hist = k.select_hist_tensor(ws, njobs) if self.comm.world > 1 else None
         for p in range(_capi.SELECT_PASSES):
             with self._t(f"select_hist[{njobs}x{n_local}]"):
@@ -180,8 +185,9 @@ class AbcEngine:
 
     # ---- shared front half: scaling, distance, tolerance cut ----------------------------------
     FAST_MIN_ROWS = 1 << 20   # below this the 6-pass radix select is launch-bound anyway
+    use_fused = True          # one-pass front half (csrc/fused.cuh) when the table qualifies
 
-    def _front(self, target, ss, tol, status, keep_dist=False, exact=False):
+    def _front(self, target, ss, tol, status, keep_dist=False, exact=False, two_pass=False):
         """MAD scaling -> distance -> exact threshold ds -> R's cap rule.  Returns the accepted rows (ascending
         global row numbers, their distances) of this rank.
 
@@ -190,11 +196,15 @@ class AbcEngine:
         S_FASTPATH_MISS, upon which abc() reruns with ``exact=True`` (6-pass radix select, always exact)."""
         k = self.k
         d, n_local = ss.shape
-        n_global, row_offset, ns = self._shard_info(n_local)
+        can_fuse = (self.use_fused and not exact and not two_pass and not keep_dist and hasattr(k, "fused_supported")
+                    and k.fused_supported(ss, n_local, d, ss.stride(0)))
+        n_global, row_offset, ns, all_fuse = self._shard_info(n_local, int(can_fuse))
         nacc = int(math.ceil(n_global * tol))
         if not (1 <= nacc <= n_global):
             raise AbcError("'tol' must give 1 <= ceiling(N * tol) <= N")
         fast = (not exact) and min(ns) >= self.FAST_MIN_ROWS   # every rank must take the same path
+        fused = fast and all_fuse
+        self.path_calls["fused" if fused else ("two_pass" if fast else "exact")] += 1
         cap = min(nacc, n_local)
         idx = k.new(cap, dtype=torch.int64)
         dacc = k.new(cap)
@@ -202,7 +212,31 @@ class AbcEngine:
         le = torch.zeros(1, dtype=torch.int64, device=self.device)
         quota = torch.full((1,), nacc, dtype=torch.int64, device=self.device)
         comm = self.comm if self.comm.world > 1 else None
-        if fast:
+        cand_ss = slot = None
+        if fused:
+            # ONE table read: medians + MADs and the candidate rows of the cut; exact distances only for the candidates
+            med, mad = k.new(d), k.new(d)
+            ccap = min(n_local, 2 * nacc + 65536)
+            dist = None
+            cand_row, cand_dist = k.new(ccap, dtype=torch.int64), k.new(ccap)
+            cand_ss = k.new(d, ccap)
+            slot = k.new(cap, dtype=torch.int64)
+            n_cand = torch.zeros(1, dtype=torch.int64, device=self.device)
+            with self._t("fused_front"):
+                k.fused_front(ss, n_local, n_global, d, ss.stride(0), target, nacc, row_offset, ccap, med, mad, cand_row,
+                              cand_dist, cand_ss, n_cand, status, comm)
+            with self._t("fused_ds"):
+                ds = self._select(cand_dist[None, :], ccap, None, nacc - 1, nacc - 1, counts=n_cand)[0, :1].contiguous()
+                k.fused_check(n_local, d, mad, ds, status)
+            with self._t("accept"):
+                ws = k.accept_workspace(ccap)
+                k.count_le(cand_dist, ccap, n_cand, ds, le, ws)
+                if comm is not None:
+                    below = comm.allgather(le).view(-1)[: comm.rank].sum()
+                    quota = (nacc - below).clamp(min=0).view(1)
+                k.accept(cand_dist, ccap, n_cand, cand_row, ds, quota, row_offset, cap, idx, dacc, n_acc, ws, status,
+                         slot_out=slot)
+        elif fast:
             med, mad = k.new(d), k.new(d)
             with self._t("mad_fast"):
                 k.mad_fast(ss, n_local, n_global, d, ss.stride(0), med, mad, status, comm)
@@ -235,7 +269,7 @@ class AbcEngine:
                 quota = (nacc - below).clamp(min=0).view(1)
             k.accept(dist, n_local, None, None, ds, quota, row_offset, cap, idx, dacc, n_acc, ws, status)
         return dict(n_global=n_global, row_offset=row_offset, nacc=nacc, mad=mad, dist=dist, ds=ds, cap=cap, idx=idx,
-                    n_acc=n_acc, dacc=dacc, fast=fast)
+                    n_acc=n_acc, dacc=dacc, fast=fast, fused=fused, cand_ss=cand_ss, slot=slot)
 
     def _zero_variance(self, ss) -> bool:
         """R: stop if every column of sumstat has a single unique value."""
@@ -251,7 +285,7 @@ class AbcEngine:
     # ---- abc() ----------------------------------------------------------------------------------
     def abc(self, target: torch.Tensor, param: torch.Tensor, sumstat: torch.Tensor, tol: float, method: str,
             hcorr: bool = True, kernel: str = "epanechnikov", keep_dist: bool = False,
-            _exact: bool = False) -> AbcResult:
+            _level: int = 0) -> AbcResult:
         """``abc::abc`` for method in {rejection, loclinear} on this rank's shard.
 
         target (d,), param (P, n_local), sumstat (d, n_local): float64 CUDA tensors, column-major tables.
@@ -271,6 +305,7 @@ class AbcEngine:
             raise AbcError("Number of summary statistics in 'target' has to be the same as in 'sumstat'.")
         if par.shape[1] != n_local:
             raise AbcError("'param' and 'sumstat' must have the same number of rows")
+        _t0 = time.perf_counter()
         if par.device.type == "cpu":
             if self.device.type == "cuda" and not par.is_pinned():
                 par = par.to(self.device)      # pageable host memory cannot be mapped: stage it
@@ -279,14 +314,18 @@ class AbcEngine:
         if ss.device != self.device:
             ss = ss.to(self.device)
         status = torch.zeros(1, dtype=torch.int32, device=self.device)
-        f = self._front(target, ss, tol, status, keep_dist=keep_dist, exact=_exact)
+        f = self._front(target, ss, tol, status, keep_dist=keep_dist, exact=_level >= 2, two_pass=_level >= 1)
         cap, idx, n_acc, ds, mad, dacc = f["cap"], f["idx"], f["n_acc"], f["ds"], f["mad"], f["dacc"]
 
         xs, y, ss_out = k.new(d, cap), k.new(P, cap), k.new(d, cap)
         w = k.new(cap)
         with self._t("gather"):
-            k.gather(ss, ss.stride(0), par, par.stride(0), dacc, idx, n_acc, f["row_offset"], cap, d, P, mad, target,
-                     ds, xs, y, ss_out, w)
+            if f["fused"]:   # the statistics of the accepted rows are already compact (candidate block)
+                k.gather_cand(f["cand_ss"], f["cand_ss"].stride(0), f["slot"], par, par.stride(0), dacc, idx, n_acc,
+                              f["row_offset"], cap, d, P, mad, target, ds, xs, y, ss_out, w)
+            else:
+                k.gather(ss, ss.stride(0), par, par.stride(0), dacc, idx, n_acc, f["row_offset"], cap, d, P, mad,
+                         target, ds, xs, y, ss_out, w)
         # zero variance inside the accepted region (R cond2)
         reg = k.new(d, 6)
         k.col_stats(ss_out, None, n_acc, cap, d, reg)
@@ -342,13 +381,19 @@ class AbcEngine:
 
         # one host read for everything data dependent
         host = torch.cat([status.to(torch.float64), n_acc.to(torch.float64), ds,
-                          region_const.to(torch.float64).view(1), all_mad_zero.to(torch.float64).view(1)]).cpu()
+                          region_const.to(torch.float64).view(1), all_mad_zero.to(torch.float64).view(1)])
+        self.host_enqueue_ms.append((time.perf_counter() - _t0) * 1e3)
+        if len(self.host_enqueue_ms) > 64:
+            del self.host_enqueue_ms[:32]
+        host = host.cpu()
         st, n_loc, ds_h = int(host[0]), int(host[1]), float(host[2])
         st = self.comm.allreduce_or_int(st)
         warnings: List[str] = []
         if (st & _capi.S_FASTPATH_MISS) and f["fast"]:
+            # fallback ladder: one-pass -> two-pass sampled brackets -> 6-pass radix select (always exact)
             self.fast_misses += 1
-            return self.abc(target, param, sumstat, tol, method, hcorr, kernel, keep_dist, _exact=True)
+            return self.abc(target, param, sumstat, tol, method, hcorr, kernel, keep_dist,
+                            _level=1 if f["fused"] else 2)
         if st & _capi.S_NONFINITE:
             raise AbcError("non-finite values in 'sumstat'/'target' (R's NA-row handling is not implemented)")
         if host[4] != 0 and self._zero_variance(ss):
@@ -398,7 +443,7 @@ class AbcEngine:
 
     # ---- postpr() -------------------------------------------------------------------------------
     def postpr(self, target: torch.Tensor, model_id: torch.Tensor, models: List[str], sumstat: torch.Tensor,
-               tol: float, method: str = "rejection", keep_dist: bool = False, _exact: bool = False) -> PostprResult:
+               tol: float, method: str = "rejection", keep_dist: bool = False, _level: int = 0) -> PostprResult:
         """``abc::postpr(method='rejection')``: model_id int32 (n_local,) indexes ``models`` (sorted levels)."""
         if method != "rejection":
             raise AbcError("postpr: only method='rejection' is implemented (mnlogistic / neuralnet stay with R's nnet)")
@@ -415,7 +460,7 @@ class AbcEngine:
             raise AbcError("'index' must be the same length as the number of rows in 'sumstat'.")
         model_id = model_id.to(device=self.device, dtype=torch.int32).contiguous()
         status = torch.zeros(1, dtype=torch.int32, device=self.device)
-        f = self._front(target, ss, tol, status, keep_dist=keep_dist, exact=_exact)
+        f = self._front(target, ss, tol, status, keep_dist=keep_dist, exact=_level >= 2, two_pass=_level >= 1)
         cap, idx, n_acc = f["cap"], f["idx"], f["n_acc"]
         counts = torch.zeros(K, dtype=torch.int64, device=self.device)
         k.postpr_counts(model_id, idx, n_acc, f["row_offset"], cap, K, counts)
@@ -426,7 +471,8 @@ class AbcEngine:
         st, n_loc, ds_h = self.comm.allreduce_or_int(int(host[0])), int(host[1]), float(host[2])
         if (st & _capi.S_FASTPATH_MISS) and f["fast"]:
             self.fast_misses += 1
-            return self.postpr(target, model_id, models, sumstat, tol, method, keep_dist, _exact=True)
+            return self.postpr(target, model_id, models, sumstat, tol, method, keep_dist,
+                               _level=1 if f["fused"] else 2)
         if st & _capi.S_NONFINITE:
             raise AbcError("non-finite values in 'sumstat'/'target' (R's NA-row handling is not implemented)")
         if host[3] != 0 and self._zero_variance(ss):
@@ -452,7 +498,7 @@ class AbcEngine:
         """Ascending GLOBAL row numbers of this rank's rows with every parameter in [lo, hi] (ABC.py:2974-2990)."""
         tab = _as_table(param_all)
         P, n = tab.shape
-        _, row_offset, _ = self._shard_info(n)
+        _, row_offset, _, _ = self._shard_info(n)
         lo = lo.to(device=self.device, dtype=torch.float64).contiguous()
         hi = hi.to(device=self.device, dtype=torch.float64).contiguous()
         idx = self.k.new(n, dtype=torch.int64)

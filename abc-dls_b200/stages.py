@@ -96,9 +96,65 @@ class CudaStages:
                          self._stream())
         self.launches += 4
 
-    def accept(self, dist, n, n_dev, src_idx, ds, quota, row_offset, cap, idx, dist_out, n_out, ws, status):
+    def accept(self, dist, n, n_dev, src_idx, ds, quota, row_offset, cap, idx, dist_out, n_out, ws, status,
+               slot_out=None):
         self.handle.call("abcdls_accept", _p(dist), n, _p(n_dev), _p(src_idx), _p(ds), _p(quota), row_offset, cap,
-                         _p(idx), _p(dist_out), _p(n_out), _p(ws), ws.numel(), _p(status), self._stream())
+                         _p(idx), _p(dist_out), _p(slot_out), _p(n_out), _p(ws), ws.numel(), _p(status), self._stream())
+        self.launches += 1
+
+    # ---- one-pass front half (csrc/fused.cuh) -----------------------------------------------------
+    def fused_supported(self, ss, n, d, ld) -> bool:
+        return bool(self.lib.abcdls_fused_supported(_p(ss), n, d, ld))
+
+    def fused_front(self, ss, n, n_global, d, ld, target, nacc, row_offset, cap, med, mad, cand_row, cand_dist, cand_ss,
+                    n_cand, status, comm=None):
+        """Medians + MADs AND the candidate rows of the tolerance cut from ONE read of the table.  Leaves the exact
+        distance of every candidate in cand_dist (row order); the caller selects ds among them (all ranks) and then
+        calls fused_check."""
+        world = comm.world if comm is not None else 1
+        ws = self.workspace("fused", self.lib.abcdls_fused_workspace_bytes(n, d))
+        p0, c0, p1, c1 = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t()
+        st = self._stream()
+        self.handle.call("abcdls_fused_sample_cols", _p(ss), n, d, ld, world, _p(ws), ws.numel(), C.byref(p0),
+                         C.byref(c0), st)
+        if world > 1:
+            comm.allreduce_sum(self._view(ws, p0, c0, torch.float64, 8))
+        self.handle.call("abcdls_fused_sample_dist", _p(ss), n, d, ld, _p(target), nacc, n_global, world, _p(ws),
+                         ws.numel(), C.byref(p0), C.byref(c0), st)
+        if world > 1:
+            comm.allreduce_sum(self._view(ws, p0, c0, torch.float64, 8))
+        with self._timed("k_fused_pass"):
+            self.handle.call("abcdls_fused_pass", _p(ss), n, d, ld, world, _p(ws), ws.numel(), _p(status), C.byref(p0),
+                             C.byref(c0), st)
+        if world > 1:
+            comm.allreduce_sum(self._view(ws, p0, c0, torch.int64, 8))
+        gs = gc = None
+        with self._timed("fused_refine"):
+            for phase in range(4):
+                self.handle.call("abcdls_fused_refine", _p(ss), n, n_global, d, ld, phase, world, _p(gs), _p(gc), _p(ws),
+                                 ws.numel(), _p(med), _p(mad), _p(status), C.byref(p0), C.byref(c0), C.byref(p1),
+                                 C.byref(c1), st)
+                if world > 1:
+                    if phase in (0, 2):
+                        gs = comm.allgather(self._view(ws, p0, c0, torch.float64, 8)).contiguous()
+                        gc = comm.allgather(self._view(ws, p1, c1, torch.int32, 4)).contiguous()
+                    elif phase == 1:
+                        comm.allreduce_sum(self._view(ws, p0, c0, torch.int64, 8))
+        with self._timed("fused_candidates"):
+            self.handle.call("abcdls_fused_candidates", _p(ss), n, d, ld, world, _p(mad), _p(target), row_offset, cap,
+                             _p(cand_row), _p(cand_dist), _p(cand_ss), _p(n_cand), _p(ws), ws.numel(), _p(status), st)
+        self.launches += 24
+
+    def fused_check(self, n, d, mad, ds, status):
+        ws = self._ws["fused"]
+        self.handle.call("abcdls_fused_check", n, d, _p(mad), _p(ds), _p(ws), ws.numel(), _p(status), self._stream())
+        self.launches += 1
+
+    def gather_cand(self, cand_ss, ld_cand, slot, param, ld_param, dist_acc, idx, n_acc, row_offset, cap, d, P, mad,
+                    target, ds, xs, y, ss_out, w):
+        self.handle.call("abcdls_gather_cand", _p(cand_ss), ld_cand, _p(slot), _p(param), ld_param, _p(dist_acc),
+                         _p(idx), _p(n_acc), row_offset, cap, d, P, _p(mad), _p(target), _p(ds), _p(xs), _p(y),
+                         _p(ss_out), _p(w), self._stream())
         self.launches += 1
 
     # ---- fast path (sampled brackets) -----------------------------------------------------------

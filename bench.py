@@ -39,7 +39,7 @@ UNIT = "sims/s"
 def _args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=float, default=1e8, help="global simulations N")
@@ -50,6 +50,7 @@ def _args():
     ap.add_argument("--cpu-rows", type=float, default=1e6, help="bounded sample for the CPU arm")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--clock-interval", type=float, default=0.02, help="seconds between NVML clock samples")
     return ap.parse_args()
 
 
@@ -64,8 +65,9 @@ class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region through NVML in-process (forking
     nvidia-smi from a process that maps tens of GB stalls the launching thread for milliseconds)."""
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, interval: float = 0.02):
         self.index, self.rows, self.stop = index, [], threading.Event()
+        self.interval, self.call_ms = interval, []
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.max_mhz, self.nv, self.h = None, None, None
         try:  # import + nvmlInit are slow (tens of ms, GIL held): do them before the timed region
@@ -75,6 +77,9 @@ class ClockSampler:
             idx = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
             self.h = nv.nvmlDeviceGetHandleByIndex(idx)
             self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            # the first query of each kind takes ~15 ms inside the driver and stalls kernel launches meanwhile
+            nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+            nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
             self.nv = nv
         except Exception as e:  # pragma: no cover
             self.err = repr(e)
@@ -85,12 +90,14 @@ class ClockSampler:
             return
         while not self.stop.is_set():
             try:
+                t0 = time.perf_counter()
                 self.rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
                                   nv.nvmlDeviceGetCurrentClocksEventReasons(h)))
+                self.call_ms.append((time.perf_counter() - t0) * 1e3)
             except Exception as e:  # pragma: no cover
                 self.err = repr(e)
                 return
-            self.stop.wait(0.01)
+            self.stop.wait(self.interval)
 
     def __enter__(self):
         self.thread.start()
@@ -107,7 +114,8 @@ class ClockSampler:
         bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
                 "hw_power_brake_slowdown": 0x80}
         reasons = [n for n, b in bits.items() if any(r[1] & b for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm),
+                "nvml_ms_per_sample": round(sum(self.call_ms) / len(self.call_ms), 3)}
 
 
 def cpu_arm(args, steps, warmup):
@@ -186,7 +194,7 @@ def main():
     eng.timers = {}
     l0 = eng.k.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, args.clock_interval)
     with sampler as clocks:
         sync()
         ev0.record()
@@ -195,6 +203,7 @@ def main():
         ev1.record()
         sync()
     ms = ev0.elapsed_time(ev1)
+    host_ms = eng.host_enqueue_ms[-args.steps:]
     launches = eng.k.launches - l0
     tms = eng.timer_ms()
     eng.timers = None
@@ -213,7 +222,8 @@ def main():
     kern = {}
     for name, v in tms.items():
         kern[name] = {"launches": len(v), "avg_ms": sum(v) / len(v), "total_ms_per_step": sum(v) / args.steps}
-    alg = {"k_bracket_pass": 8.0 * d * n_local,      # one read of the N x d table (all medians + MADs)
+    alg = {"k_fused_pass": 8.0 * d * n_local,        # THE one read of the N x d table (medians, MADs and the cut)
+           "k_bracket_pass": 8.0 * d * n_local,      # one read of the N x d table (all medians + MADs)
            "k_dist_pass": 8.0 * d * n_local,         # one read of the table; dist is not materialised
            "scale_dist": (8.0 * d + 8.0) * n_local}
     for name in list(kern):
@@ -282,7 +292,8 @@ def main():
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "roofline": roofline,
                 "cpu_baseline": base, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
-                "nacc": res.nacc, "ds": res.ds, "fast_path_misses": eng.fast_misses}
+                "nacc": res.nacc, "ds": res.ds, "fast_path_misses": eng.fast_misses,
+                "host_enqueue_ms": round(sum(host_ms) / max(1, len(host_ms)), 3)}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -119,10 +119,11 @@ int abcdls_count_le(abcdls_handle_t h, const double* dist, int64_t n, const int6
                     int64_t* le_count, void* ws, size_t ws_bytes, void* stream);
 /* must follow abcdls_count_le on the same ws; quota is a device int64.  src_idx (may be NULL): entry i of
  * `dist` belongs to global row src_idx[i] (candidate list) instead of row_offset + i.  dist_out (may be
- * NULL) receives the distances of the accepted rows. */
+ * NULL) receives the distances of the accepted rows, slot_out (may be NULL) their positions i in `dist`. */
 int abcdls_accept(abcdls_handle_t h, const double* dist, int64_t n, const int64_t* n_dev, const int64_t* src_idx,
                   const double* ds, const int64_t* quota, int64_t row_offset, int64_t cap, int64_t* idx_out,
-                  double* dist_out, int64_t* n_out, void* ws, size_t ws_bytes, int* status_dev, void* stream);
+                  double* dist_out, int64_t* slot_out, int64_t* n_out, void* ws, size_t ws_bytes, int* status_dev,
+                  void* stream);
 
 /* ---- fast path: sampled brackets, one table pass each (csrc/bracket.cu) -----------------------
  * Exact results or ABCDLS_S_FASTPATH_MISS in status_dev (then rerun with the radix select above).
@@ -164,6 +165,37 @@ int abcdls_dist_fast_refine(abcdls_handle_t h, int64_t n, int64_t nacc, int64_t 
                             void* ws, size_t ws_bytes, int* status_dev, void** x0, size_t* x0_count, void** x1,
                             size_t* x1_count, void* stream);
 
+/* ---- one-pass front half (csrc/fused.cuh): medians + MADs AND the tolerance cut from ONE table read ------------
+ * R's dependency "MAD before distance" is broken by interval reasoning: sampled MAD estimates with a relative
+ * uncertainty eps give an approximate squared distance q~; the pass keeps every row whose q~ could still be
+ * <= ds^2, the exact MADs then give those ~1.5 nacc rows R's exact distance, and the device proves that no
+ * unmarked row can have dist <= ds (else ABCDLS_S_FASTPATH_MISS: rerun with the two-pass path above).
+ *   sample_cols -> [all-reduce est] -> sample_dist -> [all-reduce est] -> pass -> [all-reduce counts]
+ *   -> refine phases 0..3 (exchanges as abcdls_mad_fast_refine) -> candidates -> [select ds among the
+ *   candidates of all ranks: abcdls_select_*] -> check -> abcdls_count_le / abcdls_accept on the candidate list.
+ * Requirements (abcdls_fused_supported): d <= 16, n >= 16384, ld even, 16-byte aligned table. */
+int abcdls_fused_supported(const double* ss, int64_t n, int d, int64_t ld);
+size_t abcdls_fused_workspace_bytes(int64_t n, int d);
+int abcdls_fused_sample_cols(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, void* ws,
+                             size_t ws_bytes, double** est_out, size_t* est_count, void* stream);
+int abcdls_fused_sample_dist(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, const double* target,
+                             int64_t nacc, int64_t n_global, int world, void* ws, size_t ws_bytes, double** est_out,
+                             size_t* est_count, void* stream);
+int abcdls_fused_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, void* ws,
+                      size_t ws_bytes, int* status_dev, int64_t** counts_out, size_t* counts_count, void* stream);
+int abcdls_fused_refine(abcdls_handle_t h, const double* ss, int64_t n, int64_t n_global, int d, int64_t ld, int phase,
+                        int world, const double* gath_small, const int32_t* gath_cnt, void* ws, size_t ws_bytes,
+                        double* med, double* mad, int* status_dev, void** x0, size_t* x0_count, void** x1,
+                        size_t* x1_count, void* stream);
+/* cand_row: ascending global rows; cand_dist: R's exact distance; cand_ss (may be NULL): raw statistics of the
+ * candidates, column-major with leading dimension cap; n_cand: device int64 */
+int abcdls_fused_candidates(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world,
+                            const double* mad, const double* target, int64_t row_offset, int64_t cap, int64_t* cand_row,
+                            double* cand_dist, double* cand_ss, int64_t* n_cand, void* ws, size_t ws_bytes,
+                            int* status_dev, void* stream);
+int abcdls_fused_check(abcdls_handle_t h, int64_t n, int d, const double* mad, const double* ds, void* ws,
+                       size_t ws_bytes, int* status_dev, void* stream);
+
 /* ---- kernel 3: local-linear adjustment -----------------------------------------------------
  * R: weights (epanechnikov) -> lsfit -> residual recentring -> hcorr -> adj.values.
  * Design is centred on the scaled target; normal equations are accumulated in fp64 with a fixed
@@ -183,6 +215,14 @@ int abcdls_gather(abcdls_handle_t h, const double* ss, int64_t ld_ss, const doub
                   const int64_t* idx, const int64_t* n_acc, int64_t row_offset, int64_t cap, int d, int P,
                   const double* mad, const double* target, const double* ds, double* xs, double* y,
                   double* ss_out, double* w, void* stream);
+/* same outputs; the statistics come from a compact candidate block (abcdls_fused_candidates: cand_ss, leading
+ * dimension ld_cand) through slot[r] (abcdls_accept slot_out), the parameters from the table through idx[r].
+ * One thread per (row, column): d + P independent scattered loads in flight per accepted row. */
+int abcdls_gather_cand(abcdls_handle_t h, const double* cand_ss, int64_t ld_cand, const int64_t* slot,
+                       const double* param, int64_t ld_param, const double* dist_acc, const int64_t* idx,
+                       const int64_t* n_acc, int64_t row_offset, int64_t cap, int d, int P, const double* mad,
+                       const double* target, const double* ds, double* xs, double* y, double* ss_out, double* w,
+                       void* stream);
 size_t abcdls_normal_workspace_bytes(int d, int P);
 int abcdls_normal(abcdls_handle_t h, const double* xs, const double* rhs, const double* w,
                   const int64_t* n_acc, int64_t cap, int d, int P, int with_gram, double* partial,

@@ -107,8 +107,11 @@ class CpuStages:
         ws.flags = dist[:m].numpy() <= ds.item()
         le_count[0] = int(ws.flags.sum())
 
-    def accept(self, dist, n, n_dev, src_idx, ds, quota, row_offset, cap, idx, dist_out, n_out, ws, status):
+    def accept(self, dist, n, n_dev, src_idx, ds, quota, row_offset, cap, idx, dist_out, n_out, ws, status,
+               slot_out=None):
         rows = np.flatnonzero(ws.flags)[: max(int(quota), 0)][:cap]
+        if slot_out is not None:
+            slot_out[: rows.size] = torch.from_numpy(rows)
         idx[: rows.size] = torch.from_numpy((src_idx.numpy()[rows] if src_idx is not None else rows + row_offset))
         if dist_out is not None:
             dist_out[: rows.size] = dist[torch.from_numpy(rows)]

@@ -202,3 +202,69 @@ def test_fast_path_is_taken_without_misses(engine):
     r2 = engine.abc(tgt, par, ss, 0.005, "loclinear")               # dist not kept: TMA kernel without the N-vector
     assert torch.equal(r2.idx, r.idx) and r2.dist is None
     assert engine.fast_misses == before
+
+
+# ---- one-pass front half (csrc/fused.cuh): medians + MADs and the tolerance cut from ONE table read ----------------
+def _check_fused(engine, par, ss, tgt, tol, method, expect="fused"):
+    before = dict(engine.path_calls)
+    misses = engine.fast_misses
+    r = engine.abc(tgt, par, ss, tol, method)                       # dist not kept -> the one-pass path qualifies
+    assert engine.path_calls[expect] == before[expect] + 1
+    assert engine.fast_misses == misses
+    o = O.abc(_np(tgt), _np(par).T, _np(ss).T, tol, method)
+    np.testing.assert_array_equal(_np(r.mad), o.mad)
+    assert r.ds == o.ds and r.nacc == o.nacc
+    np.testing.assert_array_equal(_np(r.idx), o.idx)
+    np.testing.assert_array_equal(_np(r.unadj_values), o.unadj_values)
+    np.testing.assert_array_equal(_np(r.ss), o.ss)
+    np.testing.assert_array_equal(_np(r.dist_accepted), o.dist[o.idx])
+    if method == "loclinear":
+        np.testing.assert_array_equal(_np(r.weights), o.weights)
+        assert _rel(_np(r.adj_values), o.adj_values) < REL_TOL
+    return r, o
+
+
+@pytest.mark.parametrize("n", [1 << 20, (1 << 21) + 14, (1 << 20) + 254])
+@pytest.mark.parametrize("d,P", [(1, 1), (3, 2), (10, 10), (16, 16)])
+def test_fused_one_pass_parity(engine, n, d, P):
+    par, ss, tgt = synth.abc_tables(n, d, P, engine.device)
+    _check_fused(engine, par, ss, tgt, 0.01, "loclinear" if d > 1 else "rejection")
+
+
+def test_fused_odd_rows_in_an_even_pitch(engine):
+    n = (1 << 20) + 77                                              # odd row count: ragged tile finished with plain stores
+    par, ss, tgt = synth.abc_tables(n, 5, 4, engine.device)
+    big = torch.zeros((5, n + 1), dtype=torch.float64, device=engine.device)
+    big[:, :n] = ss
+    _check_fused(engine, par, big[:, :n], tgt, 0.003, "loclinear")
+    _check_fused(engine, par, ss, tgt, 0.003, "loclinear", expect="two_pass")   # odd pitch: TMA cannot stream it
+
+
+def test_fused_small_and_large_tolerance(engine):
+    par, ss, tgt = synth.abc_tables(1 << 21, 8, 8, engine.device)
+    _check_fused(engine, par, ss, tgt, 0.0002, "loclinear")
+    _check_fused(engine, par, ss, tgt, 0.2, "rejection")
+
+
+def test_fused_miss_falls_back_and_stays_exact(engine):
+    """Ties (integer statistics): the sampled MAD band collapses / MAD may be 0, the proof cannot hold -> the ladder
+    falls back, the result is still R's."""
+    g = torch.Generator(device="cpu").manual_seed(5)
+    n = 1 << 20
+    ss = torch.randint(0, 9, (3, n), generator=g).to(torch.float64).to(engine.device)
+    par = torch.rand((2, n), generator=g, dtype=torch.float64).to(engine.device)
+    tgt = torch.tensor([4.0, 3.0, 5.0], dtype=torch.float64, device=engine.device)
+    r = engine.abc(tgt, par, ss, 0.01, "rejection")
+    o = O.abc(_np(tgt), _np(par).T, _np(ss).T, 0.01, "rejection")
+    np.testing.assert_array_equal(_np(r.idx), o.idx)
+    assert r.ds == o.ds
+
+
+def test_fused_postpr(engine):
+    ids, ss, tgt = synth.postpr_tables(3000000, engine.device)
+    models = ["BNDX", "MNDX", "SNDX"]
+    r = engine.postpr(tgt, ids, models, ss, 0.05)
+    o = O.postpr(_np(tgt), np.array(models)[_np(ids)], _np(ss).T, 0.05)
+    np.testing.assert_array_equal(_np(r.idx), o.idx)
+    np.testing.assert_array_equal(_np(r.counts), o.counts)
+    assert r.ds == o.ds
