@@ -21,7 +21,39 @@
 // two lanes (even / odd columns) and combined with one shuffle; the 16-bit ballot of the warp is one store into
 // the row bitmap, so candidate rows come out in row order without any barrier, atomic or staging.
 
+#include <cuda.h>
+
 namespace {
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// one 2-D tile (256 rows x d columns of the column-major table) per TMA instruction; rows beyond n arrive as NaN
+__device__ __forceinline__ void tma_tile_g2s(void* dst_smem, const CUtensorMap* tmap, int row0, int col0,
+                                             unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(tmap), "r"(row0), "r"(col0), "r"(smem_u32(bar))
+        : "memory");
+}
 
 constexpr int kFRows = 256;
 constexpr int kFMaxD = 16;
@@ -29,13 +61,12 @@ constexpr int kFWarps = 16;
 constexpr int kFConsumers = kFWarps * 32;
 constexpr int kFThreads = kFConsumers + 32;
 constexpr int kFMaxStages = 8;
-constexpr int kFRingBytes = 96 * 1024;
+constexpr int kFRingBytes = 160 * 1024;
 constexpr int kFChunk = 256;
 constexpr int kFHeader = 1024;   // bytes in front of the ring
-constexpr int kFQCapM = 12;      // per-lane queue slots, M band (flushed when a lane holds more than cap - 8)
-constexpr int kFQCapU = 16;      //   ... U band
-constexpr int kFQWarpBytes = (kFQCapM + kFQCapU) * 256;   // per consumer warp
-constexpr int kFQBytes = kFWarps * kFQWarpBytes;          // 112 KB
+constexpr int kFQCap = 16;       // per-lane queue slots (both bands share it; flushed when a lane holds more than 8)
+constexpr int kFQWarpBytes = kFQCap * 256;                // per consumer warp
+constexpr int kFQBytes = kFWarps * kFQWarpBytes;          // 64 KB
 
 struct FusedPar {
     double rho[kFMaxD];   // 1 / (1.4826 * sampled MAD estimate)
@@ -49,7 +80,7 @@ struct FusedPar {
 
 struct FusedSmem {
     unsigned long long full[kFMaxStages], empty[kFMaxStages];
-    double2 sc[kFMaxD];   // (target, rho)
+    double2 sc[kFMaxD];   // (-target * rho, rho)
 };
 static_assert(sizeof(FusedSmem) <= kFHeader, "header");
 
@@ -140,7 +171,7 @@ __global__ void k_make_fused_thr(const double* __restrict__ est, int G, double i
 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kFThreads, 1)
-k_fused_pass(const double* __restrict__ ss, long long n, long long ntiles, int d, long long ld, int nstages,
+k_fused_pass(const __grid_constant__ CUtensorMap tmap, long long n, long long ntiles, int d, int nstages,
              const ColBrk* __restrict__ brk, const FusedPar* __restrict__ par, unsigned long long* __restrict__ counts,
              double* __restrict__ candM, long long capM, double* __restrict__ candU, long long capU,
              unsigned long long* __restrict__ cnt, unsigned short* __restrict__ mask16, long long tpc, int* status) {
@@ -148,7 +179,8 @@ k_fused_pass(const double* __restrict__ ss, long long n, long long ntiles, int d
     FusedSmem& sm = *reinterpret_cast<FusedSmem*>(smem_raw);
     double* ring = reinterpret_cast<double*>(smem_raw + kFHeader);
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x < kFMaxD) sm.sc[threadIdx.x] = make_double2(par->tgt[threadIdx.x], par->rho[threadIdx.x]);
+    if (threadIdx.x < kFMaxD)   // a = x * rho - t * rho as one fma
+        sm.sc[threadIdx.x] = make_double2(-par->tgt[threadIdx.x] * par->rho[threadIdx.x], par->rho[threadIdx.x]);
     if (threadIdx.x == 0) {
         for (int s2 = 0; s2 < nstages; ++s2) {
             mbar_init(&sm.full[s2], 1);
@@ -159,40 +191,17 @@ k_fused_pass(const double* __restrict__ ss, long long n, long long ntiles, int d
     __syncthreads();
     const long long t_begin = (long long)blockIdx.x * tpc, t_end = min(ntiles, t_begin + tpc);
     const size_t stage_doubles = (size_t)d * kFRows;
-    const double nan = __longlong_as_double(0x7ff8000000000000ll);
-
     if (wid == kFWarps) {
-        // ===== producer warp: lane 0 feeds the ring; the ragged last tile is completed with plain stores =====
-        int st = 0;
-        unsigned ph = 0;
-        for (long long tile = t_begin; tile < t_end; ++tile) {
-            if (lane == 0) mbar_wait(&sm.empty[st], ph ^ 1u);
-            __syncwarp();
-            double* dst = ring + (size_t)st * stage_doubles;
-            const double* src0 = ss + tile * kFRows;
-            const long long left = n - tile * kFRows;
-            if (left >= kFRows) {
-                if (lane == 0) {
-                    mbar_expect_tx(&sm.full[st], (unsigned)(stage_doubles * 8));
-                    for (int c = 0; c < d; ++c)
-                        bulk_g2s(dst + c * kFRows, src0 + (size_t)c * ld, kFRows * 8, &sm.full[st]);
-                }
-            } else {
-                const int rows = (int)left, nb = rows & ~1;   // bulk copies move multiples of 16 bytes
-                for (int c = 0; c < d; ++c)
-                    for (int r = nb + lane; r < kFRows; r += 32)
-                        dst[c * kFRows + r] = r < rows ? src0[(size_t)c * ld + r] : nan;
-                __syncwarp();
-                if (lane == 0) {
-                    if (nb > 0) {
-                        mbar_expect_tx(&sm.full[st], (unsigned)(d * nb * 8));
-                        for (int c = 0; c < d; ++c) bulk_g2s(dst + c * kFRows, src0 + (size_t)c * ld, nb * 8, &sm.full[st]);
-                    } else {
-                        mbar_arrive(&sm.full[st]);
-                    }
-                }
+        // ===== producer: one elected lane, ONE 2-D TMA tile copy per stage =====
+        if (lane == 0) {
+            int st = 0;
+            unsigned ph = 0;
+            for (long long tile = t_begin; tile < t_end; ++tile) {
+                mbar_wait(&sm.empty[st], ph ^ 1u);
+                mbar_expect_tx(&sm.full[st], (unsigned)(stage_doubles * 8));   // out-of-bounds rows count too
+                tma_tile_g2s(ring + (size_t)st * stage_doubles, &tmap, (int)(tile * kFRows), 0, &sm.full[st]);
+                if (++st == nstages) { st = 0; ph ^= 1u; }
             }
-            if (++st == nstages) { st = 0; ph ^= 1u; }
         }
         return;
     }
@@ -209,14 +218,14 @@ k_fused_pass(const double* __restrict__ ss, long long n, long long ntiles, int d
     const unsigned hiW = (unsigned)__double2hiint(__dsub_rn(B.r2, B.r1));
     const double thr = par->thr;
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
-    // Band candidates go to per-LANE queues in shared memory ([slot][lane]: conflict free, no votes, no branches:
-    // one predicated store + one predicated pointer bump per band and element).  When some lane could overflow
-    // in the next tile the warp flushes: one scan, ONE global atomic, dense coalesced-by-runs copy.
+    // Band candidates (either band) go to a per-LANE queue in shared memory ([slot][lane]: conflict free, no votes, no
+    // branches: one predicated store + one predicated pointer bump per element).  When some lane could overflow in
+    // the next tile the warp flushes: entries are re-classified (M: |x - c| <= r0, else U), two scans, two global
+    // atomics, dense copies.
     unsigned char* qbase = smem_raw + kFHeader + (size_t)nstages * stage_doubles * 8 + (size_t)wid * kFQWarpBytes;
-    const unsigned qM0 = smem_u32(qbase) + lane * 8;                       // my M queue: slot s at qM0 + s * 256
-    const unsigned qU0 = qM0 + kFQCapM * 256;                              // my U queue
-    unsigned pM = qM0, pU = qU0;
-    const unsigned limM = qM0 + (kFQCapM - 8) * 256, limU = qU0 + (kFQCapU - 8) * 256;
+    const unsigned q0 = smem_u32(qbase) + lane * 8;                        // my queue: slot s at q0 + s * 256
+    unsigned pq = q0;
+    const unsigned qlim = q0 + (kFQCap - 8) * 256;
     double* __restrict__ gM = candM + (size_t)jc * capM;
     double* __restrict__ gU = candU + (size_t)jc * capU;
     unsigned long long* cntM = &cnt[jc * 2 + 0];
@@ -225,50 +234,66 @@ k_fused_pass(const double* __restrict__ ss, long long n, long long ntiles, int d
     bool bad = false;
     const int row = (wid << 4) | (lane & 15);    // row of the tile this lane helps with
     const int half = lane >> 4;                  // 0: even columns, 1: odd columns
-    // scaling constants of this lane's (up to 8) columns in registers: a = x * rho - t * rho as one fma
-    double rh[8], mt[8];
+    auto flush = [&]() {
+        const int fill = (int)((pq - q0) >> 8);
+        const int mx = __reduce_max_sync(0xffffffffu, fill);
+        // my entries, split by band: packed (nM | nU << 16) inclusive scan
+        double v[kFQCap];
+        int mine = 0;
+        unsigned isM = 0;
 #pragma unroll
-    for (int q8 = 0; q8 < 8; ++q8) {
-        const int cc = 2 * q8 + half;
-        rh[q8] = cc < d ? sm.sc[cc].y : 0.0;
-        mt[q8] = cc < d ? -sm.sc[cc].x * sm.sc[cc].y : 0.0;
-    }
-
-    auto flush = [&](unsigned& p, unsigned q0, double* __restrict__ g, long long cap, unsigned long long* cntp) {
-        const int fill = (int)((p - q0) >> 8);
-        int incl = fill;
+        for (int t = 0; t < kFQCap; ++t) {
+            if (t < mx) {
+                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v[t]) : "r"(q0 + t * 256));
+                if (t < fill) {
+                    const bool m = fabs(__dsub_rn(v[t], c)) <= r0;
+                    isM |= m ? (1u << t) : 0u;
+                    mine += m ? 1 : 0x10000;
+                }
+            }
+        }
+        int incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += t;
         }
         const int tot = __shfl_sync(0xffffffffu, incl, 31);
-        const int mx = __reduce_max_sync(0xffffffffu, fill);
-        unsigned long long b = 0ull;
-        if (lane == 0) b = atomicAdd(cntp, (unsigned long long)tot);
-        b = __shfl_sync(0xffffffffu, b, 0);
-        const long long dst0 = (long long)b + (incl - fill);
-        for (int t = 0; t < mx; ++t) {
-            if (t < fill && dst0 + t < cap) {
-                double v;
-                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(q0 + t * 256));
-                g[dst0 + t] = v;
+        unsigned long long bM = 0ull, bU = 0ull;
+        if (lane == 0) {
+            if (tot & 0xffff) bM = atomicAdd(cntM, (unsigned long long)(tot & 0xffff));
+            if (tot >> 16) bU = atomicAdd(cntU, (unsigned long long)(tot >> 16));
+        }
+        bM = __shfl_sync(0xffffffffu, bM, 0);
+        bU = __shfl_sync(0xffffffffu, bU, 0);
+        long long dM = (long long)bM + ((incl - mine) & 0xffff);
+        long long dU = (long long)bU + ((incl - mine) >> 16);
+#pragma unroll
+        for (int t = 0; t < kFQCap; ++t) {
+            if (t < fill) {
+                if (isM & (1u << t)) {
+                    if (dM < capM) gM[dM] = v[t];
+                    ++dM;
+                } else {
+                    if (dU < capU) gU[dU] = v[t];
+                    ++dU;
+                }
             }
         }
-        p = q0;
+        pq = q0;
         __syncwarp();
     };
 
     int st = 0;
     unsigned ph = 0;
+    unsigned short* mptr = mask16 + t_begin * kFWarps + wid;
+    const long long tail_tile = (n % kFRows) ? ntiles - 1 : -1;   // the ragged tile (rows >= tail_rows hold NaN)
+    const int tail_rows = (int)(n % kFRows);
     for (long long tile = t_begin; tile < t_end; ++tile) {
         mbar_wait(&sm.full[st], ph);
         const double* __restrict__ stage = ring + (size_t)st * stage_doubles;
         if (has_col) {
-            if (__any_sync(0xffffffffu, pM > limM || pU > limU)) {
-                if (__any_sync(0xffffffffu, pM > limM)) flush(pM, qM0, gM, capM, cntM);
-                if (__any_sync(0xffffffffu, pU > limU)) flush(pU, qU0, gU, capU, cntU);
-            }
+            if (__any_sync(0xffffffffu, pq > qlim)) flush();
             const double* __restrict__ colp = stage + j * kFRows + 2 * lane;
             double x[8];
 #pragma unroll
@@ -284,54 +309,51 @@ k_fused_pass(const double* __restrict__ ss, long long n, long long ntiles, int d
                 const unsigned hu = (unsigned)__double2hiint(uu);
                 c_neg += (unsigned)__double2hiint(sgn) >> 31;
                 c_in += hu >> 31;
-                const bool inM = fabs(sgn) <= r0;
-                const bool inU = hu <= hiW;
+                const bool cand = (fabs(sgn) <= r0) || (hu <= hiW);   // M band or U band
                 asm volatile(
                     "{\n\t"
-                    ".reg .pred pm, pu;\n\t"
-                    "setp.ne.u32 pm, %2, 0;\n\t"
-                    "setp.ne.u32 pu, %3, 0;\n\t"
-                    "@pm st.shared.f64 [%0], %4;\n\t"
-                    "@pu st.shared.f64 [%1], %4;\n\t"
-                    "@pm add.u32 %0, %0, 256;\n\t"
-                    "@pu add.u32 %1, %1, 256;\n\t"
+                    ".reg .pred pc;\n\t"
+                    "setp.ne.u32 pc, %1, 0;\n\t"
+                    "@pc st.shared.f64 [%0], %2;\n\t"
+                    "@pc add.u32 %0, %0, 256;\n\t"
                     "}"
-                    : "+r"(pM), "+r"(pU)
-                    : "r"((unsigned)inM), "r"((unsigned)inU), "d"(x[u])
+                    : "+r"(pq)
+                    : "r"((unsigned)cand), "d"(x[u])
                     : "memory");
             }
         }
         // approximate squared distance of row `row`: this lane sums the columns of its parity
         double q = 0.0;
-        if (d == kFMaxD) {
+        {
+            const double* __restrict__ xp = stage + half * kFRows + row;
+            const double2* __restrict__ sp = sm.sc + half;      // (-t rho, rho) of this lane's columns: broadcast loads
+            if (d == kFMaxD) {
 #pragma unroll
-            for (int q8 = 0; q8 < 8; ++q8) {
-                const double a = fma(stage[(2 * q8 + half) * kFRows + row], rh[q8], mt[q8]);
-                q = fma(a, a, q);
-            }
-        } else {
-#pragma unroll
-            for (int q8 = 0; q8 < 8; ++q8) {
-                const int cc = 2 * q8 + half;
-                if (cc < d) {
-                    const double a = fma(stage[cc * kFRows + row], rh[q8], mt[q8]);
+                for (int q8 = 0; q8 < 8; ++q8) {
+                    const double2 s2 = sp[2 * q8];
+                    const double a = fma(xp[2 * q8 * kFRows], s2.y, s2.x);
+                    q = fma(a, a, q);
+                }
+            } else {
+                for (int cc = half; cc < d; cc += 2) {
+                    const double2 s2 = sm.sc[cc];
+                    const double a = fma(stage[cc * kFRows + row], s2.y, s2.x);
                     q = fma(a, a, q);
                 }
             }
         }
         q += __shfl_xor_sync(0xffffffffu, q, 16);
-        const bool valid = (tile + 1) * kFRows <= n || tile * kFRows + row < n;
-        bad |= valid && !(q < inf);
+        bad |= !(q < inf) && (tile != tail_tile || row < tail_rows);
         const unsigned bal = __ballot_sync(0xffffffffu, q <= thr);
         if (lane == 0) {
-            mask16[tile * kFWarps + wid] = (unsigned short)(bal & 0xffffu);
+            *mptr = (unsigned short)(bal & 0xffffu);
             mbar_arrive(&sm.empty[st]);   // every lane's shared loads completed before the shuffle / ballot
         }
+        mptr += kFWarps;
         if (++st == nstages) { st = 0; ph ^= 1u; }
     }
     if (has_col) {
-        flush(pM, qM0, gM, capM, cntM);
-        flush(pU, qU0, gU, capU, cntU);
+        flush();
         c_neg = warp_sum(c_neg);
         c_in = warp_sum(c_in);
         if (lane == 0) {
@@ -535,10 +557,10 @@ size_t abcdls_fused_workspace_bytes(int64_t n, int d) { return carve_fused(nullp
 
 // 1 if the one-pass path can stream this table (TMA needs 16-byte aligned columns; d <= 16 fits one ring stage)
 int abcdls_fused_supported(const double* ss, int64_t n, int d, int64_t ld) {
-    if (!(d >= 1 && d <= kFMaxD && n >= 4 * kSample && ld >= n && (ld & 1) == 0 &&
+    if (!(d >= 1 && d <= kFMaxD && n >= 4 * kSample && n < (1ll << 31) && ld >= n && (ld & 1) == 0 &&
           (reinterpret_cast<uintptr_t>(ss) & 15) == 0))
         return 0;
-    return 1;
+    return encode_tiled_fn() ? 1 : 0;
 }
 
 #define FUSED_PROLOGUE(name)                                                                                        \
@@ -600,7 +622,26 @@ int abcdls_fused_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int
     long long grid = h->sm_count;
     if (grid > ntiles) grid = ntiles;
     const long long tpc = (ntiles + grid - 1) / grid;
-    k_fused_pass<<<(unsigned)grid, kFThreads, smem, st>>>(ss, n, ntiles, d, ld, nstages, w.m.brk, w.par, w.m.counts,
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) {
+        h->err = "cuTensorMapEncodeTiled is not available from this driver";
+        return ABCDLS_E_CUDA;
+    }
+    alignas(64) CUtensorMap tmap;
+    {
+        const cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)d};
+        const cuuint64_t gstr[1] = {(cuuint64_t)ld * 8};
+        const cuuint32_t box[2] = {(cuuint32_t)kFRows, (cuuint32_t)d};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ss), gdim, gstr, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA);
+        if (r != CUDA_SUCCESS) {
+            h->err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")";
+            return ABCDLS_E_CUDA;
+        }
+    }
+    k_fused_pass<<<(unsigned)grid, kFThreads, smem, st>>>(tmap, n, ntiles, d, nstages, w.m.brk, w.par, w.m.counts,
                                                          w.m.candM, w.capM, w.m.candU, w.capU, w.m.cnt, w.mask16, tpc,
                                                          status_dev);
     ABCDLS_LAUNCH_CHECK(h);

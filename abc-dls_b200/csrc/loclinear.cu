@@ -100,12 +100,24 @@ __global__ void __launch_bounds__(256) k_gather_cand(const double* __restrict__ 
 
 // ---- weighted normal equations ------------------------------------------------------------------
 // T_r = [1, xs_r (d), rhs_r (P)] (width W = M + P);  C[a][b] = sum_r w_r * T_r[a] * T_r[b] for a < M, b < W.
-// Register blocking: the (M x W) result is cut into 4x4 blocks; a thread owns one block per "slot" and keeps
-// its 16 accumulators in registers, so a row costs 8 shared-memory doubles per 16 FMAs.  The 256 threads of a
-// CTA form `groups` row-groups that take alternate rows of a staged tile; groups are summed in a fixed order.
+// The operands are column-major (k-major), so tiles of 64 rows are staged AS THEY ARE ([column][row], odd pitch:
+// conflict-free stores) with 8-byte cp.async copies into a double buffer; nothing is transposed.  Every warp walks
+// its own rows of the tile; lane (ablk, bblk) owns the 6 x 4 outputs {a = ablk + nA*i} x {b = bblk + nB*j} in
+// registers.  The interleaved index sets make the lanes of one shared load hit consecutive columns (distinct banks)
+// while lanes with the same block share one broadcast.  Per row and warp: 10 shared loads, 6 multiplies, 24 FMAs.
+// Warps, then CTAs, are summed in a fixed order: deterministic for a given (n_acc, cap).
 constexpr int kNormThreads = 256;
-constexpr int kNormRows = 64;   // rows staged per tile
-constexpr int kBlk = 4;
+constexpr int kNormWarps = kNormThreads / 32;
+constexpr int kNormRows = 64;            // rows per staged tile
+constexpr int kNormPitch = kNormRows + 1;
+constexpr int kBA = 6, kBB = 4;
+
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(kNormThreads) k_normal_partial(const double* __restrict__ xs,
                                                                  const double* __restrict__ rhs,
@@ -113,93 +125,109 @@ __global__ void __launch_bounds__(kNormThreads) k_normal_partial(const double* _
                                                                  const long long* __restrict__ n_acc_ptr,
                                                                  long long cap, int d, int P, int with_gram,
                                                                  double* __restrict__ partials) {
-    extern __shared__ __align__(32) double smn[];
-    double* sm = smn;
-    const int M = d + 1;
-    const int W = M + P;
-    const int Wp = (W + kBlk - 1) / kBlk * kBlk;       // row pitch, zero padded, 32-byte aligned rows
-    const int nbA = (M + kBlk - 1) / kBlk;
-    const int b_first = with_gram ? 0 : M / kBlk;      // without gram only columns >= M are needed
-    const int nbB = Wp / kBlk - b_first;
-    const int nblocks = nbA * nbB;
-    double* T = sm;                                    // [kNormRows][Wp]
-    double* wr = sm + (size_t)kNormRows * Wp;          // [kNormRows]
+    extern __shared__ __align__(16) double smn[];
+    const int M = d + 1, W = M + P;
+    const int b0 = with_gram ? 0 : M;                  // first output column
+    const int Wb = W - b0;
+    const int nA = (M + kBA - 1) / kBA, nB = (Wb + kBB - 1) / kBB;
+    const int npairs = nA * nB;
+    const int nslots = (npairs + 31) / 32;
+    // tile columns: 0 = ones, 1..d = xs, M..W-1 = rhs, W = weights, W + 1 = zeros (padding target)
+    const int ncols = W + 2;
+    double* buf[2] = {smn, smn + (size_t)ncols * kNormPitch};
+    double* red = smn + (size_t)2 * ncols * kNormPitch;    // [kNormWarps][32][24]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     long long n_acc = *n_acc_ptr;
     if (n_acc > cap) n_acc = cap;
-
-    // thread -> (group, block).  groups = how many disjoint row subsets run side by side
-    const int groups = max(1, kNormThreads / nblocks);
-    const int slots = (nblocks + kNormThreads - 1) / kNormThreads;   // >1 only when nblocks > 256
-    const int grp = (slots == 1) ? threadIdx.x / nblocks : 0;
-    const int blk0 = (slots == 1) ? threadIdx.x % nblocks : threadIdx.x;
-    const bool active = (slots == 1) ? (grp < groups) : true;
-
+    const long long ntile = (n_acc + kNormRows - 1) / kNormRows;
+    const long long per = (ntile + gridDim.x - 1) / gridDim.x;
+    const long long t_begin = (long long)blockIdx.x * per, t_end = min(ntile, t_begin + per);
     const int E = (with_gram ? M * M : 0) + M * P;
     double* out = partials + (size_t)blockIdx.x * E;
     for (int e = threadIdx.x; e < E; e += kNormThreads) out[e] = 0.0;
+    for (int t = threadIdx.x; t < 2 * kNormPitch; t += kNormThreads) {   // constant columns of both buffers
+        const int bsel = t / kNormPitch, rr = t % kNormPitch;
+        buf[bsel][rr] = 1.0;
+        buf[bsel][(size_t)(W + 1) * kNormPitch + rr] = 0.0;
+    }
 
-    for (int slot = 0; slot < slots; ++slot) {
-        const int blk = blk0 + slot * kNormThreads;
-        const bool on = active && blk < nblocks;
-        const int ba = on ? (blk / nbB) * kBlk : 0;
-        const int bb = on ? (blk % nbB + b_first) * kBlk : 0;
-        double acc[kBlk][kBlk];
-#pragma unroll
-        for (int i = 0; i < kBlk; ++i)
-#pragma unroll
-            for (int j = 0; j < kBlk; ++j) acc[i][j] = 0.0;
-
-        const long long ntile = (n_acc + kNormRows - 1) / kNormRows;
-        for (long long tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
-            const long long r0 = tile * kNormRows;
-            __syncthreads();
-            for (int t = threadIdx.x; t < kNormRows * Wp; t += kNormThreads) {
-                const int c = t / kNormRows, rr = t % kNormRows;   // consecutive threads -> consecutive rows
-                const long long r = r0 + rr;
-                double v = 0.0;
-                if (r < n_acc && c < W) {
-                    if (c == 0) v = 1.0;
-                    else if (c < M) v = xs[(size_t)(c - 1) * cap + r];
-                    else v = rhs[(size_t)(c - M) * cap + r];
-                }
-                T[rr * Wp + c] = v;
-            }
-            if (threadIdx.x < kNormRows) {
-                const long long r = r0 + threadIdx.x;
-                wr[threadIdx.x] = r < n_acc ? w[r] : 0.0;
-            }
-            __syncthreads();
-            if (on) {
-                for (int rr = grp; rr < kNormRows; rr += groups) {
-                    const double wv = wr[rr];
-                    const double4 a4 = *reinterpret_cast<const double4*>(T + rr * Wp + ba);
-                    const double4 b4 = *reinterpret_cast<const double4*>(T + rr * Wp + bb);
-                    const double av[4] = {a4.x * wv, a4.y * wv, a4.z * wv, a4.w * wv};
-                    const double bv[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-                    for (int i = 0; i < kBlk; ++i)
-#pragma unroll
-                        for (int j = 0; j < kBlk; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
-                }
-            }
+    auto stage = [&](long long tile, double* T) {
+        const long long r0 = tile * kNormRows;
+        const int nr = (int)min((long long)kNormRows, n_acc - r0);
+        for (int t = threadIdx.x; t < W * kNormRows; t += kNormThreads) {
+            const int c = 1 + t / kNormRows, rr = t % kNormRows;       // c = 1 .. W  (W = the weight column)
+            double* dst = T + (size_t)c * kNormPitch + rr;
+            const double* src = (c < M ? xs + (size_t)(c - 1) * cap : (c < W ? rhs + (size_t)(c - M) * cap : w)) + r0 + rr;
+            if (rr < nr) cp_async8(dst, src);
+            else *dst = 0.0;
         }
-        // combine the row-groups in a fixed order (deterministic): group g adds in turn
-        for (int g = 0; g < groups; ++g) {
+    };
+
+    for (int slot = 0; slot < nslots; ++slot) {
+        const int pair = slot * 32 + lane;
+        const bool on = pair < npairs;
+        const int ablk = on ? pair / nB : 0, bblk = on ? pair % nB : 0;
+        int ai[kBA], bi[kBB];                                            // tile columns (padding -> the zero column)
+#pragma unroll
+        for (int i = 0; i < kBA; ++i) {
+            const int a = ablk + nA * i;
+            ai[i] = (on && a < M) ? a * kNormPitch : (W + 1) * kNormPitch;
+        }
+#pragma unroll
+        for (int j = 0; j < kBB; ++j) {
+            const int b = b0 + bblk + nB * j;
+            bi[j] = (on && b < W) ? b * kNormPitch : (W + 1) * kNormPitch;
+        }
+        double acc[kBA][kBB];
+#pragma unroll
+        for (int i = 0; i < kBA; ++i)
+#pragma unroll
+            for (int j = 0; j < kBB; ++j) acc[i][j] = 0.0;
+
+        __syncthreads();
+        if (t_begin < t_end) stage(t_begin, buf[0]);
+        cp_async_commit();
+        for (long long tile = t_begin; tile < t_end; ++tile) {
+            const int cur = (int)((tile - t_begin) & 1);
+            if (tile + 1 < t_end) stage(tile + 1, buf[cur ^ 1]);
+            cp_async_commit();
+            cp_async_wait<1>();
             __syncthreads();
-            if (on && grp == g) {
+            const double* __restrict__ T = buf[cur];
+            const double* __restrict__ wt = T + (size_t)W * kNormPitch;
+#pragma unroll 2
+            for (int rr = wid; rr < kNormRows; rr += kNormWarps) {
+                const double wv = wt[rr];
+                double av[kBA], bv[kBB];
 #pragma unroll
-                for (int i = 0; i < kBlk; ++i)
+                for (int i = 0; i < kBA; ++i) av[i] = T[ai[i] + rr] * wv;
 #pragma unroll
-                    for (int j = 0; j < kBlk; ++j) {
-                        const int a = ba + i, b = bb + j;
-                        if (a < M && b < W) {
-                            int e = -1;
-                            if (b < M) { if (with_gram) e = a * M + b; }
-                            else e = (with_gram ? M * M : 0) + a * P + (b - M);
-                            if (e >= 0) out[e] += acc[i][j];
-                        }
-                    }
+                for (int j = 0; j < kBB; ++j) bv[j] = T[bi[j] + rr];
+#pragma unroll
+                for (int i = 0; i < kBA; ++i)
+#pragma unroll
+                    for (int j = 0; j < kBB; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
             }
+            __syncthreads();   // everyone is done with buf[cur] before it is refilled
+        }
+        cp_async_wait<0>();
+        // warps -> CTA partial in warp order
+        double* mine = red + ((size_t)wid * 32 + lane) * (kBA * kBB);
+#pragma unroll
+        for (int i = 0; i < kBA; ++i)
+#pragma unroll
+            for (int j = 0; j < kBB; ++j) mine[i * kBB + j] = acc[i][j];
+        __syncthreads();
+        for (int t = threadIdx.x; t < 32 * kBA * kBB; t += kNormThreads) {
+            const int ln = t / (kBA * kBB), ij = t % (kBA * kBB);
+            const int pr = slot * 32 + ln;
+            if (pr >= npairs) continue;
+            const int a = pr / nB + nA * (ij / kBB), b = b0 + pr % nB + nB * (ij % kBB);
+            if (a >= M || b >= W) continue;
+            double sum = 0.0;
+            for (int wq = 0; wq < kNormWarps; ++wq) sum += red[((size_t)wq * 32 + ln) * (kBA * kBB) + ij];
+            const int e = (b < M) ? a * M + b : (with_gram ? M * M : 0) + a * P + (b - M);
+            out[e] = sum;
         }
         __syncthreads();
     }
@@ -323,9 +351,8 @@ __global__ void __launch_bounds__(256) k_adjust(const double* __restrict__ xs, d
                 double g0 = sg[p];
                 double lin = g0;
                 for (int j = 0; j < d; ++j) lin = fma(xs[(size_t)j * cap + r], sg[(j + 1) * P + p], lin);
-                double sd = sqrt(exp(g0));
-                double si = sqrt(exp(lin));
-                rv = (sd * rv) / si;
+                // pred.sd * res / pred.si = res * sqrt(exp(g0)) / sqrt(exp(lin)) = res * exp((g0 - lin) / 2): one exp
+                rv = rv * exp(0.5 * (g0 - lin));
                 res[(size_t)p * cap + r] = rv;
             }
             adj[(size_t)p * cap + r] = (beta[p] + the_m[p]) + rv;
@@ -501,8 +528,7 @@ int abcdls_normal(abcdls_handle_t h, const double* xs, const double* rhs, const 
         h->err = "normal workspace too small";
         return ABCDLS_E_WORKSPACE;
     }
-    const int Wp = (M + P + kBlk - 1) / kBlk * kBlk;
-    size_t smem = (size_t)(kNormRows * Wp + kNormRows) * sizeof(double);
+    size_t smem = ((size_t)2 * (M + P + 2) * kNormPitch + (size_t)kNormWarps * 32 * kBA * kBB) * sizeof(double);
     cudaStream_t st = (cudaStream_t)stream;
     if (smem > 48 * 1024)
         ABCDLS_CUDA(h, cudaFuncSetAttribute(k_normal_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
