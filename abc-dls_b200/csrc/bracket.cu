@@ -35,24 +35,94 @@ constexpr int kSmallCap = 8192;    // values gathered for the final in-smem sort
 constexpr int kMaxD = 64;
 
 // ---------------------------------------------------------------------------------------------------
-// shared-memory bitonic sort of n = power of two doubles
-__device__ void bitonic_sort(double* s, int n) {
-    for (int k = 2; k <= n; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                int ixj = i ^ j;
-                if (ixj > i) {
-                    double a = s[i], b = s[ixj];
-                    bool up = ((i & k) == 0);
-                    if ((a > b) == up) {
-                        s[i] = b;
-                        s[ixj] = a;
+// shared-memory bitonic sort of n = power of two doubles (n >= 8, blockDim.x * 8 >= ... any block size).
+// Steps with partner distance j >= 8 work on pairs (every thread busy, two loads + two stores per pair); the last
+// three steps of every merge (j = 4, 2, 1) stay inside 8 consecutive elements and run in registers.
+__device__ __forceinline__ void bitonic_tail8(double* s, int n, int k) {
+    // steps j = 4, 2, 1 of the merge with run length k (k >= 8): direction is constant inside an aligned block of 8
+    for (int blk = threadIdx.x; blk < n / 8; blk += blockDim.x) {
+        double v[8];
+        double* p = s + blk * 8;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = p[t];
+        const bool up = (((blk * 8) & k) == 0);
+#pragma unroll
+        for (int j = 4; j > 0; j >>= 1) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                if ((t & j) == 0) {
+                    const double a = v[t], b = v[t | j];
+                    const bool sw = (a > b) == up;
+                    v[t] = sw ? b : a;
+                    v[t | j] = sw ? a : b;
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) p[t] = v[t];
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void bitonic_step(double* s, int n, int k, int j) {
+    for (int p = threadIdx.x; p < n / 2; p += blockDim.x) {
+        const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+        const double a = s[i], b = s[i | j];
+        const bool up = ((i & k) == 0);
+        if ((a > b) == up) {
+            s[i] = b;
+            s[i | j] = a;
+        }
+    }
+    __syncthreads();
+}
+
+// sorts the first 8 elements' worth of runs (k = 2, 4, 8) entirely in registers
+__device__ __forceinline__ void bitonic_head8(double* s, int n) {
+    for (int blk = threadIdx.x; blk < n / 8; blk += blockDim.x) {
+        double v[8];
+        double* p = s + blk * 8;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = p[t];
+#pragma unroll
+        for (int k = 2; k <= 8; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    if ((t & j) == 0) {
+                        const bool up = (((blk * 8 + t) & k) == 0);
+                        const double a = v[t], b = v[t | j];
+                        const bool sw = (a > b) == up;
+                        v[t] = sw ? b : a;
+                        v[t | j] = sw ? a : b;
                     }
                 }
             }
-            __syncthreads();
         }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) p[t] = v[t];
     }
+    __syncthreads();
+}
+
+__device__ void bitonic_sort(double* s, int n) {
+    if (n < 8) {   // tiny inputs: plain network
+        for (int k = 2; k <= n; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) bitonic_step(s, n, k, j);
+        return;
+    }
+    bitonic_head8(s, n);
+    for (int k = 16; k <= n; k <<= 1) {
+        for (int j = k >> 1; j >= 8; j >>= 1) bitonic_step(s, n, k, j);
+        bitonic_tail8(s, n, k);
+    }
+}
+
+// s is already bitonic (e.g. decreasing then increasing): one ascending merge sorts it
+__device__ void bitonic_merge_up(double* s, int n) {
+    for (int j = n >> 1; j >= 8; j >>= 1) bitonic_step(s, n, n << 1, j);   // k = 2n: (i & k) == 0 for every i -> ascending
+    bitonic_tail8(s, n, n << 1);
 }
 
 __device__ __forceinline__ unsigned hash3(unsigned a, unsigned b, unsigned c) {
@@ -83,9 +153,10 @@ __global__ void __launch_bounds__(512) k_sample_cols(const double* __restrict__ 
     __syncthreads();
     bitonic_sort(s, kSample);
     const double mhat = s[kSample / 2];
+    // |s - mhat| of the sorted sample falls to 0 at the median and rises again: already bitonic -> one merge
     for (int t = threadIdx.x; t < kSample; t += blockDim.x) a[t] = fabs(s[t] - mhat);
     __syncthreads();
-    bitonic_sort(a, kSample);
+    bitonic_merge_up(a, kSample);
     if (threadIdx.x == 0) {
         int il = (int)floor((0.5 - delta) * kSample), ih = (int)ceil((0.5 + delta) * kSample);
         il = max(0, min(kSample - 1, il));

@@ -530,8 +530,11 @@ int abcdls_normal(abcdls_handle_t h, const double* xs, const double* rhs, const 
     }
     size_t smem = ((size_t)2 * (M + P + 2) * kNormPitch + (size_t)kNormWarps * 32 * kBA * kBB) * sizeof(double);
     cudaStream_t st = (cudaStream_t)stream;
-    if (smem > 48 * 1024)
+    static size_t smem_set = 48 * 1024;   // raise the opt-in limit only when a call needs more than any before
+    if (smem > smem_set) {
         ABCDLS_CUDA(h, cudaFuncSetAttribute(k_normal_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
     k_normal_partial<<<grid, kNormThreads, smem, st>>>(xs, rhs, w, (const long long*)n_acc, cap, d, P, with_gram,
                                                        reinterpret_cast<double*>(ws));
     ABCDLS_LAUNCH_CHECK(h);

@@ -120,6 +120,10 @@ class AbcEngine:
         self.fast_misses = 0  # how often a sampled bracket missed and the next path of the ladder reran the call
         self.path_calls = {"fused": 0, "two_pass": 0, "exact": 0}   # front-half path taken, per call
         self.host_enqueue_ms = []   # per abc() call: host time spent enqueueing before the one blocking read
+        self.use_graphs = True      # replay the device work of a repeated call as one CUDA graph
+        self.copy_results = True    # results of a replayed graph are copied out of the graph's buffers
+        self.max_graphs = 4
+        self._graphs, self._seen = {}, {}
         if hasattr(stages, "timer"):
             stages.timer = self._t
 
@@ -187,24 +191,33 @@ class AbcEngine:
     FAST_MIN_ROWS = 1 << 20   # below this the 6-pass radix select is launch-bound anyway
     use_fused = True          # one-pass front half (csrc/fused.cuh) when the table qualifies
 
-    def _front(self, target, ss, tol, status, keep_dist=False, exact=False, two_pass=False):
-        """MAD scaling -> distance -> exact threshold ds -> R's cap rule.  Returns the accepted rows (ascending
-        global row numbers, their distances) of this rank.
-
-        Fast path (single rank, big tables): sampled brackets, ONE table read for all medians/MADs and ONE for
-        the distances (csrc/bracket.cu); every bracket is verified on the device and a miss raises
-        S_FASTPATH_MISS, upon which abc() reruns with ``exact=True`` (6-pass radix select, always exact)."""
+    def _plan(self, ss, tol, keep_dist=False, level=0):
+        """Host-side decisions for one call (the only place that may need a host collective: shard sizes).
+        level 0: one-pass front half if the table qualifies; 1: two-pass sampled brackets; 2: 6-pass radix select."""
         k = self.k
         d, n_local = ss.shape
-        can_fuse = (self.use_fused and not exact and not two_pass and not keep_dist and hasattr(k, "fused_supported")
+        can_fuse = (self.use_fused and level == 0 and not keep_dist and hasattr(k, "fused_supported")
                     and k.fused_supported(ss, n_local, d, ss.stride(0)))
         n_global, row_offset, ns, all_fuse = self._shard_info(n_local, int(can_fuse))
         nacc = int(math.ceil(n_global * tol))
         if not (1 <= nacc <= n_global):
             raise AbcError("'tol' must give 1 <= ceiling(N * tol) <= N")
-        fast = (not exact) and min(ns) >= self.FAST_MIN_ROWS   # every rank must take the same path
+        fast = level < 2 and min(ns) >= self.FAST_MIN_ROWS   # every rank must take the same path
         fused = fast and all_fuse
-        self.path_calls["fused" if fused else ("two_pass" if fast else "exact")] += 1
+        return dict(n_global=n_global, row_offset=row_offset, nacc=nacc, fast=fast, fused=fused, keep_dist=keep_dist,
+                    path="fused" if fused else ("two_pass" if fast else "exact"))
+
+    def _front(self, target, ss, status, pl):
+        """MAD scaling -> distance -> exact threshold ds -> R's cap rule (device work only).  Returns the accepted rows
+        (ascending global row numbers, their distances) of this rank.
+
+        Paths (csrc/fused.cuh, csrc/bracket.cu, csrc/select.cu): one-pass front half (ONE table read), two-pass
+        sampled brackets, 6-pass radix select.  The first two verify themselves on the device and raise
+        S_FASTPATH_MISS; abc() then reruns one level down the ladder."""
+        k = self.k
+        d, n_local = ss.shape
+        n_global, row_offset, nacc = pl["n_global"], pl["row_offset"], pl["nacc"]
+        fast, fused, keep_dist = pl["fast"], pl["fused"], pl["keep_dist"]
         cap = min(nacc, n_local)
         idx = k.new(cap, dtype=torch.int64)
         dacc = k.new(cap)
@@ -268,8 +281,8 @@ class AbcEngine:
                 below = allc[: self.comm.rank].sum()
                 quota = (nacc - below).clamp(min=0).view(1)
             k.accept(dist, n_local, None, None, ds, quota, row_offset, cap, idx, dacc, n_acc, ws, status)
-        return dict(n_global=n_global, row_offset=row_offset, nacc=nacc, mad=mad, dist=dist, ds=ds, cap=cap, idx=idx,
-                    n_acc=n_acc, dacc=dacc, fast=fast, fused=fused, cand_ss=cand_ss, slot=slot)
+        return dict(row_offset=row_offset, mad=mad, dist=dist, ds=ds, cap=cap, idx=idx, n_acc=n_acc, dacc=dacc, fast=fast,
+                    fused=fused, cand_ss=cand_ss, slot=slot)
 
     def _zero_variance(self, ss) -> bool:
         """R: stop if every column of sumstat has a single unique value."""
@@ -313,8 +326,108 @@ class AbcEngine:
             par = par.to(self.device)
         if ss.device != self.device:
             ss = ss.to(self.device)
+        pl = self._plan(ss, tol, keep_dist, _level)
+        self.path_calls[pl["path"]] += 1
+
+        # The device work of one call is a fixed sequence of ~90 launches whose shapes depend only on the key below, so
+        # it is captured into a CUDA graph the second time a key is seen and replayed afterwards (one launch per call).
+        o = None
+        key = (ss.data_ptr(), tuple(ss.shape), ss.stride(0), par.data_ptr(), tuple(par.shape), par.stride(0),
+               par.device.type, float(tol), method, bool(hcorr), bool(keep_dist), int(_level), self.comm.world,
+               pl["n_global"], pl["row_offset"])
+        graphable = (self.use_graphs and self.timers is None and self.device.type == "cuda" and not keep_dist)
+        plan = self._graphs.get(key) if graphable else None
+        if plan is not None:
+            plan["target"].copy_(target)
+            plan["graph"].replay()
+            self.k.launches += plan["launches"]
+            self._graphs[key] = self._graphs.pop(key)          # LRU order
+            o = plan["out"]
+        elif graphable and self._seen.get(key, 0) >= 1:
+            plan = self._capture(key, target, ss, par, pl, method, hcorr)
+            o = plan["out"]
+        else:
+            if graphable:
+                if len(self._seen) > 64:
+                    self._seen.clear()
+                self._seen[key] = self._seen.get(key, 0) + 1
+            o = self._abc_device(target, ss, par, pl, method, hcorr)
+        from_graph = plan is not None
+
+        self.host_enqueue_ms.append((time.perf_counter() - _t0) * 1e3)
+        if len(self.host_enqueue_ms) > 64:
+            del self.host_enqueue_ms[:32]
+        host = o["host"].cpu()    # the one blocking read: everything data dependent
+        st, n_loc, ds_h = int(host[0]), int(host[1]), float(host[2])
+        st = self.comm.allreduce_or_int(st)
+        warnings: List[str] = []
+        if (st & _capi.S_FASTPATH_MISS) and pl["fast"]:
+            # fallback ladder: one-pass -> two-pass sampled brackets -> 6-pass radix select (always exact)
+            self.fast_misses += 1
+            return self.abc(target, param, sumstat, tol, method, hcorr, kernel, keep_dist,
+                            _level=1 if pl["fused"] else 2)
+        if st & _capi.S_NONFINITE:
+            raise AbcError("non-finite values in 'sumstat'/'target' (R's NA-row handling is not implemented)")
+        if host[4] != 0 and self._zero_variance(ss):
+            raise AbcError("Zero variance in the summary statistics.")
+        if host[3] != 0:
+            msg = "Zero variance in the summary statistics in the selected region."
+            if method != "rejection":
+                raise AbcError(msg + " Try: checking summary statistics, choosing larger tolerance, or rejection method.")
+            warnings.append(msg + " Check summary statistics, consider larger tolerance.")
+        if st & _capi.S_SINGULAR:
+            raise AbcError("lsfit: X matrix deemed to be singular (collinear summary statistics in the accepted region)")
+        if st & _capi.S_CAPACITY:
+            raise AbcError("internal: accepted-row buffer overflow")
+
+        # results of a replayed graph live in the graph's buffers (overwritten by the next call with the same key)
+        own = (lambda t: t.clone()) if (from_graph and self.copy_results) else (lambda t: t)
+        mad, nacc = own(o["mad"]), pl["nacc"]
+        r = AbcResult(method=method, tol=tol, nacc=nacc, n_global=pl["n_global"], ds=ds_h, mad=mad,
+                      idx=own(o["idx"][:n_loc]), unadj_values=own(o["y"][:, :n_loc]).t(),
+                      ss=own(o["ss_out"][:, :n_loc]).t(),
+                      weights=(own(o["w"][:n_loc]) if method != "rejection"
+                               else torch.ones(n_loc, dtype=torch.float64, device=self.device)),
+                      dist_accepted=own(o["dacc"][:n_loc]), stats=own(o["stats"]), warnings=warnings, numparam=P,
+                      numstat=d, dist=o["dist"] if keep_dist else None)
+        if method == "loclinear":
+            tsc = torch.where(mad == 0, target, target / torch.where(mad == 0, torch.ones_like(mad), mad))
+            r.adj_values, r.residuals = own(o["adj"][:, :n_loc]).t(), own(o["res"][:, :n_loc]).t()
+            r.pred = o["beta"][0] + o["the_m"]
+            r.sigma2 = own(o["sig"])
+            r.coef = self._uncentre(o["beta"], tsc)
+            if hcorr:
+                r.coef_h = self._uncentre(o["gamma"], tsc)
+            ls = float(host[5])
+            r.aic = nacc * ls + 2 * (d + 1) * P
+            r.bic = nacc * ls + math.log(nacc) * (d + 1) * P
+        return r
+
+    def _capture(self, key, target, ss, par, pl, method, hcorr):
+        """Capture the device work of this call into a CUDA graph (torch allocates its temporaries and outputs from a
+        pool owned by the graph).  The tables are NOT referenced by the plan: the key pins their addresses."""
+        while len(self._graphs) >= self.max_graphs:
+            self._graphs.pop(next(iter(self._graphs)))
+        tgt = target.clone()
+        g = torch.cuda.CUDAGraph()
+        l0 = self.k.launches
+        torch.cuda.synchronize(self.device)
+        with torch.cuda.graph(g):
+            out = self._abc_device(tgt, ss, par, pl, method, hcorr)
+        plan = dict(graph=g, out=out, target=tgt, launches=self.k.launches - l0,
+                    keep=list(getattr(self.k, "_ws", {}).values()))   # workspaces must outlive the graph
+        self._graphs[key] = plan
+        g.replay()
+        return plan
+
+    def _abc_device(self, target, ss, par, pl, method, hcorr):
+        """All device work of abc() — no host synchronisation — ending in the packed `host` vector
+        [status, n_acc, ds, region_const, all_mad_zero, sum log sigma2]."""
+        k = self.k
+        d, n_local = ss.shape
+        P = par.shape[0]
         status = torch.zeros(1, dtype=torch.int32, device=self.device)
-        f = self._front(target, ss, tol, status, keep_dist=keep_dist, exact=_level >= 2, two_pass=_level >= 1)
+        f = self._front(target, ss, status, pl)
         cap, idx, n_acc, ds, mad, dacc = f["cap"], f["idx"], f["n_acc"], f["ds"], f["mad"], f["dacc"]
 
         xs, y, ss_out = k.new(d, cap), k.new(P, cap), k.new(d, cap)
@@ -336,6 +449,7 @@ class AbcEngine:
         all_mad_zero = (mad == 0).all()
 
         beta = gamma = the_m = res = adj = sig = None
+        logsig = torch.zeros(1, dtype=torch.float64, device=self.device)
         stats = k.new(P, 6)
         _tl = self._t("loclinear")
         _tl.__enter__()
@@ -360,6 +474,7 @@ class AbcEngine:
             sg = torch.cat([rs[:, 4], rs[:1, 5]])
             self.comm.allreduce_sum(sg)
             sig = sg[:P] / sg[P]
+            logsig = torch.log(sig).sum().view(1)
             if hcorr:
                 part2 = k.new(M * P)
                 k.normal(xs, logres2, w, n_acc, cap, d, P, False, part2)
@@ -378,54 +493,10 @@ class AbcEngine:
             self.comm.allreduce_max(mx)
             self.comm.allreduce_sum(sm)
             stats = torch.cat([mn[:, None], mx[:, None], sm], dim=1)
-
-        # one host read for everything data dependent
         host = torch.cat([status.to(torch.float64), n_acc.to(torch.float64), ds,
-                          region_const.to(torch.float64).view(1), all_mad_zero.to(torch.float64).view(1)])
-        self.host_enqueue_ms.append((time.perf_counter() - _t0) * 1e3)
-        if len(self.host_enqueue_ms) > 64:
-            del self.host_enqueue_ms[:32]
-        host = host.cpu()
-        st, n_loc, ds_h = int(host[0]), int(host[1]), float(host[2])
-        st = self.comm.allreduce_or_int(st)
-        warnings: List[str] = []
-        if (st & _capi.S_FASTPATH_MISS) and f["fast"]:
-            # fallback ladder: one-pass -> two-pass sampled brackets -> 6-pass radix select (always exact)
-            self.fast_misses += 1
-            return self.abc(target, param, sumstat, tol, method, hcorr, kernel, keep_dist,
-                            _level=1 if f["fused"] else 2)
-        if st & _capi.S_NONFINITE:
-            raise AbcError("non-finite values in 'sumstat'/'target' (R's NA-row handling is not implemented)")
-        if host[4] != 0 and self._zero_variance(ss):
-            raise AbcError("Zero variance in the summary statistics.")
-        if host[3] != 0:
-            msg = "Zero variance in the summary statistics in the selected region."
-            if method != "rejection":
-                raise AbcError(msg + " Try: checking summary statistics, choosing larger tolerance, or rejection method.")
-            warnings.append(msg + " Check summary statistics, consider larger tolerance.")
-        if st & _capi.S_SINGULAR:
-            raise AbcError("lsfit: X matrix deemed to be singular (collinear summary statistics in the accepted region)")
-        if st & _capi.S_CAPACITY:
-            raise AbcError("internal: accepted-row buffer overflow")
-
-        r = AbcResult(method=method, tol=tol, nacc=f["nacc"], n_global=f["n_global"], ds=ds_h, mad=mad,
-                      idx=idx[:n_loc], unadj_values=y.t()[:n_loc], ss=ss_out.t()[:n_loc],
-                      weights=(w[:n_loc] if method != "rejection" else torch.ones(n_loc, dtype=torch.float64,
-                                                                                 device=self.device)),
-                      dist_accepted=dacc[:n_loc], stats=stats, warnings=warnings, numparam=P, numstat=d,
-                      dist=f["dist"] if keep_dist else None)
-        if method == "loclinear":
-            tsc = torch.where(mad == 0, target, target / torch.where(mad == 0, torch.ones_like(mad), mad))
-            r.adj_values, r.residuals = adj.t()[:n_loc], res.t()[:n_loc]
-            r.pred = beta[0] + the_m
-            r.sigma2 = sig
-            r.coef = self._uncentre(beta, tsc)
-            if hcorr:
-                r.coef_h = self._uncentre(gamma, tsc)
-            ls = torch.log(sig).sum().item()
-            r.aic = f["nacc"] * ls + 2 * (d + 1) * P
-            r.bic = f["nacc"] * ls + math.log(f["nacc"]) * (d + 1) * P
-        return r
+                          region_const.to(torch.float64).view(1), all_mad_zero.to(torch.float64).view(1), logsig])
+        return dict(host=host, mad=mad, idx=idx, y=y, ss_out=ss_out, w=w, dacc=dacc, stats=stats, dist=f["dist"],
+                    adj=adj, res=res, beta=beta, gamma=gamma, the_m=the_m, sig=sig)
 
     @staticmethod
     def _uncentre(b: torch.Tensor, t_scaled: torch.Tensor) -> torch.Tensor:
@@ -460,7 +531,10 @@ class AbcEngine:
             raise AbcError("'index' must be the same length as the number of rows in 'sumstat'.")
         model_id = model_id.to(device=self.device, dtype=torch.int32).contiguous()
         status = torch.zeros(1, dtype=torch.int32, device=self.device)
-        f = self._front(target, ss, tol, status, keep_dist=keep_dist, exact=_level >= 2, two_pass=_level >= 1)
+        pl = self._plan(ss, tol, keep_dist, _level)
+        self.path_calls[pl["path"]] += 1
+        f = self._front(target, ss, status, pl)
+        f.update(n_global=pl["n_global"], nacc=pl["nacc"], row_offset=pl["row_offset"])
         cap, idx, n_acc = f["cap"], f["idx"], f["n_acc"]
         counts = torch.zeros(K, dtype=torch.int64, device=self.device)
         k.postpr_counts(model_id, idx, n_acc, f["row_offset"], cap, K, counts)

@@ -188,10 +188,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(args.warmup, 3)):   # call 1 runs eagerly, call 2 captures the CUDA graph, call 3+ replay it
         step()
     sync()
-    eng.timers = {}
     l0 = eng.k.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local_rank, args.clock_interval)
@@ -205,6 +204,11 @@ def main():
     ms = ev0.elapsed_time(ev1)
     host_ms = eng.host_enqueue_ms[-args.steps:]
     launches = eng.k.launches - l0
+    # per-stage / per-kernel durations: the same call enqueued eagerly with CUDA events around every stage
+    eng.timers = {}
+    for _ in range(min(args.steps, 5)):
+        step()
+    sync()
     tms = eng.timer_ms()
     eng.timers = None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -221,7 +225,7 @@ def main():
     peak, peak_src = _peaks()
     kern = {}
     for name, v in tms.items():
-        kern[name] = {"launches": len(v), "avg_ms": sum(v) / len(v), "total_ms_per_step": sum(v) / args.steps}
+        kern[name] = {"launches": len(v), "avg_ms": sum(v) / len(v), "total_ms_per_step": sum(v) / min(args.steps, 5)}
     alg = {"k_fused_pass": 8.0 * d * n_local,        # THE one read of the N x d table (medians, MADs and the cut)
            "k_bracket_pass": 8.0 * d * n_local,      # one read of the N x d table (all medians + MADs)
            "k_dist_pass": 8.0 * d * n_local,         # one read of the table; dist is not materialised
@@ -293,7 +297,8 @@ def main():
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "roofline": roofline,
                 "cpu_baseline": base, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
                 "nacc": res.nacc, "ds": res.ds, "fast_path_misses": eng.fast_misses,
-                "host_enqueue_ms": round(sum(host_ms) / max(1, len(host_ms)), 3)}
+                "host_enqueue_ms": round(sum(host_ms) / max(1, len(host_ms)), 3),
+                "cuda_graph": bool(eng._graphs), "front_half": dict(eng.path_calls)}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

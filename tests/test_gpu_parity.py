@@ -268,3 +268,26 @@ def test_fused_postpr(engine):
     np.testing.assert_array_equal(_np(r.idx), o.idx)
     np.testing.assert_array_equal(_np(r.counts), o.counts)
     assert r.ds == o.ds
+
+
+def test_cuda_graph_replay_matches_eager_and_tracks_the_target(engine):
+    """Call 1 runs eagerly, call 2 captures the device work into a CUDA graph, later calls replay it.  The replayed
+    results must equal the eager ones bit for bit, follow a changed target (copied into the graph's buffer), and stay
+    valid after the next call (results are copied out of the graph's buffers)."""
+    par, ss, tgt = synth.abc_tables((1 << 20) + 64, 6, 5, engine.device)
+    engine._graphs.clear(); engine._seen.clear()
+    r1 = engine.abc(tgt, par, ss, 0.01, "loclinear")
+    r2 = engine.abc(tgt, par, ss, 0.01, "loclinear")
+    assert len(engine._graphs) == 1
+    r3 = engine.abc(tgt, par, ss, 0.01, "loclinear")
+    for r in (r2, r3):
+        assert torch.equal(r.idx, r1.idx) and torch.equal(r.adj_values, r1.adj_values) and r.ds == r1.ds
+        assert torch.equal(r.stats, r1.stats) and r.aic == r1.aic
+    keep = r3.adj_values.clone()
+    tgt2 = tgt * 1.01
+    r4 = engine.abc(tgt2, par, ss, 0.01, "loclinear")                 # same key, new target values: replay
+    assert torch.equal(r3.adj_values, keep)                           # earlier results were not overwritten
+    o = O.abc(_np(tgt2), _np(par).T, _np(ss).T, 0.01, "loclinear")
+    np.testing.assert_array_equal(_np(r4.idx), o.idx)
+    assert r4.ds == o.ds and _rel(_np(r4.adj_values), o.adj_values) < REL_TOL
+    assert abs(r4.aic - o.aic) <= 1e-9 * abs(o.aic)
