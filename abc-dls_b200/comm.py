@@ -22,11 +22,20 @@ class Comm:
         else:
             self.world, self.rank = 1, 0
         self.calls = 0
+        # set by the engine while it records a call as CUDA-graph segments: collectives are not captured, they end the
+        # current segment, run eagerly (and are replayed eagerly) between two graph launches
+        self.recorder = None
+
+    def _do(self, fn):
+        self.calls += 1
+        if self.recorder is not None:
+            self.recorder.split(fn)
+        else:
+            fn()
 
     def _red(self, t: torch.Tensor, op):
         if self.world > 1:
-            dist.all_reduce(t, op=op, group=self.group)
-            self.calls += 1
+            self._do(lambda: dist.all_reduce(t, op=op, group=self.group))
         return t
 
     def allreduce_sum(self, t):
@@ -43,8 +52,8 @@ class Comm:
         if self.world == 1:
             return t[None]
         out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(out.view(-1), t.contiguous().view(-1), group=self.group)
-        self.calls += 1
+        src = t.contiguous().view(-1)
+        self._do(lambda: dist.all_gather_into_tensor(out.view(-1), src, group=self.group))
         return out
 
     def allgather_ints(self, vals: List[int]) -> List[List[int]]:

@@ -19,6 +19,7 @@ min/max), with the arithmetic of CRAN abc 2.2.1.
 from __future__ import annotations
 
 import math
+import os
 import time
 from dataclasses import dataclass, field
 from typing import List, Optional
@@ -101,6 +102,43 @@ def _as_table(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+class _SegmentedGraph:
+    """The device work of one call as CUDA-graph segments.  Kernels, memsets and torch ops are captured; every
+    collective ends the running segment, runs eagerly and is replayed eagerly between two graph launches (NCCL is
+    never captured).  A single-rank call is one segment = one graph launch.  All segments allocate from one pool."""
+
+    def __init__(self, device):
+        self.device = device
+        self.stream = torch.cuda.Stream(device)
+        self.pool = torch.cuda.graph_pool_handle()
+        self.items = []
+        self.cur = None
+
+    def begin(self):
+        g = torch.cuda.CUDAGraph()
+        # thread_local: other threads (NCCL watchdog, NVML sampler) may keep calling the CUDA API while we capture
+        g.capture_begin(pool=self.pool, capture_error_mode="thread_local")
+        self.cur = g
+
+    def end(self):
+        self.cur.capture_end()
+        self.items.append(self.cur)
+        self.cur = None
+
+    def split(self, fn):
+        self.end()
+        fn()
+        self.items.append(fn)
+        self.begin()
+
+    def replay(self):
+        for it in self.items:
+            if isinstance(it, torch.cuda.CUDAGraph):
+                it.replay()
+            else:
+                it()
+
+
 class AbcEngine:
     """Drop-in compute engine for abc()/postpr() on device tables.  See ``rabc.py`` for the facade that
     keeps rpy2's call surface."""
@@ -123,6 +161,8 @@ class AbcEngine:
         self.use_graphs = True      # replay the device work of a repeated call as one CUDA graph
         self.copy_results = True    # results of a replayed graph are copied out of the graph's buffers
         self.max_graphs = 4
+        if os.environ.get("ABCDLS_NO_GRAPH", "0") == "1":
+            self.use_graphs = False
         self._graphs, self._seen = {}, {}
         if hasattr(stages, "timer"):
             stages.timer = self._t
@@ -191,14 +231,26 @@ class AbcEngine:
     FAST_MIN_ROWS = 1 << 20   # below this the 6-pass radix select is launch-bound anyway
     use_fused = True          # one-pass front half (csrc/fused.cuh) when the table qualifies
 
-    def _plan(self, ss, tol, keep_dist=False, level=0):
+    def _plan(self, ss, tol, keep_dist=False, level=0, shard=None):
         """Host-side decisions for one call (the only place that may need a host collective: shard sizes).
-        level 0: one-pass front half if the table qualifies; 1: two-pass sampled brackets; 2: 6-pass radix select."""
+        level 0: one-pass front half if the table qualifies; 1: two-pass sampled brackets; 2: 6-pass radix select.
+        shard = (n_global, row_offset): the caller vouches for the standard contiguous split (rank r holds rows
+        [r * ceil(N / world), ...)) with the same table layout on every rank, which saves the blocking exchange."""
         k = self.k
         d, n_local = ss.shape
         can_fuse = (self.use_fused and level == 0 and not keep_dist and hasattr(k, "fused_supported")
                     and k.fused_supported(ss, n_local, d, ss.stride(0)))
-        n_global, row_offset, ns, all_fuse = self._shard_info(n_local, int(can_fuse))
+        if shard is not None and self.comm.world > 1:
+            n_global, row_offset = int(shard[0]), int(shard[1])
+            per = -(-n_global // self.comm.world)
+            ns = [max(0, min(per, n_global - r * per)) for r in range(self.comm.world)]
+            if ns[self.comm.rank] != n_local or row_offset != self.comm.rank * per:
+                raise AbcError("shard=(n_global, row_offset) does not describe the standard contiguous split")
+            all_fuse = can_fuse
+            if (self.use_fused and level == 0 and not keep_dist and min(ns) >= 16384 and d <= 16 and not can_fuse):
+                raise AbcError("shard= promises the same 16-byte aligned, even-pitch table layout on every rank")
+        else:
+            n_global, row_offset, ns, all_fuse = self._shard_info(n_local, int(can_fuse))
         nacc = int(math.ceil(n_global * tol))
         if not (1 <= nacc <= n_global):
             raise AbcError("'tol' must give 1 <= ceiling(N * tol) <= N")
@@ -298,7 +350,7 @@ class AbcEngine:
     # ---- abc() ----------------------------------------------------------------------------------
     def abc(self, target: torch.Tensor, param: torch.Tensor, sumstat: torch.Tensor, tol: float, method: str,
             hcorr: bool = True, kernel: str = "epanechnikov", keep_dist: bool = False,
-            _level: int = 0) -> AbcResult:
+            shard=None, _level: int = 0) -> AbcResult:
         """``abc::abc`` for method in {rejection, loclinear} on this rank's shard.
 
         target (d,), param (P, n_local), sumstat (d, n_local): float64 CUDA tensors, column-major tables.
@@ -326,7 +378,7 @@ class AbcEngine:
             par = par.to(self.device)
         if ss.device != self.device:
             ss = ss.to(self.device)
-        pl = self._plan(ss, tol, keep_dist, _level)
+        pl = self._plan(ss, tol, keep_dist, _level, shard)
         self.path_calls[pl["path"]] += 1
 
         # The device work of one call is a fixed sequence of ~90 launches whose shapes depend only on the key below, so
@@ -358,13 +410,12 @@ class AbcEngine:
         if len(self.host_enqueue_ms) > 64:
             del self.host_enqueue_ms[:32]
         host = o["host"].cpu()    # the one blocking read: everything data dependent
-        st, n_loc, ds_h = int(host[0]), int(host[1]), float(host[2])
-        st = self.comm.allreduce_or_int(st)
+        st, n_loc, ds_h = int(host[0]), int(host[1]), float(host[2])    # status is already OR-ed over the ranks
         warnings: List[str] = []
         if (st & _capi.S_FASTPATH_MISS) and pl["fast"]:
             # fallback ladder: one-pass -> two-pass sampled brackets -> 6-pass radix select (always exact)
             self.fast_misses += 1
-            return self.abc(target, param, sumstat, tol, method, hcorr, kernel, keep_dist,
+            return self.abc(target, param, sumstat, tol, method, hcorr, kernel, keep_dist, shard,
                             _level=1 if pl["fused"] else 2)
         if st & _capi.S_NONFINITE:
             raise AbcError("non-finite values in 'sumstat'/'target' (R's NA-row handling is not implemented)")
@@ -404,20 +455,28 @@ class AbcEngine:
         return r
 
     def _capture(self, key, target, ss, par, pl, method, hcorr):
-        """Capture the device work of this call into a CUDA graph (torch allocates its temporaries and outputs from a
-        pool owned by the graph).  The tables are NOT referenced by the plan: the key pins their addresses."""
+        """Record the device work of this call as CUDA-graph segments (torch allocates its temporaries and outputs from
+        a pool owned by the plan).  The tables are NOT referenced by the plan: the key pins their addresses."""
         while len(self._graphs) >= self.max_graphs:
             self._graphs.pop(next(iter(self._graphs)))
         tgt = target.clone()
-        g = torch.cuda.CUDAGraph()
+        sg = _SegmentedGraph(self.device)
         l0 = self.k.launches
         torch.cuda.synchronize(self.device)
-        with torch.cuda.graph(g):
-            out = self._abc_device(tgt, ss, par, pl, method, hcorr)
-        plan = dict(graph=g, out=out, target=tgt, launches=self.k.launches - l0,
-                    keep=list(getattr(self.k, "_ws", {}).values()))   # workspaces must outlive the graph
+        sg.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(sg.stream):
+            sg.begin()
+            self.comm.recorder = sg
+            try:
+                out = self._abc_device(tgt, ss, par, pl, method, hcorr)
+            finally:
+                self.comm.recorder = None
+                sg.end()
+        torch.cuda.current_stream(self.device).wait_stream(sg.stream)
+        plan = dict(graph=sg, out=out, target=tgt, launches=self.k.launches - l0,
+                    keep=list(getattr(self.k, "_ws", {}).values()))   # workspaces must outlive the graphs
         self._graphs[key] = plan
-        g.replay()
+        sg.replay()
         return plan
 
     def _abc_device(self, target, ss, par, pl, method, hcorr):
@@ -493,6 +552,10 @@ class AbcEngine:
             self.comm.allreduce_max(mx)
             self.comm.allreduce_sum(sm)
             stats = torch.cat([mn[:, None], mx[:, None], sm], dim=1)
+        if self.comm.world > 1:   # OR of the status words over the ranks = max of every bit
+            bits = (status.view(1) >> torch.arange(8, device=self.device, dtype=torch.int32)) & 1
+            self.comm.allreduce_max(bits)
+            status = (bits << torch.arange(8, device=self.device, dtype=torch.int32)).sum().to(torch.int32).view(1)
         host = torch.cat([status.to(torch.float64), n_acc.to(torch.float64), ds,
                           region_const.to(torch.float64).view(1), all_mad_zero.to(torch.float64).view(1), logsig])
         return dict(host=host, mad=mad, idx=idx, y=y, ss_out=ss_out, w=w, dacc=dacc, stats=stats, dist=f["dist"],

@@ -181,7 +181,7 @@ def main():
     par, ss, tgt = synth.abc_tables(n_local, d, P, dev, row_start=r0)
 
     def step():
-        return eng.abc(tgt, par, ss, args.tol, args.method)
+        return eng.abc(tgt, par, ss, args.tol, args.method, shard=(N, r0))
 
     def sync():
         if world > 1:
@@ -264,7 +264,7 @@ def main():
             # rows are read by the gather kernel through UVA (counted below as H2D traffic)
             dss = h_ss.to(dev, non_blocking=True)
             dt_ = h_tgt.to(dev, non_blocking=True)
-            r = eng.abc(dt_, h_par, dss, args.tol, args.method)
+            r = eng.abc(dt_, h_par, dss, args.tol, args.method, shard=(N, r0))
             out = (r.adj_values if r.adj_values is not None else r.unadj_values).contiguous().cpu()
             st = r.stats.cpu()
             d2h[0] = out.numel() * 8 + st.numel() * 8
