@@ -72,6 +72,9 @@ SIGNATURES = {
     "abcdls_normal": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "abcdls_solve": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "abcdls_residual": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "abcdls_residual_workspace_bytes": (_sz, [_i32]),
+    "abcdls_residual_stats": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "abcdls_normal_logres": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
     "abcdls_recentre_log": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "abcdls_adjust": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "abcdls_col_stats_workspace_bytes": (_sz, [_i32]),

@@ -124,7 +124,11 @@ __global__ void __launch_bounds__(kNormThreads) k_normal_partial(const double* _
                                                                  const double* __restrict__ w,
                                                                  const long long* __restrict__ n_acc_ptr,
                                                                  long long cap, int d, int P, int with_gram,
+                                                                 const double* __restrict__ the_m,
+                                                                 double* __restrict__ res_io,
                                                                  double* __restrict__ partials) {
+    // the_m != NULL ("hcorr" fit): rhs = res_io holds the raw residuals; they are centred in place (res -= the_m)
+    // and the staged right-hand side becomes log(res^2) - R's fit2 without a log(res^2) round trip through HBM
     extern __shared__ __align__(16) double smn[];
     const int M = d + 1, W = M + P;
     const int b0 = with_gram ? 0 : M;                  // first output column
@@ -193,6 +197,24 @@ __global__ void __launch_bounds__(kNormThreads) k_normal_partial(const double* _
             cp_async_commit();
             cp_async_wait<1>();
             __syncthreads();
+            if (the_m) {
+                double* Tm = buf[cur];
+                const long long r0 = tile * kNormRows;
+                const int nr = (int)min((long long)kNormRows, n_acc - r0);
+                for (int t = threadIdx.x; t < P * kNormRows; t += kNormThreads) {
+                    const int p = t / kNormRows, rr = t % kNormRows;
+                    if (rr < nr) {
+                        double* cell = Tm + (size_t)(M + p) * kNormPitch + rr;
+                        double v = *cell;
+                        if (slot == 0) {               // later slots re-stage residuals that are already centred
+                            v -= the_m[p];
+                            res_io[(size_t)p * cap + r0 + rr] = v;
+                        }
+                        *cell = log(v * v);
+                    }
+                }
+                __syncthreads();
+            }
             const double* __restrict__ T = buf[cur];
             const double* __restrict__ wt = T + (size_t)W * kNormPitch;
 #pragma unroll 2
@@ -233,43 +255,57 @@ __global__ void __launch_bounds__(kNormThreads) k_normal_partial(const double* _
     }
 }
 
-__global__ void k_reduce_partials(const double* __restrict__ partials, int nparts, int E, double* __restrict__ out) {
-    int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= E) return;
+// out[e] = sum over the CTA partials, 8 lanes per entry: lane q adds parts q, q + 8, ... in order, then a fixed
+// shuffle tree combines the 8 sums => deterministic
+__global__ void __launch_bounds__(256) k_reduce_partials(const double* __restrict__ partials, int nparts, int E,
+                                                         double* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int e = t >> 3, q = t & 7;
     double a = 0.0;
-    for (int p = 0; p < nparts; ++p) a += partials[(size_t)p * E + e];  // fixed order: deterministic
-    out[e] = a;
+    if (e < E)
+        for (int p = q; p < nparts; p += 8) a += partials[(size_t)p * E + e];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o, 8);
+    if (e < E && q == 0) out[e] = a;
 }
 
 // Cholesky solve of the (M x M) SPD gram against P right-hand sides. beta[a*P + p].
-__global__ void __launch_bounds__(64) k_solve(const double* __restrict__ gram, const double* __restrict__ rhs, int M,
-                                              int P, double* __restrict__ beta, int* status) {
+// Column c: thread c finishes the diagonal, then the rows below it are updated in parallel (thread r owns row r).
+__global__ void __launch_bounds__(128) k_solve(const double* __restrict__ gram, const double* __restrict__ rhs, int M,
+                                               int P, double* __restrict__ beta, int* status) {
     extern __shared__ double sm[];
     double* L = sm;  // M*M
     __shared__ int bad;
+    __shared__ double dmax_sh;
     for (int t = threadIdx.x; t < M * M; t += blockDim.x) L[t] = gram[t];
     if (threadIdx.x == 0) bad = 0;
     __syncthreads();
     if (threadIdx.x == 0) {
         double dmax = 0.0;
         for (int a = 0; a < M; ++a) dmax = fmax(dmax, fabs(L[a * M + a]));
-        for (int c = 0; c < M; ++c) {
+        dmax_sh = dmax;
+    }
+    __syncthreads();
+    for (int c = 0; c < M; ++c) {
+        if (threadIdx.x == 0) {
             double s = L[c * M + c];
+            const double orig = s;
             for (int k = 0; k < c; ++k) s -= L[c * M + k] * L[c * M + k];
-            if (!(s > 1e-13 * L[c * M + c]) || !(s > 0.0) || !(dmax > 0.0)) {
+            if (!(s > 1e-13 * orig) || !(s > 0.0) || !(dmax_sh > 0.0)) {
                 bad = 1;
                 s = 1.0;
             }
-            double lcc = sqrt(s);
-            L[c * M + c] = lcc;
-            for (int r = c + 1; r < M; ++r) {
-                double t = L[r * M + c];
-                for (int k = 0; k < c; ++k) t -= L[r * M + k] * L[c * M + k];
-                L[r * M + c] = t / lcc;
-            }
+            L[c * M + c] = sqrt(s);
         }
+        __syncthreads();
+        const double lcc = L[c * M + c];
+        for (int r = c + 1 + threadIdx.x; r < M; r += blockDim.x) {
+            double t = L[r * M + c];
+            for (int k = 0; k < c; ++k) t -= L[r * M + k] * L[c * M + k];
+            L[r * M + c] = t / lcc;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     for (int p = threadIdx.x; p < P; p += blockDim.x) {
         double z[kMaxD + 1];
         for (int a = 0; a < M; ++a) {
@@ -317,6 +353,88 @@ __global__ void __launch_bounds__(256) k_residual(const double* __restrict__ xs,
     }
 }
 
+// Same residuals, 8 parameters per thread (blockIdx.y picks the group), fused with the three column sums the next
+// steps need:  stat[0][p] = sum res, stat[1][p] = sum w res, stat[2][p] = sum w res^2   (the_m = stat0 / n;
+// sigma2 = (stat2 - 2 m stat1 + m^2 sum w) / sum w).  Block partials are combined by the last block of each group
+// in block order => deterministic.
+constexpr int kResBlocks = 296;
+__global__ void __launch_bounds__(256) k_residual_stats(const double* __restrict__ xs, const double* __restrict__ y,
+                                                        const double* __restrict__ beta, const double* __restrict__ w,
+                                                        const long long* __restrict__ n_acc_ptr, long long cap, int d,
+                                                        int P, double* __restrict__ res, double* __restrict__ part,
+                                                        unsigned* __restrict__ done, double* __restrict__ stat) {
+    extern __shared__ double sb[];  // (d+1)*8 coefficients of this group | 8 warps x 24 partials
+    double* sred = sb + (d + 1) * 8;
+    __shared__ bool last;
+    const int p0 = blockIdx.y * 8, pe = min(8, P - p0);
+    for (int t = threadIdx.x; t < (d + 1) * 8; t += blockDim.x) {
+        const int j = t / 8, q = t % 8;
+        sb[t] = q < pe ? beta[j * P + p0 + q] : 0.0;
+    }
+    __syncthreads();
+    long long n_acc = *n_acc_ptr;
+    if (n_acc > cap) n_acc = cap;
+    double s0[8], s1[8], s2[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s0[q] = s1[q] = s2[q] = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_acc; r += stride) {
+        double f[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) f[q] = sb[q];
+        for (int j = 0; j < d; ++j) {
+            const double x = xs[(size_t)j * cap + r];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[q] = fma(x, sb[(j + 1) * 8 + q], f[q]);
+        }
+        const double wr = w[r];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (q < pe) {
+                const double v = y[(size_t)(p0 + q) * cap + r] - f[q];
+                res[(size_t)(p0 + q) * cap + r] = v;
+                s0[q] += v;
+                s1[q] = fma(wr, v, s1[q]);
+                s2[q] = fma(wr * v, v, s2[q]);
+            }
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        s0[q] = warp_sum(s0[q]);
+        s1[q] = warp_sum(s1[q]);
+        s2[q] = warp_sum(s2[q]);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            sred[wid * 24 + q] = s0[q];
+            sred[wid * 24 + 8 + q] = s1[q];
+            sred[wid * 24 + 16 + q] = s2[q];
+        }
+    }
+    __syncthreads();
+    // part[(y * gridDim.x + x) * 24 + k*8 + q]
+    if (threadIdx.x < 24) {
+        double a = 0.0;
+        for (int wq = 0; wq < 8; ++wq) a += sred[wq * 24 + threadIdx.x];
+        part[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 24 + threadIdx.x] = a;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(&done[blockIdx.y], 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (last && threadIdx.x < 24) {
+        __threadfence();
+        const int k = threadIdx.x / 8, q = threadIdx.x % 8;
+        double a = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b)
+            a += reinterpret_cast<const volatile double*>(part)[((size_t)blockIdx.y * gridDim.x + b) * 24 + threadIdx.x];
+        if (q < pe) stat[(size_t)k * P + p0 + q] = a;
+        if (threadIdx.x == 0) done[blockIdx.y] = 0u;   // ready for the next call on this workspace
+    }
+}
+
 __global__ void __launch_bounds__(256) k_recentre_log(double* __restrict__ res, const double* __restrict__ the_m,
                                                       const long long* __restrict__ n_acc_ptr, long long cap, int P,
                                                       double* __restrict__ logres2) {
@@ -345,12 +463,24 @@ __global__ void __launch_bounds__(256) k_adjust(const double* __restrict__ xs, d
     if (n_acc > cap) n_acc = cap;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_acc; r += stride) {
+        double xr[16];
+        const bool small = hcorr && d <= 16;     // the row's statistics stay in registers for all P parameters
+        if (small) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) xr[j] = j < d ? xs[(size_t)j * cap + r] : 0.0;
+        }
         for (int p = 0; p < P; ++p) {
             double rv = res[(size_t)p * cap + r];
             if (hcorr) {
                 double g0 = sg[p];
                 double lin = g0;
-                for (int j = 0; j < d; ++j) lin = fma(xs[(size_t)j * cap + r], sg[(j + 1) * P + p], lin);
+                if (small) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (j < d) lin = fma(xr[j], sg[(j + 1) * P + p], lin);
+                } else {
+                    for (int j = 0; j < d; ++j) lin = fma(xs[(size_t)j * cap + r], sg[(j + 1) * P + p], lin);
+                }
                 // pred.sd * res / pred.si = res * sqrt(exp(g0)) / sqrt(exp(lin)) = res * exp((g0 - lin) / 2): one exp
                 rv = rv * exp(0.5 * (g0 - lin));
                 res[(size_t)p * cap + r] = rv;
@@ -516,9 +646,26 @@ size_t abcdls_normal_workspace_bytes(int d, int P) {
     return align_up((size_t)148 * 2 * 2 * E * sizeof(double), 256);  // up to 592 partial blocks
 }
 
+static int normal_impl(abcdls_handle_t h, const double* xs, const double* rhs, const double* w, const int64_t* n_acc,
+                       int64_t cap, int d, int P, int with_gram, const double* the_m, double* partial, void* ws,
+                       size_t ws_bytes, void* stream);
+
 int abcdls_normal(abcdls_handle_t h, const double* xs, const double* rhs, const double* w, const int64_t* n_acc,
                   int64_t cap, int d, int P, int with_gram, double* partial, void* ws, size_t ws_bytes,
                   void* stream) {
+    return normal_impl(h, xs, rhs, w, n_acc, cap, d, P, with_gram, nullptr, partial, ws, ws_bytes, stream);
+}
+
+int abcdls_normal_logres(abcdls_handle_t h, const double* xs, double* res, const double* the_m, const double* w,
+                         const int64_t* n_acc, int64_t cap, int d, int P, double* partial, void* ws, size_t ws_bytes,
+                         void* stream) {
+    ABCDLS_CHECK_ARG(h, the_m, "normal_logres: null pointer");
+    return normal_impl(h, xs, res, w, n_acc, cap, d, P, 0, the_m, partial, ws, ws_bytes, stream);
+}
+
+static int normal_impl(abcdls_handle_t h, const double* xs, const double* rhs, const double* w, const int64_t* n_acc,
+                       int64_t cap, int d, int P, int with_gram, const double* the_m, double* partial, void* ws,
+                       size_t ws_bytes, void* stream) {
     ABCDLS_CHECK_ARG(h, h && xs && rhs && w && n_acc && partial && ws, "normal: null pointer");
     ABCDLS_CHECK_ARG(h, d >= 1 && d <= kMaxD && P >= 1 && P <= kMaxP && cap >= 1, "normal: shape");
     const int M = d + 1;
@@ -535,10 +682,11 @@ int abcdls_normal(abcdls_handle_t h, const double* xs, const double* rhs, const 
         ABCDLS_CUDA(h, cudaFuncSetAttribute(k_normal_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
-    k_normal_partial<<<grid, kNormThreads, smem, st>>>(xs, rhs, w, (const long long*)n_acc, cap, d, P, with_gram,
+    k_normal_partial<<<grid, kNormThreads, smem, st>>>(xs, rhs, w, (const long long*)n_acc, cap, d, P, with_gram, the_m,
+                                                       the_m ? const_cast<double*>(rhs) : nullptr,
                                                        reinterpret_cast<double*>(ws));
     ABCDLS_LAUNCH_CHECK(h);
-    k_reduce_partials<<<(E + 127) / 128, 128, 0, st>>>(reinterpret_cast<const double*>(ws), grid, E, partial);
+    k_reduce_partials<<<(E * 8 + 255) / 256, 256, 0, st>>>(reinterpret_cast<const double*>(ws), grid, E, partial);
     ABCDLS_LAUNCH_CHECK(h);
     return ABCDLS_OK;
 }
@@ -548,7 +696,7 @@ int abcdls_solve(abcdls_handle_t h, const double* gram, const double* rhs, int d
     ABCDLS_CHECK_ARG(h, h && gram && rhs && beta && status_dev, "solve: null pointer");
     ABCDLS_CHECK_ARG(h, d >= 1 && d <= kMaxD && P >= 1 && P <= kMaxP, "solve: shape");
     const int M = d + 1;
-    k_solve<<<1, 64, (size_t)M * M * sizeof(double), (cudaStream_t)stream>>>(gram, rhs, M, P, beta, status_dev);
+    k_solve<<<1, 128, (size_t)M * M * sizeof(double), (cudaStream_t)stream>>>(gram, rhs, M, P, beta, status_dev);
     ABCDLS_LAUNCH_CHECK(h);
     return ABCDLS_OK;
 }
@@ -559,6 +707,35 @@ int abcdls_residual(abcdls_handle_t h, const double* xs, const double* y, const 
     ABCDLS_CHECK_ARG(h, d >= 1 && d <= kMaxD && P >= 1 && P <= kMaxP && cap >= 1, "residual: shape");
     k_residual<<<grid_for(h, cap, 256, 8), 256, (size_t)(d + 1) * P * sizeof(double), (cudaStream_t)stream>>>(
         xs, y, beta, (const long long*)n_acc, cap, d, P, res);
+    ABCDLS_LAUNCH_CHECK(h);
+    return ABCDLS_OK;
+}
+
+size_t abcdls_residual_workspace_bytes(int P) {
+    const int groups = (P + 7) / 8;
+    return align_up((size_t)groups * kResBlocks * 24 * sizeof(double), 256) + align_up((size_t)groups * 4, 256);
+}
+
+// ws must be zero-initialised once by the caller (the kernel leaves its counters zeroed again).
+// stat: [3][P] = {sum res, sum w res, sum w res^2} over the first n_acc rows
+int abcdls_residual_stats(abcdls_handle_t h, const double* xs, const double* y, const double* beta, const double* w,
+                          const int64_t* n_acc, int64_t cap, int d, int P, double* res, double* stat, void* ws,
+                          size_t ws_bytes, void* stream) {
+    ABCDLS_CHECK_ARG(h, h && xs && y && beta && w && n_acc && res && stat && ws, "residual_stats: null pointer");
+    ABCDLS_CHECK_ARG(h, d >= 1 && d <= kMaxD && P >= 1 && P <= kMaxP && cap >= 1, "residual_stats: shape");
+    if (ws_bytes < abcdls_residual_workspace_bytes(P)) {
+        h->err = "residual workspace too small";
+        return ABCDLS_E_WORKSPACE;
+    }
+    const int groups = (P + 7) / 8;
+    double* part = reinterpret_cast<double*>(ws);
+    unsigned* done = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) +
+                                                 align_up((size_t)groups * kResBlocks * 24 * sizeof(double), 256));
+    unsigned gx = grid_for(h, cap, 256, 2);
+    if (gx > (unsigned)kResBlocks) gx = kResBlocks;
+    const size_t smem = (size_t)((d + 1) * 8 + 8 * 24) * sizeof(double);
+    k_residual_stats<<<dim3(gx, groups), 256, smem, (cudaStream_t)stream>>>(xs, y, beta, w, (const long long*)n_acc, cap,
+                                                                          d, P, res, part, done, stat);
     ABCDLS_LAUNCH_CHECK(h);
     return ABCDLS_OK;
 }

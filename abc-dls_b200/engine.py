@@ -521,25 +521,22 @@ class AbcEngine:
             beta = k.new(M, P)
             k.solve(gram, rhs, d, P, beta, status)
             res = k.new(P, cap)
-            k.residual(xs, y, beta, n_acc, cap, d, P, res)
-            rs = k.new(P, 6)
-            k.col_stats(res, None, n_acc, cap, P, rs)
-            sums = torch.cat([rs[:, 2], n_acc.to(torch.float64)])
+            rstat = k.new(3, P)      # sum res | sum w res | sum w res^2
+            k.residual_stats(xs, y, beta, w, n_acc, cap, d, P, res, rstat)
+            sums = torch.cat([rstat.view(-1), n_acc.to(torch.float64)])
             self.comm.allreduce_sum(sums)
-            the_m = (sums[:P] / sums[P]).contiguous()
-            logres2 = k.new(P, cap) if hcorr else None
-            k.recentre_log(res, the_m, n_acc, cap, P, logres2)
-            k.col_stats(res, w, n_acc, cap, P, rs)
-            sg = torch.cat([rs[:, 4], rs[:1, 5]])
-            self.comm.allreduce_sum(sg)
-            sig = sg[:P] / sg[P]
+            the_m = (sums[:P] / sums[3 * P]).contiguous()          # UNWEIGHTED mean of the residuals (R: colMeans)
+            sw = gram[0]                                           # sum of the weights (already reduced over ranks)
+            sig = (sums[2 * P:3 * P] - 2.0 * the_m * sums[P:2 * P] + the_m * the_m * sw) / sw
             logsig = torch.log(sig).sum().view(1)
             if hcorr:
                 part2 = k.new(M * P)
-                k.normal(xs, logres2, w, n_acc, cap, d, P, False, part2)
+                k.normal_logres(xs, res, the_m, w, n_acc, cap, d, P, part2)   # centres res in place
                 self.comm.allreduce_sum(part2)
                 gamma = k.new(M, P)
                 k.solve(gram, part2, d, P, gamma, status)
+            else:
+                k.recentre_log(res, the_m, n_acc, cap, P, None)
             adj = k.new(P, cap)
             k.adjust(xs, res, beta, the_m, gamma, n_acc, cap, d, P, hcorr, adj)
             k.col_stats(adj, w, n_acc, cap, P, stats)

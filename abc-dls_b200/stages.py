@@ -245,6 +245,21 @@ class CudaStages:
         self.handle.call("abcdls_residual", _p(xs), _p(y), _p(beta), _p(n_acc), cap, d, P, _p(res), self._stream())
         self.launches += 1
 
+    def residual_stats(self, xs, y, beta, w, n_acc, cap, d, P, res, stat):
+        key = f"resid{P}"
+        if key not in self._ws:
+            self.workspace(key, self.lib.abcdls_residual_workspace_bytes(P)).zero_()
+        ws = self._ws[key]
+        self.handle.call("abcdls_residual_stats", _p(xs), _p(y), _p(beta), _p(w), _p(n_acc), cap, d, P, _p(res),
+                         _p(stat), _p(ws), ws.numel(), self._stream())
+        self.launches += 1
+
+    def normal_logres(self, xs, res, the_m, w, n_acc, cap, d, P, partial):
+        ws = self.workspace("normal", self.lib.abcdls_normal_workspace_bytes(d, P))
+        self.handle.call("abcdls_normal_logres", _p(xs), _p(res), _p(the_m), _p(w), _p(n_acc), cap, d, P, _p(partial),
+                         _p(ws), ws.numel(), self._stream())
+        self.launches += 2
+
     def recentre_log(self, res, the_m, n_acc, cap, P, logres2):
         self.handle.call("abcdls_recentre_log", _p(res), _p(the_m), _p(n_acc), cap, P, _p(logres2), self._stream())
         self.launches += 1

@@ -231,6 +231,17 @@ int abcdls_solve(abcdls_handle_t h, const double* gram, const double* rhs, int d
                  int* status_dev, void* stream);
 int abcdls_residual(abcdls_handle_t h, const double* xs, const double* y, const double* beta,
                     const int64_t* n_acc, int64_t cap, int d, int P, double* res, void* stream);
+/* residual fused with the column sums of the next steps: stat[3][P] = {sum res, sum w res, sum w res^2}
+ * (the_m = stat[0] / n; sigma2 = (stat[2] - 2 m stat[1] + m^2 sum w) / sum w).  ws: zero it once. */
+size_t abcdls_residual_workspace_bytes(int P);
+int abcdls_residual_stats(abcdls_handle_t h, const double* xs, const double* y, const double* beta, const double* w,
+                          const int64_t* n_acc, int64_t cap, int d, int P, double* res, double* stat, void* ws,
+                          size_t ws_bytes, void* stream);
+/* the hcorr fit in one step: res (raw residuals) is centred in place (res -= the_m) and
+ * partial[M*P] = X'W log(res^2), without materialising log(res^2) */
+int abcdls_normal_logres(abcdls_handle_t h, const double* xs, double* res, const double* the_m, const double* w,
+                         const int64_t* n_acc, int64_t cap, int d, int P, double* partial, void* ws, size_t ws_bytes,
+                         void* stream);
 int abcdls_recentre_log(abcdls_handle_t h, double* res, const double* the_m, const int64_t* n_acc,
                         int64_t cap, int P, double* logres2 /* may be NULL */, void* stream);
 int abcdls_adjust(abcdls_handle_t h, const double* xs, double* res, const double* beta,

@@ -149,6 +149,17 @@ class CpuStages:
         X = np.column_stack([np.ones(n)] + [xs[j, :n].numpy() for j in range(d)])
         res[:, :n] = torch.from_numpy((y[:, :n].numpy().T - X @ beta.numpy()).T.copy())
 
+    def residual_stats(self, xs, y, beta, w, n_acc, cap, d, P, res, stat):
+        self.residual(xs, y, beta, n_acc, cap, d, P, res)
+        n = int(n_acc)
+        r, ww = res[:, :n], w[:n]
+        stat[0], stat[1], stat[2] = r.sum(dim=1), (r * ww).sum(dim=1), (r * r * ww).sum(dim=1)
+
+    def normal_logres(self, xs, res, the_m, w, n_acc, cap, d, P, partial):
+        n = int(n_acc)
+        res[:, :n] -= the_m[:, None]
+        self.normal(xs, torch.log(res ** 2), w, n_acc, cap, d, P, False, partial)
+
     def recentre_log(self, res, the_m, n_acc, cap, P, logres2):
         n = int(n_acc)
         res[:, :n] -= the_m[:, None]
