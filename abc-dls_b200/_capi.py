@@ -39,7 +39,7 @@ SIGNATURES = {
     "abcdls_accept_workspace_bytes": (_sz, [_i64]),
     "abcdls_count_le": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "abcdls_accept": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
-    "abcdls_gather_cand": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp,
+    "abcdls_gather_cand": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp,
                                   _vp, _vp, _vp, _vp, _vp]),
     "abcdls_fused_supported": (_i32, [_vp, _i64, _i32, _i64]),
     "abcdls_fused_workspace_bytes": (_sz, [_i64, _i32]),
@@ -47,11 +47,13 @@ SIGNATURES = {
                                         _vp]),
     "abcdls_fused_sample_dist": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _i64, _i64, _i32, _vp, _sz, C.POINTER(_vp),
                                         C.POINTER(_sz), _vp]),
-    "abcdls_fused_pass": (_i32, [_vp, _vp, _i64, _i32, _i64, _i32, _vp, _sz, _vp, C.POINTER(_vp), C.POINTER(_sz), _vp]),
+    "abcdls_fused_emit_cap": (_i64, [_i64]),
+    "abcdls_fused_pass": (_i32, [_vp, _vp, _i64, _i32, _i64, _i32, _vp, _vp, _i64, _vp, _sz, _vp, C.POINTER(_vp),
+                                 C.POINTER(_sz), _vp]),
     "abcdls_fused_refine": (_i32, [_vp, _vp, _i64, _i64, _i32, _i64, _i32, _i32, _vp, _vp, _vp, _sz, _vp, _vp, _vp,
                                    C.POINTER(_vp), C.POINTER(_sz), C.POINTER(_vp), C.POINTER(_sz), _vp]),
-    "abcdls_fused_candidates": (_i32, [_vp, _vp, _i64, _i32, _i64, _i32, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp,
-                                       _sz, _vp, _vp]),
+    "abcdls_fused_candidates": (_i32, [_vp, _vp, _i64, _i32, _i64, _i32, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64,
+                                       _vp, _vp, _vp, _sz, _vp, _vp]),
     "abcdls_fused_check": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp, _vp]),
     "abcdls_gather": (_i32, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp,
                              _vp, _vp, _vp, _vp, _vp]),

@@ -63,6 +63,7 @@ constexpr int kFThreads = kFConsumers + 32;
 constexpr int kFMaxStages = 8;
 constexpr int kFRingBytes = 160 * 1024;
 constexpr int kFChunk = 256;
+constexpr int kFEChunk = 64;     // candidate-row slots a warp allocates at a time
 constexpr int kFHeader = 1024;   // bytes in front of the ring
 constexpr int kFQCap = 16;       // per-lane queue slots (both bands share it; flushed when a lane holds more than 8)
 constexpr int kFQWarpBytes = kFQCap * 256;                // per consumer warp
@@ -174,7 +175,9 @@ __global__ void __launch_bounds__(kFThreads, 1)
 k_fused_pass(const __grid_constant__ CUtensorMap tmap, long long n, long long ntiles, int d, int nstages,
              const ColBrk* __restrict__ brk, const FusedPar* __restrict__ par, unsigned long long* __restrict__ counts,
              double* __restrict__ candM, long long capM, double* __restrict__ candU, long long capU,
-             unsigned long long* __restrict__ cnt, unsigned short* __restrict__ mask16, long long tpc, int* status) {
+             unsigned long long* __restrict__ cnt, unsigned short* __restrict__ mask16, double* __restrict__ cand_e,
+             long long ecap, int* __restrict__ erow, unsigned long long* __restrict__ ealloc, long long tpc,
+             int* status) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FusedSmem& sm = *reinterpret_cast<FusedSmem*>(smem_raw);
     double* ring = reinterpret_cast<double*>(smem_raw + kFHeader);
@@ -231,6 +234,8 @@ k_fused_pass(const __grid_constant__ CUtensorMap tmap, long long n, long long nt
     unsigned long long* cntM = &cnt[jc * 2 + 0];
     unsigned long long* cntU = &cnt[jc * 2 + 1];
     unsigned c_neg = 0, c_in = 0;                // per lane: x < c, |x - c| < r1
+    unsigned eoff = 0;                           // candidate-row emission: next free slot of this warp's 64-slot chunk
+    int eroom = 0;
     bool bad = false;
     const int row = (wid << 4) | (lane & 15);    // row of the tile this lane helps with
     const int half = lane >> 4;                  // 0: even columns, 1: odd columns
@@ -345,11 +350,44 @@ k_fused_pass(const __grid_constant__ CUtensorMap tmap, long long n, long long nt
         q += __shfl_xor_sync(0xffffffffu, q, 16);
         bad |= !(q < inf) && (tile != tail_tile || row < tail_rows);
         const unsigned bal = __ballot_sync(0xffffffffu, q <= thr);
-        if (lane == 0) {
-            *mptr = (unsigned short)(bal & 0xffffu);
-            mbar_arrive(&sm.empty[st]);   // every lane's shared loads completed before the shuffle / ballot
-        }
+        const unsigned m16 = bal & 0xffffu;
+        if (lane == 0) *mptr = (unsigned short)m16;
         mptr += kFWarps;
+        if (m16) {
+            // candidate rows leave the SM right here (statistics + row number, to a slot of this warp's chunk), so
+            // that their exact distance later needs no second, scattered read of the table
+            const int k = __popc(m16);
+            eroom -= k;
+            if (eroom < 0) {
+                unsigned nb = 0;
+                if (lane == 0) nb = (unsigned)atomicAdd(ealloc, (unsigned long long)kFEChunk);
+                eoff = __shfl_sync(0xffffffffu, nb, 0);
+                eroom = kFEChunk - k;
+            }
+            const int r16 = lane & 15;
+            if ((m16 >> r16) & 1u) {
+                const unsigned slot = eoff + __popc(m16 & ((1u << r16) - 1u));
+                if ((long long)slot < ecap) {
+                    // row-major block: 128 bytes per candidate; this lane writes columns [8 half, 8 half + 8)
+                    if (half == 0) erow[slot] = (int)(tile * kFRows + row);
+                    double* dst = cand_e + (size_t)slot * kFMaxD + 8 * half;
+                    const double* src = stage + (size_t)(8 * half) * kFRows + row;
+#pragma unroll
+                    for (int q2 = 0; q2 < 4; ++q2) {
+                        const int c0 = 8 * half + 2 * q2;
+                        if (c0 < d) {
+                            double2 v;
+                            v.x = src[(2 * q2) * kFRows];
+                            v.y = (c0 + 1 < d) ? src[(2 * q2 + 1) * kFRows] : 0.0;
+                            *reinterpret_cast<double2*>(dst + 2 * q2) = v;
+                        }
+                    }
+                }
+            }
+            eoff += k;
+            __syncwarp();
+        }
+        if (lane == 0) mbar_arrive(&sm.empty[st]);   // every lane is done with the stage
         if (++st == nstages) { st = 0; ph ^= 1u; }
     }
     if (has_col) {
@@ -421,6 +459,7 @@ __global__ void __launch_bounds__(256) k_mask_count(const unsigned* __restrict__
 __global__ void __launch_bounds__(256) k_mask_write(const unsigned* __restrict__ bitmap, long long nwords,
                                                     const long long* __restrict__ tile_off, long long row_offset,
                                                     long long cap, long long* __restrict__ rows_out,
+                                                    int* __restrict__ wprefix,
                                                     const unsigned long long* __restrict__ total,
                                                     long long* __restrict__ n_out, int* status) {
     __shared__ int sh[33];
@@ -438,6 +477,7 @@ __global__ void __launch_bounds__(256) k_mask_write(const unsigned* __restrict__
 #pragma unroll
     for (int t = 0; t < kMWords; ++t) {
         unsigned m = wv[t];
+        if (base + t < nwords) wprefix[base + t] = (int)pos;   // candidates before the first row of this word
         while (m) {
             const int b = __ffs(m) - 1;
             m &= m - 1;
@@ -452,45 +492,46 @@ __global__ void __launch_bounds__(256) k_mask_write(const unsigned* __restrict__
     }
 }
 
-// R's exact distance of the candidate rows (same arithmetic as k_dist_pass) + their raw statistics, compacted
-__global__ void __launch_bounds__(256) k_cand_exact(const double* __restrict__ ss, int d, long long ld,
+// R's exact distance of the emitted candidate rows (same arithmetic as k_dist_pass).  One thread per slot: coalesced
+// reads of the compact row-major block (16 doubles per slot); the position of the row in the ascending candidate list comes from the bitmap
+// (prefix of its word + bits below it), where the distance and the slot number are scattered to.
+__global__ void __launch_bounds__(256) k_cand_exact(const double* __restrict__ cand_e, long long ecap,
+                                                    const int* __restrict__ erow,
+                                                    const unsigned long long* __restrict__ ealloc, int d,
                                                     const double* __restrict__ mad, const double* __restrict__ target,
-                                                    const long long* __restrict__ cand_row,
-                                                    const long long* __restrict__ n_cand, long long row_offset,
+                                                    const unsigned* __restrict__ bitmap, const int* __restrict__ wprefix,
                                                     long long cap, double* __restrict__ cand_dist,
-                                                    double* __restrict__ cand_ss, int* status) {
+                                                    long long* __restrict__ perm, int* status) {
     __shared__ ColScale S;
     load_scale(S, mad, target, d);
     __syncthreads();
-    long long nc = *n_cand;
-    if (nc > cap) nc = cap;
+    long long ns = (long long)*ealloc;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && ns > ecap) atomicOr(status, ABCDLS_S_FASTPATH_MISS);   // rows were lost
+    if (ns > ecap) ns = ecap;
     bool nonfinite = false;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += stride) {
-        const long long r = cand_row[i] - row_offset;
-        const double* p = ss + r;
+    for (long long sl = (long long)blockIdx.x * blockDim.x + threadIdx.x; sl < ns; sl += stride) {
+        const int r = erow[sl];
+        if (r < 0) continue;   // unused tail of a chunk
         double s0 = 0.0;
-        int jj = 0;
-        for (; jj + 4 <= d; jj += 4) {
-            double x[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) x[q] = ld_stream(p + (size_t)(jj + q) * ld);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (cand_ss) cand_ss[(size_t)(jj + q) * cap + i] = x[q];
-                const double a = __dsub_rn(scaled_value(x[q], S.dr[jj + q]), S.tgt[jj + q]);
-                s0 = __dadd_rn(s0, __dmul_rn(a, a));
-            }
-        }
-        for (; jj < d; ++jj) {
-            const double x = ld_stream(p + (size_t)jj * ld);
-            if (cand_ss) cand_ss[(size_t)jj * cap + i] = x;
-            const double a = __dsub_rn(scaled_value(x, S.dr[jj]), S.tgt[jj]);
+        const double* __restrict__ rowp = cand_e + (size_t)sl * kFMaxD;
+        for (int j = 0; j < d; j += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(rowp + j);
+            const double a = __dsub_rn(scaled_value(v.x, S.dr[j]), S.tgt[j]);
             s0 = __dadd_rn(s0, __dmul_rn(a, a));
+            if (j + 1 < d) {
+                const double b = __dsub_rn(scaled_value(v.y, S.dr[j + 1]), S.tgt[j + 1]);
+                s0 = __dadd_rn(s0, __dmul_rn(b, b));
+            }
         }
         const double dd = __dsqrt_rn(s0);
         nonfinite |= !isfinite(dd);
-        cand_dist[i] = dd;
+        const int word = r >> 5;
+        const long long pos = (long long)wprefix[word] + __popc(bitmap[word] & ((1u << (r & 31)) - 1u));
+        if (pos < cap) {
+            cand_dist[pos] = dd;
+            perm[pos] = sl;
+        }
     }
     if (__any_sync(0xffffffffu, nonfinite) && (threadIdx.x & 31) == 0) atomicOr(status, ABCDLS_S_NONFINITE);
 }
@@ -520,6 +561,8 @@ struct FusedWs {
     unsigned short* mask16;        // [ntiles * 16]
     int* tile_cnt;
     long long* tile_off;
+    int* wprefix;                  // [nwords] candidates before every 32-row word
+    unsigned long long* ealloc;    // emission slots handed out
     size_t total_bytes;
 };
 
@@ -545,6 +588,8 @@ inline FusedWs carve_fused(void* ws, int64_t n, int d) {
     w.mask16 = (unsigned short*)take((size_t)ntiles * kFWarps * 2 + 64);
     w.tile_cnt = (int*)take((size_t)nblk * 4);
     w.tile_off = (long long*)take((size_t)nblk * 8);
+    w.wprefix = (int*)take((size_t)nwords * 4);
+    w.ealloc = (unsigned long long*)take(8);
     w.total_bytes = o;
     return w;
 }
@@ -583,6 +628,7 @@ int abcdls_fused_sample_cols(abcdls_handle_t h, const double* ss, int64_t n, int
     ABCDLS_ONCE(h, cudaFuncSetAttribute(k_sample_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ABCDLS_CUDA(h, cudaMemsetAsync(w.m.cnt, 0, w.m.zero_bytes, st));
     ABCDLS_CUDA(h, cudaMemsetAsync(w.total, 0, 8, st));
+    ABCDLS_CUDA(h, cudaMemsetAsync(w.ealloc, 0, 8, st));
     k_sample_cols<<<dim3(G, d), 512, smem, st>>>(ss, n, ld, 0x5EEDu, delta, w.m.est);
     ABCDLS_LAUNCH_CHECK(h);
     if (est_out) *est_out = w.m.est;
@@ -609,10 +655,14 @@ int abcdls_fused_sample_dist(abcdls_handle_t h, const double* ss, int64_t n, int
 }
 
 // Stage 3: THE table pass.  counts_out: int64 block (counts | band counts | median histogram) to all-reduce (sum).
-int abcdls_fused_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, void* ws,
-                      size_t ws_bytes, int* status_dev, int64_t** counts_out, size_t* counts_count, void* stream) {
+int64_t abcdls_fused_emit_cap(int64_t cap) { return cap + (int64_t)160 * kFWarps * kFEChunk; }
+
+int abcdls_fused_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, double* cand_ss,
+                      int32_t* cand_lrow, int64_t ecap, void* ws, size_t ws_bytes, int* status_dev, int64_t** counts_out,
+                      size_t* counts_count, void* stream) {
     FUSED_PROLOGUE("fused_pass");
-    ABCDLS_CHECK_ARG(h, status_dev, "fused_pass: status");
+    ABCDLS_CHECK_ARG(h, status_dev && cand_ss && cand_lrow && ecap >= 1 && ecap < (1ll << 31), "fused_pass: args");
+    ABCDLS_CUDA(h, cudaMemsetAsync(cand_lrow, 0xff, (size_t)ecap * 4, st));   // -1 = unused slot
     k_make_fused_thr<<<1, 32, 0, st>>>(w.est2, kFG2, 1.0 / world, d, w.par);
     const int nstages = fused_stages(d);
     const size_t smem = kFHeader + (size_t)nstages * d * kFRows * 8 + kFQBytes;
@@ -642,8 +692,8 @@ int abcdls_fused_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int
         }
     }
     k_fused_pass<<<(unsigned)grid, kFThreads, smem, st>>>(tmap, n, ntiles, d, nstages, w.m.brk, w.par, w.m.counts,
-                                                         w.m.candM, w.capM, w.m.candU, w.capU, w.m.cnt, w.mask16, tpc,
-                                                         status_dev);
+                                                         w.m.candM, w.capM, w.m.candU, w.capU, w.m.cnt, w.mask16, cand_ss,
+                                                         ecap, cand_lrow, w.ealloc, tpc, status_dev);
     ABCDLS_LAUNCH_CHECK(h);
     {
         long long gx = (w.capM + 256 * 8 - 1) / (256 * 8);
@@ -670,14 +720,17 @@ int abcdls_fused_refine(abcdls_handle_t h, const double* ss, int64_t n, int64_t 
                        status_dev, x0, x0_count, x1, x1_count, st);
 }
 
-// Stage 5: marked rows -> ascending global candidate rows, R's exact distance for each, their raw statistics
-// (cand_ss: column-major, leading dimension cap; may be NULL).  n_cand: device int64.
+// Stage 5: marked rows -> ascending global candidate rows (cand_row), R's exact distance of each from the block the
+// pass emitted (cand_ss / cand_lrow / ecap as given to the pass), perm[i] = slot of candidate i in that block.
+// n_cand: device int64.
 int abcdls_fused_candidates(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world,
                             const double* mad, const double* target, int64_t row_offset, int64_t cap, int64_t* cand_row,
-                            double* cand_dist, double* cand_ss, int64_t* n_cand, void* ws, size_t ws_bytes,
-                            int* status_dev, void* stream) {
+                            double* cand_dist, const double* cand_ss, const int32_t* cand_lrow, int64_t ecap,
+                            int64_t* perm, int64_t* n_cand, void* ws, size_t ws_bytes, int* status_dev, void* stream) {
     FUSED_PROLOGUE("fused_candidates");
-    ABCDLS_CHECK_ARG(h, mad && target && cand_row && cand_dist && n_cand && status_dev && cap >= 1, "fused_candidates");
+    ABCDLS_CHECK_ARG(h, mad && target && cand_row && cand_dist && cand_ss && cand_lrow && perm && n_cand && status_dev &&
+                            cap >= 1 && ecap >= 1,
+                     "fused_candidates");
     const long long ntiles = (n + kFRows - 1) / kFRows;
     const long long nwords = ntiles * (kFRows / 32);
     const long long nblk = (nwords + 256 * kMWords - 1) / (256 * kMWords);
@@ -685,12 +738,12 @@ int abcdls_fused_candidates(abcdls_handle_t h, const double* ss, int64_t n, int 
     k_mask_count<<<(unsigned)nblk, 256, 0, st>>>(bitmap, nwords, w.tile_cnt, w.total);
     k_scan_tiles<<<1, 1024, 0, st>>>(w.tile_cnt, nblk, w.tile_off);
     k_mask_write<<<(unsigned)nblk, 256, 0, st>>>(bitmap, nwords, w.tile_off, row_offset, cap, (long long*)cand_row,
-                                                 w.total, (long long*)n_cand, status_dev);
+                                                 w.wprefix, w.total, (long long*)n_cand, status_dev);
     ABCDLS_LAUNCH_CHECK(h);
-    long long g = (cap + 255) / 256;
+    long long g = (ecap + 255) / 256;
     if (g > (long long)h->sm_count * 16) g = (long long)h->sm_count * 16;
-    k_cand_exact<<<(unsigned)g, 256, 0, st>>>(ss, d, ld, mad, target, (const long long*)cand_row,
-                                              (const long long*)n_cand, row_offset, cap, cand_dist, cand_ss, status_dev);
+    k_cand_exact<<<(unsigned)g, 256, 0, st>>>(cand_ss, ecap, cand_lrow, w.ealloc, d, mad, target, bitmap, w.wprefix, cap,
+                                              cand_dist, (long long*)perm, status_dev);
     ABCDLS_LAUNCH_CHECK(h);
     return ABCDLS_OK;
 }

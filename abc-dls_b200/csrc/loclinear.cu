@@ -55,10 +55,13 @@ __global__ void __launch_bounds__(256) k_gather(const double* __restrict__ ss, l
     }
 }
 
-// same outputs, one thread per (accepted row, column): blockIdx.y < d -> statistic column (from the compact
-// candidate block through slot[]), else parameter column (from the table, possibly pinned host memory, through idx[]).
-__global__ void __launch_bounds__(256) k_gather_cand(const double* __restrict__ cand_ss, long long ld_cand,
+// same outputs from the block of candidate rows the one-pass kernel emitted (row-major, `pitch` doubles per slot,
+// reached through perm[slot[r]]) and the parameter table (possibly pinned host memory) through idx[r].
+// blockIdx.y == 0: one thread per accepted row copies / scales its d statistics and computes its weight;
+// blockIdx.y == 1 + p: one thread per accepted row gathers parameter p (P independent scattered loads in flight).
+__global__ void __launch_bounds__(256) k_gather_cand(const double* __restrict__ cand_e, long long pitch,
                                                      const long long* __restrict__ slot,
+                                                     const long long* __restrict__ perm,
                                                      const double* __restrict__ param, long long ld_param,
                                                      const double* __restrict__ dist_acc,
                                                      const long long* __restrict__ idx,
@@ -68,31 +71,34 @@ __global__ void __launch_bounds__(256) k_gather_cand(const double* __restrict__ 
                                                      const double* __restrict__ ds_ptr, double* __restrict__ xs,
                                                      double* __restrict__ y, double* __restrict__ ss_out,
                                                      double* __restrict__ w) {
+    __shared__ double sdiv[kMaxD], stgt[kMaxD];
     long long n_acc = *n_acc_ptr;
     if (n_acc > cap) n_acc = cap;
-    const int col = blockIdx.y;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long r0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (col < d) {
-        const double m = mad[col];
-        const double dv = (m == 0.0) ? 1.0 : m;
-        const double tj = (m == 0.0) ? target[col] : target[col] / dv;
-        const double* __restrict__ src = cand_ss + (size_t)col * ld_cand;
-        for (long long r = r0; r < n_acc; r += stride) {
-            const double x = src[slot[r]];
-            ss_out[(size_t)col * cap + r] = x;
-            const double sc = (dv == 1.0) ? x : x / dv;   // IEEE division == R's x/mad
-            xs[(size_t)col * cap + r] = __dsub_rn(sc, tj);
+    if (blockIdx.y == 0) {
+        for (int j = threadIdx.x; j < d; j += blockDim.x) {
+            const double m = mad[j];
+            const double dv = (m == 0.0) ? 1.0 : m;
+            sdiv[j] = dv;
+            stgt[j] = (m == 0.0) ? target[j] : target[j] / dv;
         }
-        if (col == 0) {
-            const double ds = *ds_ptr;
-            for (long long r = r0; r < n_acc; r += stride) {
-                const double q = dist_acc[r] / ds;
-                w[r] = __dsub_rn(1.0, __dmul_rn(q, q));
+        __syncthreads();
+        const double ds = *ds_ptr;
+        for (long long r = r0; r < n_acc; r += stride) {
+            const long long sl = perm ? perm[slot[r]] : slot[r];
+            const double* __restrict__ rowp = cand_e + (size_t)sl * pitch;
+            for (int j = 0; j < d; ++j) {
+                const double x = rowp[j];
+                ss_out[(size_t)j * cap + r] = x;
+                const double sc = (sdiv[j] == 1.0) ? x : x / sdiv[j];   // IEEE division == R's x/mad
+                xs[(size_t)j * cap + r] = __dsub_rn(sc, stgt[j]);
             }
+            const double q = dist_acc[r] / ds;
+            w[r] = __dsub_rn(1.0, __dmul_rn(q, q));
         }
     } else {
-        const int p = col - d;
+        const int p = blockIdx.y - 1;
         const double* __restrict__ src = param + (size_t)p * ld_param - row_offset;
         for (long long r = r0; r < n_acc; r += stride) y[(size_t)p * cap + r] = src[idx[r]];
     }
@@ -100,7 +106,7 @@ __global__ void __launch_bounds__(256) k_gather_cand(const double* __restrict__ 
 
 // ---- weighted normal equations ------------------------------------------------------------------
 // T_r = [1, xs_r (d), rhs_r (P)] (width W = M + P);  C[a][b] = sum_r w_r * T_r[a] * T_r[b] for a < M, b < W.
-// The operands are column-major (k-major), so tiles of 64 rows are staged AS THEY ARE ([column][row], odd pitch:
+// The operands are column-major (k-major), so tiles of 128 rows are staged AS THEY ARE ([column][row], odd pitch:
 // conflict-free stores) with 8-byte cp.async copies into a double buffer; nothing is transposed.  Every warp walks
 // its own rows of the tile; lane (ablk, bblk) owns the 6 x 4 outputs {a = ablk + nA*i} x {b = bblk + nB*j} in
 // registers.  The interleaved index sets make the lanes of one shared load hit consecutive columns (distinct banks)
@@ -108,7 +114,7 @@ __global__ void __launch_bounds__(256) k_gather_cand(const double* __restrict__ 
 // Warps, then CTAs, are summed in a fixed order: deterministic for a given (n_acc, cap).
 constexpr int kNormThreads = 256;
 constexpr int kNormWarps = kNormThreads / 32;
-constexpr int kNormRows = 64;            // rows per staged tile
+constexpr int kNormRows = 128;           // rows per staged tile
 constexpr int kNormPitch = kNormRows + 1;
 constexpr int kBA = 6, kBB = 4;
 
@@ -139,7 +145,7 @@ __global__ void __launch_bounds__(kNormThreads) k_normal_partial(const double* _
     // tile columns: 0 = ones, 1..d = xs, M..W-1 = rhs, W = weights, W + 1 = zeros (padding target)
     const int ncols = W + 2;
     double* buf[2] = {smn, smn + (size_t)ncols * kNormPitch};
-    double* red = smn + (size_t)2 * ncols * kNormPitch;    // [kNormWarps][32][24]
+    double* red = smn;   // [kNormWarps][32][24], aliases the tile buffers (used only between the tile loops)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     long long n_acc = *n_acc_ptr;
     if (n_acc > cap) n_acc = cap;
@@ -149,11 +155,6 @@ __global__ void __launch_bounds__(kNormThreads) k_normal_partial(const double* _
     const int E = (with_gram ? M * M : 0) + M * P;
     double* out = partials + (size_t)blockIdx.x * E;
     for (int e = threadIdx.x; e < E; e += kNormThreads) out[e] = 0.0;
-    for (int t = threadIdx.x; t < 2 * kNormPitch; t += kNormThreads) {   // constant columns of both buffers
-        const int bsel = t / kNormPitch, rr = t % kNormPitch;
-        buf[bsel][rr] = 1.0;
-        buf[bsel][(size_t)(W + 1) * kNormPitch + rr] = 0.0;
-    }
 
     auto stage = [&](long long tile, double* T) {
         const long long r0 = tile * kNormRows;
@@ -189,6 +190,11 @@ __global__ void __launch_bounds__(kNormThreads) k_normal_partial(const double* _
             for (int j = 0; j < kBB; ++j) acc[i][j] = 0.0;
 
         __syncthreads();
+        for (int t = threadIdx.x; t < 2 * kNormPitch; t += kNormThreads) {   // constant columns of both buffers
+            const int bsel = t / kNormPitch, rr = t % kNormPitch;
+            buf[bsel][rr] = 1.0;
+            buf[bsel][(size_t)(W + 1) * kNormPitch + rr] = 0.0;
+        }
         if (t_begin < t_end) stage(t_begin, buf[0]);
         cp_async_commit();
         for (long long tile = t_begin; tile < t_end; ++tile) {
@@ -233,6 +239,7 @@ __global__ void __launch_bounds__(kNormThreads) k_normal_partial(const double* _
             __syncthreads();   // everyone is done with buf[cur] before it is refilled
         }
         cp_async_wait<0>();
+        __syncthreads();
         // warps -> CTA partial in warp order
         double* mine = red + ((size_t)wid * 32 + lane) * (kBA * kBB);
 #pragma unroll
@@ -357,7 +364,7 @@ __global__ void __launch_bounds__(256) k_residual(const double* __restrict__ xs,
 // steps need:  stat[0][p] = sum res, stat[1][p] = sum w res, stat[2][p] = sum w res^2   (the_m = stat0 / n;
 // sigma2 = (stat2 - 2 m stat1 + m^2 sum w) / sum w).  Block partials are combined by the last block of each group
 // in block order => deterministic.
-constexpr int kResBlocks = 296;
+constexpr int kResBlocks = 592;
 __global__ void __launch_bounds__(256) k_residual_stats(const double* __restrict__ xs, const double* __restrict__ y,
                                                         const double* __restrict__ beta, const double* __restrict__ w,
                                                         const long long* __restrict__ n_acc_ptr, long long cap, int d,
@@ -382,6 +389,7 @@ __global__ void __launch_bounds__(256) k_residual_stats(const double* __restrict
         double f[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) f[q] = sb[q];
+#pragma unroll 8
         for (int j = 0; j < d; ++j) {
             const double x = xs[(size_t)j * cap + r];
 #pragma unroll
@@ -424,13 +432,23 @@ __global__ void __launch_bounds__(256) k_residual_stats(const double* __restrict
     __syncthreads();
     if (threadIdx.x == 0) last = (atomicAdd(&done[blockIdx.y], 1u) == gridDim.x - 1);
     __syncthreads();
-    if (last && threadIdx.x < 24) {
+    if (last) {
+        // 10 threads per output sum the block partials b = g, g + 10, ... in order; the 10 sums are added in order
         __threadfence();
-        const int k = threadIdx.x / 8, q = threadIdx.x % 8;
+        const int o = threadIdx.x % 24, g = threadIdx.x / 24;   // g = 0..9 (threads 240..255 idle)
         double a = 0.0;
-        for (unsigned b = 0; b < gridDim.x; ++b)
-            a += reinterpret_cast<const volatile double*>(part)[((size_t)blockIdx.y * gridDim.x + b) * 24 + threadIdx.x];
-        if (q < pe) stat[(size_t)k * P + p0 + q] = a;
+        if (g < 10)
+            for (unsigned b = g; b < gridDim.x; b += 10)
+                a += reinterpret_cast<const volatile double*>(part)[((size_t)blockIdx.y * gridDim.x + b) * 24 + o];
+        __syncthreads();
+        if (g < 10) sred[g * 24 + o] = a;
+        __syncthreads();
+        if (threadIdx.x < 24) {
+            double t = 0.0;
+            for (int gg = 0; gg < 10; ++gg) t += sred[gg * 24 + threadIdx.x];
+            const int k = threadIdx.x / 8, q = threadIdx.x % 8;
+            if (q < pe) stat[(size_t)k * P + p0 + q] = t;
+        }
         if (threadIdx.x == 0) done[blockIdx.y] = 0u;   // ready for the next call on this workspace
     }
 }
@@ -555,17 +573,32 @@ __global__ void __launch_bounds__(256) k_col_stats(const double* __restrict__ v,
         last = (atomicAdd(&done[c], 1u) == (unsigned)kStatChunks - 1);
     }
     __syncthreads();
-    if (last && threadIdx.x == 0) {
+    if (last) {
+        // thread k < 64 holds chunk k; fixed shuffle tree inside each of the two warps, then warp 0 + warp 1
         __threadfence();
         double r6[6] = {inf, -inf, 0, 0, 0, 0};
-        for (int k = 0; k < kStatChunks; ++k) {
-            const volatile double* p6 = part + ((size_t)c * kStatChunks + k) * 6;
-            r6[0] = fmin(r6[0], p6[0]);
-            r6[1] = fmax(r6[1], p6[1]);
-            for (int q = 2; q < 6; ++q) r6[q] += p6[q];
+        if (threadIdx.x < kStatChunks) {
+            const volatile double* p6 = part + ((size_t)c * kStatChunks + threadIdx.x) * 6;
+            for (int q = 0; q < 6; ++q) r6[q] = p6[q];
         }
-        for (int q = 0; q < 6; ++q) out[(size_t)c * 6 + q] = r6[q];
-        done[c] = 0u;   // ready for the next call on this workspace
+        if (threadIdx.x < 64) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                r6[0] = fmin(r6[0], __shfl_down_sync(0xffffffffu, r6[0], o));
+                r6[1] = fmax(r6[1], __shfl_down_sync(0xffffffffu, r6[1], o));
+#pragma unroll
+                for (int q = 2; q < 6; ++q) r6[q] += __shfl_down_sync(0xffffffffu, r6[q], o);
+            }
+            if ((threadIdx.x & 31) == 0)
+                for (int q = 0; q < 6; ++q) sh[q][threadIdx.x >> 5] = r6[q];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            out[(size_t)c * 6 + 0] = fmin(sh[0][0], sh[0][1]);
+            out[(size_t)c * 6 + 1] = fmax(sh[1][0], sh[1][1]);
+            for (int q = 2; q < 6; ++q) out[(size_t)c * 6 + q] = sh[q][0] + sh[q][1];
+            done[c] = 0u;   // ready for the next call on this workspace
+        }
     }
 }
 
@@ -623,7 +656,7 @@ int abcdls_gather(abcdls_handle_t h, const double* ss, int64_t ld_ss, const doub
 }
 
 int abcdls_gather_cand(abcdls_handle_t h, const double* cand_ss, int64_t ld_cand, const int64_t* slot,
-                       const double* param, int64_t ld_param, const double* dist_acc, const int64_t* idx,
+                       const int64_t* perm, const double* param, int64_t ld_param, const double* dist_acc, const int64_t* idx,
                        const int64_t* n_acc, int64_t row_offset, int64_t cap, int d, int P, const double* mad,
                        const double* target, const double* ds, double* xs, double* y, double* ss_out, double* w,
                        void* stream) {
@@ -633,8 +666,8 @@ int abcdls_gather_cand(abcdls_handle_t h, const double* cand_ss, int64_t ld_cand
     ABCDLS_CHECK_ARG(h, d >= 1 && d <= kMaxD && P >= 1 && P <= kMaxP && cap >= 1 && ld_cand >= 1, "gather_cand: shape");
     unsigned gx = grid_for(h, cap, 256, 16);
     if (gx > 2048) gx = 2048;
-    k_gather_cand<<<dim3(gx, (unsigned)(d + P)), 256, 0, (cudaStream_t)stream>>>(
-        cand_ss, ld_cand, (const long long*)slot, param, ld_param, dist_acc, (const long long*)idx,
+    k_gather_cand<<<dim3(gx, (unsigned)(1 + P)), 256, 0, (cudaStream_t)stream>>>(
+        cand_ss, ld_cand, (const long long*)slot, (const long long*)perm, param, ld_param, dist_acc, (const long long*)idx,
         (const long long*)n_acc, row_offset, cap, d, mad, target, ds, xs, y, ss_out, w);
     ABCDLS_LAUNCH_CHECK(h);
     return ABCDLS_OK;
@@ -675,7 +708,9 @@ static int normal_impl(abcdls_handle_t h, const double* xs, const double* rhs, c
         h->err = "normal workspace too small";
         return ABCDLS_E_WORKSPACE;
     }
-    size_t smem = ((size_t)2 * (M + P + 2) * kNormPitch + (size_t)kNormWarps * 32 * kBA * kBB) * sizeof(double);
+    size_t smem = (size_t)2 * (M + P + 2) * kNormPitch;
+    if (smem < (size_t)kNormWarps * 32 * kBA * kBB) smem = (size_t)kNormWarps * 32 * kBA * kBB;
+    smem *= sizeof(double);
     cudaStream_t st = (cudaStream_t)stream;
     static size_t smem_set = 48 * 1024;   // raise the opt-in limit only when a call needs more than any before
     if (smem > smem_set) {
@@ -731,9 +766,9 @@ int abcdls_residual_stats(abcdls_handle_t h, const double* xs, const double* y, 
     double* part = reinterpret_cast<double*>(ws);
     unsigned* done = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) +
                                                  align_up((size_t)groups * kResBlocks * 24 * sizeof(double), 256));
-    unsigned gx = grid_for(h, cap, 256, 2);
+    unsigned gx = grid_for(h, cap, 256, 4);
     if (gx > (unsigned)kResBlocks) gx = kResBlocks;
-    const size_t smem = (size_t)((d + 1) * 8 + 8 * 24) * sizeof(double);
+    const size_t smem = (size_t)((d + 1) * 8 + 10 * 24) * sizeof(double);
     k_residual_stats<<<dim3(gx, groups), 256, smem, (cudaStream_t)stream>>>(xs, y, beta, w, (const long long*)n_acc, cap,
                                                                           d, P, res, part, done, stat);
     ABCDLS_LAUNCH_CHECK(h);

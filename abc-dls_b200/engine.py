@@ -277,19 +277,22 @@ class AbcEngine:
         le = torch.zeros(1, dtype=torch.int64, device=self.device)
         quota = torch.full((1,), nacc, dtype=torch.int64, device=self.device)
         comm = self.comm if self.comm.world > 1 else None
-        cand_ss = slot = None
+        cand_ss = slot = perm = None
         if fused:
             # ONE table read: medians + MADs and the candidate rows of the cut; exact distances only for the candidates
             med, mad = k.new(d), k.new(d)
             ccap = min(n_local, 2 * nacc + 65536)
             dist = None
             cand_row, cand_dist = k.new(ccap, dtype=torch.int64), k.new(ccap)
-            cand_ss = k.new(d, ccap)
+            ecap = k.fused_emit_cap(ccap)                     # the pass emits candidate rows in 64-slot chunks per warp
+            cand_ss = k.new(ecap, 16)                         # row-major: 16 doubles per emitted row
+            cand_lrow = k.new(ecap, dtype=torch.int32)
+            perm = k.new(ccap, dtype=torch.int64)
             slot = k.new(cap, dtype=torch.int64)
             n_cand = torch.zeros(1, dtype=torch.int64, device=self.device)
             with self._t("fused_front"):
                 k.fused_front(ss, n_local, n_global, d, ss.stride(0), target, nacc, row_offset, ccap, med, mad, cand_row,
-                              cand_dist, cand_ss, n_cand, status, comm)
+                              cand_dist, cand_ss, cand_lrow, perm, n_cand, status, comm)
             with self._t("fused_ds"):
                 ds = self._select(cand_dist[None, :], ccap, None, nacc - 1, nacc - 1, counts=n_cand)[0, :1].contiguous()
                 k.fused_check(n_local, d, mad, ds, status)
@@ -334,7 +337,7 @@ class AbcEngine:
                 quota = (nacc - below).clamp(min=0).view(1)
             k.accept(dist, n_local, None, None, ds, quota, row_offset, cap, idx, dacc, n_acc, ws, status)
         return dict(row_offset=row_offset, mad=mad, dist=dist, ds=ds, cap=cap, idx=idx, n_acc=n_acc, dacc=dacc, fast=fast,
-                    fused=fused, cand_ss=cand_ss, slot=slot)
+                    fused=fused, cand_ss=cand_ss, slot=slot, perm=perm)
 
     def _zero_variance(self, ss) -> bool:
         """R: stop if every column of sumstat has a single unique value."""
@@ -493,7 +496,7 @@ class AbcEngine:
         w = k.new(cap)
         with self._t("gather"):
             if f["fused"]:   # the statistics of the accepted rows are already compact (candidate block)
-                k.gather_cand(f["cand_ss"], f["cand_ss"].stride(0), f["slot"], par, par.stride(0), dacc, idx, n_acc,
+                k.gather_cand(f["cand_ss"], f["cand_ss"].stride(0), f["slot"], f["perm"], par, par.stride(0), dacc, idx, n_acc,
                               f["row_offset"], cap, d, P, mad, target, ds, xs, y, ss_out, w)
             else:
                 k.gather(ss, ss.stride(0), par, par.stride(0), dacc, idx, n_acc, f["row_offset"], cap, d, P, mad,

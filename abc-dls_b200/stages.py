@@ -106,8 +106,11 @@ class CudaStages:
     def fused_supported(self, ss, n, d, ld) -> bool:
         return bool(self.lib.abcdls_fused_supported(_p(ss), n, d, ld))
 
+    def fused_emit_cap(self, cap) -> int:
+        return int(self.lib.abcdls_fused_emit_cap(cap))
+
     def fused_front(self, ss, n, n_global, d, ld, target, nacc, row_offset, cap, med, mad, cand_row, cand_dist, cand_ss,
-                    n_cand, status, comm=None):
+                    cand_lrow, perm, n_cand, status, comm=None):
         """Medians + MADs AND the candidate rows of the tolerance cut from ONE read of the table.  Leaves the exact
         distance of every candidate in cand_dist (row order); the caller selects ds among them (all ranks) and then
         calls fused_check."""
@@ -124,8 +127,8 @@ class CudaStages:
         if world > 1:
             comm.allreduce_sum(self._view(ws, p0, c0, torch.float64, 8))
         with self._timed("k_fused_pass"):
-            self.handle.call("abcdls_fused_pass", _p(ss), n, d, ld, world, _p(ws), ws.numel(), _p(status), C.byref(p0),
-                             C.byref(c0), st)
+            self.handle.call("abcdls_fused_pass", _p(ss), n, d, ld, world, _p(cand_ss), _p(cand_lrow), cand_ss.shape[0],
+                             _p(ws), ws.numel(), _p(status), C.byref(p0), C.byref(c0), st)
         if world > 1:
             comm.allreduce_sum(self._view(ws, p0, c0, torch.int64, 8))
         gs = gc = None
@@ -142,7 +145,8 @@ class CudaStages:
                         comm.allreduce_sum(self._view(ws, p0, c0, torch.int64, 8))
         with self._timed("fused_candidates"):
             self.handle.call("abcdls_fused_candidates", _p(ss), n, d, ld, world, _p(mad), _p(target), row_offset, cap,
-                             _p(cand_row), _p(cand_dist), _p(cand_ss), _p(n_cand), _p(ws), ws.numel(), _p(status), st)
+                             _p(cand_row), _p(cand_dist), _p(cand_ss), _p(cand_lrow), cand_ss.shape[0], _p(perm),
+                             _p(n_cand), _p(ws), ws.numel(), _p(status), st)
         self.launches += 24
 
     def fused_check(self, n, d, mad, ds, status):
@@ -150,9 +154,9 @@ class CudaStages:
         self.handle.call("abcdls_fused_check", n, d, _p(mad), _p(ds), _p(ws), ws.numel(), _p(status), self._stream())
         self.launches += 1
 
-    def gather_cand(self, cand_ss, ld_cand, slot, param, ld_param, dist_acc, idx, n_acc, row_offset, cap, d, P, mad,
-                    target, ds, xs, y, ss_out, w):
-        self.handle.call("abcdls_gather_cand", _p(cand_ss), ld_cand, _p(slot), _p(param), ld_param, _p(dist_acc),
+    def gather_cand(self, cand_ss, ld_cand, slot, perm, param, ld_param, dist_acc, idx, n_acc, row_offset, cap, d, P,
+                    mad, target, ds, xs, y, ss_out, w):
+        self.handle.call("abcdls_gather_cand", _p(cand_ss), ld_cand, _p(slot), _p(perm), _p(param), ld_param, _p(dist_acc),
                          _p(idx), _p(n_acc), row_offset, cap, d, P, _p(mad), _p(target), _p(ds), _p(xs), _p(y),
                          _p(ss_out), _p(w), self._stream())
         self.launches += 1

@@ -181,18 +181,23 @@ int abcdls_fused_sample_cols(abcdls_handle_t h, const double* ss, int64_t n, int
 int abcdls_fused_sample_dist(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, const double* target,
                              int64_t nacc, int64_t n_global, int world, void* ws, size_t ws_bytes, double** est_out,
                              size_t* est_count, void* stream);
-int abcdls_fused_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, void* ws,
-                      size_t ws_bytes, int* status_dev, int64_t** counts_out, size_t* counts_count, void* stream);
+/* the pass also EMITS every marked row (its d statistics + local row number) into the caller's block
+ * cand_ss[ecap][16] (row-major) / cand_lrow[ecap] (unordered, 64-slot chunks per warp, -1 = unused slot);
+ * ecap = abcdls_fused_emit_cap(cap of the candidate list) */
+int64_t abcdls_fused_emit_cap(int64_t cap);
+int abcdls_fused_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, double* cand_ss,
+                      int32_t* cand_lrow, int64_t ecap, void* ws, size_t ws_bytes, int* status_dev, int64_t** counts_out,
+                      size_t* counts_count, void* stream);
 int abcdls_fused_refine(abcdls_handle_t h, const double* ss, int64_t n, int64_t n_global, int d, int64_t ld, int phase,
                         int world, const double* gath_small, const int32_t* gath_cnt, void* ws, size_t ws_bytes,
                         double* med, double* mad, int* status_dev, void** x0, size_t* x0_count, void** x1,
                         size_t* x1_count, void* stream);
-/* cand_row: ascending global rows; cand_dist: R's exact distance; cand_ss (may be NULL): raw statistics of the
- * candidates, column-major with leading dimension cap; n_cand: device int64 */
+/* cand_row: ascending global rows; cand_dist: R's exact distance, computed from the emitted block; perm[i] = slot of
+ * candidate i in that block; n_cand: device int64 */
 int abcdls_fused_candidates(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world,
                             const double* mad, const double* target, int64_t row_offset, int64_t cap, int64_t* cand_row,
-                            double* cand_dist, double* cand_ss, int64_t* n_cand, void* ws, size_t ws_bytes,
-                            int* status_dev, void* stream);
+                            double* cand_dist, const double* cand_ss, const int32_t* cand_lrow, int64_t ecap,
+                            int64_t* perm, int64_t* n_cand, void* ws, size_t ws_bytes, int* status_dev, void* stream);
 int abcdls_fused_check(abcdls_handle_t h, int64_t n, int d, const double* mad, const double* ds, void* ws,
                        size_t ws_bytes, int* status_dev, void* stream);
 
@@ -215,11 +220,12 @@ int abcdls_gather(abcdls_handle_t h, const double* ss, int64_t ld_ss, const doub
                   const int64_t* idx, const int64_t* n_acc, int64_t row_offset, int64_t cap, int d, int P,
                   const double* mad, const double* target, const double* ds, double* xs, double* y,
                   double* ss_out, double* w, void* stream);
-/* same outputs; the statistics come from a compact candidate block (abcdls_fused_candidates: cand_ss, leading
- * dimension ld_cand) through slot[r] (abcdls_accept slot_out), the parameters from the table through idx[r].
+/* same outputs; the statistics come from a compact candidate block (cand_ss, leading dimension ld_cand) through
+ * perm[slot[r]] (slot: abcdls_accept slot_out; perm: abcdls_fused_candidates, may be NULL = identity; the block is ROW-major, ld_cand doubles per candidate), the
+ * parameters from the table through idx[r].
  * One thread per (row, column): d + P independent scattered loads in flight per accepted row. */
 int abcdls_gather_cand(abcdls_handle_t h, const double* cand_ss, int64_t ld_cand, const int64_t* slot,
-                       const double* param, int64_t ld_param, const double* dist_acc, const int64_t* idx,
+                       const int64_t* perm, const double* param, int64_t ld_param, const double* dist_acc, const int64_t* idx,
                        const int64_t* n_acc, int64_t row_offset, int64_t cap, int d, int P, const double* mad,
                        const double* target, const double* ds, double* xs, double* y, double* ss_out, double* w,
                        void* stream);
