@@ -242,20 +242,12 @@ k_fused_pass(const __grid_constant__ CUtensorMap tmap, long long n, long long nt
     auto flush = [&]() {
         const int fill = (int)((pq - q0) >> 8);
         const int mx = __reduce_max_sync(0xffffffffu, fill);
-        // my entries, split by band: packed (nM | nU << 16) inclusive scan
-        double v[kFQCap];
+        // my entries, split by band: packed (nM | nU << 16) inclusive scan over the lanes
         int mine = 0;
-        unsigned isM = 0;
-#pragma unroll
-        for (int t = 0; t < kFQCap; ++t) {
-            if (t < mx) {
-                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v[t]) : "r"(q0 + t * 256));
-                if (t < fill) {
-                    const bool m = fabs(__dsub_rn(v[t], c)) <= r0;
-                    isM |= m ? (1u << t) : 0u;
-                    mine += m ? 1 : 0x10000;
-                }
-            }
+        for (int t = 0; t < mx; ++t) {
+            double v;
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(q0 + t * 256));
+            if (t < fill) mine += (fabs(__dsub_rn(v, c)) <= r0) ? 1 : 0x10000;
         }
         int incl = mine;
 #pragma unroll
@@ -273,16 +265,15 @@ k_fused_pass(const __grid_constant__ CUtensorMap tmap, long long n, long long nt
         bU = __shfl_sync(0xffffffffu, bU, 0);
         long long dM = (long long)bM + ((incl - mine) & 0xffff);
         long long dU = (long long)bU + ((incl - mine) >> 16);
-#pragma unroll
-        for (int t = 0; t < kFQCap; ++t) {
-            if (t < fill) {
-                if (isM & (1u << t)) {
-                    if (dM < capM) gM[dM] = v[t];
-                    ++dM;
-                } else {
-                    if (dU < capU) gU[dU] = v[t];
-                    ++dU;
-                }
+        for (int t = 0; t < fill; ++t) {
+            double v;
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(q0 + t * 256));
+            if (fabs(__dsub_rn(v, c)) <= r0) {
+                if (dM < capM) gM[dM] = v;
+                ++dM;
+            } else {
+                if (dU < capU) gU[dU] = v;
+                ++dU;
             }
         }
         pq = q0;
