@@ -86,6 +86,14 @@ SIGNATURES = {
     "abcdls_smc_oldrange": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _sz, _vp]),
     "abcdls_smc_box_filter": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _sz, _vp,
                                      _vp]),
+    "abcdls_peer_handle_bytes": (_sz, []),
+    "abcdls_peer_create": (_i32, [C.POINTER(_vp), _i32, _i32, _sz, _vp]),
+    "abcdls_peer_connect": (_i32, [_vp, _vp]),
+    "abcdls_peer_destroy": (_i32, [_vp]),
+    "abcdls_peer_last_error": (C.c_char_p, [_vp]),
+    "abcdls_peer_slot_bytes": (_sz, [_vp]),
+    "abcdls_peer_allreduce": (_i32, [_vp, _vp, _sz, _i32, _i32, _vp]),
+    "abcdls_peer_allgather": (_i32, [_vp, _vp, _sz, _vp, _vp]),
 }
 
 _lib = None

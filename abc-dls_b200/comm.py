@@ -6,10 +6,14 @@ partial, 2P min/max) so every call is latency bound; callers pack what they can 
 """
 from __future__ import annotations
 
+import ctypes as C
+import os
 from typing import List
 
 import torch
 import torch.distributed as dist
+
+PEER_SLOT_BYTES = 2 << 20   # largest message that goes through the NVLink mailboxes (bigger ones use NCCL)
 
 
 class Comm:
@@ -22,9 +26,44 @@ class Comm:
         else:
             self.world, self.rank = 1, 0
         self.calls = 0
-        # set by the engine while it records a call as CUDA-graph segments: collectives are not captured, they end the
-        # current segment, run eagerly (and are replayed eagerly) between two graph launches
+        # set by the engine while it records a call as CUDA-graph segments: NCCL collectives are not captured, they end
+        # the current segment, run eagerly (and are replayed eagerly) between two graph launches
         self.recorder = None
+        # NVLink peer-memory mailboxes (csrc/peer.cu): every small exchange is ONE kernel, no NCCL, graph capturable
+        self.peer = None
+        self.peer_calls = 0
+        if (self.world > 1 and device is not None and torch.device(device).type == "cuda"
+                and os.environ.get("ABCDLS_NO_PEER", "0") != "1"):
+            self._init_peer()
+
+    def _init_peer(self):
+        from . import _capi
+        lib = _capi.load()
+        hb = lib.abcdls_peer_handle_bytes()
+        handle = (C.c_ubyte * hb)()
+        p = C.c_void_p()
+        ok = lib.abcdls_peer_create(C.byref(p), self.rank, self.world, PEER_SLOT_BYTES, handle) == 0
+        mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=self.device)
+        allh = torch.empty(self.world * hb, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(allh, mine, group=self.group)          # bootstrap only: the IPC handles
+        blob = bytes(allh.cpu().tolist())
+        if ok:
+            ok = lib.abcdls_peer_connect(p, blob) == 0
+        bad = torch.tensor([0 if ok else 1], dtype=torch.int64, device=self.device)
+        dist.all_reduce(bad, group=self.group)                             # every rank uses the mailboxes, or none
+        if int(bad.item()) == 0:
+            self.peer, self._lib = p, lib
+        elif p:
+            lib.abcdls_peer_destroy(p)
+        dist.barrier(group=self.group)
+
+    def close(self):
+        if self.peer is not None:
+            self._lib.abcdls_peer_destroy(self.peer)
+            self.peer = None
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _do(self, fn):
         self.calls += 1
@@ -33,19 +72,28 @@ class Comm:
         else:
             fn()
 
-    def _red(self, t: torch.Tensor, op):
+    def _red(self, t: torch.Tensor, op, opcode):
         if self.world > 1:
-            self._do(lambda: dist.all_reduce(t, op=op, group=self.group))
+            if (self.peer is not None and t.is_cuda and t.is_contiguous() and t.dtype in (torch.float64, torch.int64)
+                    and t.numel() * 8 <= PEER_SLOT_BYTES):
+                rc = self._lib.abcdls_peer_allreduce(self.peer, C.c_void_p(t.data_ptr()), t.numel(),
+                                                     0 if t.dtype == torch.float64 else 1, opcode, self._stream())
+                if rc != 0:
+                    raise RuntimeError("abcdls_peer_allreduce failed")
+                self.calls += 1
+                self.peer_calls += 1
+            else:
+                self._do(lambda: dist.all_reduce(t, op=op, group=self.group))
         return t
 
     def allreduce_sum(self, t):
-        return self._red(t, dist.ReduceOp.SUM)
+        return self._red(t, dist.ReduceOp.SUM, 0)
 
     def allreduce_min(self, t):
-        return self._red(t, dist.ReduceOp.MIN)
+        return self._red(t, dist.ReduceOp.MIN, 1)
 
     def allreduce_max(self, t):
-        return self._red(t, dist.ReduceOp.MAX)
+        return self._red(t, dist.ReduceOp.MAX, 2)
 
     def allgather(self, t: torch.Tensor) -> torch.Tensor:
         """(world, *t.shape) stacked copies, rank order."""
@@ -53,7 +101,18 @@ class Comm:
             return t[None]
         out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
         src = t.contiguous().view(-1)
-        self._do(lambda: dist.all_gather_into_tensor(out.view(-1), src, group=self.group))
+        nbytes = src.numel() * src.element_size()
+        if self.peer is not None and t.is_cuda and nbytes % 8 == 0 and 0 < nbytes <= PEER_SLOT_BYTES:
+            rc = self._lib.abcdls_peer_allgather(self.peer, C.c_void_p(src.data_ptr()), nbytes,
+                                                 C.c_void_p(out.data_ptr()), self._stream())
+            if rc != 0:
+                raise RuntimeError("abcdls_peer_allgather failed")
+            self.calls += 1
+            self.peer_calls += 1
+            if src.data_ptr() != t.data_ptr():
+                out._abcdls_keep = src      # a temporary contiguous copy must outlive the enqueued kernel
+        else:
+            self._do(lambda: dist.all_gather_into_tensor(out.view(-1), src, group=self.group))
         return out
 
     def allgather_ints(self, vals: List[int]) -> List[List[int]]:

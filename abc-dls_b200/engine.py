@@ -553,9 +553,10 @@ class AbcEngine:
             self.comm.allreduce_sum(sm)
             stats = torch.cat([mn[:, None], mx[:, None], sm], dim=1)
         if self.comm.world > 1:   # OR of the status words over the ranks = max of every bit
-            bits = (status.view(1) >> torch.arange(8, device=self.device, dtype=torch.int32)) & 1
+            sh = torch.arange(8, device=self.device, dtype=torch.int64)
+            bits = (status.view(1).to(torch.int64) >> sh) & 1
             self.comm.allreduce_max(bits)
-            status = (bits << torch.arange(8, device=self.device, dtype=torch.int32)).sum().to(torch.int32).view(1)
+            status = (bits << sh).sum().to(torch.int32).view(1)
         host = torch.cat([status.to(torch.float64), n_acc.to(torch.float64), ds,
                           region_const.to(torch.float64).view(1), all_mad_zero.to(torch.float64).view(1), logsig])
         return dict(host=host, mad=mad, idx=idx, y=y, ss_out=ss_out, w=w, dacc=dacc, stats=stats, dist=f["dist"],

@@ -303,7 +303,9 @@ def main():
                 "cpu_baseline": base, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
                 "nacc": res.nacc, "ds": res.ds, "fast_path_misses": eng.fast_misses,
                 "host_enqueue_ms": round(sum(host_ms) / max(1, len(host_ms)), 3),
-                "cuda_graph": bool(eng._graphs), "front_half": dict(eng.path_calls)}
+                "cuda_graph": bool(eng._graphs), "front_half": dict(eng.path_calls),
+                "collectives": {"total": eng.comm.calls, "nvlink_mailbox_kernels": eng.comm.peer_calls,
+                                "nccl": eng.comm.calls - eng.comm.peer_calls}}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -279,6 +279,25 @@ int abcdls_smc_box_filter(abcdls_handle_t h, const double* param_all, int64_t n,
                           int64_t* idx_out, int64_t* n_out, void* ws, size_t ws_bytes, int* status_dev,
                           void* stream);
 
+/* ---- collectives over NVLink peer memory (csrc/peer.cu) ---------------------------------------
+ * The exchanges of the path are tiny and latency bound.  Every rank owns a mailbox (cudaMalloc + CUDA
+ * IPC) that all peers map; one kernel per exchange writes the contribution, pushes a sequence number to the peers,
+ * waits for theirs and reduces / concatenates the peers' slots in RANK ORDER over NVLink.  No host involvement and
+ * no NCCL on the data path: the kernels are ordinary graph nodes.  Bootstrap (exchanging the IPC handles) is the
+ * caller's job (the Python host uses torch.distributed for it).
+ *   create (per rank) -> all-gather the handles by any channel -> connect -> barrier -> exchanges ... -> destroy */
+typedef struct abcdls_peer_s* abcdls_peer_t;
+size_t abcdls_peer_handle_bytes(void);
+int abcdls_peer_create(abcdls_peer_t* out, int rank, int world, size_t slot_bytes, void* handle_out);
+int abcdls_peer_connect(abcdls_peer_t p, const void* all_handles /* world x handle_bytes, rank order */);
+int abcdls_peer_destroy(abcdls_peer_t p);
+const char* abcdls_peer_last_error(abcdls_peer_t p);
+size_t abcdls_peer_slot_bytes(abcdls_peer_t p);
+/* in place; dtype 0 = double, 1 = int64; op 0 = sum, 1 = min, 2 = max; count * 8 <= slot bytes */
+int abcdls_peer_allreduce(abcdls_peer_t p, void* data, size_t count, int dtype, int op, void* stream);
+/* dst[world * bytes] <- every rank's src[bytes] (multiple of 8, <= slot bytes), rank order */
+int abcdls_peer_allgather(abcdls_peer_t p, const void* src, size_t bytes, void* dst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
