@@ -49,17 +49,6 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
     asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ double ld_volatile_f64(const double* p) {
-    double v;
-    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ long long ld_volatile_s64(const long long* p) {
-    long long v;
-    asm volatile("ld.volatile.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
 // all CTAs of this launch have arrived (monotonic counter; *bar_cum = arrivals before this exchange)
 __device__ __forceinline__ void grid_arrive_wait(const PeerDev& P) {
     __syncthreads();
