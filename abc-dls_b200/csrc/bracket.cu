@@ -180,14 +180,23 @@ struct ColBrk {
     double loM, scaleM;   // fine histogram of the M band: bin((x - loM) * scaleM), loM = c - r0
 };
 
-// K1b: average the G local estimates (already summed over ranks when world > 1) -> brackets. 1 thread/column.
-__global__ void k_make_brackets(const double* __restrict__ est, int G, int d, double inv_world, ColBrk* __restrict__ brk) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
+// K1b: average the G local estimates (already summed over ranks when world > 1) -> brackets.  One warp per column:
+// lane l adds estimates l, l + 32, ... in order, then a fixed shuffle tree (deterministic).
+__global__ void __launch_bounds__(32) k_make_brackets(const double* __restrict__ est, int G, int d, double inv_world,
+                                                      ColBrk* __restrict__ brk) {
+    const int j = blockIdx.x, lane = threadIdx.x;
     if (j >= d) return;
     double m[4] = {0, 0, 0, 0};
-    for (int g = 0; g < G; ++g)
+    for (int g = lane; g < G; g += 32)
+#pragma unroll
         for (int q = 0; q < 4; ++q) m[q] += est[((size_t)g * d + j) * 4 + q];
-    for (int q = 0; q < 4; ++q) m[q] = m[q] / G * inv_world;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m[q] += __shfl_down_sync(0xffffffffu, m[q], o);
+        m[q] = m[q] / G * inv_world;
+    }
+    if (lane != 0) return;
     // m = {m_lo, m_hi, r_lo, r_hi}
     ColBrk B;
     B.c = 0.5 * m[0] + 0.5 * m[1];
@@ -358,7 +367,6 @@ struct RefJob {
     const double* src;                    // candidate values
     const unsigned long long* src_count;  // entries appended (may exceed src_cap => miss)
     long long src_cap;
-    const int* dir;                       // chunked source (one-pass kernel): slot i is valid iff (i & 255) < dir[i >> 8]
     int transform;                        // 1: v = |x - center|
     int valid;                            // 0 => the bracket missed; results are NaN and MISS is flagged
     double center;
@@ -444,16 +452,25 @@ __global__ void __launch_bounds__(256) k_refine_gather(RefJob* jobs, long long n
     const double lo = J.lo, scale = J.scale, c = J.center, vmin = J.vmin;
     const bool tr = J.transform != 0;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    const int* __restrict__ dir = J.dir;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        if (dir && (int)(i & 255) >= dir[i >> 8]) continue;
-        double x = J.src[i];
-        double v = tr ? fabs(__dsub_rn(x, c)) : x;
-        if (v >= vmin) {
-            int b = bin_of(v, lo, scale);
-            if (b >= b0 && b <= b1) {
-                unsigned p = atomicAdd(J.small_count, 1u);
-                if (p < (unsigned)kSmallCap) J.small[p] = v;
+    // four independent streaming loads in flight per thread (the candidate lists are read once, from HBM)
+    const double* __restrict__ src = J.src;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
+        double xv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long i = i0 + u * stride;
+            xv[u] = i < n ? ld_stream(src + i) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (i0 + u * stride >= n) continue;
+            const double v = tr ? fabs(__dsub_rn(xv[u], c)) : xv[u];
+            if (v >= vmin) {
+                const int b = bin_of(v, lo, scale);
+                if (b >= b0 && b <= b1) {
+                    unsigned p = atomicAdd(J.small_count, 1u);
+                    if (p < (unsigned)kSmallCap) J.small[p] = v;
+                }
             }
         }
     }
@@ -521,16 +538,15 @@ __global__ void k_plan_median(RefJob* jobs, int d, const ColBrk* __restrict__ br
                               const unsigned long long* __restrict__ counts, unsigned long long* histM,
                               const double* candM, long long capM, const unsigned long long* cnt,
                               const unsigned long long* gcnt, double* small, unsigned* small_count, long long k0,
-                              long long k1, const int* dirM, int* status) {
+                              long long k1, int* status) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= d) return;
     RefJob J;
-    J.dir = dirM ? dirM + (size_t)j * (capM / 256) : nullptr;
     // counts / gcnt are summed over ranks; cnt is what THIS rank appended (every band value is appended)
     const long long c_lt = (long long)counts[j * 4 + 0], c_m = (long long)gcnt[j * 2 + 0];
     J.src = candM + (size_t)j * capM;
     J.src_count = cnt + j * 2 + 0;
-    J.src_cap = dirM ? capM - 256 : capM;   // chunked source: the last chunk is the overflow sink
+    J.src_cap = capM;
     J.transform = 0;
     J.center = 0.0;
     J.lo = brk[j].loM;
@@ -556,8 +572,7 @@ __global__ void k_plan_mad(RefJob* jobs, int d, const ColBrk* __restrict__ brk,
                            const unsigned long long* __restrict__ counts, unsigned long long* histU,
                            const double* candU, long long capU, const unsigned long long* cnt,
                            const unsigned long long* gcnt, double* small, unsigned* small_count, long long k0,
-                           long long k1, double* __restrict__ med, double* __restrict__ guard, const int* dirU,
-                           int* status) {
+                           long long k1, double* __restrict__ med, double* __restrict__ guard, int* status) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= d) return;
     const RefJob& Jm = jobs[j];
@@ -565,11 +580,10 @@ __global__ void k_plan_mad(RefJob* jobs, int d, const ColBrk* __restrict__ brk,
     med[j] = m;
     const ColBrk B = brk[j];
     RefJob J;
-    J.dir = dirU ? dirU + (size_t)j * (capU / 256) : nullptr;
     const long long c_in = (long long)counts[j * 4 + 2], c_u = (long long)gcnt[j * 2 + 1];
     J.src = candU + (size_t)j * capU;
     J.src_count = cnt + j * 2 + 1;
-    J.src_cap = dirU ? capU - 256 : capU;
+    J.src_cap = capU;
     J.transform = 1;
     J.center = m;
     // x in U has fl|x - c| in [r1, r2]; with e = |c - m| its |x - m| lies in [r1 - e, r2 + e] up to rounding
@@ -612,12 +626,20 @@ __global__ void __launch_bounds__(256) k_refine_hist(RefJob* jobs, long long n_m
     const double lo = J.lo, scale = J.scale, c = J.center, vmin = J.vmin;
     const bool tr = J.transform != 0;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    const int* __restrict__ dir = J.dir;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        if (dir && (int)(i & 255) >= dir[i >> 8]) continue;
-        double x = J.src[i];
-        double v = tr ? fabs(__dsub_rn(x, c)) : x;
-        if (v >= vmin) atomicAdd(&hist[bin_of(v, lo, scale)], 1u);
+    const double* __restrict__ src = J.src;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
+        double xv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long i = i0 + u * stride;
+            xv[u] = i < n ? ld_stream(src + i) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (i0 + u * stride >= n) continue;
+            const double v = tr ? fabs(__dsub_rn(xv[u], c)) : xv[u];
+            if (v >= vmin) atomicAdd(&hist[bin_of(v, lo, scale)], 1u);
+        }
     }
     __syncthreads();
     for (int t = threadIdx.x; t < kNB; t += blockDim.x)
@@ -1082,7 +1104,6 @@ __global__ void k_plan_ds(RefJob* job, const DistBrk* __restrict__ brk, const un
                           int* status) {
     if (threadIdx.x || blockIdx.x) return;
     RefJob J;
-    J.dir = nullptr;
     const long long c_lt = (long long)*n_lt, c_all = (long long)*gcand_cnt;   // summed over ranks
     J.src = cand_dist;
     J.src_count = cand_cnt;
@@ -1126,8 +1147,6 @@ struct MadWs {
     double* small;                  // [2d*kSmallCap]
     double* candM;                  // [d*capM]
     double* candU;                  // [d*capU]
-    int* dirM;                      // [d*capM/256] chunk fills (one-pass kernel only)
-    int* dirU;                      // [d*capU/256]
     size_t total;
 };
 
@@ -1156,8 +1175,6 @@ inline MadWs carve_mad(void* ws, int d, int G, long long capM, long long capU) {
     w.small = (double*)take((size_t)2 * d * kSmallCap * 8);
     w.candM = (double*)take((size_t)d * capM * 8);
     w.candU = (double*)take((size_t)d * capU * 8);
-    w.dirM = (int*)take((size_t)d * (capM / 256 + 1) * 4);
-    w.dirU = (int*)take((size_t)d * (capU / 256 + 1) * 4);
     w.total = o;
     return w;
 }
@@ -1284,7 +1301,7 @@ int abcdls_mad_fast_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, 
         return ABCDLS_E_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    k_make_brackets<<<1, 64, 0, st>>>(w.est, G, d, 1.0 / world, w.brk);
+    k_make_brackets<<<d, 32, 0, st>>>(w.est, G, d, 1.0 / world, w.brk);
     ABCDLS_LAUNCH_CHECK(h);
     long long gx = ((n + kATile - 1) / kATile);
     long long mx = (long long)h->sm_count * 8 / d;
@@ -1307,8 +1324,7 @@ int abcdls_mad_fast_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, 
 //   phase 2: locate bins + gather (MAD)                 -> exchange: all-gather x0 = small block, x1 = counts
 //   phase 3: sort -> MAD, guards
 // gath_small / gath_cnt: the all-gathered exchange block of the previous phase (NULL on a single rank).
-// shared by the two-pass path (fused = false: histM was built by the pass) and the one-pass path (fused.cuh:
-// candidates live in 256-slot chunks described by dirM / dirU)
+// shared by the two-pass path and the one-pass path (fused.cuh)
 static int refine_impl(abcdls_handle_t h, const MadWs& w, long long capM, long long capU, bool fused, int64_t n_global,
                        int d, int phase, int world, const double* gath_small, const int32_t* gath_cnt, double* med,
                        double* mad, int* status_dev, void** x0, size_t* x0_count, void** x1, size_t* x1_count,
@@ -1328,7 +1344,7 @@ static int refine_impl(abcdls_handle_t h, const MadWs& w, long long capM, long l
     switch (phase) {
         case 0:
             k_plan_median<<<1, 64, 0, st>>>(w.jobs, d, w.brk, w.counts, w.histM, w.candM, capM, w.cnt, w.gcnt, w.small,
-                                            w.small_count, k0, k1, fused ? w.dirM : nullptr, status_dev);
+                                            w.small_count, k0, k1, status_dev);
             k_refine_pick<<<d, 256, 0, st>>>(w.jobs, status_dev);
             k_refine_gather<<<dim3(gx_for(capM), d), 256, 0, st>>>(w.jobs, capM);
             if (x0) { *x0 = w.small; *x0_count = (size_t)d * kSmallCap; }
@@ -1337,7 +1353,7 @@ static int refine_impl(abcdls_handle_t h, const MadWs& w, long long capM, long l
         case 1:
             k_refine_final<<<d, 1024, smem, st>>>(w.jobs, gath_small, gc, gath_small ? world : 1, d, status_dev);
             k_plan_mad<<<1, 64, 0, st>>>(w.jobs, d, w.brk, w.counts, w.histU, w.candU, capU, w.cnt, w.gcnt, w.small,
-                                         w.small_count, k0, k1, med, w.guard, fused ? w.dirU : nullptr, status_dev);
+                                         w.small_count, k0, k1, med, w.guard, status_dev);
             k_refine_hist<<<dim3(gx_for(capU), d), 256, 0, st>>>(w.jobs + d, capU);
             if (x0) { *x0 = w.histU; *x0_count = w.redB_count; }
             break;

@@ -98,6 +98,7 @@ __global__ void k_make_fused_scale(const double* __restrict__ est, int G, int d,
     bool ok = true;
     if (j < d) {
         double a = 0.0, b = 0.0;
+#pragma unroll 8
         for (int g = 0; g < G; ++g) {
             a += est[((size_t)g * d + j) * 4 + 2];
             b += est[((size_t)g * d + j) * 4 + 3];
@@ -415,10 +416,19 @@ __global__ void __launch_bounds__(256) k_fused_histM(const double* __restrict__ 
     const double* __restrict__ src = candM + (size_t)j * capM;
     const long long stride = (long long)gridDim.x * blockDim.x;
     unsigned neg = 0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
-        const double x = src[i];
-        atomicAdd(&hist[bin_of(x, lo, scale)], 1u);
-        neg += (unsigned)__double2hiint(__dsub_rn(x, c)) >> 31;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < nv; i0 += 4 * stride) {
+        double xv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long i = i0 + u * stride;
+            xv[u] = i < nv ? ld_stream(src + i) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (i0 + u * stride >= nv) continue;
+            atomicAdd(&hist[bin_of(xv[u], lo, scale)], 1u);
+            neg += (unsigned)__double2hiint(__dsub_rn(xv[u], c)) >> 31;
+        }
     }
     neg = warp_sum(neg);
     if ((threadIdx.x & 31) == 0 && neg) atomicAdd(&negs, neg);
@@ -634,7 +644,7 @@ int abcdls_fused_sample_dist(abcdls_handle_t h, const double* ss, int64_t n, int
                              size_t* est_count, void* stream) {
     FUSED_PROLOGUE("fused_sample_dist");
     ABCDLS_CHECK_ARG(h, target && nacc >= 1 && n_global >= nacc, "fused_sample_dist: nacc");
-    k_make_brackets<<<1, 64, 0, st>>>(w.m.est, G, d, 1.0 / world, w.m.brk);
+    k_make_brackets<<<d, 32, 0, st>>>(w.m.est, G, d, 1.0 / world, w.m.brk);
     k_make_fused_scale<<<1, 32, 0, st>>>(w.m.est, G, d, 1.0 / world, target, w.par);
     const double p = (double)nacc / (double)n_global;
     const double delta = kZ * sqrt(p * (1.0 - p) / ((double)kFG2 * kSample * world));

@@ -291,3 +291,45 @@ def test_cuda_graph_replay_matches_eager_and_tracks_the_target(engine):
     np.testing.assert_array_equal(_np(r4.idx), o.idx)
     assert r4.ds == o.ds and _rel(_np(r4.adj_values), o.adj_values) < REL_TOL
     assert abs(r4.aic - o.aic) <= 1e-9 * abs(o.aic)
+
+
+# ---- BASELINE.json full sizes ------------------------------------------------------------------------------------------
+def test_cfg3_full_size_against_the_oracle(engine):
+    """BASELINE config 3: 1e7 simulations x 10 statistics x 10 parameters, loclinear, tol 0.001, one GPU."""
+    par, ss, tgt = synth.abc_tables(10_000_000, 10, 10, engine.device)
+    r, o = _check_fused(engine, par, ss, tgt, 0.001, "loclinear")
+    assert r.nacc == 10_000 and r.idx.numel() == 10_000
+    mn, mx = r.minmax()
+    assert _rel(_np(mn)[None, :], o.adj_values.min(axis=0)[None, :]) < REL_TOL
+    assert _rel(_np(mx)[None, :], o.adj_values.max(axis=0)[None, :]) < REL_TOL
+
+
+def test_cfg5_full_size_three_independent_paths_agree(engine):
+    """BASELINE config 5 at its full size (1e8 x 16 x 16, tol 0.01): too big for the CPU oracle in a test, so the three
+    front halves - one table read with interval reasoning, two reads with sampled brackets, thirteen reads with the
+    distribution-independent radix select - must give bit-identical MADs, ds and accepted rows, and the accepted set
+    must satisfy R's definition against the full distance vector (size-independent properties)."""
+    N = 100_000_000
+    par, ss, tgt = synth.abc_tables(N, 16, 16, engine.device)
+    engine._graphs.clear()
+    before, misses = dict(engine.path_calls), engine.fast_misses
+    a = engine.abc(tgt, par, ss, 0.01, "loclinear")                              # one-pass
+    b = engine.abc(tgt, par, ss, 0.01, "loclinear", keep_dist=True)              # two-pass (returns dist)
+    c = engine.abc(tgt, par, ss, 0.01, "loclinear", keep_dist=True, _level=2)    # radix select
+    assert engine.path_calls["fused"] == before["fused"] + 1
+    assert engine.path_calls["two_pass"] == before["two_pass"] + 1
+    assert engine.path_calls["exact"] == before["exact"] + 1 and engine.fast_misses == misses
+    for r in (b, c):
+        assert torch.equal(r.mad, a.mad) and r.ds == a.ds and torch.equal(r.idx, a.idx)
+        assert torch.equal(r.unadj_values, a.unadj_values) and torch.equal(r.weights, a.weights)
+        assert _rel(_np(r.adj_values), _np(a.adj_values)) < 1e-12
+    assert torch.equal(b.dist, c.dist)
+    # R's definition on the full vector: nacc = ceil(N tol); ds = nacc-th smallest; first nacc rows with dist <= ds
+    nacc = 1_000_000
+    assert a.nacc == nacc and a.idx.numel() == nacc
+    assert int((b.dist < a.ds).sum()) < nacc <= int((b.dist <= a.ds).sum())
+    assert bool((a.idx[1:] > a.idx[:-1]).all())
+    assert torch.equal(b.dist[a.idx], a.dist_accepted) and bool((a.dist_accepted <= a.ds).all())
+    first = torch.nonzero(b.dist <= a.ds).view(-1)[:nacc]
+    assert torch.equal(first, a.idx)
+    del b, c
