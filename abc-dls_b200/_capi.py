@@ -39,7 +39,11 @@ SIGNATURES = {
     "abcdls_accept_workspace_bytes": (_sz, [_i64]),
     "abcdls_count_le": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "abcdls_accept": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
-    "abcdls_gather_cand": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp,
+    "abcdls_gather_rows": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _i64, _vp, _vp]),
+    "abcdls_fused_rows": (_i32, [_vp, _vp, _i64, _i32, _i64, _i32, _i64, _i64, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "abcdls_fused_exact": (_i32, [_vp, _vp, _i64, _i32, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _sz,
+                                  _vp, _vp]),
+    "abcdls_gather_cand": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp,
                                   _vp, _vp, _vp, _vp, _vp]),
     "abcdls_fused_supported": (_i32, [_vp, _i64, _i32, _i64]),
     "abcdls_fused_workspace_bytes": (_sz, [_i64, _i32]),

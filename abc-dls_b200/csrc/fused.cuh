@@ -721,17 +721,14 @@ int abcdls_fused_refine(abcdls_handle_t h, const double* ss, int64_t n, int64_t 
                        status_dev, x0, x0_count, x1, x1_count, st);
 }
 
-// Stage 5: marked rows -> ascending global candidate rows (cand_row), R's exact distance of each from the block the
-// pass emitted (cand_ss / cand_lrow / ecap as given to the pass), perm[i] = slot of candidate i in that block.
-// n_cand: device int64.
-int abcdls_fused_candidates(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world,
-                            const double* mad, const double* target, int64_t row_offset, int64_t cap, int64_t* cand_row,
-                            double* cand_dist, const double* cand_ss, const int32_t* cand_lrow, int64_t ecap,
-                            int64_t* perm, int64_t* n_cand, void* ws, size_t ws_bytes, int* status_dev, void* stream) {
-    FUSED_PROLOGUE("fused_candidates");
-    ABCDLS_CHECK_ARG(h, mad && target && cand_row && cand_dist && cand_ss && cand_lrow && perm && n_cand && status_dev &&
-                            cap >= 1 && ecap >= 1,
-                     "fused_candidates");
+// Stage 5a (needs only the pass): marked rows -> ascending global candidate rows (cand_row), n_cand (device int64).
+// Independent of the median / MAD refinement, so a caller can start work that only needs the candidate rows
+// (e.g. pre-gathering their parameters on a second stream) while stage 4 runs.
+int abcdls_fused_rows(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, int64_t row_offset,
+                      int64_t cap, int64_t* cand_row, int64_t* n_cand, void* ws, size_t ws_bytes, int* status_dev,
+                      void* stream) {
+    FUSED_PROLOGUE("fused_rows");
+    ABCDLS_CHECK_ARG(h, cand_row && n_cand && status_dev && cap >= 1, "fused_rows");
     const long long ntiles = (n + kFRows - 1) / kFRows;
     const long long nwords = ntiles * (kFRows / 32);
     const long long nblk = (nwords + 256 * kMWords - 1) / (256 * kMWords);
@@ -741,12 +738,37 @@ int abcdls_fused_candidates(abcdls_handle_t h, const double* ss, int64_t n, int 
     k_mask_write<<<(unsigned)nblk, 256, 0, st>>>(bitmap, nwords, w.tile_off, row_offset, cap, (long long*)cand_row,
                                                  w.wprefix, w.total, (long long*)n_cand, status_dev);
     ABCDLS_LAUNCH_CHECK(h);
+    return ABCDLS_OK;
+}
+
+// Stage 5b (needs the exact MADs): R's exact distance of every candidate from the block the pass emitted
+// (cand_ss / cand_lrow / ecap as given to the pass), scattered to its position in the ascending candidate list;
+// perm[i] = slot of candidate i in that block.
+int abcdls_fused_exact(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, const double* mad,
+                       const double* target, int64_t cap, double* cand_dist, const double* cand_ss,
+                       const int32_t* cand_lrow, int64_t ecap, int64_t* perm, void* ws, size_t ws_bytes, int* status_dev,
+                       void* stream) {
+    FUSED_PROLOGUE("fused_exact");
+    ABCDLS_CHECK_ARG(h, mad && target && cand_dist && cand_ss && cand_lrow && perm && status_dev && cap >= 1 && ecap >= 1,
+                     "fused_exact");
+    const unsigned* bitmap = reinterpret_cast<const unsigned*>(w.mask16);
     long long g = (ecap + 255) / 256;
     if (g > (long long)h->sm_count * 16) g = (long long)h->sm_count * 16;
     k_cand_exact<<<(unsigned)g, 256, 0, st>>>(cand_ss, ecap, cand_lrow, w.ealloc, d, mad, target, bitmap, w.wprefix, cap,
                                               cand_dist, (long long*)perm, status_dev);
     ABCDLS_LAUNCH_CHECK(h);
     return ABCDLS_OK;
+}
+
+// Stage 5 = 5a + 5b
+int abcdls_fused_candidates(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world,
+                            const double* mad, const double* target, int64_t row_offset, int64_t cap, int64_t* cand_row,
+                            double* cand_dist, const double* cand_ss, const int32_t* cand_lrow, int64_t ecap,
+                            int64_t* perm, int64_t* n_cand, void* ws, size_t ws_bytes, int* status_dev, void* stream) {
+    int rc = abcdls_fused_rows(h, ss, n, d, ld, world, row_offset, cap, cand_row, n_cand, ws, ws_bytes, status_dev, stream);
+    if (rc) return rc;
+    return abcdls_fused_exact(h, ss, n, d, ld, world, mad, target, cap, cand_dist, cand_ss, cand_lrow, ecap, perm, ws,
+                              ws_bytes, status_dev, stream);
 }
 
 // Stage 6 (after the exact ds has been selected among the candidates of all ranks): completeness proof.

@@ -55,6 +55,24 @@ __global__ void __launch_bounds__(256) k_gather(const double* __restrict__ ss, l
     }
 }
 
+// out[p][i] = table[p][rows[i] - row_offset] for the first *n_rows rows (column-major table, possibly pinned host
+// memory): the scattered half of a gather, runnable as soon as the row numbers exist.  grid (gx, P)
+__global__ void __launch_bounds__(256) k_gather_rows(const double* __restrict__ table, long long ld,
+                                                     const long long* __restrict__ rows,
+                                                     const long long* __restrict__ n_rows_ptr, long long row_offset,
+                                                     long long cap, double* __restrict__ out) {
+    long long n = *n_rows_ptr;
+    if (n > cap) n = cap;
+    const int p = blockIdx.y;
+    const double* __restrict__ src = table + (size_t)p * ld - row_offset;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double v;
+        asm volatile("ld.global.L2::64B.f64 %0, [%1];" : "=d"(v) : "l"(src + rows[i]));
+        out[(size_t)p * cap + i] = v;
+    }
+}
+
 // same outputs from the block of candidate rows the one-pass kernel emitted (row-major, `pitch` doubles per slot,
 // reached through perm[slot[r]]) and the parameter table (possibly pinned host memory) through idx[r].
 // blockIdx.y == 0: one thread per accepted row copies / scales its d statistics and computes its weight;
@@ -63,6 +81,7 @@ __global__ void __launch_bounds__(256) k_gather_cand(const double* __restrict__ 
                                                      const long long* __restrict__ slot,
                                                      const long long* __restrict__ perm,
                                                      const double* __restrict__ param, long long ld_param,
+                                                     const double* __restrict__ cand_par, long long ld_cpar,
                                                      const double* __restrict__ dist_acc,
                                                      const long long* __restrict__ idx,
                                                      const long long* __restrict__ n_acc_ptr, long long row_offset,
@@ -99,6 +118,11 @@ __global__ void __launch_bounds__(256) k_gather_cand(const double* __restrict__ 
         }
     } else {
         const int p = blockIdx.y - 1;
+        if (cand_par) {   // the candidates' parameters were pre-gathered (abcdls_gather_rows): compact, near-sequential
+            const double* __restrict__ cp = cand_par + (size_t)p * ld_cpar;
+            for (long long r = r0; r < n_acc; r += stride) y[(size_t)p * cap + r] = cp[slot[r]];
+            return;
+        }
         const double* __restrict__ src = param + (size_t)p * ld_param - row_offset;
         // scattered 8-byte reads: ask L2 for 64-byte fills instead of the default 128 (halves the DRAM traffic)
         for (long long r = r0; r < n_acc; r += stride) {
@@ -660,8 +684,20 @@ int abcdls_gather(abcdls_handle_t h, const double* ss, int64_t ld_ss, const doub
     return ABCDLS_OK;
 }
 
+int abcdls_gather_rows(abcdls_handle_t h, const double* table, int64_t ld, int P, const int64_t* rows,
+                       const int64_t* n_rows, int64_t row_offset, int64_t cap, double* out, void* stream) {
+    ABCDLS_CHECK_ARG(h, h && table && rows && n_rows && out && P >= 1 && P <= kMaxP && cap >= 1, "gather_rows");
+    unsigned gx = grid_for(h, cap, 256, 16);
+    if (gx > 2048) gx = 2048;
+    k_gather_rows<<<dim3(gx, (unsigned)P), 256, 0, (cudaStream_t)stream>>>(table, ld, (const long long*)rows,
+                                                                         (const long long*)n_rows, row_offset, cap, out);
+    ABCDLS_LAUNCH_CHECK(h);
+    return ABCDLS_OK;
+}
+
 int abcdls_gather_cand(abcdls_handle_t h, const double* cand_ss, int64_t ld_cand, const int64_t* slot,
-                       const int64_t* perm, const double* param, int64_t ld_param, const double* dist_acc, const int64_t* idx,
+                       const int64_t* perm, const double* param, int64_t ld_param, const double* cand_par,
+                       int64_t ld_cpar, const double* dist_acc, const int64_t* idx,
                        const int64_t* n_acc, int64_t row_offset, int64_t cap, int d, int P, const double* mad,
                        const double* target, const double* ds, double* xs, double* y, double* ss_out, double* w,
                        void* stream) {
@@ -672,7 +708,8 @@ int abcdls_gather_cand(abcdls_handle_t h, const double* cand_ss, int64_t ld_cand
     unsigned gx = grid_for(h, cap, 256, 16);
     if (gx > 2048) gx = 2048;
     k_gather_cand<<<dim3(gx, (unsigned)(1 + P)), 256, 0, (cudaStream_t)stream>>>(
-        cand_ss, ld_cand, (const long long*)slot, (const long long*)perm, param, ld_param, dist_acc, (const long long*)idx,
+        cand_ss, ld_cand, (const long long*)slot, (const long long*)perm, param, ld_param, cand_par, ld_cpar, dist_acc,
+        (const long long*)idx,
         (const long long*)n_acc, row_offset, cap, d, mad, target, ds, xs, y, ss_out, w);
     ABCDLS_LAUNCH_CHECK(h);
     return ABCDLS_OK;

@@ -161,6 +161,11 @@ class AbcEngine:
         self.use_graphs = True      # replay the device work of a repeated call as one CUDA graph
         self.copy_results = True    # results of a replayed graph are copied out of the graph's buffers
         self.max_graphs = 4
+        # Gather the parameters of ALL candidates on a second stream during the refinement.  Measured at 1e8 x 16: the
+        # scattered reads (1.6x more rows) slow the memory-bound refinement kernels by more than the later gather
+        # saves (4.94 -> 5.2 ms per call), so it stays off.
+        self.pregather = False
+        self._side = None
         if os.environ.get("ABCDLS_NO_GRAPH", "0") == "1":
             self.use_graphs = False
         self._graphs, self._seen = {}, {}
@@ -259,7 +264,7 @@ class AbcEngine:
         return dict(n_global=n_global, row_offset=row_offset, nacc=nacc, fast=fast, fused=fused, keep_dist=keep_dist,
                     path="fused" if fused else ("two_pass" if fast else "exact"))
 
-    def _front(self, target, ss, status, pl):
+    def _front(self, target, ss, status, pl, par=None):
         """MAD scaling -> distance -> exact threshold ds -> R's cap rule (device work only).  Returns the accepted rows
         (ascending global row numbers, their distances) of this rank.
 
@@ -277,7 +282,7 @@ class AbcEngine:
         le = torch.zeros(1, dtype=torch.int64, device=self.device)
         quota = torch.full((1,), nacc, dtype=torch.int64, device=self.device)
         comm = self.comm if self.comm.world > 1 else None
-        cand_ss = slot = perm = None
+        cand_ss = slot = perm = cand_par = None
         if fused:
             # ONE table read: medians + MADs and the candidate rows of the cut; exact distances only for the candidates
             med, mad = k.new(d), k.new(d)
@@ -290,9 +295,17 @@ class AbcEngine:
             perm = k.new(ccap, dtype=torch.int64)
             slot = k.new(cap, dtype=torch.int64)
             n_cand = torch.zeros(1, dtype=torch.int64, device=self.device)
+            pre = None
+            if (par is not None and par.device.type == "cuda" and self.pregather
+                    and (self.comm.world == 1 or self.comm.peer is not None)):   # NCCL segments cannot span a fork
+                # device-resident parameters: gather them for ALL candidates on a second stream while this one refines
+                if self._side is None:
+                    self._side = torch.cuda.Stream(self.device)
+                cand_par = k.new(par.shape[0], ccap)
+                pre = (par, cand_par, self._side)
             with self._t("fused_front"):
                 k.fused_front(ss, n_local, n_global, d, ss.stride(0), target, nacc, row_offset, ccap, med, mad, cand_row,
-                              cand_dist, cand_ss, cand_lrow, perm, n_cand, status, comm)
+                              cand_dist, cand_ss, cand_lrow, perm, n_cand, status, comm, pregather=pre)
             with self._t("fused_ds"):
                 ds = self._select(cand_dist[None, :], ccap, None, nacc - 1, nacc - 1, counts=n_cand)[0, :1].contiguous()
                 k.fused_check(n_local, d, mad, ds, status)
@@ -337,7 +350,7 @@ class AbcEngine:
                 quota = (nacc - below).clamp(min=0).view(1)
             k.accept(dist, n_local, None, None, ds, quota, row_offset, cap, idx, dacc, n_acc, ws, status)
         return dict(row_offset=row_offset, mad=mad, dist=dist, ds=ds, cap=cap, idx=idx, n_acc=n_acc, dacc=dacc, fast=fast,
-                    fused=fused, cand_ss=cand_ss, slot=slot, perm=perm)
+                    fused=fused, cand_ss=cand_ss, slot=slot, perm=perm, cand_par=cand_par)
 
     def _zero_variance(self, ss) -> bool:
         """R: stop if every column of sumstat has a single unique value."""
@@ -489,15 +502,17 @@ class AbcEngine:
         d, n_local = ss.shape
         P = par.shape[0]
         status = torch.zeros(1, dtype=torch.int32, device=self.device)
-        f = self._front(target, ss, status, pl)
+        f = self._front(target, ss, status, pl, par)
         cap, idx, n_acc, ds, mad, dacc = f["cap"], f["idx"], f["n_acc"], f["ds"], f["mad"], f["dacc"]
 
         xs, y, ss_out = k.new(d, cap), k.new(P, cap), k.new(d, cap)
         w = k.new(cap)
         with self._t("gather"):
             if f["fused"]:   # the statistics of the accepted rows are already compact (candidate block)
+                if f["cand_par"] is not None:
+                    torch.cuda.current_stream(self.device).wait_stream(self._side)   # join the parameter pre-gather
                 k.gather_cand(f["cand_ss"], f["cand_ss"].stride(0), f["slot"], f["perm"], par, par.stride(0), dacc, idx, n_acc,
-                              f["row_offset"], cap, d, P, mad, target, ds, xs, y, ss_out, w)
+                              f["row_offset"], cap, d, P, mad, target, ds, xs, y, ss_out, w, cand_par=f["cand_par"])
             else:
                 k.gather(ss, ss.stride(0), par, par.stride(0), dacc, idx, n_acc, f["row_offset"], cap, d, P, mad,
                          target, ds, xs, y, ss_out, w)

@@ -110,7 +110,7 @@ class CudaStages:
         return int(self.lib.abcdls_fused_emit_cap(cap))
 
     def fused_front(self, ss, n, n_global, d, ld, target, nacc, row_offset, cap, med, mad, cand_row, cand_dist, cand_ss,
-                    cand_lrow, perm, n_cand, status, comm=None):
+                    cand_lrow, perm, n_cand, status, comm=None, pregather=None):
         """Medians + MADs AND the candidate rows of the tolerance cut from ONE read of the table.  Leaves the exact
         distance of every candidate in cand_dist (row order); the caller selects ds among them (all ranks) and then
         calls fused_check."""
@@ -131,6 +131,18 @@ class CudaStages:
                              _p(ws), ws.numel(), _p(status), C.byref(p0), C.byref(c0), st)
         if world > 1:
             comm.allreduce_sum(self._view(ws, p0, c0, torch.int64, 8))
+        # the candidate rows need only the pass: compact them now; their parameters can then be gathered on a second
+        # stream (16 scattered 8-byte reads per row) while this stream refines medians / MADs and selects ds
+        self.handle.call("abcdls_fused_rows", _p(ss), n, d, ld, world, row_offset, cap, _p(cand_row), _p(n_cand), _p(ws),
+                         ws.numel(), _p(status), st)
+        if pregather is not None:
+            par, cand_par, side = pregather
+            main = torch.cuda.current_stream(self.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self.handle.call("abcdls_gather_rows", _p(par), par.stride(0), par.shape[0], _p(cand_row), _p(n_cand),
+                                 row_offset, cap, _p(cand_par), C.c_void_p(side.cuda_stream))
+            self.launches += 1
         gs = gc = None
         with self._timed("fused_refine"):
             for phase in range(4):
@@ -144,9 +156,8 @@ class CudaStages:
                     elif phase == 1:
                         comm.allreduce_sum(self._view(ws, p0, c0, torch.int64, 8))
         with self._timed("fused_candidates"):
-            self.handle.call("abcdls_fused_candidates", _p(ss), n, d, ld, world, _p(mad), _p(target), row_offset, cap,
-                             _p(cand_row), _p(cand_dist), _p(cand_ss), _p(cand_lrow), cand_ss.shape[0], _p(perm),
-                             _p(n_cand), _p(ws), ws.numel(), _p(status), st)
+            self.handle.call("abcdls_fused_exact", _p(ss), n, d, ld, world, _p(mad), _p(target), cap, _p(cand_dist),
+                             _p(cand_ss), _p(cand_lrow), cand_ss.shape[0], _p(perm), _p(ws), ws.numel(), _p(status), st)
         self.launches += 24
 
     def fused_check(self, n, d, mad, ds, status):
@@ -155,8 +166,9 @@ class CudaStages:
         self.launches += 1
 
     def gather_cand(self, cand_ss, ld_cand, slot, perm, param, ld_param, dist_acc, idx, n_acc, row_offset, cap, d, P,
-                    mad, target, ds, xs, y, ss_out, w):
-        self.handle.call("abcdls_gather_cand", _p(cand_ss), ld_cand, _p(slot), _p(perm), _p(param), ld_param, _p(dist_acc),
+                    mad, target, ds, xs, y, ss_out, w, cand_par=None):
+        self.handle.call("abcdls_gather_cand", _p(cand_ss), ld_cand, _p(slot), _p(perm), _p(param), ld_param,
+                         _p(cand_par), cand_par.stride(0) if cand_par is not None else 0, _p(dist_acc),
                          _p(idx), _p(n_acc), row_offset, cap, d, P, _p(mad), _p(target), _p(ds), _p(xs), _p(y),
                          _p(ss_out), _p(w), self._stream())
         self.launches += 1

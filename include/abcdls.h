@@ -192,6 +192,16 @@ int abcdls_fused_refine(abcdls_handle_t h, const double* ss, int64_t n, int64_t 
                         int world, const double* gath_small, const int32_t* gath_cnt, void* ws, size_t ws_bytes,
                         double* med, double* mad, int* status_dev, void** x0, size_t* x0_count, void** x1,
                         size_t* x1_count, void* stream);
+/* stage 5 in two halves: abcdls_fused_rows needs only the pass (ascending global candidate rows + their count), so
+ * work that only needs the row numbers (abcdls_gather_rows of the parameters on a second stream) can overlap the
+ * refinement; abcdls_fused_exact needs the exact MADs.  abcdls_fused_candidates = both. */
+int abcdls_fused_rows(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, int64_t row_offset,
+                      int64_t cap, int64_t* cand_row, int64_t* n_cand, void* ws, size_t ws_bytes, int* status_dev,
+                      void* stream);
+int abcdls_fused_exact(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, const double* mad,
+                       const double* target, int64_t cap, double* cand_dist, const double* cand_ss,
+                       const int32_t* cand_lrow, int64_t ecap, int64_t* perm, void* ws, size_t ws_bytes, int* status_dev,
+                       void* stream);
 /* cand_row: ascending global rows; cand_dist: R's exact distance, computed from the emitted block; perm[i] = slot of
  * candidate i in that block; n_cand: device int64 */
 int abcdls_fused_candidates(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world,
@@ -224,8 +234,14 @@ int abcdls_gather(abcdls_handle_t h, const double* ss, int64_t ld_ss, const doub
  * perm[slot[r]] (slot: abcdls_accept slot_out; perm: abcdls_fused_candidates, may be NULL = identity; the block is ROW-major, ld_cand doubles per candidate), the
  * parameters from the table through idx[r].
  * One thread per (row, column): d + P independent scattered loads in flight per accepted row. */
+/* out[p][i] = table[p][rows[i] - row_offset], i < *n_rows (device int64), leading dimension of out = cap */
+int abcdls_gather_rows(abcdls_handle_t h, const double* table, int64_t ld, int P, const int64_t* rows,
+                       const int64_t* n_rows, int64_t row_offset, int64_t cap, double* out, void* stream);
+/* cand_par (may be NULL): parameters of ALL candidates pre-gathered with abcdls_gather_rows (leading dimension
+ * ld_cpar), indexed by slot[r]; when given, the parameter table is not touched */
 int abcdls_gather_cand(abcdls_handle_t h, const double* cand_ss, int64_t ld_cand, const int64_t* slot,
-                       const int64_t* perm, const double* param, int64_t ld_param, const double* dist_acc, const int64_t* idx,
+                       const int64_t* perm, const double* param, int64_t ld_param, const double* cand_par,
+                       int64_t ld_cpar, const double* dist_acc, const int64_t* idx,
                        const int64_t* n_acc, int64_t row_offset, int64_t cap, int d, int P, const double* mad,
                        const double* target, const double* ds, double* xs, double* y, double* ss_out, double* w,
                        void* stream);
