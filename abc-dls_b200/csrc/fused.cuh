@@ -289,9 +289,35 @@ k_fused_pass(const __grid_constant__ CUtensorMap tmap, long long n, long long nt
     for (long long tile = t_begin; tile < t_end; ++tile) {
         mbar_wait(&sm.full[st], ph);
         const double* __restrict__ stage = ring + (size_t)st * stage_doubles;
-        if (has_col) {
+        double q = 0.0;
+        // One element of the column strip: two subtractions, two sign-bit counters, one integer and one fp64 compare,
+        // a predicated store + predicated pointer bump into this lane's queue.  (No "memory" clobber: the queue is only
+        // touched by volatile asm, which keeps its own order, so the compiler may interleave the distance math.)
+#define ABCDLS_CLASSIFY(xv)                                                                          \
+        {                                                                                            \
+            const double sgn = __dsub_rn((xv), c);                                                   \
+            const double uu = __dadd_rn(fabs(sgn), mr1); /* |x - c| - r1 */                          \
+            const unsigned hu = (unsigned)__double2hiint(uu);                                        \
+            c_neg += (unsigned)__double2hiint(sgn) >> 31;                                            \
+            c_in += hu >> 31;                                                                        \
+            const bool cand = (fabs(sgn) <= r0) || (hu <= hiW); /* M band or U band */               \
+            asm volatile(                                                                            \
+                "{\n\t"                                                                              \
+                ".reg .pred pc;\n\t"                                                                 \
+                "setp.ne.u32 pc, %1, 0;\n\t"                                                         \
+                "@pc st.shared.f64 [%0], %2;\n\t"                                                    \
+                "@pc add.u32 %0, %0, 256;\n\t"                                                       \
+                "}"                                                                                  \
+                : "+r"(pq)                                                                           \
+                : "r"((unsigned)cand), "d"(xv));                                                     \
+        }
+        if (d == kFMaxD) {
+            // every warp owns a column: ONE straight-line block, so that the classification chains and the distance
+            // FMAs of the tile overlap in the pipeline
             if (__any_sync(0xffffffffu, pq > qlim)) flush();
             const double* __restrict__ colp = stage + j * kFRows + 2 * lane;
+            const double* __restrict__ xp = stage + half * kFRows + row;
+            const double2* __restrict__ sp = sm.sc + half;      // (-t rho, rho) of this lane's columns: broadcast loads
             double x[8];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -301,44 +327,33 @@ k_fused_pass(const __grid_constant__ CUtensorMap tmap, long long n, long long nt
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const double sgn = __dsub_rn(x[u], c);
-                const double uu = __dadd_rn(fabs(sgn), mr1);          // |x - c| - r1
-                const unsigned hu = (unsigned)__double2hiint(uu);
-                c_neg += (unsigned)__double2hiint(sgn) >> 31;
-                c_in += hu >> 31;
-                const bool cand = (fabs(sgn) <= r0) || (hu <= hiW);   // M band or U band
-                asm volatile(
-                    "{\n\t"
-                    ".reg .pred pc;\n\t"
-                    "setp.ne.u32 pc, %1, 0;\n\t"
-                    "@pc st.shared.f64 [%0], %2;\n\t"
-                    "@pc add.u32 %0, %0, 256;\n\t"
-                    "}"
-                    : "+r"(pq)
-                    : "r"((unsigned)cand), "d"(x[u])
-                    : "memory");
+                const double2 s2 = sp[2 * u];
+                const double a = fma(xp[2 * u * kFRows], s2.y, s2.x);
+                q = fma(a, a, q);
+                ABCDLS_CLASSIFY(x[u]);
             }
-        }
-        // approximate squared distance of row `row`: this lane sums the columns of its parity
-        double q = 0.0;
-        {
-            const double* __restrict__ xp = stage + half * kFRows + row;
-            const double2* __restrict__ sp = sm.sc + half;      // (-t rho, rho) of this lane's columns: broadcast loads
-            if (d == kFMaxD) {
+        } else {
+            if (has_col) {
+                if (__any_sync(0xffffffffu, pq > qlim)) flush();
+                const double* __restrict__ colp = stage + j * kFRows + 2 * lane;
+                double x[8];
 #pragma unroll
-                for (int q8 = 0; q8 < 8; ++q8) {
-                    const double2 s2 = sp[2 * q8];
-                    const double a = fma(xp[2 * q8 * kFRows], s2.y, s2.x);
-                    q = fma(a, a, q);
+                for (int u = 0; u < 4; ++u) {
+                    const double2 v = *reinterpret_cast<const double2*>(colp + 64 * u);
+                    x[2 * u] = v.x;
+                    x[2 * u + 1] = v.y;
                 }
-            } else {
-                for (int cc = half; cc < d; cc += 2) {
-                    const double2 s2 = sm.sc[cc];
-                    const double a = fma(stage[cc * kFRows + row], s2.y, s2.x);
-                    q = fma(a, a, q);
-                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) ABCDLS_CLASSIFY(x[u]);
+            }
+            // approximate squared distance of row `row`: this lane sums the columns of its parity
+            for (int cc = half; cc < d; cc += 2) {
+                const double2 s2 = sm.sc[cc];
+                const double a = fma(stage[cc * kFRows + row], s2.y, s2.x);
+                q = fma(a, a, q);
             }
         }
+#undef ABCDLS_CLASSIFY
         q += __shfl_xor_sync(0xffffffffu, q, 16);
         bad |= !(q < inf) && (tile != tail_tile || row < tail_rows);
         const unsigned bal = __ballot_sync(0xffffffffu, q <= thr);
