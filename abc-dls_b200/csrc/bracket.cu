@@ -1241,10 +1241,22 @@ inline int sample_ctas(long long n) {
     return (int)g;
 }
 
+// The estimates of all ranks are averaged, so each of `world` ranks only has to contribute 1/world of the sample:
+// the sampling kernels (a fixed cost that does not shrink with the shard) get `world` times cheaper.
+inline int sample_ctas_w(long long n, int world) {
+    int g = sample_ctas(n);
+    if (world > 1) {
+        int cap = 64 / world;
+        if (cap < 8) cap = 8;
+        if (g > cap) g = cap;
+    }
+    return g;
+}
+
 constexpr double kZ = 5.5;  // bracket half-width in standard deviations of the sample-quantile estimate
 
 inline double col_delta(long long n, int world) {
-    double s_tot = (double)sample_ctas(n) * kSample * world;
+    double s_tot = (double)sample_ctas_w(n, world) * kSample * world;
     double delta = kZ * 0.5 / sqrt(s_tot);
     return delta < 2.0 / kSample ? 2.0 / kSample : delta;
 }
@@ -1281,10 +1293,11 @@ int abcdls_mad_fast_sample(abcdls_handle_t h, const double* ss, int64_t n, int d
     const size_t smem = (size_t)2 * kSample * sizeof(double);
     ABCDLS_ONCE(h, cudaFuncSetAttribute(k_sample_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ABCDLS_CUDA(h, cudaMemsetAsync(w.cnt, 0, w.zero_bytes, st));
-    k_sample_cols<<<dim3(G, d), 512, smem, st>>>(ss, n, ld, 0x5EEDu, delta, w.est);
+    const int Gw = sample_ctas_w(n, world);
+    k_sample_cols<<<dim3(Gw, d), 512, smem, st>>>(ss, n, ld, 0x5EEDu, delta, w.est);
     ABCDLS_LAUNCH_CHECK(h);
     if (est_out) *est_out = w.est;
-    if (est_count) *est_count = (size_t)G * d * 4;
+    if (est_count) *est_count = (size_t)Gw * d * 4;
     return ABCDLS_OK;
 }
 
@@ -1301,7 +1314,7 @@ int abcdls_mad_fast_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, 
         return ABCDLS_E_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    k_make_brackets<<<d, 32, 0, st>>>(w.est, G, d, 1.0 / world, w.brk);
+    k_make_brackets<<<d, 32, 0, st>>>(w.est, sample_ctas_w(n, world), d, 1.0 / world, w.brk);
     ABCDLS_LAUNCH_CHECK(h);
     long long gx = ((n + kATile - 1) / kATile);
     long long mx = (long long)h->sm_count * 8 / d;

@@ -632,8 +632,10 @@ int abcdls_fused_supported(const double* ss, int64_t n, int d, int64_t ld) {
         return ABCDLS_E_WORKSPACE;                                                                                  \
     }                                                                                                               \
     cudaStream_t st = (cudaStream_t)stream;                                                                         \
-    const int G = sample_ctas(n);                                                                                   \
-    (void)G
+    const int G = sample_ctas_w(n, world);  /* CTAs per column of the sampling kernels */                           \
+    const int G2 = (world > 1 && kFG2 / world < 8) ? 8 : kFG2 / (world > 1 ? world : 1);                            \
+    (void)G;                                                                                                        \
+    (void)G2
 
 // Stage 1: column samples.  est_out: doubles a multi-rank caller all-reduces (sum) before stage 2.
 int abcdls_fused_sample_cols(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, void* ws,
@@ -662,11 +664,11 @@ int abcdls_fused_sample_dist(abcdls_handle_t h, const double* ss, int64_t n, int
     k_make_brackets<<<d, 32, 0, st>>>(w.m.est, G, d, 1.0 / world, w.m.brk);
     k_make_fused_scale<<<1, 32, 0, st>>>(w.m.est, G, d, 1.0 / world, target, w.par);
     const double p = (double)nacc / (double)n_global;
-    const double delta = kZ * sqrt(p * (1.0 - p) / ((double)kFG2 * kSample * world));
-    k_sample_qdist<<<kFG2, 512, (size_t)kSample * sizeof(double), st>>>(ss, n, d, ld, w.par, 0xD157u, p, delta, w.est2);
+    const double delta = kZ * sqrt(p * (1.0 - p) / ((double)G2 * kSample * world));
+    k_sample_qdist<<<G2, 512, (size_t)kSample * sizeof(double), st>>>(ss, n, d, ld, w.par, 0xD157u, p, delta, w.est2);
     ABCDLS_LAUNCH_CHECK(h);
     if (est_out) *est_out = w.est2;
-    if (est_count) *est_count = (size_t)kFG2;
+    if (est_count) *est_count = (size_t)G2;
     return ABCDLS_OK;
 }
 
@@ -679,7 +681,7 @@ int abcdls_fused_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int
     FUSED_PROLOGUE("fused_pass");
     ABCDLS_CHECK_ARG(h, status_dev && cand_ss && cand_lrow && ecap >= 1 && ecap < (1ll << 31), "fused_pass: args");
     ABCDLS_CUDA(h, cudaMemsetAsync(cand_lrow, 0xff, (size_t)ecap * 4, st));   // -1 = unused slot
-    k_make_fused_thr<<<1, 32, 0, st>>>(w.est2, kFG2, 1.0 / world, d, w.par);
+    k_make_fused_thr<<<1, 32, 0, st>>>(w.est2, G2, 1.0 / world, d, w.par);
     const int nstages = fused_stages(d);
     const size_t smem = kFHeader + (size_t)nstages * d * kFRows * 8 + kFQBytes;
     ABCDLS_ONCE(h, cudaFuncSetAttribute(k_fused_pass, cudaFuncAttributeMaxDynamicSharedMemorySize,
