@@ -516,13 +516,9 @@ class AbcEngine:
             else:
                 k.gather(ss, ss.stride(0), par, par.stride(0), dacc, idx, n_acc, f["row_offset"], cap, d, P, mad,
                          target, ds, xs, y, ss_out, w)
-        # zero variance inside the accepted region (R cond2)
+        # zero variance inside the accepted region (R cond2): local min / max now, reduced over the ranks at the end
         reg = k.new(d, 6)
         k.col_stats(ss_out, None, n_acc, cap, d, reg)
-        rmin, rmax = reg[:, 0].clone(), reg[:, 1].clone()
-        self.comm.allreduce_min(rmin)
-        self.comm.allreduce_max(rmax)
-        region_const = (rmin == rmax).all()
         all_mad_zero = (mad == 0).all()
 
         beta = gamma = the_m = res = adj = sig = None
@@ -561,17 +557,21 @@ class AbcEngine:
         else:
             k.col_stats(y, None, n_acc, cap, P, stats)
         _tl.__exit__()
+        rmin, rmax = reg[:, 0], reg[:, 1]
         if self.comm.world > 1:
-            mn, mx, sm = stats[:, 0].contiguous(), stats[:, 1].contiguous(), stats[:, 2:].contiguous()
-            self.comm.allreduce_min(mn)
-            self.comm.allreduce_max(mx)
-            self.comm.allreduce_sum(sm)
-            stats = torch.cat([mn[:, None], mx[:, None], sm], dim=1)
-        if self.comm.world > 1:   # OR of the status words over the ranks = max of every bit
+            # ONE min-exchange for everything that is a min, a max (negated) or an OR (negated bits):
+            # region min / max of the statistics, min / max of the posterior sample, the status word
             sh = torch.arange(8, device=self.device, dtype=torch.int64)
-            bits = (status.view(1).to(torch.int64) >> sh) & 1
-            self.comm.allreduce_max(bits)
+            bits = ((status.view(1).to(torch.int64) >> sh) & 1).to(torch.float64)
+            pack = torch.cat([rmin, -rmax, stats[:, 0], -stats[:, 1], -bits])
+            self.comm.allreduce_min(pack)
+            sm = stats[:, 2:].contiguous()
+            self.comm.allreduce_sum(sm)
+            rmin, rmax = pack[:d], -pack[d:2 * d]
+            stats = torch.cat([pack[2 * d:2 * d + P, None], -pack[2 * d + P:2 * d + 2 * P, None], sm], dim=1)
+            bits = (-pack[2 * d + 2 * P:]).to(torch.int64)
             status = (bits << sh).sum().to(torch.int32).view(1)
+        region_const = (rmin == rmax).all()
         host = torch.cat([status.to(torch.float64), n_acc.to(torch.float64), ds,
                           region_const.to(torch.float64).view(1), all_mad_zero.to(torch.float64).view(1), logsig])
         return dict(host=host, mad=mad, idx=idx, y=y, ss_out=ss_out, w=w, dacc=dacc, stats=stats, dist=f["dist"],
