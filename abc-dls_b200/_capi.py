@@ -58,6 +58,8 @@ SIGNATURES = {
                                    C.POINTER(_vp), C.POINTER(_sz), C.POINTER(_vp), C.POINTER(_sz), _vp]),
     "abcdls_fused_candidates": (_i32, [_vp, _vp, _i64, _i32, _i64, _i32, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64,
                                        _vp, _vp, _vp, _sz, _vp, _vp]),
+    "abcdls_fused_ds": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _sz, _vp, C.POINTER(_vp),
+                               C.POINTER(_sz), _vp]),
     "abcdls_fused_check": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp, _vp]),
     "abcdls_gather": (_i32, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp,
                              _vp, _vp, _vp, _vp, _vp]),

@@ -368,6 +368,7 @@ struct RefJob {
     const unsigned long long* src_count;  // entries appended (may exceed src_cap => miss)
     long long src_cap;
     int transform;                        // 1: v = |x - center|
+    int pow2k;                            // > 0: bin(v) = int(kNB * (v * lo)^(2^pow2k)) (monotone; lo = 1 / upper bound)
     int valid;                            // 0 => the bracket missed; results are NaN and MISS is flagged
     double center;
     double lo, scale;                     // bin(v) = clamp(int((v - lo) * scale))
@@ -381,6 +382,14 @@ struct RefJob {
     unsigned* small_count;
     double result[2];
 };
+
+__device__ __forceinline__ int job_bin(double v, double lo, double scale, int pow2k) {
+    if (pow2k == 0) return bin_of(v, lo, scale);
+    double t = __dmul_rn(v, lo);                      // v >= 0; every step is monotone in v
+    for (int i = 0; i < pow2k; ++i) t = __dmul_rn(t, t);
+    const int b = (int)(t * (double)kNB);
+    return b < 0 ? 0 : (b >= kNB ? kNB - 1 : b);
+}
 
 // one block per job: locate the bins.  (after the histogram is complete / all-reduced)
 __global__ void __launch_bounds__(256) k_refine_pick(RefJob* jobs, int* status) {
@@ -451,6 +460,7 @@ __global__ void __launch_bounds__(256) k_refine_gather(RefJob* jobs, long long n
     const int b0 = J.bq[0], b1 = J.bq[1];
     const double lo = J.lo, scale = J.scale, c = J.center, vmin = J.vmin;
     const bool tr = J.transform != 0;
+    const int pow2k = J.pow2k;
     const long long stride = (long long)gridDim.x * blockDim.x;
     // four independent streaming loads in flight per thread (the candidate lists are read once, from HBM)
     const double* __restrict__ src = J.src;
@@ -466,7 +476,7 @@ __global__ void __launch_bounds__(256) k_refine_gather(RefJob* jobs, long long n
             if (i0 + u * stride >= n) continue;
             const double v = tr ? fabs(__dsub_rn(xv[u], c)) : xv[u];
             if (v >= vmin) {
-                const int b = bin_of(v, lo, scale);
+                const int b = job_bin(v, lo, scale, pow2k);
                 if (b >= b0 && b <= b1) {
                     unsigned p = atomicAdd(J.small_count, 1u);
                     if (p < (unsigned)kSmallCap) J.small[p] = v;
@@ -548,6 +558,7 @@ __global__ void k_plan_median(RefJob* jobs, int d, const ColBrk* __restrict__ br
     J.src_count = cnt + j * 2 + 0;
     J.src_cap = capM;
     J.transform = 0;
+    J.pow2k = 0;
     J.center = 0.0;
     J.lo = brk[j].loM;
     J.scale = brk[j].scaleM;
@@ -585,6 +596,7 @@ __global__ void k_plan_mad(RefJob* jobs, int d, const ColBrk* __restrict__ brk,
     J.src_count = cnt + j * 2 + 1;
     J.src_cap = capU;
     J.transform = 1;
+    J.pow2k = 0;
     J.center = m;
     // x in U has fl|x - c| in [r1, r2]; with e = |c - m| its |x - m| lies in [r1 - e, r2 + e] up to rounding
     const double e = fabs(__dsub_rn(B.c, m));
@@ -625,6 +637,7 @@ __global__ void __launch_bounds__(256) k_refine_hist(RefJob* jobs, long long n_m
     if (n > n_max) n = n_max;
     const double lo = J.lo, scale = J.scale, c = J.center, vmin = J.vmin;
     const bool tr = J.transform != 0;
+    const int pow2k = J.pow2k;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const double* __restrict__ src = J.src;
     for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
@@ -638,7 +651,7 @@ __global__ void __launch_bounds__(256) k_refine_hist(RefJob* jobs, long long n_m
         for (int u = 0; u < 4; ++u) {
             if (i0 + u * stride >= n) continue;
             const double v = tr ? fabs(__dsub_rn(xv[u], c)) : xv[u];
-            if (v >= vmin) atomicAdd(&hist[bin_of(v, lo, scale)], 1u);
+            if (v >= vmin) atomicAdd(&hist[job_bin(v, lo, scale, pow2k)], 1u);
         }
     }
     __syncthreads();
@@ -1109,6 +1122,7 @@ __global__ void k_plan_ds(RefJob* job, const DistBrk* __restrict__ brk, const un
     J.src_count = cand_cnt;
     J.src_cap = cap;
     J.transform = 0;
+    J.pow2k = 0;
     J.center = 0.0;
     J.lo = brk->lo;
     J.scale = brk->scale;

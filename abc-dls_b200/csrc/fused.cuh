@@ -552,6 +552,89 @@ __global__ void __launch_bounds__(256) k_cand_exact(const double* __restrict__ c
     if (__any_sync(0xffffffffu, nonfinite) && (threadIdx.x & 31) == 0) atomicOr(status, ABCDLS_S_NONFINITE);
 }
 
+// ds = the (nacc - 1)-th (0-based, over all ranks) smallest exact candidate distance, with the histogram -> bin ->
+// gather -> sort machinery of the brackets instead of six radix passes.  The candidate distances crowd towards the
+// top (count(dist <= r) ~ r^d), so bins are uniform in (dist / hi)^(2^k), 2^k >= d: a monotone map that spreads them
+// evenly (~n_cand / 1024 per bin).  hi bounds every candidate's distance: q~ <= thr  =>  dist <= sqrt(thr) / (1 - eps).
+__global__ void k_plan_ds_fused(RefJob* job, const FusedPar* __restrict__ par, const long long* n_cand,
+                                const double* cand_dist, long long cap, unsigned long long* hist, double* small,
+                                unsigned* small_count, long long k, int d, int* status) {
+    if (threadIdx.x || blockIdx.x) return;
+    RefJob J;
+    const bool ok = par->ok != 0 && par->thr > 0.0;
+    const double hi = ok ? sqrt(par->thr) / (1.0 - par->eps) * (1.0 + 1e-6) : 1.0;
+    int pk = 0;
+    while ((1 << pk) < d) ++pk;
+    J.src = cand_dist;
+    J.src_count = reinterpret_cast<const unsigned long long*>(n_cand);
+    J.src_cap = cap;
+    J.transform = 0;
+    J.pow2k = pk;
+    J.center = 0.0;
+    J.lo = pk ? 1.0 / hi : 0.0;
+    J.scale = pk ? 0.0 : (double)kNB / hi;
+    J.vmin = -__longlong_as_double(0x7ff0000000000000ll);
+    J.kk[0] = J.kk[1] = k;
+    J.nq = 1;
+    J.bq[0] = J.bq[1] = -1;
+    J.before = 0;
+    J.hist = hist;
+    J.small = small;
+    J.small_count = small_count;
+    J.result[0] = J.result[1] = 0.0;
+    J.valid = ok ? 1 : 0;
+    if (!ok) atomicOr(status, ABCDLS_S_FASTPATH_MISS);
+    *job = J;
+}
+
+// the exchange block of a rank: kSmallCap gathered values followed by their count (as a double)
+__global__ void k_ds_pack(const RefJob* job) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) job->small[kSmallCap] = (double)*job->small_count;
+}
+
+// blocks[world][kSmallCap + 1] (or the job's own block when world == 1): sort, read the rank -> ds
+__global__ void __launch_bounds__(1024) k_ds_final(RefJob* job, const double* __restrict__ blocks, int world,
+                                                   double* __restrict__ ds_out, int* status) {
+    extern __shared__ double sm[];
+    __shared__ unsigned off[65];
+    RefJob& J = *job;
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    const double* src = blocks ? blocks : J.small;
+    if (threadIdx.x == 0) {
+        unsigned a = 0;
+        for (int r = 0; r < world; ++r) {
+            off[r] = a;
+            const double c = src[(size_t)r * (kSmallCap + 1) + kSmallCap];
+            a += (c >= 0.0 && c <= 4.0e9) ? (unsigned)c : 0xffffffffu / 64;
+        }
+        off[world] = a;
+    }
+    __syncthreads();
+    const unsigned cnt = off[world];
+    const long long rk = J.kk[0] - J.before;
+    const bool ok = J.valid != 0 && world <= 64 && cnt > 0 && cnt <= (unsigned)kSmallCap && rk >= 0 && rk < (long long)cnt;
+    if (!ok) {
+        if (threadIdx.x == 0) {
+            *ds_out = nan;
+            atomicOr(status, ABCDLS_S_FASTPATH_MISS);
+        }
+        return;
+    }
+    int np2 = 32;
+    while (np2 < (int)cnt) np2 <<= 1;
+    for (int t = threadIdx.x; t < np2; t += blockDim.x) sm[t] = inf;
+    __syncthreads();
+    for (int r = 0; r < world; ++r) {
+        const unsigned c = off[r + 1] - off[r];
+        const double* from = src + (size_t)r * (kSmallCap + 1);
+        for (int t = threadIdx.x; t < (int)c; t += blockDim.x) sm[off[r] + t] = from[t];
+    }
+    __syncthreads();
+    bitonic_sort(sm, np2);
+    if (threadIdx.x == 0) *ds_out = sm[rk];
+}
+
 // the completeness proof (header comment, item 4)
 __global__ void k_fused_check(const FusedPar* __restrict__ par, const double* __restrict__ mad, int d,
                               const double* __restrict__ ds_ptr, int* status) {
@@ -579,6 +662,11 @@ struct FusedWs {
     long long* tile_off;
     int* wprefix;                  // [nwords] candidates before every 32-row word
     unsigned long long* ealloc;    // emission slots handed out
+    unsigned long long* ds_hist;   // [kNB]    } zeroed together
+    unsigned* ds_small_count;      //          }
+    size_t ds_zero_bytes;
+    RefJob* ds_job;
+    double* ds_small;              // [kSmallCap + 1]
     size_t total_bytes;
 };
 
@@ -606,6 +694,12 @@ inline FusedWs carve_fused(void* ws, int64_t n, int d) {
     w.tile_off = (long long*)take((size_t)nblk * 8);
     w.wprefix = (int*)take((size_t)nwords * 4);
     w.ealloc = (unsigned long long*)take(8);
+    size_t z0 = o;
+    w.ds_hist = (unsigned long long*)take((size_t)kNB * 8);
+    w.ds_small_count = (unsigned*)take(8);
+    w.ds_zero_bytes = o - z0;
+    w.ds_job = (RefJob*)take(sizeof(RefJob));
+    w.ds_small = (double*)take((size_t)(kSmallCap + 1) * 8);
     w.total_bytes = o;
     return w;
 }
@@ -647,6 +741,7 @@ int abcdls_fused_sample_cols(abcdls_handle_t h, const double* ss, int64_t n, int
     ABCDLS_CUDA(h, cudaMemsetAsync(w.m.cnt, 0, w.m.zero_bytes, st));
     ABCDLS_CUDA(h, cudaMemsetAsync(w.total, 0, 8, st));
     ABCDLS_CUDA(h, cudaMemsetAsync(w.ealloc, 0, 8, st));
+    ABCDLS_CUDA(h, cudaMemsetAsync(w.ds_hist, 0, w.ds_zero_bytes, st));
     k_sample_cols<<<dim3(G, d), 512, smem, st>>>(ss, n, ld, 0x5EEDu, delta, w.m.est);
     ABCDLS_LAUNCH_CHECK(h);
     if (est_out) *est_out = w.m.est;
@@ -786,6 +881,44 @@ int abcdls_fused_candidates(abcdls_handle_t h, const double* ss, int64_t n, int 
     if (rc) return rc;
     return abcdls_fused_exact(h, ss, n, d, ld, world, mad, target, cap, cand_dist, cand_ss, cand_lrow, ecap, perm, ws,
                               ws_bytes, status_dev, stream);
+}
+
+// Stage 5c: exact ds among the candidates of all ranks.
+//   phase 0: plan + histogram of this rank's candidate distances   -> exchange: all-reduce (sum) x0 (kNB int64)
+//   phase 1: locate the bin + gather its values                     -> exchange: all-gather x0 (8193 doubles: values, count)
+//   phase 2: sort the gathered values -> ds_out (gath = the gathered blocks, NULL on a single rank)
+int abcdls_fused_ds(abcdls_handle_t h, int64_t n, int d, int phase, int world, const double* gath,
+                    const double* cand_dist, const int64_t* n_cand, int64_t cap, int64_t nacc, double* ds_out, void* ws,
+                    size_t ws_bytes, int* status_dev, void** x0, size_t* x0_count, void* stream) {
+    ABCDLS_CHECK_ARG(h, h && ws && cand_dist && n_cand && ds_out && status_dev && d >= 1 && d <= kFMaxD && phase >= 0 &&
+                            phase <= 2 && world >= 1 && world <= 64 && nacc >= 1 && cap >= 1,
+                     "fused_ds");
+    FusedWs w = carve_fused(ws, n, d);
+    if (ws_bytes < w.total_bytes) {
+        h->err = "fused workspace too small";
+        return ABCDLS_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    long long gg = (cap + 2047) / 2048;
+    if (gg > (long long)h->sm_count * 4) gg = (long long)h->sm_count * 4;
+    if (x0) *x0 = nullptr;
+    if (phase == 0) {
+        k_plan_ds_fused<<<1, 32, 0, st>>>(w.ds_job, w.par, (const long long*)n_cand, cand_dist, cap, w.ds_hist, w.ds_small,
+                                          w.ds_small_count, nacc - 1, d, status_dev);
+        k_refine_hist<<<dim3((unsigned)gg, 1), 256, 0, st>>>(w.ds_job, cap);
+        if (x0) { *x0 = w.ds_hist; *x0_count = (size_t)kNB; }
+    } else if (phase == 1) {
+        k_refine_pick<<<1, 256, 0, st>>>(w.ds_job, status_dev);
+        k_refine_gather<<<dim3((unsigned)gg, 1), 256, 0, st>>>(w.ds_job, cap);
+        k_ds_pack<<<1, 32, 0, st>>>(w.ds_job);
+        if (x0) { *x0 = w.ds_small; *x0_count = (size_t)kSmallCap + 1; }
+    } else {
+        const size_t smem = (size_t)kSmallCap * sizeof(double);
+        ABCDLS_ONCE(h, cudaFuncSetAttribute(k_ds_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_ds_final<<<1, 1024, smem, st>>>(w.ds_job, gath, gath ? world : 1, ds_out, status_dev);
+    }
+    ABCDLS_LAUNCH_CHECK(h);
+    return ABCDLS_OK;
 }
 
 // Stage 6 (after the exact ds has been selected among the candidates of all ranks): completeness proof.

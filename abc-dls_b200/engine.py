@@ -307,7 +307,8 @@ class AbcEngine:
                 k.fused_front(ss, n_local, n_global, d, ss.stride(0), target, nacc, row_offset, ccap, med, mad, cand_row,
                               cand_dist, cand_ss, cand_lrow, perm, n_cand, status, comm, pregather=pre)
             with self._t("fused_ds"):
-                ds = self._select(cand_dist[None, :], ccap, None, nacc - 1, nacc - 1, counts=n_cand)[0, :1].contiguous()
+                ds = k.new(1)
+                k.fused_ds(n_local, d, nacc, ccap, cand_dist, n_cand, ds, status, comm)
                 k.fused_check(n_local, d, mad, ds, status)
             with self._t("accept"):
                 ws = k.accept_workspace(ccap)

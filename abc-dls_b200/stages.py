@@ -160,6 +160,21 @@ class CudaStages:
                              _p(cand_ss), _p(cand_lrow), cand_ss.shape[0], _p(perm), _p(ws), ws.numel(), _p(status), st)
         self.launches += 24
 
+    def fused_ds(self, n, d, nacc, cap, cand_dist, n_cand, ds, status, comm=None):
+        """Exact ds = nacc-th smallest candidate distance over all ranks (3 small kernels-stages, 2 exchanges)."""
+        world = comm.world if comm is not None else 1
+        ws = self._ws["fused"]
+        p0, c0 = C.c_void_p(), C.c_size_t()
+        gath = None
+        for phase in range(3):
+            self.handle.call("abcdls_fused_ds", n, d, phase, world, _p(gath), _p(cand_dist), _p(n_cand), cap, nacc,
+                             _p(ds), _p(ws), ws.numel(), _p(status), C.byref(p0), C.byref(c0), self._stream())
+            if world > 1 and phase == 0:
+                comm.allreduce_sum(self._view(ws, p0, c0, torch.int64, 8))
+            elif world > 1 and phase == 1:
+                gath = comm.allgather(self._view(ws, p0, c0, torch.float64, 8)).contiguous()
+        self.launches += 7
+
     def fused_check(self, n, d, mad, ds, status):
         ws = self._ws["fused"]
         self.handle.call("abcdls_fused_check", n, d, _p(mad), _p(ds), _p(ws), ws.numel(), _p(status), self._stream())

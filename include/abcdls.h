@@ -208,6 +208,12 @@ int abcdls_fused_candidates(abcdls_handle_t h, const double* ss, int64_t n, int 
                             const double* mad, const double* target, int64_t row_offset, int64_t cap, int64_t* cand_row,
                             double* cand_dist, const double* cand_ss, const int32_t* cand_lrow, int64_t ecap,
                             int64_t* perm, int64_t* n_cand, void* ws, size_t ws_bytes, int* status_dev, void* stream);
+/* exact ds among the candidates of all ranks (histogram -> bin -> gather -> sort; bins uniform in dist^(2^k)):
+ * phase 0 -> all-reduce(sum) x0 (int64); phase 1 -> all-gather x0 (doubles: 8192 values + their count);
+ * phase 2 (gath = gathered blocks, NULL on one rank) -> ds_out */
+int abcdls_fused_ds(abcdls_handle_t h, int64_t n, int d, int phase, int world, const double* gath,
+                    const double* cand_dist, const int64_t* n_cand, int64_t cap, int64_t nacc, double* ds_out, void* ws,
+                    size_t ws_bytes, int* status_dev, void** x0, size_t* x0_count, void* stream);
 int abcdls_fused_check(abcdls_handle_t h, int64_t n, int d, const double* mad, const double* ds, void* ws,
                        size_t ws_bytes, int* status_dev, void* stream);
 
