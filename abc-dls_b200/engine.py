@@ -160,7 +160,7 @@ class AbcEngine:
         self.host_enqueue_ms = []   # per abc() call: host time spent enqueueing before the one blocking read
         self.use_graphs = True      # replay the device work of a repeated call as one CUDA graph
         self.copy_results = True    # results of a replayed graph are copied out of the graph's buffers
-        self.max_graphs = 4
+        self.max_graphs = 8
         # Gather the parameters of ALL candidates on a second stream during the refinement.  Measured at 1e8 x 16: the
         # scattered reads (1.6x more rows) slow the memory-bound refinement kernels by more than the later gather
         # saves (4.94 -> 5.2 ms per call), so it stays off.

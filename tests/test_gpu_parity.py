@@ -333,3 +333,40 @@ def test_cfg5_full_size_three_independent_paths_agree(engine):
     first = torch.nonzero(b.dist <= a.ds).view(-1)[:nacc]
     assert torch.equal(first, a.idx)
     del b, c
+
+
+@pytest.mark.parametrize("d,P", [(2, 2), (7, 3), (15, 4)])
+def test_fused_odd_column_counts(engine, d, P):
+    """Column counts that do not fill the 16-warp CTA / the paired 16-byte emission stores."""
+    par, ss, tgt = synth.abc_tables((1 << 20) + 512, d, P, engine.device)
+    _check_fused(engine, par, ss, tgt, 0.02, "loclinear")
+
+
+def test_fused_tiny_tolerance_and_half_the_table(engine):
+    """nacc = 21 (the sampled threshold is far above ds: many more candidates than needed, still exact) and
+    tol = 0.5 (every second row is accepted: the candidate list is the whole table)."""
+    par, ss, tgt = synth.abc_tables(1 << 21, 4, 2, engine.device)
+    misses = engine.fast_misses
+    r = engine.abc(tgt, par, ss, 1e-5, "rejection")
+    o = O.abc(_np(tgt), _np(par).T, _np(ss).T, 1e-5, "rejection")
+    assert o.nacc == 21 and r.ds == o.ds
+    np.testing.assert_array_equal(_np(r.idx), o.idx)
+    r = engine.abc(tgt, par, ss, 0.5, "rejection")
+    o = O.abc(_np(tgt), _np(par).T, _np(ss).T, 0.5, "rejection")
+    assert r.ds == o.ds
+    np.testing.assert_array_equal(_np(r.idx), o.idx)
+    assert engine.fast_misses - misses <= 2           # a miss is allowed here (ladder), a wrong answer is not
+
+
+def test_fused_target_far_from_the_data(engine):
+    """Large offset between target and data relative to the spread: the rounding slack eta of the proof must cover
+    R's cancellation in (x/m - t/m)."""
+    g = torch.Generator(device="cpu").manual_seed(11)
+    n = 1 << 20
+    ss = (1.0e6 + torch.randn((3, n), generator=g, dtype=torch.float64)).to(engine.device)
+    par = torch.rand((2, n), generator=g, dtype=torch.float64).to(engine.device)
+    tgt = torch.tensor([1.0e6 + 0.1, 1.0e6 - 0.2, 1.0e6], dtype=torch.float64, device=engine.device)
+    r = engine.abc(tgt, par, ss, 0.01, "loclinear")
+    o = O.abc(_np(tgt), _np(par).T, _np(ss).T, 0.01, "loclinear")
+    np.testing.assert_array_equal(_np(r.idx), o.idx)
+    assert r.ds == o.ds and _rel(_np(r.adj_values), o.adj_values) < REL_TOL
