@@ -34,6 +34,22 @@ class AbcError(RuntimeError):
     """Mirrors an R ``stop()`` inside abc()/postpr() (surfaced by rpy2 as RRuntimeError)."""
 
 
+class _Deferred:
+    """A result array that still lives in the buffers of a replayed CUDA graph.  It is copied out on first access; if
+    the same plan has been replayed in the meantime the data is gone and the access raises instead of returning the
+    newer call's values."""
+
+    def __init__(self, plan, view, post=None):
+        self.plan, self.gen, self.view, self.post = plan, plan["gen"], view, post
+
+    def resolve(self):
+        if self.plan["gen"] != self.gen:
+            raise RuntimeError("this array of an earlier abc() result was not read before the next call with the same "
+                               "tables reused the graph's buffers; read it first, or set engine.lazy_results = False")
+        t = self.view.clone()
+        return self.post(t) if self.post is not None else t
+
+
 @dataclass
 class AbcResult:
     method: str
@@ -60,6 +76,13 @@ class AbcResult:
     warnings: List[str] = field(default_factory=list)
     numparam: int = 0
     numstat: int = 0
+
+    def __getattribute__(self, name):
+        v = object.__getattribute__(self, name)
+        if isinstance(v, _Deferred):
+            v = v.resolve()
+            object.__setattr__(self, name, v)
+        return v
 
     @property
     def values(self) -> torch.Tensor:
@@ -159,7 +182,8 @@ class AbcEngine:
         self.path_calls = {"fused": 0, "two_pass": 0, "exact": 0}   # front-half path taken, per call
         self.host_enqueue_ms = []   # per abc() call: host time spent enqueueing before the one blocking read
         self.use_graphs = True      # replay the device work of a repeated call as one CUDA graph
-        self.copy_results = True    # results of a replayed graph are copied out of the graph's buffers
+        self.copy_results = True    # results of a replayed graph are copied out of the graph's buffers ...
+        self.lazy_results = True    # ... the rarely read ones (ss, residuals, unadj of loclinear, dist) on first access
         self.max_graphs = 8
         # Gather the parameters of ALL candidates on a second stream during the refinement.  Measured at 1e8 x 16: the
         # scattered reads (1.6x more rows) slow the memory-bound refinement kernels by more than the later gather
@@ -408,6 +432,7 @@ class AbcEngine:
         plan = self._graphs.get(key) if graphable else None
         if plan is not None:
             plan["target"].copy_(target)
+            plan["gen"] += 1
             plan["graph"].replay()
             self.k.launches += plan["launches"]
             self._graphs[key] = self._graphs.pop(key)          # LRU order
@@ -448,19 +473,30 @@ class AbcEngine:
         if st & _capi.S_CAPACITY:
             raise AbcError("internal: accepted-row buffer overflow")
 
-        # results of a replayed graph live in the graph's buffers (overwritten by the next call with the same key)
-        own = (lambda t: t.clone()) if (from_graph and self.copy_results) else (lambda t: t)
+        # Results of a replayed graph live in the graph's buffers (overwritten by the next call with the same key): what
+        # a caller normally reads (rows, posterior sample, weights, summary statistics) is copied out now, the rest on
+        # first access (_Deferred).
+        if from_graph and self.copy_results:
+            own = lambda t: t.clone()
+            later = (lambda t, post=None: _Deferred(plan, t, post)) if self.lazy_results else \
+                    (lambda t, post=None: post(t.clone()) if post else t.clone())
+        else:
+            own = lambda t: t
+            later = lambda t, post=None: post(t) if post else t
+        tr = lambda t: t.t()
         mad, nacc = own(o["mad"]), pl["nacc"]
+        lin = method == "loclinear"
         r = AbcResult(method=method, tol=tol, nacc=nacc, n_global=pl["n_global"], ds=ds_h, mad=mad,
-                      idx=own(o["idx"][:n_loc]), unadj_values=own(o["y"][:, :n_loc]).t(),
-                      ss=own(o["ss_out"][:, :n_loc]).t(),
-                      weights=(own(o["w"][:n_loc]) if method != "rejection"
+                      idx=own(o["idx"][:n_loc]),
+                      unadj_values=(later(o["y"][:, :n_loc], tr) if lin else own(o["y"][:, :n_loc]).t()),
+                      ss=later(o["ss_out"][:, :n_loc], tr),
+                      weights=(own(o["w"][:n_loc]) if lin
                                else torch.ones(n_loc, dtype=torch.float64, device=self.device)),
-                      dist_accepted=own(o["dacc"][:n_loc]), stats=own(o["stats"]), warnings=warnings, numparam=P,
+                      dist_accepted=later(o["dacc"][:n_loc]), stats=own(o["stats"]), warnings=warnings, numparam=P,
                       numstat=d, dist=o["dist"] if keep_dist else None)
-        if method == "loclinear":
+        if lin:
             tsc = torch.where(mad == 0, target, target / torch.where(mad == 0, torch.ones_like(mad), mad))
-            r.adj_values, r.residuals = own(o["adj"][:, :n_loc]).t(), own(o["res"][:, :n_loc]).t()
+            r.adj_values, r.residuals = own(o["adj"][:, :n_loc]).t(), later(o["res"][:, :n_loc], tr)
             r.pred = o["beta"][0] + o["the_m"]
             r.sigma2 = own(o["sig"])
             r.coef = self._uncentre(o["beta"], tsc)
@@ -490,7 +526,7 @@ class AbcEngine:
                 self.comm.recorder = None
                 sg.end()
         torch.cuda.current_stream(self.device).wait_stream(sg.stream)
-        plan = dict(graph=sg, out=out, target=tgt, launches=self.k.launches - l0,
+        plan = dict(graph=sg, out=out, target=tgt, gen=0, launches=self.k.launches - l0,
                     keep=list(getattr(self.k, "_ws", {}).values()))   # workspaces must outlive the graphs
         self._graphs[key] = plan
         sg.replay()

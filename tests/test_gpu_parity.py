@@ -291,6 +291,12 @@ def test_cuda_graph_replay_matches_eager_and_tracks_the_target(engine):
     np.testing.assert_array_equal(_np(r4.idx), o.idx)
     assert r4.ds == o.ds and _rel(_np(r4.adj_values), o.adj_values) < REL_TOL
     assert abs(r4.aic - o.aic) <= 1e-9 * abs(o.aic)
+    # rarely read arrays are copied out of the graph's buffers on first access: fine for the latest call, an error
+    # (never the newer call's data) once the buffers have been reused
+    np.testing.assert_array_equal(_np(r4.ss), o.ss)
+    np.testing.assert_array_equal(_np(r4.unadj_values), o.unadj_values)
+    with pytest.raises(RuntimeError, match="reused the graph's buffers"):
+        r3.ss
 
 
 # ---- BASELINE.json full sizes ------------------------------------------------------------------------------------------
