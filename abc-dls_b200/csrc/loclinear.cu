@@ -808,7 +808,7 @@ int abcdls_residual_stats(abcdls_handle_t h, const double* xs, const double* y, 
     double* part = reinterpret_cast<double*>(ws);
     unsigned* done = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) +
                                                  align_up((size_t)groups * kResBlocks * 24 * sizeof(double), 256));
-    unsigned gx = grid_for(h, cap, 256, 4);
+    unsigned gx = grid_for(h, cap, 256, 2);   // fat blocks: the 24-value block reduction is a fixed cost per block
     if (gx > (unsigned)kResBlocks) gx = kResBlocks;
     const size_t smem = (size_t)((d + 1) * 8 + 10 * 24) * sizeof(double);
     k_residual_stats<<<dim3(gx, groups), 256, smem, (cudaStream_t)stream>>>(xs, y, beta, w, (const long long*)n_acc, cap,

@@ -572,8 +572,12 @@ class AbcEngine:
             beta = k.new(M, P)
             k.solve(gram, rhs, d, P, beta, status)
             res = k.new(P, cap)
-            rstat = k.new(3, P)      # sum res | sum w res | sum w res^2
-            k.residual_stats(xs, y, beta, w, n_acc, cap, d, P, res, rstat)
+            # residuals, then sum res | sum w res | sum w res^2 in one statistics pass (measured faster than the fused
+            # k_residual_stats, whose 48 running sums per thread cost occupancy: 0.15 vs 0.20 ms)
+            k.residual(xs, y, beta, n_acc, cap, d, P, res)
+            rs = k.new(P, 6)
+            k.col_stats(res, w, n_acc, cap, P, rs)
+            rstat = rs[:, 2:5].t().contiguous()
             sums = torch.cat([rstat.view(-1), n_acc.to(torch.float64)])
             self.comm.allreduce_sum(sums)
             the_m = (sums[:P] / sums[3 * P]).contiguous()          # UNWEIGHTED mean of the residuals (R: colMeans)
