@@ -38,14 +38,18 @@ constexpr int kMaxD = 64;
 // shared-memory bitonic sort of n = power of two doubles (n >= 8, blockDim.x * 8 >= ... any block size).
 // Steps with partner distance j >= 8 work on pairs (every thread busy, two loads + two stores per pair); the last
 // three steps of every merge (j = 4, 2, 1) stay inside 8 consecutive elements and run in registers.
-__device__ __forceinline__ void bitonic_tail8(double* s, int n, int k) {
-    // steps j = 4, 2, 1 of the merge with run length k (k >= 8): direction is constant inside an aligned block of 8
-    for (int blk = threadIdx.x; blk < n / 8; blk += blockDim.x) {
+// Three consecutive levels j = 4 jlo, 2 jlo, jlo of the merge with run length k (k >= 8 jlo) in ONE round trip through
+// shared memory: a thread owns the 8 elements base + t * jlo (t = 0..7) whose indices differ exactly in the three bits
+// those levels compare, and runs the three compare-exchange rounds in registers.  The sorts are shared-memory
+// bandwidth bound (every level used to be a full read + write of the array), so this is ~2x.
+__device__ __forceinline__ void bitonic_block8(double* s, int n, int k, int jlo) {
+    const int sh = 31 - __clz(jlo);
+    for (int g = threadIdx.x; g < n / 8; g += blockDim.x) {
+        const int base = ((g >> sh) << (sh + 3)) | (g & (jlo - 1));
         double v[8];
-        double* p = s + blk * 8;
 #pragma unroll
-        for (int t = 0; t < 8; ++t) v[t] = p[t];
-        const bool up = (((blk * 8) & k) == 0);
+        for (int t = 0; t < 8; ++t) v[t] = s[base + t * jlo];
+        const bool up = ((base & k) == 0);
 #pragma unroll
         for (int j = 4; j > 0; j >>= 1) {
 #pragma unroll
@@ -59,10 +63,11 @@ __device__ __forceinline__ void bitonic_tail8(double* s, int n, int k) {
             }
         }
 #pragma unroll
-        for (int t = 0; t < 8; ++t) p[t] = v[t];
+        for (int t = 0; t < 8; ++t) s[base + t * jlo] = v[t];
     }
     __syncthreads();
 }
+
 
 __device__ __forceinline__ void bitonic_step(double* s, int n, int k, int j) {
     for (int p = threadIdx.x; p < n / 2; p += blockDim.x) {
@@ -106,6 +111,19 @@ __device__ __forceinline__ void bitonic_head8(double* s, int n) {
     __syncthreads();
 }
 
+// levels j = jtop .. 1 of one merge.  Three levels at a time (bitonic_block8) where the 8 elements of a thread are at
+// least 32 apart (consecutive lanes then touch consecutive words: conflict free) and for the last three levels; pair
+// steps in between (a block with a small stride would serialise on bank conflicts and lose more than it saves).
+__device__ __forceinline__ void bitonic_merge_levels(double* s, int n, int k, int jtop) {
+    int j = jtop;
+    while (j >= 128) {            // levels j, j/2, j/4 with stride j/4 >= 32
+        bitonic_block8(s, n, k, j >> 2);
+        j >>= 3;
+    }
+    for (; j >= 8; j >>= 1) bitonic_step(s, n, k, j);
+    bitonic_block8(s, n, k, 1);   // levels 4, 2, 1
+}
+
 __device__ void bitonic_sort(double* s, int n) {
     if (n < 8) {   // tiny inputs: plain network
         for (int k = 2; k <= n; k <<= 1)
@@ -113,16 +131,12 @@ __device__ void bitonic_sort(double* s, int n) {
         return;
     }
     bitonic_head8(s, n);
-    for (int k = 16; k <= n; k <<= 1) {
-        for (int j = k >> 1; j >= 8; j >>= 1) bitonic_step(s, n, k, j);
-        bitonic_tail8(s, n, k);
-    }
+    for (int k = 16; k <= n; k <<= 1) bitonic_merge_levels(s, n, k, k >> 1);
 }
 
 // s is already bitonic (e.g. decreasing then increasing): one ascending merge sorts it
 __device__ void bitonic_merge_up(double* s, int n) {
-    for (int j = n >> 1; j >= 8; j >>= 1) bitonic_step(s, n, n << 1, j);   // k = 2n: (i & k) == 0 for every i -> ascending
-    bitonic_tail8(s, n, n << 1);
+    bitonic_merge_levels(s, n, n << 1, n >> 1);   // k = 2n: (i & k) == 0 for every i -> ascending
 }
 
 __device__ __forceinline__ unsigned hash3(unsigned a, unsigned b, unsigned c) {

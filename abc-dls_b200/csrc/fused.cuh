@@ -64,6 +64,8 @@ constexpr int kFMaxStages = 8;
 constexpr int kFRingBytes = 160 * 1024;
 constexpr int kFChunk = 256;
 constexpr int kFEChunk = 64;     // candidate-row slots a warp allocates at a time
+constexpr int kFG2 = 128;        // CTAs of the row sample, kSampleQ rows each (262144 rows in total)
+constexpr int kSampleQ = 2048;
 constexpr int kFHeader = 1024;   // bytes in front of the ring
 constexpr int kFQCap = 16;       // per-lane queue slots (both bands share it; flushed when a lane holds more than 8)
 constexpr int kFQWarpBytes = kFQCap * 256;                // per consumer warp
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(512) k_sample_qdist(const double* __restrict__
     __shared__ double2 sc[kFMaxD];
     if (threadIdx.x < kFMaxD) sc[threadIdx.x] = make_double2(par->tgt[threadIdx.x], par->rho[threadIdx.x]);
     __syncthreads();
-    for (int t = threadIdx.x; t < kSample; t += blockDim.x) {
+    for (int t = threadIdx.x; t < kSampleQ; t += blockDim.x) {
         const long long r = sample_row(seed, blockIdx.x, t, n);
         double q = 0.0;
         for (int j = 0; j < d; ++j) {
@@ -145,10 +147,10 @@ __global__ void __launch_bounds__(512) k_sample_qdist(const double* __restrict__
         sm[t] = (q == q) ? q : __longlong_as_double(0x7ff0000000000000ll);   // NaN rows sort last
     }
     __syncthreads();
-    bitonic_sort(sm, kSample);
+    bitonic_sort(sm, kSampleQ);
     if (threadIdx.x == 0) {
-        int ih = (int)ceil((p + delta) * kSample) + 1;
-        ih = max(0, min(kSample - 1, ih));
+        int ih = (int)ceil((p + delta) * kSampleQ) + 1;
+        ih = max(0, min(kSampleQ - 1, ih));
         est[blockIdx.x] = sm[ih];
     }
 }
@@ -670,7 +672,6 @@ struct FusedWs {
     size_t total_bytes;
 };
 
-constexpr int kFG2 = 64;
 
 inline long long round_chunk(long long x) { return (x + kFChunk - 1) / kFChunk * kFChunk; }
 
@@ -759,8 +760,8 @@ int abcdls_fused_sample_dist(abcdls_handle_t h, const double* ss, int64_t n, int
     k_make_brackets<<<d, 32, 0, st>>>(w.m.est, G, d, 1.0 / world, w.m.brk);
     k_make_fused_scale<<<1, 32, 0, st>>>(w.m.est, G, d, 1.0 / world, target, w.par);
     const double p = (double)nacc / (double)n_global;
-    const double delta = kZ * sqrt(p * (1.0 - p) / ((double)G2 * kSample * world));
-    k_sample_qdist<<<G2, 512, (size_t)kSample * sizeof(double), st>>>(ss, n, d, ld, w.par, 0xD157u, p, delta, w.est2);
+    const double delta = kZ * sqrt(p * (1.0 - p) / ((double)G2 * kSampleQ * world));
+    k_sample_qdist<<<G2, 512, (size_t)kSampleQ * sizeof(double), st>>>(ss, n, d, ld, w.par, 0xD157u, p, delta, w.est2);
     ABCDLS_LAUNCH_CHECK(h);
     if (est_out) *est_out = w.est2;
     if (est_count) *est_count = (size_t)G2;
