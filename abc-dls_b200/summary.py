@@ -3,7 +3,8 @@
 Min / Max / (weighted) Mean come from the ``k_col_stats`` kernel (they are what ABC-DLS's SMC reads,
 ABC.py:2833, 2837).  The percentile rows are SURVEY §8f "next" work: they are computed here with a
 device sort (R ``quantile`` type 7 for rejection; weighted order statistic = ``quantreg::rq(x ~ 1)`` for
-loclinear).  The Mode row (argmax of R ``density``) is not implemented and reads NaN.
+loclinear).  The Mode row is ``abc:::getmode``: the grid point of R's ``density()`` (gaussian kernel, ``bw.nrd0``, linear
+binning onto 1024 points + FFT convolution, 512 output points) with the largest (weighted) density.
 """
 from __future__ import annotations
 
@@ -44,6 +45,45 @@ def _quantile7(xs: torch.Tensor, p: float) -> torch.Tensor:
     return torch.where(xl == xh, xl, (1 - h) * xl + h * xh)
 
 
+def _density_mode(xs: torch.Tensor, ws, n_grid: int = 512, cut: float = 3.0) -> torch.Tensor:
+    """Mode of R's ``density(x, weights = w / sum(w))`` (stats::density.default of R 4.3).  xs: the sample SORTED
+    ascending, ws: its weights in the same order (None = equal weights).  Deterministic: the linear binning is done
+    with prefix sums over the sorted sample instead of atomic adds."""
+    n = xs.numel()
+    dev, f64 = xs.device, torch.float64
+    sd = xs.std(unbiased=True)
+    iqr = _quantile7(xs, 0.75) - _quantile7(xs, 0.25)
+    lo_ = torch.minimum(sd, iqr / 1.34)
+    lo_ = torch.where(lo_ == 0, torch.where(sd == 0, torch.where(xs[0] == 0, torch.ones_like(sd), xs[0].abs()), sd), lo_)
+    bw = 0.9 * lo_ * n ** (-0.2)                                   # bw.nrd0 (of the UNWEIGHTED sample, like R)
+    frm, to = xs[0] - cut * bw, xs[-1] + cut * bw
+    lo, up = frm - 4.0 * bw, to + 4.0 * bw
+    w = torch.full((n,), 1.0 / n, dtype=f64, device=dev) if ws is None else ws / ws.sum()
+    N = n_grid
+    xdelta = (up - lo) / (N - 1)
+    xpos = (xs - lo) / xdelta
+    ix = torch.floor(xpos)
+    fx = xpos - ix
+    ix = ix.to(torch.int64).clamp_(0, N - 2)                        # the data lies 7 bw inside [lo, up]
+    # C_BinDist: y[ix] += w (1 - fx); y[ix + 1] += w fx   -- ix is non-decreasing, so segment sums = prefix differences
+    c0 = torch.cat([torch.zeros(1, dtype=f64, device=dev), torch.cumsum(w * (1 - fx), 0)])
+    c1 = torch.cat([torch.zeros(1, dtype=f64, device=dev), torch.cumsum(w * fx, 0)])
+    edges = torch.searchsorted(ix, torch.arange(N + 1, device=dev, dtype=torch.int64), right=False)
+    y = torch.zeros(2 * N, dtype=f64, device=dev)
+    y[:N] += c0[edges[1:]] - c0[edges[:-1]]
+    y[1:N + 1] += c1[edges[1:]] - c1[edges[:-1]]
+    k = torch.linspace(0.0, 1.0, 2 * N, dtype=f64, device=dev) * (2.0 * (up - lo))
+    k = torch.cat([k[:N + 1], -k[1:N].flip(0)])
+    k = torch.exp(-0.5 * (k / bw) ** 2) / (bw * (2.0 * np.pi) ** 0.5)
+    dens = torch.fft.ifft(torch.fft.fft(y) * torch.conj(torch.fft.fft(k))).real[:N].clamp_min(0.0)
+    xout = torch.arange(N, dtype=f64, device=dev) * ((to - frm) / (N - 1)) + frm     # numpy / R seq(): i * step + from
+    t = (xout - lo) / xdelta
+    i0 = torch.floor(t).to(torch.int64).clamp_(0, N - 2)
+    fr = t - i0
+    yout = dens[i0] * (1 - fr) + dens[i0 + 1] * fr
+    return xout[torch.argmax(yout)]
+
+
 def summary_table(values: torch.Tensor, weights, stats: torch.Tensor, weighted: bool, intvl: float = 0.95, names=None):
     """values (n, P) global posterior sample, weights (n,) or None, stats (P, 6) from k_col_stats."""
     a = (1 - intvl) / 2
@@ -54,8 +94,11 @@ def summary_table(values: torch.Tensor, weights, stats: torch.Tensor, weighted: 
         out[3] = stats[:, 3] / stats[:, 5]
         for p in range(P):
             xs, order = torch.sort(values[:, p], stable=True)
-            cw = torch.cumsum(weights[order], 0)
+            ws = weights[order]
+            cw = torch.cumsum(ws, 0)
             W = cw[-1]
+            if n >= 2:
+                out[4, p] = _density_mode(xs, ws)
             for row, tau in ((1, a), (2, 0.5), (5, 1 - a)):
                 kk = torch.searchsorted(cw, (tau * W).reshape(1), right=False).clamp(max=n - 1)
                 out[row, p] = xs[kk[0]]
@@ -64,6 +107,8 @@ def summary_table(values: torch.Tensor, weights, stats: torch.Tensor, weighted: 
         for p in range(P):
             xs, _ = torch.sort(values[:, p])
             out[1, p], out[2, p], out[5, p] = _quantile7(xs, a), _quantile7(xs, 0.5), _quantile7(xs, 1 - a)
+            if n >= 2:
+                out[4, p] = _density_mode(xs, None)
     return SummaryTable(out.cpu().numpy(), names)
 
 

@@ -345,25 +345,76 @@ def postpr(target, index, sumstat, tol: float, method: str = "rejection",
 SUMMARY_ROWS = ("Min.:", "2.5% Perc.:", "Median:", "Mean:", "Mode:", "97.5% Perc.:", "Max.:")
 
 
+def r_bw_nrd0(x: np.ndarray) -> float:
+    """stats::bw.nrd0 (R 4.3): 0.9 * min(sd, IQR / 1.34) * n^-0.2, with R's fallbacks when that is 0."""
+    x = np.asarray(x, dtype=np.float64)
+    hi = float(np.std(x, ddof=1))
+    q = r_quantile7(x, [0.25, 0.75])
+    lo = min(hi, float(q[1] - q[0]) / 1.34)
+    if not lo:
+        lo = hi or abs(float(x[0])) or 1.0
+    return 0.9 * lo * x.size ** (-0.2)
+
+
+def r_density(x: np.ndarray, weights=None, n: int = 512, cut: float = 3.0):
+    """stats::density.default (R 4.3, gaussian kernel, bw = "nrd0", old grid coordinates): linear binning of the
+    (weighted) sample onto 2n points over [lo, up] = [min - 7 bw, max + 7 bw], circular convolution with the normal
+    kernel by FFT, clamping at 0, linear interpolation onto n points over [min - 3 bw, max + 3 bw]."""
+    x = np.asarray(x, dtype=np.float64)
+    nx = x.size
+    w = np.full(nx, 1.0 / nx) if weights is None else np.asarray(weights, dtype=np.float64)
+    bw = r_bw_nrd0(x)
+    frm, to = x.min() - cut * bw, x.max() + cut * bw
+    lo, up = frm - 4.0 * bw, to + 4.0 * bw
+    # C_BinDist
+    y = np.zeros(2 * n)
+    xdelta = (up - lo) / (n - 1)
+    xpos = (x - lo) / xdelta
+    ix = np.floor(xpos).astype(np.int64)
+    fx = xpos - ix
+    inside = (ix >= 0) & (ix <= n - 2)
+    np.add.at(y, ix[inside], w[inside] * (1 - fx[inside]))
+    np.add.at(y, ix[inside] + 1, w[inside] * fx[inside])
+    left = ix == -1
+    np.add.at(y, np.zeros(int(left.sum()), dtype=np.int64), w[left] * fx[left])
+    right = ix == n - 1
+    np.add.at(y, ix[right], w[right] * (1 - fx[right]))
+    kords = np.linspace(0.0, 2.0 * (up - lo), 2 * n)
+    kords[n + 1:] = -kords[n - 1:0:-1]
+    kords = np.exp(-0.5 * (kords / bw) ** 2) / (bw * np.sqrt(2.0 * np.pi))
+    conv = np.fft.ifft(np.fft.fft(y) * np.conj(np.fft.fft(kords))) * (2 * n)    # R's inverse fft is unnormalised
+    dens = np.maximum(0.0, conv.real[:n] / (2 * n))
+    xords = np.linspace(lo, up, n)
+    xout = np.linspace(frm, to, n)
+    return xout, np.interp(xout, xords, dens)
+
+
+def r_density_mode(x: np.ndarray, weights=None) -> float:
+    """abc:::getmode: the grid point of ``density(x, weights = w / sum(w))`` with the largest density (first one)."""
+    if weights is not None:
+        weights = np.asarray(weights, dtype=np.float64)
+        weights = weights / weights.sum()
+    gx, gy = r_density(x, weights)
+    return float(gx[int(np.argmax(gy))])
+
+
 def summary_abc(res: AbcOracleResult, intvl: float = 0.95) -> np.ndarray:
     """``summary.abc``: rejection -> plain statistics of unadj.values; loclinear -> min/max plain,
-    weighted mean, weighted quantiles (rq).  The Mode row (argmax of R ``density``) is left NaN:
-    ABC-DLS reads rows 0 and 6 (ABC.py:2833, 2837) and prints the table; the kernel-density mode is
-    on SURVEY §8f's "next" list."""
+    weighted mean, weighted quantiles (rq), mode = argmax of the (weighted) kernel density."""
     a = (1 - intvl) / 2
     if res.method == "rejection":
         x = res.unadj_values
         out = np.full((7, x.shape[1]), np.nan)
         for p in range(x.shape[1]):
             q = r_quantile7(x[:, p], [a, 0.5, 1 - a])
-            out[:, p] = [x[:, p].min(), q[0], q[1], r_mean(x[:, p]), np.nan, q[2], x[:, p].max()]
+            out[:, p] = [x[:, p].min(), q[0], q[1], r_mean(x[:, p]), r_density_mode(x[:, p]), q[2], x[:, p].max()]
         return out
     x, w = res.adj_values, res.weights
     out = np.full((7, x.shape[1]), np.nan)
     for p in range(x.shape[1]):
         q = r_weighted_quantile(x[:, p], w, [a, 0.5, 1 - a])
-        out[:, p] = [x[:, p].min(), q[0], q[1], float((x[:, p] * w).sum() / w.sum()), np.nan, q[2],
-                     x[:, p].max()]
+        out[:, p] = [x[:, p].min(), q[0], q[1], float((x[:, p] * w).sum() / w.sum()), r_density_mode(x[:, p], w),
+                     q[2], x[:, p].max()]
     return out
 
 

@@ -226,3 +226,48 @@ def test_narrowing_and_lmrd():
     keep = (par[:, 0] >= .1) & (par[:, 0] <= .9) & (par[:, 1] >= .2) & (par[:, 1] <= .8)
     np.testing.assert_array_equal(lines, np.flatnonzero(keep) + 2)
     assert math.isclose(O.lmrd_calculation([0, 0], [1, 2], [0, 0], [2, 4]), math.log(0.5))
+
+
+# ---- summary.abc Mode row: R density() restated (stats::density.default, bw.nrd0, C_BinDist, FFT convolution) --------
+def test_bw_nrd0_known_answer():
+    x = np.array([1.0, 2.0, 3.0, 4.0, 100.0])
+    # sd = 43.60619, IQR (type 7) = 4 - 2 = 2 -> lo = 2 / 1.34; bw = 0.9 * lo * 5^-0.2
+    assert abs(O.r_bw_nrd0(x) - 0.9 * (2.0 / 1.34) * 5 ** (-0.2)) < 1e-15
+    assert O.r_bw_nrd0(np.array([3.0, 3.0, 3.0])) == 0.9 * 3.0 * 3 ** (-0.2)       # sd = IQR = 0 -> |x[1]|
+
+
+def test_density_matches_the_exact_kernel_sum_and_integrates_to_one():
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.normal(0.0, 1.0, 3000), rng.normal(6.0, 0.5, 1000)])
+    w = rng.random(x.size)
+    w /= w.sum()
+    for weights in (None, w):
+        gx, gy = O.r_density(x, weights)
+        bw = O.r_bw_nrd0(x)
+        ww = np.full(x.size, 1.0 / x.size) if weights is None else weights
+        exact = (ww[None, :] * np.exp(-0.5 * ((gx[:, None] - x[None, :]) / bw) ** 2)).sum(1) / (bw * np.sqrt(2 * np.pi))
+        assert np.abs(gy - exact).max() < 5e-3 * exact.max()                      # linear binning onto 512 points
+        assert abs(np.sum(0.5 * (gy[1:] + gy[:-1]) * np.diff(gx)) - 1.0) < 5e-3
+        assert gx.size == 512 and gx[0] == x.min() - 3 * bw
+    assert abs(O.r_density_mode(x) - 0.0) < 0.3 and abs(O.r_density_mode(x, np.where(x > 3, 50.0, 1.0)) - 6.0) < 0.2
+
+
+def test_product_summary_table_matches_the_oracle_including_the_mode_row():
+    """summary.py is pure torch (device sort, prefix-sum binning, torch.fft): check it on CPU tensors against the oracle."""
+    import torch
+    from abc_dls_b200 import summary as S
+    rng = np.random.default_rng(9)
+    n, P = 4000, 3
+    vals = rng.normal(size=(n, P)) * np.array([1.0, 10.0, 0.01]) + np.array([0.0, 50.0, 1.0])
+    w = rng.random(n)
+    res = O.AbcOracleResult.__new__(O.AbcOracleResult)
+    for method in ("rejection", "loclinear"):
+        res.method, res.unadj_values, res.adj_values, res.weights = method, vals, vals, w
+        want = O.summary_abc(res)
+        ww = w if method == "loclinear" else np.ones(n)
+        stats = np.stack([vals.min(0), vals.max(0), vals.sum(0), (ww[:, None] * vals).sum(0),
+                          (ww[:, None] * vals * vals).sum(0), np.full(P, ww.sum())], axis=1)
+        got = S.summary_table(torch.from_numpy(vals), torch.from_numpy(w), torch.from_numpy(stats),
+                              weighted=(method == "loclinear"))
+        np.testing.assert_allclose(np.asarray(got), want, rtol=1e-9, atol=1e-15)
+        assert not np.isnan(np.asarray(got)).any()
