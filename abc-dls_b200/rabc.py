@@ -4,6 +4,9 @@ Same attribute names and keyword arguments as the reference's call sites:
 
     abc.abc(target=, param=, sumstat=, method=, tol=)            ABC.py:1950-1953, 1964, 2806-2809, 2817
     abc.postpr(target=, index=, sumstat=, tol=, method=)         ABC.py:919
+    abc.cv4abc(param=, sumstat=, nval=, tols=, method=, trace=)  ABC.py:1900-1902, 1913
+    abc.cv4postpr(index=, sumstat=, nval=, tol=, method=)        ABC.py:886
+    abc.gfit(target, ss, repeats, tol=)                          ABC.py:961
 
 Inputs may be pandas DataFrame/Series, numpy arrays or torch tensors (host or CUDA).  Host inputs are
 copied to HBM once per call; the arithmetic runs in the CUDA engine (``engine.py``) — there is no CPU
@@ -19,6 +22,7 @@ import torch
 
 from .engine import AbcEngine, AbcError, AbcResult, PostprResult
 from . import summary as _summary
+from . import cv as _cv
 
 _engine: Optional[AbcEngine] = None
 
@@ -171,15 +175,68 @@ def postpr(target, index, sumstat, tol, method="rejection", subset=None, **_igno
     eng = engine()
     ss = to_table(sumstat, eng.device)
     tgt = _to_vec(target, eng.device)
-    if torch.is_tensor(index) and index.dtype in (torch.int32, torch.int64):
-        ids = index
-        models = [str(m) for m in range(int(index.max().item()) + 1)]
-    else:
-        if eng.comm.world > 1:
-            raise AbcError("postpr over several ranks needs integer model ids shared by all ranks")
-        labels = np.asarray(index.to_numpy() if hasattr(index, "to_numpy") else index).astype(str)
-        models, inv = np.unique(labels, return_inverse=True)   # sorted levels, like factor()
-        models = models.tolist()
-        ids = torch.from_numpy(inv.astype(np.int32))
+    ids, models = _model_ids(index, eng)
     res = eng.postpr(tgt, ids, models, ss, float(tol), method)
     return PostprFit(res)
+
+
+def _model_ids(index, eng: AbcEngine):
+    """R's factor(index): sorted levels + integer codes."""
+    if torch.is_tensor(index) and index.dtype in (torch.int32, torch.int64):
+        return index, [str(m) for m in range(int(index.max().item()) + 1)]
+    if eng.comm.world > 1:
+        raise AbcError("postpr over several ranks needs integer model ids shared by all ranks")
+    labels = np.asarray(index.to_numpy() if hasattr(index, "to_numpy") else index).astype(str)
+    models, inv = np.unique(labels, return_inverse=True)   # sorted levels, like factor()
+    return torch.from_numpy(inv.astype(np.int32)), models.tolist()
+
+
+def cv4abc(param, sumstat, nval, tols, method, statistic: str = "median", hcorr: bool = True, transf: str = "none",
+           subset=None, kernel: str = "epanechnikov", trace: bool = False, abc_out=None, cvsamples=None, seed=None,
+           **_ignored) -> _cv.Cv4abcResult:
+    """``abc::cv4abc`` (leave-one-out prediction error of the point estimate).  ``cvsamples`` (0-based rows) / ``seed``
+    are extras: R draws the rows with its own sample() stream, which is not reproduced."""
+    if transf != "none" or subset is not None or kernel != "epanechnikov":
+        raise AbcError("cv4abc: only transf='none', subset=NULL, kernel='epanechnikov' are implemented")
+    if method not in ("rejection", "loclinear"):
+        raise AbcError("Method must be rejection or loclinear (neuralnet / ridge stay with R's nnet)")
+    eng = engine()
+    ss, par = to_table(sumstat, eng.device), to_table(param, eng.device)
+    if par.shape[1] != ss.shape[1]:
+        raise AbcError("'param' and 'sumstat' must have the same number of rows")
+    names = {"parameter.names": _names(param, par.shape[0], "P"), "statistics.names": _names(sumstat, ss.shape[0], "S")}
+    return _cv.cv4abc(eng, par, ss, int(nval), tols, method, statistic, hcorr, cvsamples, seed, names)
+
+
+def cv4postpr(index, sumstat, nval, tols=None, method="rejection", subset=None, kernel: str = "epanechnikov",
+              trace: bool = False, postpr_out=None, cvsamples=None, seed=None, tol=None, **_ignored) -> _cv.Cv4postprResult:
+    """``abc::cv4postpr``.  ABC-DLS passes ``tol=`` (ABC.py:886), which R partial-matches to ``tols``."""
+    if tols is None:
+        tols = tol
+    if tols is None:
+        raise AbcError("'tols' is missing")
+    if subset is not None:
+        raise AbcError("'subset' is not implemented")
+    eng = engine()
+    ss = to_table(sumstat, eng.device)
+    ids, models = _model_ids(index, eng)
+    if ids.numel() != ss.shape[1]:
+        raise AbcError("'index' must be the same length as the number of rows in 'sumstat'.")
+    if len(models) < 2:
+        raise AbcError("At least two different models must be given.")
+    return _cv.cv4postpr(eng, ids, models, ss, int(nval), tols, method, cvsamples, seed)
+
+
+def gfit(target, sumstat, nb_replicate, tol, statistic="mean", subset=None, trace: bool = False, samples=None,
+         seed=None, **_ignored) -> _cv.GfitResult:
+    """``abc::gfit(target, sumstat, nb.replicate, tol, statistic = mean)``."""
+    if subset is not None:
+        raise AbcError("'subset' is not implemented")
+    if callable(statistic):
+        statistic = getattr(statistic, "__name__", "mean")
+    eng = engine()
+    ss = to_table(sumstat, eng.device)
+    tgt = _to_vec(target, eng.device)
+    if tgt.numel() != ss.shape[0]:
+        raise AbcError("Number of summary statistics in 'target' has to be the same as in 'sumstat'.")
+    return _cv.gfit(eng, tgt, ss, int(nb_replicate), float(tol), statistic, samples, seed)

@@ -13,7 +13,7 @@ import numpy as np
 
 class _R:
     def __init__(self):
-        self._sink = None
+        self._sink_file = None
         self._stdout = None
 
     def options(self, **_kw):
@@ -27,12 +27,12 @@ class _R:
 
     def _sink(self, path=None):  # R sink(file) / sink()
         if path is not None:
-            self._stdout, self._sink = sys.stdout, open(path, "w")
-            sys.stdout = self._sink
+            self._stdout, self._sink_file = sys.stdout, open(path, "w")
+            sys.stdout = self._sink_file
         elif self._stdout is not None:
             sys.stdout = self._stdout
-            self._sink.close()
-            self._stdout = self._sink = None
+            self._sink_file.close()
+            self._stdout = self._sink_file = None
 
     def _pdf(self, *_a, **_k):
         return None

@@ -112,6 +112,29 @@ def summary_table(values: torch.Tensor, weights, stats: torch.Tensor, weighted: 
     return SummaryTable(out.cpu().numpy(), names)
 
 
+def point_estimate(values: torch.Tensor, weights, stats: torch.Tensor, weighted: bool, statistic: str) -> torch.Tensor:
+    """Row ``statistic`` (median | mean | mode) of the summary.abc table only, as a (P,) device tensor: what cv4abc keeps
+    of every leave-one-out fit (abc::cv4abc: ``summary.abc(subres)[3 | 4 | 5, ]``).  All parameters in one sort."""
+    n, P = values.shape
+    if statistic == "mean":
+        return stats[:, 3] / stats[:, 5] if weighted else stats[:, 2] / n
+    if statistic == "median":
+        if not weighted:
+            return _quantile7(torch.sort(values, dim=0).values, 0.5)
+        xs, order = torch.sort(values, dim=0, stable=True)
+        cw = torch.cumsum(weights[order], dim=0).t().contiguous()                # (P, n)
+        kk = torch.searchsorted(cw, 0.5 * cw[:, -1:], right=False).clamp(max=n - 1)
+        return xs.gather(0, kk.t())[0]
+    if statistic == "mode":
+        out = torch.full((P,), float("nan"), dtype=torch.float64, device=values.device)
+        for p in range(P):
+            xs, order = torch.sort(values[:, p], stable=True)
+            if n >= 2:
+                out[p] = _density_mode(xs, weights[order] if weighted else None)
+        return out
+    raise ValueError(statistic)
+
+
 def summary_text(tab: SummaryTable, n_samples: int, weighted: bool, names=None, digits: int = 4) -> str:
     """Text from the ``Data:`` line on (what ABC-DLS prints, ABC.py:844-861)."""
     names = names or tab.names or [f"P{p + 1}" for p in range(np.asarray(tab).shape[1])]

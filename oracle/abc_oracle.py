@@ -507,3 +507,138 @@ def smc_round(target, param, sumstat, tol, method, param_all, decrease=0.95, inc
     out.update({"min": nmin, "max": nmax, "decrease": dec,
                 "lines": narrowing_params(param_all, nmin, nmax)})
     return out
+
+
+# --------------------------------------------------------------------------------------
+# Leave-one-out tools of the R package: abc::cv4abc, abc::cv4postpr, abc::gfit and their summaries.
+# Reference call sites: ABC.py:1900-1902, 1913 (cv4abc + summary()[0][0] / the 1 x P table), ABC.py:886-892 (cv4postpr +
+# summary), ABC.py:961-963 (gfit + summary).  Restated from the published R sources (abc 2.2.1: cv4abc.R, cv4postpr.R,
+# gfit.R), unpinned like the rest.  R draws the held-out rows with sample() (Mersenne twister + R's rejection sampling):
+# that stream is not restated; the rows are an explicit argument (``cvsamples``) and default to a numpy draw.
+# --------------------------------------------------------------------------------------
+_CV_ROW = {"median": 2, "mean": 3, "mode": 4}
+
+
+@dataclass
+class Cv4abcOracleResult:
+    cvsamples: np.ndarray  # int64[nval] 0-based held-out rows
+    tols: np.ndarray  # sorted ascending (R: tols <- sort(tols))
+    true: np.ndarray  # nval x P   param[cvsamples, ]
+    estim: Dict[float, np.ndarray]  # tol -> nval x P point estimates
+
+
+def cv4abc(param, sumstat, nval: int, tols, method: str, statistic: str = "median", hcorr: bool = True,
+           cvsamples=None, rng=None) -> Cv4abcOracleResult:
+    """``abc::cv4abc``: for every tolerance and every held-out row i: abc(target = sumstat[i, ], param = param[-i, ],
+    sumstat = sumstat[-i, ]) -- the row is physically removed, so N - 1 rows enter the MADs and nacc =
+    ceiling((N - 1) * tol) -- and the point estimate is row ``statistic`` of summary.abc."""
+    param, sumstat = _as_matrix(param), _as_matrix(sumstat)
+    N = sumstat.shape[0]
+    if cvsamples is None:
+        rng = rng if rng is not None else np.random.default_rng()
+        cvsamples = rng.choice(N, size=nval, replace=False)       # sample(1:numsim, nval)
+    cvsamples = np.asarray(cvsamples, dtype=np.int64)
+    tols = np.sort(np.atleast_1d(np.asarray(tols, dtype=np.float64)))
+    estim: Dict[float, np.ndarray] = {}
+    for tol in tols:
+        res = np.empty((cvsamples.size, param.shape[1]))
+        for i, s in enumerate(cvsamples):
+            keep = np.ones(N, dtype=bool)
+            keep[s] = False
+            sub = abc(sumstat[s], param[keep], sumstat[keep], float(tol), method, hcorr=hcorr)
+            res[i] = summary_abc(sub)[_CV_ROW[statistic]]
+        estim[float(tol)] = res
+    return Cv4abcOracleResult(cvsamples=cvsamples, tols=tols, true=param[cvsamples], estim=estim)
+
+
+def summary_cv4abc(cv: Cv4abcOracleResult) -> np.ndarray:
+    """``summary.cv4abc``: prediction error, one row per tolerance: colSums((estim - true)^2) / (var(true) * nval)."""
+    nval = cv.true.shape[0]
+    truevar = cv.true.var(axis=0, ddof=1) * nval
+    return np.stack([((cv.estim[float(t)] - cv.true) ** 2).sum(axis=0) / truevar for t in cv.tols])
+
+
+@dataclass
+class Cv4postprOracleResult:
+    cvsamples: np.ndarray  # nval rows per model, models in sorted-level order (R: unlist(tapply(..., sample, nval)))
+    tols: np.ndarray
+    true: np.ndarray  # model label of every held-out row
+    models: List[str]
+    estim: Dict[float, np.ndarray]  # tol -> (nval * K) x K posterior model probabilities
+
+
+def cv4postpr(index, sumstat, nval: int, tols, method: str = "rejection", cvsamples=None, rng=None) -> Cv4postprOracleResult:
+    """``abc::cv4postpr``: ``nval`` held-out rows PER MODEL; each is classified with postpr() on the remaining N - 1
+    rows (physically removed) and the posterior model probabilities are recorded."""
+    sumstat = _as_matrix(sumstat)
+    index = np.asarray(index).astype(str)
+    N = sumstat.shape[0]
+    models = sorted(set(index.tolist()))
+    if cvsamples is None:
+        rng = rng if rng is not None else np.random.default_rng()
+        cvsamples = np.concatenate([rng.choice(np.flatnonzero(index == m), size=nval, replace=False) for m in models])
+    cvsamples = np.asarray(cvsamples, dtype=np.int64)
+    tols = np.sort(np.atleast_1d(np.asarray(tols, dtype=np.float64)))
+    estim: Dict[float, np.ndarray] = {}
+    for tol in tols:
+        res = np.zeros((cvsamples.size, len(models)))
+        for i, s in enumerate(cvsamples):
+            keep = np.ones(N, dtype=bool)
+            keep[s] = False
+            sub = postpr(sumstat[s], index[keep], sumstat[keep], float(tol), method)
+            for m, p in zip(sub.models, sub.pred):            # a model whose last row was held out may be missing
+                res[i, models.index(m)] = p
+        estim[float(tol)] = res
+    return Cv4postprOracleResult(cvsamples=cvsamples, tols=tols, true=index[cvsamples], models=models, estim=estim)
+
+
+def summary_cv4postpr(cv: Cv4postprOracleResult):
+    """``summary.cv4postpr``: per tolerance the confusion matrix table(true, argmax posterior) (ties: first model, R's
+    which.max) and the mean posterior model probabilities per true model."""
+    K = len(cv.models)
+    ti = np.array([cv.models.index(m) for m in cv.true])
+    conf, probs = {}, {}
+    for t in cv.tols:
+        e = cv.estim[float(t)]
+        pm = e.argmax(axis=1)
+        cm = np.zeros((K, K), dtype=np.int64)
+        np.add.at(cm, (ti, pm), 1)
+        conf[float(t)] = cm
+        probs[float(t)] = np.stack([e[ti == k].mean(axis=0) for k in range(K)])
+    return {"conf.matrix": conf, "probs": probs}
+
+
+@dataclass
+class GfitOracleResult:
+    dist_obs: float
+    dist_sim: np.ndarray
+
+
+def gfit(target, sumstat, nb_replicate: int, tol: float, statistic: str = "mean", samples=None, rng=None) -> GfitOracleResult:
+    """``abc::gfit``: goodness-of-fit statistic = ``statistic`` of the distances of the accepted simulations
+    (abc(method = "rejection")); its null distribution treats ``nb_replicate`` simulations in turn as the observation,
+    each against the table with that row removed."""
+    sumstat = _as_matrix(sumstat)
+    target = np.asarray(target, dtype=np.float64).ravel()
+    N = sumstat.shape[0]
+    stat = {"mean": r_mean, "median": r_median}[statistic]
+    if samples is None:
+        rng = rng if rng is not None else np.random.default_rng()
+        samples = rng.choice(N, size=nb_replicate, replace=False)
+    samples = np.asarray(samples, dtype=np.int64)
+    obs = abc(target, sumstat[:, 0], sumstat, tol, "rejection")
+    dist_sim = np.empty(samples.size)
+    for i, s in enumerate(samples):
+        keep = np.ones(N, dtype=bool)
+        keep[s] = False
+        r = abc(sumstat[s], sumstat[keep, 0], sumstat[keep], tol, "rejection")
+        dist_sim[i] = stat(r.dist[r.region])
+    return GfitOracleResult(dist_obs=stat(obs.dist[obs.region]), dist_sim=dist_sim)
+
+
+def summary_gfit(g: GfitOracleResult):
+    """``summary.gfit``: p-value = share of null statistics above the observed one, summary() of the null."""
+    q = r_quantile7(g.dist_sim, [0.0, 0.25, 0.5, 0.75, 1.0])
+    return {"pvalue": float((g.dist_sim > g.dist_obs).sum() / g.dist_sim.size),
+            "s.dist.sim": np.array([q[0], q[1], q[2], r_mean(g.dist_sim), q[3], q[4]]),   # Min 1stQu Median Mean 3rdQu Max
+            "dist.obs": g.dist_obs}

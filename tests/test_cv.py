@@ -1,0 +1,173 @@
+"""cv4abc / cv4postpr / gfit: the leave-one-out sequencing against the oracle with the same held-out
+rows.  CPU tests run the host logic (``cv.py``: in-place hole buffers, point estimates, summaries) over the numpy stage
+double; the ``gpu`` tests run the same comparisons through the CUDA engine and the rpy2-shaped facade."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import abc_oracle as O
+from abc_dls_b200 import cv as CV
+from abc_dls_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def _cpu_engine():
+    from abc_dls_b200.engine import AbcEngine
+    from cpu_stages import CpuStages
+    return AbcEngine(stages=CpuStages())
+
+
+def test_leave_one_out_buffers_follow_any_hole_sequence():
+    rng = np.random.default_rng(3)
+    for n in (3, 8, 101):
+        a = torch.from_numpy(rng.normal(size=(3, n)))
+        b = torch.from_numpy(rng.integers(0, 5, size=(1, n)).astype(np.int32))
+        loo = CV.LeaveOneOut([a, b])
+        for s in [0, n - 1, 0, 1, n - 2] + rng.integers(0, n, 20).tolist():
+            ba, bb = loo.hold_out(int(s))
+            np.testing.assert_array_equal(ba.numpy(), np.delete(a.numpy(), s, axis=1))
+            np.testing.assert_array_equal(bb.numpy(), np.delete(b.numpy(), s, axis=1))
+            assert ba.stride(1) == 1 and ba.shape == (3, n - 1)
+    with pytest.raises(CV.AbcError):
+        CV.LeaveOneOut([torch.zeros(1, 2, dtype=torch.float64)])
+
+
+def _check_cv4abc(eng, method, statistic, N=400, P=2, nval=6, tols=(0.2, 0.1)):
+    par, ss, _ = synth.abc_tables(N, P, P, "cpu")
+    samp = np.random.default_rng(11).choice(N, nval, replace=False)
+    dev = eng.device
+    got = CV.cv4abc(eng, par.to(dev), ss.to(dev), nval, tols, method, statistic=statistic, cvsamples=samp)
+    want = O.cv4abc(par.numpy().T, ss.numpy().T, nval, tols, method, statistic=statistic, cvsamples=samp)
+    np.testing.assert_array_equal(got.tols, want.tols)
+    np.testing.assert_array_equal(got.true, want.true)
+    scale = np.abs(want.true).max(axis=0)
+    for t in want.tols:
+        assert np.max(np.abs(got.estim[float(t)] - want.estim[float(t)]) / scale) < 1e-9
+    np.testing.assert_allclose(got.summary(print_=False), O.summary_cv4abc(want), rtol=1e-7)
+    assert got.summary_text().startswith("Prediction error based on a cross-validation sample of %d" % nval)
+    return got
+
+
+@pytest.mark.parametrize("method,statistic", [("rejection", "median"), ("loclinear", "median"), ("loclinear", "mean"),
+                                              ("rejection", "mode")])
+def test_cv4abc_host_logic_matches_oracle(method, statistic):
+    _check_cv4abc(_cpu_engine(), method, statistic)
+
+
+def test_cv4postpr_and_gfit_host_logic_match_oracle():
+    eng = _cpu_engine()
+    N, nval = 600, 3
+    ids, ss, _ = synth.postpr_tables(N, "cpu")
+    labels = np.array(["BNDX", "MNDX", "SNDX"])[ids.numpy()]
+    rng = np.random.default_rng(5)
+    samp = np.concatenate([rng.choice(np.flatnonzero(ids.numpy() == k), nval, replace=False) for k in range(3)])
+    got = CV.cv4postpr(eng, ids, ["BNDX", "MNDX", "SNDX"], ss, nval, [0.1, 0.05], cvsamples=samp)
+    want = O.cv4postpr(labels, ss.numpy().T, nval, [0.1, 0.05], cvsamples=samp)
+    assert got.true == want.true.tolist()
+    for t in want.tols:
+        np.testing.assert_array_equal(got.estim[float(t)], want.estim[float(t)])          # counts / nacc: exact
+    gs, ws = got.summary(print_=False), O.summary_cv4postpr(want)
+    for t in want.tols:
+        np.testing.assert_array_equal(gs["conf.matrix"][float(t)], ws["conf.matrix"][float(t)])
+        np.testing.assert_allclose(gs["probs"][float(t)], ws["probs"][float(t)], rtol=1e-12)
+    assert got.summary_text().startswith("Confusion matrix based on 3 samples for each model.")
+
+    par, ss2, tgt = synth.abc_tables(500, 3, 3, "cpu")
+    s2 = rng.choice(500, 8, replace=False)
+    for statistic in ("mean", "median"):
+        g = CV.gfit(eng, tgt, ss2, 8, 0.1, statistic=statistic, samples=s2)
+        w = O.gfit(tgt.numpy(), ss2.numpy().T, 8, 0.1, statistic=statistic, samples=s2)
+        np.testing.assert_allclose(g.dist_sim, w.dist_sim, rtol=1e-12)
+        assert abs(g.dist_obs - w.dist_obs) <= 1e-12 * w.dist_obs
+        a, b = g.summary(print_=False), O.summary_gfit(w)
+        assert a["pvalue"] == b["pvalue"]
+        np.testing.assert_allclose(a["s.dist.sim"], b["s.dist.sim"], rtol=1e-12)
+
+
+def test_rshim_verbs(tmp_path):
+    """robjects.r[...] verbs ABC-DLS uses around the results (ABC.py:887-896, 1778, 1896-1925)."""
+    from abc_dls_b200.rshim import r
+
+    class Obj:
+        def summary(self, **kw):
+            print("first line")
+            return np.array([[0.25]])
+
+    r.options(width=10000)
+    p = tmp_path / "sink.txt"
+    r["sink"](str(p))
+    x = r["summary"](Obj())
+    r["sink"]()
+    assert open(p).readline() == "first line\n" and x[0][0] == 0.25
+    assert r["pdf"]("x.pdf") is None and r["dev.off"]() is None and r["plot"](Obj(), ask=False) is None
+    np.testing.assert_allclose(r["sapply"](np.array([[1.0, 2.0], [3.0, 2.0]]), "sd"), [np.sqrt(2.0), 0.0])
+
+
+# ---- the same through the CUDA engine ---------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("method,statistic", [("rejection", "median"), ("loclinear", "median"), ("loclinear", "mode")])
+def test_cv4abc_cuda_matches_oracle(engine, method, statistic):
+    l0 = engine.k.launches
+    _check_cv4abc(engine, method, statistic, N=3000, P=3, nval=5, tols=(0.05,))
+    assert engine.k.launches > l0
+
+
+@pytest.mark.gpu
+def test_cv_facade_like_abcdls_calls_it(engine):
+    """ABC.py:1900-1904 (per-column cv4abc + summary[0][0]), 886-892 (cv4postpr), 961-963 (gfit)."""
+    import pandas as pd
+    from abc_dls_b200 import rabc
+    rabc.set_engine(engine)
+    par, ss, tgt = synth.abc_tables(2000, 2, 2, "cpu")
+    names = ["N_A", "T_B"]
+    dfp, dfs = pd.DataFrame(par.T.numpy(), columns=names), pd.DataFrame(ss.T.numpy(), columns=names)
+    samp = np.random.default_rng(2).choice(2000, 4, replace=False)
+    for c in range(2):
+        cvres = rabc.cv4abc(param=pd.DataFrame(dfp.iloc[:, c]), sumstat=pd.DataFrame(dfs.iloc[:, c]), nval=4, tols=0.05,
+                            method="loclinear", trace=False, cvsamples=samp)
+        want = O.cv4abc(par.numpy()[c], ss.numpy()[c], 4, 0.05, "loclinear", cvsamples=samp)
+        s = cvres.summary(print_=False)
+        assert abs(s[0][0] - O.summary_cv4abc(want)[0][0]) <= 1e-7 * O.summary_cv4abc(want)[0][0]
+        assert cvres.names["parameter.names"] == [names[c]]
+    joint = rabc.cv4abc(param=dfp, sumstat=dfs, nval=4, tols=0.05, method="rejection", cvsamples=samp)
+    wj = O.cv4abc(par.numpy().T, ss.numpy().T, 4, 0.05, "rejection", cvsamples=samp)
+    np.testing.assert_array_equal(joint.estim[0.05], wj.estim[0.05])       # type-7 medians of identical accepted sets
+    assert pd.DataFrame(joint.summary(print_=False), columns=dfp.columns, index=[0.05]).shape == (1, 2)
+
+    ids, ssp, _ = synth.postpr_tables(3000, "cpu")
+    index = pd.Series(np.array(["BNDX", "MNDX", "SNDX"])[ids.numpy()])
+    rng = np.random.default_rng(4)
+    sp = np.concatenate([rng.choice(np.flatnonzero(ids.numpy() == k), 2, replace=False) for k in range(3)])
+    cvm = rabc.cv4postpr(index=index, sumstat=pd.DataFrame(ssp.T.numpy()), nval=2, tol=0.05, method="rejection",
+                         cvsamples=sp)
+    wm = O.cv4postpr(index.to_numpy(), ssp.T.numpy(), 2, 0.05, cvsamples=sp)
+    np.testing.assert_array_equal(cvm.estim[0.05], wm.estim[0.05])
+    assert "Mean model posterior probabilities (rejection)" in cvm.summary_text()
+    with pytest.raises(rabc.AbcError):
+        rabc.cv4postpr(index=index, sumstat=pd.DataFrame(ssp.T.numpy()), nval=2, tol=0.05, method="mnlogistic")
+
+    gs = np.random.default_rng(6).choice(2000, 5, replace=False)
+    fit = rabc.gfit(pd.DataFrame(tgt.numpy()[None, :], columns=names), dfs, 5, tol=0.05, samples=gs)
+    wg = O.gfit(tgt.numpy(), ss.numpy().T, 5, 0.05, samples=gs)
+    np.testing.assert_allclose(fit.dist_sim, wg.dist_sim, rtol=1e-12)
+    assert abs(fit.dist_obs - wg.dist_obs) <= 1e-12 * wg.dist_obs
+    assert fit.summary(print_=False)["pvalue"] == O.summary_gfit(wg)["pvalue"]
+
+
+@pytest.mark.gpu
+def test_cv4abc_large_table_replays_the_graph_on_the_fast_path(engine):
+    """N - 1 rows >= 2^20: the sampled-bracket front half runs on the hole buffer and the third validation on replays
+    the CUDA graph of the second (same buffers, same shapes)."""
+    N = (1 << 20) + 2
+    par, ss, _ = synth.abc_tables(N, 2, 2, engine.device)
+    samp = np.array([N - 1, 5, 700001, 0], dtype=np.int64)
+    before = dict(engine.path_calls)
+    got = CV.cv4abc(engine, par, ss, 4, 0.001, "rejection", cvsamples=samp)
+    assert engine.path_calls["exact"] == before["exact"]                  # never the small-table path
+    want = O.cv4abc(par.cpu().numpy().T, ss.cpu().numpy().T, 4, 0.001, "rejection", cvsamples=samp)
+    np.testing.assert_array_equal(got.estim[0.001], want.estim[0.001])
