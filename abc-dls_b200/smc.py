@@ -67,3 +67,62 @@ def lmrd_calculation(rng: RangeTable, hard_min, hard_max) -> float:
     new_w = np.abs(rng.max - rng.min)
     hard_w = np.abs(np.asarray(hard_max, dtype=np.float64) - np.asarray(hard_min, dtype=np.float64))
     return float(np.log(np.mean(new_w / hard_w)))
+
+
+# ---- cross-round file formats of the Snakemake loop ------------------------------------------------
+# Newrange.csv / hardrange.csv: no header, one row per parameter: name, min, max[, decrease]  (ABC.py:2729;
+# src/SFS/Class.py:706-796, 850-863).  P-sized host work; the table-sized parts stay with engine.oldrange / box_filter.
+def read_range_csv(path: str):
+    """-> (names, min, max) of a header-less range file (Newrange.csv, hardrange.csv)."""
+    names, lo, hi = [], [], []
+    with open(path) as fh:
+        for line in fh:
+            cells = line.rstrip("\n").split(",")
+            if len(cells) < 3 or not cells[0]:
+                continue
+            names.append(cells[0])
+            lo.append(float(cells[1]))
+            hi.append(float(cells[2]))
+    return names, np.array(lo, dtype=np.float64), np.array(hi, dtype=np.float64)
+
+
+def median_newrange(files):
+    """Per-parameter median of the min and of the max over the Newrange.csv files of ``abc_repeats`` independent
+    repeats (src/SFS/Class.py:736-749; an even number of files averages the two middle values, like pandas)."""
+    tabs = [read_range_csv(f) for f in files]
+    names = tabs[0][0]
+    return names, np.median(np.stack([t[1] for t in tabs]), axis=0), np.median(np.stack([t[2] for t in tabs]), axis=0)
+
+
+def multiple_newrange2updatednewrange(newrange_files, old_min, old_max, decrease: float = 0.95, increase: float = 0.0,
+                                      hardrange_file: Optional[str] = None, outfile: Optional[str] = "Newrange.csv"):
+    """src/SFS/Class.py:706-734: median over the repeats -> updating_newrange -> [noise_injection_update] -> csv.
+    ``old_min`` / ``old_max`` are the per-parameter extremes of the simulated table (``engine.oldrange`` on the device
+    table replaces the reference's second read of the csv, Class.py:751-763)."""
+    names, lo, hi = median_newrange(newrange_files)
+    rng = updating_newrange(lo, hi, old_min, old_max, decrease)
+    if increase > 0:
+        hmin = hmax = None
+        if hardrange_file:
+            hnames, hmin, hmax = read_range_csv(hardrange_file)
+            order = [hnames.index(n) for n in names]            # pandas aligns the hard range on the parameter names
+            hmin, hmax = hmin[order], hmax[order]
+        rng = noise_injection_update(rng, old_min, old_max, increase, hmin, hmax, decrease)
+    if outfile:
+        rng.to_csv(outfile, names)
+    return names, rng
+
+
+def lmrd4mcsv(hardrange_file: str, newrange_file: str) -> float:
+    """src/SFS/Class.py:850-863: log of the mean range decrease straight from the two files."""
+    hnames, hmin, hmax = read_range_csv(hardrange_file)
+    names, lo, hi = read_range_csv(newrange_file)
+    order = [hnames.index(n) for n in names]
+    return lmrd_calculation(RangeTable(lo, hi, np.zeros_like(lo)), hmin[order], hmax[order])
+
+
+def csv_linenumbers(rows, header: bool = True) -> np.ndarray:
+    """0-based table rows (``engine.box_filter``) -> the 1-based csv line numbers the reference extracts:
+    row + 2 for a file with a header line (ABC.py:2974-2990), row + 1 without (src/SFS/Class.py:817-818)."""
+    rows = np.asarray(rows.cpu() if hasattr(rows, "cpu") else rows, dtype=np.int64)
+    return rows + (2 if header else 1)

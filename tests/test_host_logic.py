@@ -93,3 +93,42 @@ def test_sharded_sequencing_world2_gloo(method, tol):
         np.testing.assert_allclose(t[5], ref.min(axis=0), rtol=1e-9)
         np.testing.assert_allclose(t[6], ref.max(axis=0), rtol=1e-9)
         assert t[7] >= 12                                    # the radix passes alone need 18 all-reduces
+
+
+def test_snakemake_range_files_roundtrip(tmp_path):
+    """§8f-3: median of repeated Newrange.csv files -> update rules -> Newrange.csv, against the reference's pandas
+    formulation (src/SFS/Class.py:706-796, 850-863) restated inline."""
+    import pandas
+    rng = np.random.default_rng(8)
+    names = ["N_A", "N_AF", "T_B", "m_AF_B"]
+    omin, omax = np.array([100.0, 1000.0, 0.0, 0.0]), np.array([5e4, 1e5, 1.0, 0.02])
+    files = []
+    for k in range(4):                       # even count: medians average the two middle files
+        lo = omin + (omax - omin) * rng.uniform(0.0, 0.3, 4)
+        hi = omax - (omax - omin) * rng.uniform(0.0, 0.3, 4)
+        if k == 0:
+            lo[2], hi[2] = omin[2], omax[2]
+        f = tmp_path / f"Newrange_{k}.csv"
+        smc.RangeTable(lo, hi, (hi - lo) / (omax - omin)).to_csv(str(f), names)
+        files.append(str(f))
+    hard = tmp_path / "hardrange.csv"
+    hmin, hmax = omin + 1.0, omax * 0.99
+    with open(hard, "w") as fh:
+        for n, a, b in reversed(list(zip(names, hmin, hmax))):          # other row order: aligned by name
+            fh.write(f"{n},{a},{b}\n")
+    out = tmp_path / "Newrange.csv"
+    got_names, got = smc.multiple_newrange2updatednewrange(files, omin, omax, 0.95, 0.02, str(hard), str(out))
+
+    alldata = [pandas.read_csv(f, header=None).iloc[:, :3] for f in files]
+    mn = pandas.DataFrame([d.iloc[:, 1] for d in alldata]).median().to_numpy()
+    mx = pandas.DataFrame([d.iloc[:, 2] for d in alldata]).median().to_numpy()
+    w = O.updating_newrange(mn, mx, omin, omax, 0.95)
+    w = O.noise_injection_update(w[0], w[1], w[2], omin, omax, 0.02, hmin, hmax, 0.95)
+    assert got_names == names
+    np.testing.assert_array_equal(got.min, w[0]); np.testing.assert_array_equal(got.max, w[1])
+    np.testing.assert_array_equal(got.decrease, w[2])
+    back = pandas.read_csv(out, header=None, index_col=0)
+    np.testing.assert_array_equal(back.iloc[:, 0].to_numpy(), w[0]); np.testing.assert_array_equal(back.iloc[:, 2].to_numpy(), w[2])
+    assert smc.lmrd4mcsv(str(hard), str(out)) == O.lmrd_calculation(w[0], w[1], hmin, hmax)
+    np.testing.assert_array_equal(smc.csv_linenumbers(np.array([0, 5])), [2, 7])
+    np.testing.assert_array_equal(smc.csv_linenumbers(np.array([0, 5]), header=False), [1, 6])
