@@ -87,6 +87,12 @@ SIGNATURES = {
     "abcdls_adjust": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "abcdls_col_stats_workspace_bytes": (_sz, [_i32]),
     "abcdls_col_stats": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _sz, _vp]),
+    "abcdls_resid_moments": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp]),
+    "abcdls_resid_finish": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "abcdls_final_small_doubles": (_sz, [_i32, _i32, _i32]),
+    "abcdls_final_pack": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "abcdls_final_small": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
+                                  _vp, _vp]),
     "abcdls_postpr_counts": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp]),
     "abcdls_smc_workspace_bytes": (_sz, [_i64, _i32]),
     "abcdls_smc_oldrange": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _sz, _vp]),

@@ -666,6 +666,138 @@ inline int normal_grid(abcdls_handle_t h, long long cap) {
     return (int)b;
 }
 
+
+// ---- the P-sized glue between the adjustment kernels (was ~35 one-block torch kernels per call) ------------------------
+// rs: [P][6] from k_col_stats(res, w).  sums = [sum res (P) | sum w res (P) | sum w res^2 (P) | n_acc]: the message of
+// the cross-rank sum (SURVEY 8e "residual mean the_m").
+__global__ void k_resid_moments(const double* __restrict__ rs, const long long* __restrict__ n_acc, int P,
+                                double* __restrict__ sums) {
+    const int p = threadIdx.x;
+    if (p < P) {
+        sums[p] = rs[p * 6 + 2];
+        sums[P + p] = rs[p * 6 + 3];
+        sums[2 * P + p] = rs[p * 6 + 4];
+    }
+    if (p == 0) sums[3 * P] = (double)*n_acc;
+}
+
+// the_m = colMeans(residuals) (UNWEIGHTED, R), sigma2 = sum w (res - the_m)^2 / sum w expanded around the raw moments,
+// logsig = sum_p log sigma2_p (aic / bic).  gram[0] = sum w.  No FMA contraction: same roundings as the host formula.
+__global__ void k_resid_finish(const double* __restrict__ sums, const double* __restrict__ gram, int P,
+                               double* __restrict__ the_m, double* __restrict__ sig, double* __restrict__ logsig) {
+    __shared__ double lg[kMaxP];
+    const int p = threadIdx.x;
+    if (p < P) {
+        const double sw = gram[0];
+        const double m = __ddiv_rn(sums[p], sums[3 * P]);
+        const double a = __dsub_rn(sums[2 * P + p], __dmul_rn(__dmul_rn(2.0, m), sums[P + p]));
+        const double s2 = __ddiv_rn(__dadd_rn(a, __dmul_rn(__dmul_rn(m, m), sw)), sw);
+        the_m[p] = m;
+        sig[p] = s2;
+        lg[p] = log(s2);
+    }
+    __syncthreads();
+    if (p == 0) {
+        double t = 0.0;
+        for (int q = 0; q < P; ++q) t += lg[q];
+        *logsig = t;
+    }
+}
+
+// Multi-rank: everything that is a min, a max (negated) or an OR (negated bits) in ONE vector for one min-exchange,
+// the sums of the summary in a second one.  pack = [region min (d) | -region max (d) | posterior min (P) | -posterior
+// max (P) | -status bits (8)], sm = stats[:, 2:6] (P x 4).
+__global__ void k_final_pack(const int* __restrict__ status, const double* __restrict__ reg,
+                             const double* __restrict__ stats, int d, int P, double* __restrict__ pack,
+                             double* __restrict__ sm) {
+    const int t = threadIdx.x;
+    if (t < d) {
+        pack[t] = reg[t * 6];
+        pack[d + t] = -reg[t * 6 + 1];
+    }
+    if (t < P) {
+        pack[2 * d + t] = stats[t * 6];
+        pack[2 * d + P + t] = -stats[t * 6 + 1];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sm[t * 4 + k] = stats[t * 6 + 2 + k];
+    }
+    if (t < 8) pack[2 * d + 2 * P + t] = -(double)((*status >> t) & 1);
+}
+
+// All small results of a call in ONE buffer (one copy-out, one blocking read of its head):
+// small = [host (8): status, n_acc, ds, region constant?, every MAD zero?, logsig, 0, 0 | mad (d) | stats (P x 6) |
+//          sigma2 (P) | pred (P) | coef (M x P) | coef_h (M x P)]      (the last four only for loclinear)
+// coef / coef_h: the fits were made on a design centred on the scaled target; R's convention is [1, scaled ss], so the
+// intercept moves by -sum_j t_j b_j.  pred = intercept + the_m.
+__global__ void k_final_small(const int* __restrict__ status, const long long* __restrict__ n_acc,
+                              const double* __restrict__ ds, const double* __restrict__ reg,
+                              const double* __restrict__ stats, const double* __restrict__ mad,
+                              const double* __restrict__ target, const double* __restrict__ logsig,
+                              const double* __restrict__ beta, const double* __restrict__ gamma,
+                              const double* __restrict__ the_m, const double* __restrict__ sig,
+                              const double* __restrict__ pack, const double* __restrict__ sm, int d, int P,
+                              double* __restrict__ small) {
+    __shared__ double tsc[kMaxD];
+    __shared__ int flags[2];
+    const int t = threadIdx.x, M = d + 1;
+    double* host = small;
+    double* o_mad = small + 8;
+    double* o_stats = o_mad + d;
+    double* o_sig = o_stats + 6 * P;
+    double* o_pred = o_sig + P;
+    double* o_coef = o_pred + P;
+    double* o_coefh = o_coef + M * P;
+    if (t < 2) flags[t] = 1;
+    __syncthreads();
+    if (t < d) {
+        const double m = mad[t];
+        o_mad[t] = m;
+        tsc[t] = (m == 0.0) ? target[t] : __ddiv_rn(target[t], m);
+        const double lo = pack ? pack[t] : reg[t * 6], hi = pack ? -pack[d + t] : reg[t * 6 + 1];
+        if (!(lo == hi)) atomicAnd(&flags[0], 0);
+        if (m != 0.0) atomicAnd(&flags[1], 0);
+    }
+    if (t < P) {
+        o_stats[t * 6] = pack ? pack[2 * d + t] : stats[t * 6];
+        o_stats[t * 6 + 1] = pack ? -pack[2 * d + P + t] : stats[t * 6 + 1];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o_stats[t * 6 + 2 + k] = sm ? sm[t * 4 + k] : stats[t * 6 + 2 + k];
+    }
+    __syncthreads();
+    if (beta && t < P) {
+        o_sig[t] = sig[t];
+        o_pred[t] = beta[t] + the_m[t];
+        double acc = 0.0, acch = 0.0;
+        for (int j = 0; j < d; ++j) {
+            const double b = beta[(j + 1) * P + t];
+            o_coef[(j + 1) * P + t] = b;
+            acc = __dadd_rn(acc, __dmul_rn(tsc[j], b));
+            if (gamma) {
+                const double g = gamma[(j + 1) * P + t];
+                o_coefh[(j + 1) * P + t] = g;
+                acch = __dadd_rn(acch, __dmul_rn(tsc[j], g));
+            }
+        }
+        o_coef[t] = beta[t] - acc;
+        if (gamma) o_coefh[t] = gamma[t] - acch;
+    }
+    if (t == 0) {
+        int st = *status;
+        if (pack) {
+            st = 0;
+            for (int b = 0; b < 8; ++b)
+                if (pack[2 * d + 2 * P + b] != 0.0) st |= 1 << b;
+        }
+        host[0] = (double)st;
+        host[1] = (double)*n_acc;
+        host[2] = *ds;
+        host[3] = (double)flags[0];
+        host[4] = (double)flags[1];
+        host[5] = logsig ? *logsig : 0.0;
+        host[6] = host[7] = 0.0;
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -855,6 +987,51 @@ int abcdls_col_stats(abcdls_handle_t h, const double* values, const double* w, c
                                                  align_up((size_t)ncols * kStatChunks * 6 * sizeof(double), 256));
     k_col_stats<<<dim3(kStatChunks, ncols), 256, 0, (cudaStream_t)stream>>>(values, w, (const long long*)n_acc, cap,
                                                                             part, done, out);
+    ABCDLS_LAUNCH_CHECK(h);
+    return ABCDLS_OK;
+}
+
+
+int abcdls_resid_moments(abcdls_handle_t h, const double* rs, const int64_t* n_acc, int P, double* sums, void* stream) {
+    ABCDLS_CHECK_ARG(h, h && rs && n_acc && sums && P >= 1 && P <= kMaxP, "resid_moments");
+    k_resid_moments<<<1, kMaxP, 0, (cudaStream_t)stream>>>(rs, (const long long*)n_acc, P, sums);
+    ABCDLS_LAUNCH_CHECK(h);
+    return ABCDLS_OK;
+}
+
+int abcdls_resid_finish(abcdls_handle_t h, const double* sums, const double* gram, int P, double* the_m, double* sig,
+                        double* logsig, void* stream) {
+    ABCDLS_CHECK_ARG(h, h && sums && gram && the_m && sig && logsig && P >= 1 && P <= kMaxP, "resid_finish");
+    k_resid_finish<<<1, kMaxP, 0, (cudaStream_t)stream>>>(sums, gram, P, the_m, sig, logsig);
+    ABCDLS_LAUNCH_CHECK(h);
+    return ABCDLS_OK;
+}
+
+size_t abcdls_final_small_doubles(int d, int P, int loclinear) {
+    return (size_t)8 + d + 6 * (size_t)P + (loclinear ? 2 * (size_t)P + 2 * (size_t)(d + 1) * P : 0);
+}
+
+int abcdls_final_pack(abcdls_handle_t h, const int* status_dev, const double* reg, const double* stats, int d, int P,
+                      double* pack, double* sm, void* stream) {
+    ABCDLS_CHECK_ARG(h, h && status_dev && reg && stats && pack && sm, "final_pack: null pointer");
+    ABCDLS_CHECK_ARG(h, d >= 1 && d <= kMaxD && P >= 1 && P <= kMaxP, "final_pack: shape");
+    k_final_pack<<<1, 64, 0, (cudaStream_t)stream>>>(status_dev, reg, stats, d, P, pack, sm);
+    ABCDLS_LAUNCH_CHECK(h);
+    return ABCDLS_OK;
+}
+
+int abcdls_final_small(abcdls_handle_t h, const int* status_dev, const int64_t* n_acc, const double* ds,
+                       const double* reg, const double* stats, const double* mad, const double* target,
+                       const double* logsig, const double* beta, const double* gamma, const double* the_m,
+                       const double* sig, const double* pack, const double* sm, int d, int P, double* small_out,
+                       void* stream) {
+    ABCDLS_CHECK_ARG(h, h && status_dev && n_acc && ds && reg && stats && mad && target && small_out,
+                     "final_small: null pointer");
+    ABCDLS_CHECK_ARG(h, d >= 1 && d <= kMaxD && P >= 1 && P <= kMaxP, "final_small: shape");
+    ABCDLS_CHECK_ARG(h, !beta || (the_m && sig), "final_small: beta without the_m / sigma2");
+    ABCDLS_CHECK_ARG(h, (pack == nullptr) == (sm == nullptr), "final_small: pack and sm come together");
+    k_final_small<<<1, 64, 0, (cudaStream_t)stream>>>(status_dev, (const long long*)n_acc, ds, reg, stats, mad, target,
+                                                       logsig, beta, gamma, the_m, sig, pack, sm, d, P, small_out);
     ABCDLS_LAUNCH_CHECK(h);
     return ABCDLS_OK;
 }

@@ -302,8 +302,8 @@ class AbcEngine:
         cap = min(nacc, n_local)
         idx = k.new(cap, dtype=torch.int64)
         dacc = k.new(cap)
-        n_acc = torch.zeros(1, dtype=torch.int64, device=self.device)
-        le = torch.zeros(1, dtype=torch.int64, device=self.device)
+        state = torch.zeros(4, dtype=torch.int64, device=self.device)      # one fill for the scalar outputs
+        n_acc, le, n_cand0 = state[0:1], state[1:2], state[2:3]
         quota = torch.full((1,), nacc, dtype=torch.int64, device=self.device)
         comm = self.comm if self.comm.world > 1 else None
         cand_ss = slot = perm = cand_par = None
@@ -318,7 +318,7 @@ class AbcEngine:
             cand_lrow = k.new(ecap, dtype=torch.int32)
             perm = k.new(ccap, dtype=torch.int64)
             slot = k.new(cap, dtype=torch.int64)
-            n_cand = torch.zeros(1, dtype=torch.int64, device=self.device)
+            n_cand = n_cand0
             pre = None
             if (par is not None and par.device.type == "cuda" and self.pregather
                     and (self.comm.world == 1 or self.comm.peer is not None)):   # NCCL segments cannot span a fork
@@ -349,7 +349,7 @@ class AbcEngine:
             ccap = min(n_local, 2 * nacc + 65536)
             dist = k.new(n_local) if keep_dist else None
             cand_row, cand_dist = k.new(ccap, dtype=torch.int64), k.new(ccap)
-            n_cand = torch.zeros(1, dtype=torch.int64, device=self.device)
+            n_cand = n_cand0
             ds = k.new(1)
             with self._t("dist_fast"):
                 k.dist_fast(ss, n_local, n_global, d, ss.stride(0), mad, target, nacc, row_offset, ccap, dist,
@@ -451,7 +451,7 @@ class AbcEngine:
         self.host_enqueue_ms.append((time.perf_counter() - _t0) * 1e3)
         if len(self.host_enqueue_ms) > 64:
             del self.host_enqueue_ms[:32]
-        host = o["host"].cpu()    # the one blocking read: everything data dependent
+        host = o["small"][:8].cpu()    # the one blocking read: everything data dependent
         st, n_loc, ds_h = int(host[0]), int(host[1]), float(host[2])    # status is already OR-ed over the ranks
         warnings: List[str] = []
         if (st & _capi.S_FASTPATH_MISS) and pl["fast"]:
@@ -484,24 +484,26 @@ class AbcEngine:
             own = lambda t: t
             later = lambda t, post=None: post(t) if post else t
         tr = lambda t: t.t()
-        mad, nacc = own(o["mad"]), pl["nacc"]
+        nacc = pl["nacc"]
         lin = method == "loclinear"
+        M = d + 1
+        small = own(o["small"])         # mad | stats | sigma2 | pred | coef | coef_h behind the 8-double host word
+        mad, stats = small[8:8 + d], small[8 + d:8 + d + 6 * P].view(P, 6)
         r = AbcResult(method=method, tol=tol, nacc=nacc, n_global=pl["n_global"], ds=ds_h, mad=mad,
                       idx=own(o["idx"][:n_loc]),
                       unadj_values=(later(o["y"][:, :n_loc], tr) if lin else own(o["y"][:, :n_loc]).t()),
                       ss=later(o["ss_out"][:, :n_loc], tr),
                       weights=(own(o["w"][:n_loc]) if lin
                                else torch.ones(n_loc, dtype=torch.float64, device=self.device)),
-                      dist_accepted=later(o["dacc"][:n_loc]), stats=own(o["stats"]), warnings=warnings, numparam=P,
+                      dist_accepted=later(o["dacc"][:n_loc]), stats=stats, warnings=warnings, numparam=P,
                       numstat=d, dist=o["dist"] if keep_dist else None)
         if lin:
-            tsc = torch.where(mad == 0, target, target / torch.where(mad == 0, torch.ones_like(mad), mad))
+            q = 8 + d + 6 * P
             r.adj_values, r.residuals = own(o["adj"][:, :n_loc]).t(), later(o["res"][:, :n_loc], tr)
-            r.pred = o["beta"][0] + o["the_m"]
-            r.sigma2 = own(o["sig"])
-            r.coef = self._uncentre(o["beta"], tsc)
+            r.sigma2, r.pred = small[q:q + P], small[q + P:q + 2 * P]
+            r.coef = small[q + 2 * P:q + 2 * P + M * P].view(M, P)
             if hcorr:
-                r.coef_h = self._uncentre(o["gamma"], tsc)
+                r.coef_h = small[q + 2 * P + M * P:q + 2 * P + 2 * M * P].view(M, P)
             ls = float(host[5])
             r.aic = nacc * ls + 2 * (d + 1) * P
             r.bic = nacc * ls + math.log(nacc) * (d + 1) * P
@@ -533,8 +535,8 @@ class AbcEngine:
         return plan
 
     def _abc_device(self, target, ss, par, pl, method, hcorr):
-        """All device work of abc() — no host synchronisation — ending in the packed `host` vector
-        [status, n_acc, ds, region_const, all_mad_zero, sum log sigma2]."""
+        """All device work of abc() — no host synchronisation — ending in the packed `small` buffer whose head is
+        [status, n_acc, ds, region_const, all_mad_zero, sum log sigma2, 0, 0] (csrc/loclinear.cu:k_final_small)."""
         k = self.k
         d, n_local = ss.shape
         P = par.shape[0]
@@ -556,10 +558,8 @@ class AbcEngine:
         # zero variance inside the accepted region (R cond2): local min / max now, reduced over the ranks at the end
         reg = k.new(d, 6)
         k.col_stats(ss_out, None, n_acc, cap, d, reg)
-        all_mad_zero = (mad == 0).all()
 
-        beta = gamma = the_m = res = adj = sig = None
-        logsig = torch.zeros(1, dtype=torch.float64, device=self.device)
+        beta = gamma = the_m = res = adj = sig = logsig = None
         stats = k.new(P, 6)
         _tl = self._t("loclinear")
         _tl.__enter__()
@@ -577,13 +577,13 @@ class AbcEngine:
             k.residual(xs, y, beta, n_acc, cap, d, P, res)
             rs = k.new(P, 6)
             k.col_stats(res, w, n_acc, cap, P, rs)
-            rstat = rs[:, 2:5].t().contiguous()
-            sums = torch.cat([rstat.view(-1), n_acc.to(torch.float64)])
+            sums = k.new(3 * P + 1)                                 # sum res | sum w res | sum w res^2 | n_acc
+            k.resid_moments(rs, n_acc, P, sums)
             self.comm.allreduce_sum(sums)
-            the_m = (sums[:P] / sums[3 * P]).contiguous()          # UNWEIGHTED mean of the residuals (R: colMeans)
-            sw = gram[0]                                           # sum of the weights (already reduced over ranks)
-            sig = (sums[2 * P:3 * P] - 2.0 * the_m * sums[P:2 * P] + the_m * the_m * sw) / sw
-            logsig = torch.log(sig).sum().view(1)
+            # the_m = UNWEIGHTED mean of the residuals (R: colMeans), sigma2 around it, sum log sigma2 (aic / bic);
+            # gram[0] = sum of the weights (already reduced over ranks)
+            the_m, sig, logsig = k.new(P), k.new(P), k.new(1)
+            k.resid_finish(sums, gram, P, the_m, sig, logsig)
             if hcorr:
                 part2 = k.new(M * P)
                 k.normal_logres(xs, res, the_m, w, n_acc, cap, d, P, part2)   # centres res in place
@@ -598,32 +598,19 @@ class AbcEngine:
         else:
             k.col_stats(y, None, n_acc, cap, P, stats)
         _tl.__exit__()
-        rmin, rmax = reg[:, 0], reg[:, 1]
+        # Everything small goes into ONE buffer (host word | mad | stats | sigma2 | pred | coef | coef_h): one kernel, one
+        # copy-out, one blocking read of its head.  Multi-rank: ONE min-exchange for everything that is a min, a max
+        # (negated) or an OR (negated bits) - region min / max of the statistics, min / max of the posterior sample, the
+        # status word - and one sum-exchange for the sums of the summary.
+        pack = sm = None
         if self.comm.world > 1:
-            # ONE min-exchange for everything that is a min, a max (negated) or an OR (negated bits):
-            # region min / max of the statistics, min / max of the posterior sample, the status word
-            sh = torch.arange(8, device=self.device, dtype=torch.int64)
-            bits = ((status.view(1).to(torch.int64) >> sh) & 1).to(torch.float64)
-            pack = torch.cat([rmin, -rmax, stats[:, 0], -stats[:, 1], -bits])
+            pack, sm = k.new(2 * d + 2 * P + 8), k.new(P, 4)
+            k.final_pack(status, reg, stats, d, P, pack, sm)
             self.comm.allreduce_min(pack)
-            sm = stats[:, 2:].contiguous()
             self.comm.allreduce_sum(sm)
-            rmin, rmax = pack[:d], -pack[d:2 * d]
-            stats = torch.cat([pack[2 * d:2 * d + P, None], -pack[2 * d + P:2 * d + 2 * P, None], sm], dim=1)
-            bits = (-pack[2 * d + 2 * P:]).to(torch.int64)
-            status = (bits << sh).sum().to(torch.int32).view(1)
-        region_const = (rmin == rmax).all()
-        host = torch.cat([status.to(torch.float64), n_acc.to(torch.float64), ds,
-                          region_const.to(torch.float64).view(1), all_mad_zero.to(torch.float64).view(1), logsig])
-        return dict(host=host, mad=mad, idx=idx, y=y, ss_out=ss_out, w=w, dacc=dacc, stats=stats, dist=f["dist"],
-                    adj=adj, res=res, beta=beta, gamma=gamma, the_m=the_m, sig=sig)
-
-    @staticmethod
-    def _uncentre(b: torch.Tensor, t_scaled: torch.Tensor) -> torch.Tensor:
-        """coefficients of the design centred on the target -> R's [1, scaled ss] convention."""
-        out = b.clone()
-        out[0] = b[0] - (t_scaled[:, None] * b[1:]).sum(dim=0)
-        return out
+        small = k.new(k.final_small_len(d, P, method == "loclinear"))
+        k.final_small(status, n_acc, ds, reg, stats, mad, target, logsig, beta, gamma, the_m, sig, pack, sm, d, P, small)
+        return dict(small=small, idx=idx, y=y, ss_out=ss_out, w=w, dacc=dacc, dist=f["dist"], adj=adj, res=res)
 
     def abc_columns(self, target, param, sumstat, tol, method, hcorr: bool = True) -> List[AbcResult]:
         """ABC-DLS's per-column mode (ABC.py:1949-1953, 2805-2809): P separate 1-D abc() problems,

@@ -52,24 +52,28 @@ def _names(x, n: int, prefix: str) -> List[str]:
 
 def to_table(x, device) -> torch.Tensor:
     """(rows, cols) host/device data -> (cols, rows) float64 CUDA table with unit stride along rows.
-    A column-major host array (pandas' usual block layout, R's layout) is copied without a transpose."""
+    A column-major host array (pandas' usual block layout, R's layout) is copied without a transpose.  float32 input
+    (what ABC-DLS hands over: Keras predictions, ABC.py:1849, 2758) crosses PCIe as float32 and is widened on the device
+    - exact, and half the bytes of rpy2's host-side conversion to R doubles."""
     if torch.is_tensor(x):
         t = x
         if t.dim() == 1:
             t = t[:, None]
-        t = t.to(device=device, dtype=torch.float64, non_blocking=True)
+        if t.dtype not in (torch.float32, torch.float64):
+            t = t.to(torch.float64)
+        t = t.to(device=device, non_blocking=True).to(torch.float64)
         tt = t.t()
         return tt if tt.stride(1) == 1 else tt.contiguous()
     if hasattr(x, "to_numpy"):
         x = x.to_numpy()
     a = np.asarray(x)
-    if a.dtype != np.float64:
+    if a.dtype not in (np.float32, np.float64):
         a = a.astype(np.float64)
     if a.ndim == 1:
         a = a[:, None]
     if a.flags.f_contiguous:
-        return torch.from_numpy(a.T).to(device)                # already (cols, rows) C-order: one H2D copy
-    return torch.from_numpy(np.ascontiguousarray(a)).to(device).t().contiguous()  # H2D + on-device transpose
+        return torch.from_numpy(a.T).to(device).to(torch.float64)        # already (cols, rows) C-order: one H2D copy
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device).to(torch.float64).t().contiguous()  # + device transpose
 
 
 def _to_vec(x, device) -> torch.Tensor:

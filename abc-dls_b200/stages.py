@@ -309,6 +309,28 @@ class CudaStages:
                          self._stream())
         self.launches += 1
 
+    def resid_moments(self, rs, n_acc, P, sums):
+        self.handle.call("abcdls_resid_moments", _p(rs), _p(n_acc), P, _p(sums), self._stream())
+        self.launches += 1
+
+    def resid_finish(self, sums, gram, P, the_m, sig, logsig):
+        self.handle.call("abcdls_resid_finish", _p(sums), _p(gram), P, _p(the_m), _p(sig), _p(logsig), self._stream())
+        self.launches += 1
+
+    def final_small_len(self, d, P, loclinear) -> int:
+        return int(self.lib.abcdls_final_small_doubles(d, P, int(loclinear)))
+
+    def final_pack(self, status, reg, stats, d, P, pack, sm):
+        self.handle.call("abcdls_final_pack", _p(status), _p(reg), _p(stats), d, P, _p(pack), _p(sm), self._stream())
+        self.launches += 1
+
+    def final_small(self, status, n_acc, ds, reg, stats, mad, target, logsig, beta, gamma, the_m, sig, pack, sm, d, P,
+                    small):
+        self.handle.call("abcdls_final_small", _p(status), _p(n_acc), _p(ds), _p(reg), _p(stats), _p(mad), _p(target),
+                         _p(logsig), _p(beta), _p(gamma), _p(the_m), _p(sig), _p(pack), _p(sm), d, P, _p(small),
+                         self._stream())
+        self.launches += 1
+
     def postpr_counts(self, model_id, idx, n_acc, row_offset, cap, K, counts):
         self.handle.call("abcdls_postpr_counts", _p(model_id), _p(idx), _p(n_acc), row_offset, cap, K, _p(counts),
                          self._stream())

@@ -283,6 +283,29 @@ size_t abcdls_col_stats_workspace_bytes(int ncols);
 int abcdls_col_stats(abcdls_handle_t h, const double* values, const double* w, const int64_t* n_acc,
                      int64_t cap, int ncols, double* out, void* ws, size_t ws_bytes, void* stream);
 
+/* P-sized glue of the adjustment (replaces ~35 one-block framework kernels per call).
+ * resid_moments: rs[P][6] (col_stats of the residuals) -> sums[3P + 1] = {sum res | sum w res | sum w res^2 | n_acc},
+ *   the message of the cross-rank sum.  resid_finish: the_m = colMeans(residuals) (unweighted, R abc()), sigma2 =
+ *   sum w (res - the_m)^2 / sum w (gram[0] = sum w), logsig = sum log sigma2 (aic / bic). */
+int abcdls_resid_moments(abcdls_handle_t h, const double* rs, const int64_t* n_acc, int P, double* sums, void* stream);
+int abcdls_resid_finish(abcdls_handle_t h, const double* sums, const double* gram, int P, double* the_m, double* sig,
+                        double* logsig, void* stream);
+/* End of a call.  final_pack (multi-rank only): pack[2d + 2P + 8] = {region min | -region max | posterior min |
+ * -posterior max | -status bits} for ONE min-exchange, sm[P][4] = stats[:, 2:6] for one sum-exchange.
+ * final_small: every small result in one buffer of abcdls_final_small_doubles(d, P, loclinear) doubles:
+ *   host[8] = {status, n_acc, ds, region constant (R cond2), every MAD zero, logsig, 0, 0} | mad[d] | stats[P][6] |
+ *   and for loclinear (beta != NULL): sigma2[P] | pred[P] = intercept + the_m | coef[(d+1)][P] | coef_h[(d+1)][P] in R's
+ *   [1, scaled ss] convention (the fits use a design centred on the scaled target).  pack / sm: the exchanged vectors
+ *   (both NULL on one rank: reg / stats / status_dev are read directly). */
+size_t abcdls_final_small_doubles(int d, int P, int loclinear);
+int abcdls_final_pack(abcdls_handle_t h, const int* status_dev, const double* reg, const double* stats, int d, int P,
+                      double* pack, double* sm, void* stream);
+int abcdls_final_small(abcdls_handle_t h, const int* status_dev, const int64_t* n_acc, const double* ds,
+                       const double* reg, const double* stats, const double* mad, const double* target,
+                       const double* logsig /* may be NULL */, const double* beta /* NULL: rejection */,
+                       const double* gamma /* NULL: no hcorr */, const double* the_m, const double* sig,
+                       const double* pack, const double* sm, int d, int P, double* small_out, void* stream);
+
 /* ---- postpr (rejection): accepted simulations per model ------------------------ */
 int abcdls_postpr_counts(abcdls_handle_t h, const int32_t* model_id, const int64_t* idx,
                          const int64_t* n_acc, int64_t row_offset, int64_t cap, int K, int64_t* counts,

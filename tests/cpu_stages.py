@@ -184,6 +184,54 @@ class CpuStages:
             out[c] = torch.tensor([x.min() if n else np.inf, x.max() if n else -np.inf, x.sum(), (ww * x).sum(),
                                    (ww * x * x).sum(), ww.sum()])
 
+    def resid_moments(self, rs, n_acc, P, sums):
+        sums[:P], sums[P:2 * P], sums[2 * P:3 * P] = rs[:, 2], rs[:, 3], rs[:, 4]
+        sums[3 * P] = float(n_acc)
+
+    def resid_finish(self, sums, gram, P, the_m, sig, logsig):
+        sw = gram[0]
+        m = sums[:P] / sums[3 * P]
+        the_m.copy_(m)
+        sig.copy_((sums[2 * P:3 * P] - 2.0 * m * sums[P:2 * P] + m * m * sw) / sw)
+        logsig[0] = torch.log(sig).sum()
+
+    def final_small_len(self, d, P, loclinear) -> int:
+        return 8 + d + 6 * P + (2 * P + 2 * (d + 1) * P if loclinear else 0)
+
+    def final_pack(self, status, reg, stats, d, P, pack, sm):
+        bits = ((int(status) >> np.arange(8)) & 1).astype(np.float64)
+        pack.copy_(torch.cat([reg[:, 0], -reg[:, 1], stats[:, 0], -stats[:, 1], -torch.from_numpy(bits)]))
+        sm.copy_(stats[:, 2:])
+
+    def final_small(self, status, n_acc, ds, reg, stats, mad, target, logsig, beta, gamma, the_m, sig, pack, sm, d, P,
+                    small):
+        M = d + 1
+        st = int(status)
+        rmin, rmax, stt = reg[:, 0], reg[:, 1], stats.clone()
+        if pack is not None:
+            rmin, rmax = pack[:d], -pack[d:2 * d]
+            stt = torch.cat([pack[2 * d:2 * d + P, None], -pack[2 * d + P:2 * d + 2 * P, None], sm], dim=1)
+            st = int(sum(1 << b for b in range(8) if float(pack[2 * d + 2 * P + b]) != 0.0))
+        small.zero_()
+        small[:6] = torch.tensor([st, float(n_acc), float(ds), float((rmin == rmax).all()), float((mad == 0).all()),
+                                  float(logsig) if logsig is not None else 0.0], dtype=torch.float64)
+        o = 8
+        small[o:o + d] = mad
+        o += d
+        small[o:o + 6 * P] = stt.reshape(-1)
+        o += 6 * P
+        if beta is not None:
+            tsc = torch.where(mad == 0, target, target / torch.where(mad == 0, torch.ones_like(mad), mad))
+            small[o:o + P] = sig
+            small[o + P:o + 2 * P] = beta[0] + the_m
+            o += 2 * P
+            for b in (beta, gamma):
+                if b is not None:
+                    c = b.clone()
+                    c[0] = b[0] - (tsc[:, None] * b[1:]).sum(dim=0)
+                    small[o:o + M * P] = c.reshape(-1)
+                o += M * P
+
     def postpr_counts(self, model_id, idx, n_acc, row_offset, cap, K, counts):
         n = int(n_acc)
         counts[:] = torch.bincount(model_id[idx[:n] - row_offset].long(), minlength=K)[:K]

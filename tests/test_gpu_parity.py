@@ -177,6 +177,10 @@ def test_facade_accepts_pandas_like_the_reference_call_sites(engine):
     np.testing.assert_array_equal(_np(joint.region_idx), oj.idx)
     np.testing.assert_allclose(np.array(joint.summary(print_=False)), O.summary_abc(oj), rtol=1e-9)
     assert not np.isnan(np.array(joint.summary(print_=False))).any()          # Mode row included
+    # float32 frames (Keras predictions, ABC.py:1849) cross PCIe as float32 and are widened on the device: same result
+    j32 = rabc.abc(target=dft, param=dfp.astype(np.float32), sumstat=dfs.astype(np.float32), method="rejection", tol=0.01)
+    np.testing.assert_array_equal(_np(j32.region_idx), oj.idx)          # synth tables are float32-representable
+    np.testing.assert_array_equal(_np(j32.unadj_values), oj.unadj_values)
     index = pd.Series(np.array(["BNDX", "MNDX", "SNDX"])[np.arange(30000) % 3])
     ids, ssp, tg = synth.postpr_tables(30000, "cpu")
     pp = rabc.postpr(target=pd.Series(tg.numpy()), index=index, sumstat=pd.DataFrame(ssp.T.numpy()), tol=0.05,
