@@ -76,6 +76,7 @@ SIGNATURES = {
                                       C.POINTER(_vp), C.POINTER(_sz), C.POINTER(_vp), C.POINTER(_sz), _vp]),
     "abcdls_dist_fast_refine": (_i32, [_vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp,
                                        C.POINTER(_vp), C.POINTER(_sz), C.POINTER(_vp), C.POINTER(_sz), _vp]),
+    "abcdls_gather_param_rows": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _i64, _vp, _vp]),
     "abcdls_normal_workspace_bytes": (_sz, [_i32, _i32]),
     "abcdls_normal": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "abcdls_solve": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),

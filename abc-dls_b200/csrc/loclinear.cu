@@ -49,7 +49,8 @@ __global__ void __launch_bounds__(256) k_gather(const double* __restrict__ ss, l
             double sc = (S.div[j] == 1.0) ? x : x / S.div[j];  // IEEE division == R's x/mad
             xs[(size_t)j * cap + r] = __dsub_rn(sc, S.tgt[j]);
         }
-        for (int p = 0; p < P; ++p) y[(size_t)p * cap + r] = param[(size_t)p * ld_param + i];
+        if (param)
+            for (int p = 0; p < P; ++p) y[(size_t)p * cap + r] = param[(size_t)p * ld_param + i];
         double q = dist_acc[r] / ds;
         w[r] = __dsub_rn(1.0, __dmul_rn(q, q));
     }
@@ -70,6 +71,53 @@ __global__ void __launch_bounds__(256) k_gather_rows(const double* __restrict__ 
         double v;
         asm volatile("ld.global.L2::64B.f64 %0, [%1];" : "=d"(v) : "l"(src + rows[i]));
         out[(size_t)p * cap + i] = v;
+    }
+}
+
+
+// y[p][r] = param[(idx[r] - row_offset) * pitch + p]: ROW-major parameter table (numpy / pandas C order - the P
+// parameters of one simulation are contiguous - which is how ABC-DLS's frames lie in memory), possibly pinned host
+// memory.  A CTA moves kGprRows accepted rows at a time: consecutive threads read consecutive doubles of a row (one
+// 128-byte request per 16 parameters instead of 16 separate sectors of a column-major table), the tile is transposed in
+// shared memory, and consecutive threads write consecutive rows of y.
+constexpr int kGprRows = 128;
+__global__ void __launch_bounds__(256) k_gather_param_rm(const double* param, long long pitch, int P,
+                                                         const long long* __restrict__ idx,
+                                                         const long long* __restrict__ n_acc_ptr, long long row_offset,
+                                                         long long cap, double* __restrict__ y) {
+    extern __shared__ double gpr_tile[];   // [P][kGprRows + 1]
+    long long n_acc = *n_acc_ptr;
+    if (n_acc > cap) n_acc = cap;
+    const long long ntile = (n_acc + kGprRows - 1) / kGprRows;
+    for (long long tl = blockIdx.x; tl < ntile; tl += gridDim.x) {
+        const long long r0 = tl * kGprRows;
+        const int nr = (int)min((long long)kGprRows, n_acc - r0);
+        const int ne = nr * P;
+        for (int e0 = threadIdx.x; e0 < ne; e0 += 256 * 4) {
+            double v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {      // four independent loads in flight per thread
+                const int e = e0 + k * 256;
+                if (e < ne) {
+                    const int rr = e / P, pp = e - rr * P;
+                    v[k] = param[(size_t)(idx[r0 + rr] - row_offset) * pitch + pp];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int e = e0 + k * 256;
+                if (e < ne) {
+                    const int rr = e / P, pp = e - rr * P;
+                    gpr_tile[pp * (kGprRows + 1) + rr] = v[k];
+                }
+            }
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < P * kGprRows; e += 256) {
+            const int pp = e / kGprRows, rr = e - pp * kGprRows;
+            if (rr < nr) y[(size_t)pp * cap + r0 + rr] = gpr_tile[pp * (kGprRows + 1) + rr];
+        }
+        __syncthreads();
     }
 }
 
@@ -806,8 +854,8 @@ int abcdls_gather(abcdls_handle_t h, const double* ss, int64_t ld_ss, const doub
                   const double* dist_acc, const int64_t* idx, const int64_t* n_acc, int64_t row_offset, int64_t cap,
                   int d, int P, const double* mad, const double* target, const double* ds, double* xs, double* y,
                   double* ss_out, double* w, void* stream) {
-    ABCDLS_CHECK_ARG(h, h && ss && param && dist_acc && idx && n_acc && mad && target && ds && xs && y && ss_out && w,
-                     "gather: null pointer");
+    ABCDLS_CHECK_ARG(h, h && ss && dist_acc && idx && n_acc && mad && target && ds && xs && y && ss_out && w,
+                     "gather: null pointer");   // param == NULL: the parameters come from abcdls_gather_param_rows
     ABCDLS_CHECK_ARG(h, d >= 1 && d <= kMaxD && P >= 1 && P <= kMaxP && cap >= 1, "gather: shape");
     k_gather<<<grid_for(h, cap, 256, 8), 256, 0, (cudaStream_t)stream>>>(
         ss, ld_ss, param, ld_param, dist_acc, (const long long*)idx, (const long long*)n_acc, row_offset, cap, d, P,
@@ -827,19 +875,37 @@ int abcdls_gather_rows(abcdls_handle_t h, const double* table, int64_t ld, int P
     return ABCDLS_OK;
 }
 
+int abcdls_gather_param_rows(abcdls_handle_t h, const double* param, int64_t row_pitch, int P, const int64_t* idx,
+                             const int64_t* n_acc, int64_t row_offset, int64_t cap, double* y, void* stream) {
+    ABCDLS_CHECK_ARG(h, h && param && idx && n_acc && y, "gather_param_rows: null pointer");
+    ABCDLS_CHECK_ARG(h, P >= 1 && P <= kMaxP && row_pitch >= P && cap >= 1, "gather_param_rows: shape");
+    long long ntile = (cap + kGprRows - 1) / kGprRows;
+    unsigned gx = (unsigned)std::min<long long>(ntile, (long long)h->sm_count * 8);
+    const size_t smem = (size_t)P * (kGprRows + 1) * sizeof(double);
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+        ABCDLS_CUDA(h, cudaFuncSetAttribute(k_gather_param_rm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    k_gather_param_rm<<<gx, 256, smem, (cudaStream_t)stream>>>(param, row_pitch, P, (const long long*)idx,
+                                                              (const long long*)n_acc, row_offset, cap, y);
+    ABCDLS_LAUNCH_CHECK(h);
+    return ABCDLS_OK;
+}
+
 int abcdls_gather_cand(abcdls_handle_t h, const double* cand_ss, int64_t ld_cand, const int64_t* slot,
                        const int64_t* perm, const double* param, int64_t ld_param, const double* cand_par,
                        int64_t ld_cpar, const double* dist_acc, const int64_t* idx,
                        const int64_t* n_acc, int64_t row_offset, int64_t cap, int d, int P, const double* mad,
                        const double* target, const double* ds, double* xs, double* y, double* ss_out, double* w,
                        void* stream) {
-    ABCDLS_CHECK_ARG(h, h && cand_ss && slot && param && dist_acc && idx && n_acc && mad && target && ds && xs && y &&
+    ABCDLS_CHECK_ARG(h, h && cand_ss && slot && dist_acc && idx && n_acc && mad && target && ds && xs && y &&
                             ss_out && w,
-                     "gather_cand: null pointer");
+                     "gather_cand: null pointer");   // param == NULL: the parameters come from abcdls_gather_param_rows
     ABCDLS_CHECK_ARG(h, d >= 1 && d <= kMaxD && P >= 1 && P <= kMaxP && cap >= 1 && ld_cand >= 1, "gather_cand: shape");
     unsigned gx = grid_for(h, cap, 256, 16);
     if (gx > 2048) gx = 2048;
-    k_gather_cand<<<dim3(gx, (unsigned)(1 + P)), 256, 0, (cudaStream_t)stream>>>(
+    k_gather_cand<<<dim3(gx, (unsigned)(1 + ((param || cand_par) ? P : 0))), 256, 0, (cudaStream_t)stream>>>(
         cand_ss, ld_cand, (const long long*)slot, (const long long*)perm, param, ld_param, cand_par, ld_cpar, dist_acc,
         (const long long*)idx,
         (const long long*)n_acc, row_offset, cap, d, mad, target, ds, xs, y, ss_out, w);

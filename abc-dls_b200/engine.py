@@ -113,14 +113,18 @@ class PostprResult:
         return self.pred[:, None] / self.pred[None, :]
 
 
-def _as_table(t: torch.Tensor) -> torch.Tensor:
+def _as_table(t: torch.Tensor, row_major_ok: bool = False) -> torch.Tensor:
     """(cols, rows) float64 view with unit stride along rows.  The tensor stays where it is: a PINNED host table is
-    legal for `param` (the gather kernel then reads the accepted rows zero-copy over PCIe/UVA)."""
+    legal for `param` (the gather kernel then reads the accepted rows zero-copy over PCIe/UVA).  `param` may also be
+    ROW-major - a (P, n) view with strides (1, pitch), i.e. ``array_n_by_P.t()``, how numpy / pandas hand the frame
+    over - and is then left as it is: its accepted rows are gathered as contiguous 8 P-byte records."""
     if t.dim() == 1:
         t = t[None, :]
     if t.dtype != torch.float64:
         t = t.to(torch.float64)
     if t.stride(1) != 1:
+        if row_major_ok and t.stride(0) == 1 and t.stride(1) >= t.shape[0]:
+            return t
         t = t.contiguous()
     return t
 
@@ -320,7 +324,7 @@ class AbcEngine:
             slot = k.new(cap, dtype=torch.int64)
             n_cand = n_cand0
             pre = None
-            if (par is not None and par.device.type == "cuda" and self.pregather
+            if (par is not None and par.device.type == "cuda" and self.pregather and par.stride(1) == 1
                     and (self.comm.world == 1 or self.comm.peer is not None)):   # NCCL segments cannot span a fork
                 # device-resident parameters: gather them for ALL candidates on a second stream while this one refines
                 if self._side is None:
@@ -403,7 +407,7 @@ class AbcEngine:
         if kernel != "epanechnikov":
             raise AbcError("only kernel='epanechnikov' (the R default ABC-DLS uses) is implemented")
         k = self.k
-        ss, par = _as_table(sumstat), _as_table(param)
+        ss, par = _as_table(sumstat), _as_table(param, row_major_ok=True)
         target = target.to(device=self.device, dtype=torch.float64).reshape(-1).contiguous()
         d, n_local = ss.shape
         P = par.shape[0]
@@ -425,7 +429,7 @@ class AbcEngine:
         # The device work of one call is a fixed sequence of ~90 launches whose shapes depend only on the key below, so
         # it is captured into a CUDA graph the second time a key is seen and replayed afterwards (one launch per call).
         o = None
-        key = (ss.data_ptr(), tuple(ss.shape), ss.stride(0), par.data_ptr(), tuple(par.shape), par.stride(0),
+        key = (ss.data_ptr(), tuple(ss.shape), ss.stride(0), par.data_ptr(), tuple(par.shape), par.stride(0), par.stride(1),
                par.device.type, float(tol), method, bool(hcorr), bool(keep_dist), int(_level), self.comm.world,
                pl["n_global"], pl["row_offset"])
         graphable = (self.use_graphs and self.timers is None and self.device.type == "cuda" and not keep_dist)
@@ -546,15 +550,19 @@ class AbcEngine:
 
         xs, y, ss_out = k.new(d, cap), k.new(P, cap), k.new(d, cap)
         w = k.new(cap)
+        row_major = par.stride(1) != 1          # (P, n) view of an n x P C-order array: see _as_table
+        pcol, pld = (None, 0) if row_major else (par, par.stride(0))
         with self._t("gather"):
             if f["fused"]:   # the statistics of the accepted rows are already compact (candidate block)
                 if f["cand_par"] is not None:
                     torch.cuda.current_stream(self.device).wait_stream(self._side)   # join the parameter pre-gather
-                k.gather_cand(f["cand_ss"], f["cand_ss"].stride(0), f["slot"], f["perm"], par, par.stride(0), dacc, idx, n_acc,
+                k.gather_cand(f["cand_ss"], f["cand_ss"].stride(0), f["slot"], f["perm"], pcol, pld, dacc, idx, n_acc,
                               f["row_offset"], cap, d, P, mad, target, ds, xs, y, ss_out, w, cand_par=f["cand_par"])
             else:
-                k.gather(ss, ss.stride(0), par, par.stride(0), dacc, idx, n_acc, f["row_offset"], cap, d, P, mad,
+                k.gather(ss, ss.stride(0), pcol, pld, dacc, idx, n_acc, f["row_offset"], cap, d, P, mad,
                          target, ds, xs, y, ss_out, w)
+            if row_major:    # one contiguous 8 P-byte record per accepted row instead of P scattered sectors
+                k.gather_param_rows(par, par.stride(1), P, idx, n_acc, f["row_offset"], cap, y)
         # zero variance inside the accepted region (R cond2): local min / max now, reduced over the ranks at the end
         reg = k.new(d, 6)
         k.col_stats(ss_out, None, n_acc, cap, d, reg)
@@ -615,7 +623,7 @@ class AbcEngine:
     def abc_columns(self, target, param, sumstat, tol, method, hcorr: bool = True) -> List[AbcResult]:
         """ABC-DLS's per-column mode (ABC.py:1949-1953, 2805-2809): P separate 1-D abc() problems,
         column c of ``sumstat`` against column c of ``param``."""
-        ss, par = _as_table(sumstat), _as_table(param)
+        ss, par = _as_table(sumstat), _as_table(param, row_major_ok=True)
         target = target.reshape(-1)
         return [self.abc(target[c:c + 1], par[c:c + 1], ss[c:c + 1], tol, method, hcorr) for c in range(par.shape[0])]
 

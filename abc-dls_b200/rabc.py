@@ -50,11 +50,13 @@ def _names(x, n: int, prefix: str) -> List[str]:
     return [f"{prefix}{i + 1}" for i in range(n)]
 
 
-def to_table(x, device) -> torch.Tensor:
+def to_table(x, device, row_major_ok: bool = False) -> torch.Tensor:
     """(rows, cols) host/device data -> (cols, rows) float64 CUDA table with unit stride along rows.
     A column-major host array (pandas' usual block layout, R's layout) is copied without a transpose.  float32 input
     (what ABC-DLS hands over: Keras predictions, ABC.py:1849, 2758) crosses PCIe as float32 and is widened on the device
-    - exact, and half the bytes of rpy2's host-side conversion to R doubles."""
+    - exact, and half the bytes of rpy2's host-side conversion to R doubles.  ``row_major_ok`` (the parameter table): a
+    row-major array is NOT transposed; the (cols, rows) view with strides (1, cols) goes to the engine, whose gather
+    reads the accepted rows as contiguous records."""
     if torch.is_tensor(x):
         t = x
         if t.dim() == 1:
@@ -63,7 +65,9 @@ def to_table(x, device) -> torch.Tensor:
             t = t.to(torch.float64)
         t = t.to(device=device, non_blocking=True).to(torch.float64)
         tt = t.t()
-        return tt if tt.stride(1) == 1 else tt.contiguous()
+        if tt.stride(1) == 1 or (row_major_ok and tt.stride(0) == 1):
+            return tt
+        return tt.contiguous()
     if hasattr(x, "to_numpy"):
         x = x.to_numpy()
     a = np.asarray(x)
@@ -73,7 +77,8 @@ def to_table(x, device) -> torch.Tensor:
         a = a[:, None]
     if a.flags.f_contiguous:
         return torch.from_numpy(a.T).to(device).to(torch.float64)        # already (cols, rows) C-order: one H2D copy
-    return torch.from_numpy(np.ascontiguousarray(a)).to(device).to(torch.float64).t().contiguous()  # + device transpose
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(device).to(torch.float64).t()
+    return t if row_major_ok else t.contiguous()                          # + device transpose
 
 
 def _to_vec(x, device) -> torch.Tensor:
@@ -165,7 +170,7 @@ def abc(target, param, sumstat, tol, method, hcorr: bool = True, transf: str = "
         raise AbcError("'subset' is not implemented")
     eng = engine()
     ss = to_table(sumstat, eng.device)
-    par = to_table(param, eng.device)
+    par = to_table(param, eng.device, row_major_ok=True)
     tgt = _to_vec(target, eng.device)
     res = eng.abc(tgt, par, ss, float(tol), method, hcorr=hcorr, kernel=kernel)
     for wmsg in res.warnings:

@@ -262,6 +262,12 @@ class CudaStages:
                          self._stream())
         self.launches += 1
 
+    def gather_param_rows(self, param, row_pitch, P, idx, n_acc, row_offset, cap, y):
+        """Parameter half of a gather for a ROW-major table (device or pinned host)."""
+        self.handle.call("abcdls_gather_param_rows", _p(param), row_pitch, P, _p(idx), _p(n_acc), row_offset, cap, _p(y),
+                         self._stream())
+        self.launches += 1
+
     def normal(self, xs, rhs, w, n_acc, cap, d, P, with_gram, partial):
         ws = self.workspace("normal", self.lib.abcdls_normal_workspace_bytes(d, P))
         self.handle.call("abcdls_normal", _p(xs), _p(rhs), _p(w), _p(n_acc), cap, d, P, int(with_gram), _p(partial),

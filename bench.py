@@ -48,7 +48,11 @@ def _args():
     ap.add_argument("--tol", type=float, default=0.01)
     ap.add_argument("--method", default="loclinear")
     ap.add_argument("--cpu-rows", type=float, default=1e6, help="bounded sample for the CPU arm")
+    ap.add_argument("--param-layout", default="row", choices=["row", "col"],
+                    help="memory layout of the parameter table: row = n x P C order (numpy / pandas, what ABC-DLS holds), "
+                         "col = P x n (R's as.matrix); sumstat is always column-major")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-e2e-f32", action="store_true", help="skip the extra end-to-end leg with float32 host tables")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--clock-interval", type=float, default=0.02, help="seconds between NVML clock samples")
     return ap.parse_args()
@@ -147,8 +151,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cfg = {"workload": f"cfg5 abc(method={args.method}, hcorr) joint: N={int(args.rows):d} sims x d={args.stats} "
-                       f"stats x P={args.params} params, tol={args.tol}, fp64 column-major tables",
-           "rows": int(args.rows), "stats": args.stats, "params": args.params, "tol": args.tol,
+                       f"stats x P={args.params} params, tol={args.tol}, fp64 tables: sumstat column-major, param "
+                       f"{'row-major (n x P C order, as numpy / pandas hand the frame over)' if args.param_layout == 'row' else 'column-major'}",
+           "param_layout": args.param_layout, "rows": int(args.rows), "stats": args.stats, "params": args.params, "tol": args.tol,
            "sharding": f"rows/{world}", "l2": "tables larger than L2 (no flush needed)"}
 
     if args.impl == "reference":
@@ -179,6 +184,8 @@ def main():
     n_local = r1 - r0
     d, P = args.stats, args.params
     par, ss, tgt = synth.abc_tables(n_local, d, P, dev, row_start=r0)
+    if args.param_layout == "row":
+        par = par.t().contiguous().t()          # (P, n) view of an (n, P) C-order table, strides (1, P)
 
     def step():
         return eng.abc(tgt, par, ss, args.tol, args.method, shard=(N, r0))
@@ -252,7 +259,10 @@ def main():
     # ---- end to end through host buffers -----------------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        h_par = torch.empty((P, n_local), dtype=torch.float64, pin_memory=True)
+        if args.param_layout == "row":
+            h_par = torch.empty((n_local, P), dtype=torch.float64, pin_memory=True).t()
+        else:
+            h_par = torch.empty((P, n_local), dtype=torch.float64, pin_memory=True)
         h_ss = torch.empty((d, n_local), dtype=torch.float64, pin_memory=True)
         h_par.copy_(par)
         h_ss.copy_(ss)
@@ -261,19 +271,31 @@ def main():
         h_stats = torch.empty((P, 6), dtype=torch.float64, pin_memory=True)
         d2h, h2d_dyn = [0], [0]
 
-        def e2e_step():
+        parts = []
+
+        def e2e_step(src=None):
             # sumstat must be resident (two passes); param stays in pinned host memory and only the accepted
             # rows are read by the gather kernel through UVA (counted below as H2D traffic)
-            dss = h_ss.to(dev, non_blocking=True)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
+            src = h_ss if src is None else src
+            dss = src.to(dev, non_blocking=True)
+            if dss.dtype != torch.float64:
+                dss = dss.to(torch.float64)        # float32 host table: half the PCIe bytes, widened (exactly) in HBM
             dt_ = h_tgt.to(dev, non_blocking=True)
+            ev[1].record()
             r = eng.abc(dt_, h_par, dss, args.tol, args.method, shard=(N, r0))
+            ev[2].record()
             vals = (r.adj_values if r.adj_values is not None else r.unadj_values).t()   # (P, n_local_acc), contiguous
             n_loc = vals.shape[1]
             h_out[:, :n_loc].copy_(vals, non_blocking=True)       # pinned destination: PCIe line rate
             h_stats.copy_(r.stats, non_blocking=True)
+            ev[3].record()
             torch.cuda.current_stream(dev).synchronize()
+            parts.append([ev[i].elapsed_time(ev[i + 1]) for i in range(3)])
             d2h[0] = n_loc * P * 8 + h_stats.numel() * 8
-            h2d_dyn[0] = h_ss.numel() * 8 + h_tgt.numel() * 8 + r.idx.numel() * P * 32   # 32-byte sectors per gathered value
+            h2d_dyn[0] = (src.numel() * src.element_size() + h_tgt.numel() * 8       # gathered parameters: one 8 P-byte
+                          + r.idx.numel() * P * (8 if args.param_layout == "row" else 32))  # record / 32-byte sectors
             return h_out, h_stats
 
         del par, ss
@@ -282,6 +304,7 @@ def main():
             e2e_step()
         sync()
         nstep = max(1, min(args.steps, 3))
+        del parts[:]
         t0 = time.perf_counter()
         for _ in range(nstep):
             e2e_step()
@@ -291,8 +314,36 @@ def main():
             dist.all_reduce(dt_e, op=dist.ReduceOp.MAX)
         e2e = {"value": N / float(dt_e.item()), "unit": UNIT, "h2d_bytes_per_step": h2d_dyn[0], "d2h_bytes_per_step": d2h[0],
                "ms_per_step": float(dt_e.item()) * 1e3, "steps": nstep,
+               "breakdown_ms": dict(zip(("h2d_sumstat", "abc_incl_zero_copy_param_gather", "d2h_results"),
+                                        [round(sum(p_[i] for p_ in parts) / len(parts), 3) for i in range(3)])),
                "api": "AbcEngine.abc(target, param, sumstat) on pinned HOST tables: sumstat H2D (PCIe line rate), param "
                       "gathered zero-copy (accepted rows only) -> posterior sample + summary D2H into pinned buffers"}
+
+        if not args.no_e2e_f32:
+            # The same call when the caller hands over float32 (what ABC-DLS does: Keras predictions, ABC.py:1849; the
+            # synthetic values are float32-representable by construction): identical results, half the H2D.
+            e2e_main, h2d_main = list(parts), h2d_dyn[0]
+            h_ss32 = torch.empty((d, n_local), dtype=torch.float32, pin_memory=True)
+            h_ss32.copy_(h_ss)
+            exact = bool((h_ss32[:, :1 << 20].double() == h_ss[:, :1 << 20]).all())
+            for _ in range(3):
+                e2e_step(h_ss32)
+            sync()
+            del parts[:]
+            t0 = time.perf_counter()
+            for _ in range(nstep):
+                e2e_step(h_ss32)
+            sync()
+            dt32 = torch.tensor([(time.perf_counter() - t0) / nstep], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(dt32, op=dist.ReduceOp.MAX)
+            e2e["float32_host_tables"] = {
+                "value": N / float(dt32.item()), "ms_per_step": float(dt32.item()) * 1e3, "h2d_bytes_per_step": h2d_dyn[0],
+                "values_identical_to_f64_tables": exact,
+                "breakdown_ms": dict(zip(("h2d_sumstat_and_widen", "abc_incl_zero_copy_param_gather", "d2h_results"),
+                                         [round(sum(p_[i] for p_ in parts) / len(parts), 3) for i in range(3)]))}
+            h2d_dyn[0] = h2d_main
+            del h_ss32
 
     if rank == 0:
         base = None

@@ -251,6 +251,12 @@ int abcdls_gather_cand(abcdls_handle_t h, const double* cand_ss, int64_t ld_cand
                        const int64_t* n_acc, int64_t row_offset, int64_t cap, int d, int P, const double* mad,
                        const double* target, const double* ds, double* xs, double* y, double* ss_out, double* w,
                        void* stream);
+/* y[p][r] = param[(idx[r] - row_offset) * row_pitch + p] for the first *n_acc accepted rows: the parameter half of
+ * a gather for a ROW-major parameter table (numpy / pandas C order, how ABC-DLS's frames lie in memory:
+ * params_unscaled, ABC.py:1825-1875), device or pinned host memory.  One 128-byte request per accepted row (P = 16)
+ * instead of P scattered sectors of a column-major table.  abcdls_gather / abcdls_gather_cand accept param == NULL then. */
+int abcdls_gather_param_rows(abcdls_handle_t h, const double* param, int64_t row_pitch, int P, const int64_t* idx,
+                             const int64_t* n_acc, int64_t row_offset, int64_t cap, double* y, void* stream);
 size_t abcdls_normal_workspace_bytes(int d, int P);
 int abcdls_normal(abcdls_handle_t h, const double* xs, const double* rhs, const double* w,
                   const int64_t* n_acc, int64_t cap, int d, int P, int with_gram, double* partial,

@@ -127,10 +127,16 @@ class CpuStages:
             col = ss[j][loc].numpy()
             ss_out[j, :n] = torch.from_numpy(col)
             xs[j, :n] = torch.from_numpy(col - target[j].item() if m == 0 else col / m - target[j].item() / m)
-        for p in range(P):
-            y[p, :n] = param[p][loc]
+        if param is not None:
+            for p in range(P):
+                y[p, :n] = param[p][loc]
         q = dist_acc[:n].numpy() / ds.item()
         w[:n] = torch.from_numpy(1.0 - q * q)
+
+    def gather_param_rows(self, par, row_pitch, P, idx, n_acc, row_offset, cap, y):
+        n = int(n_acc)
+        assert par.stride(0) == 1 and par.stride(1) == row_pitch
+        y[:, :n] = par[:, idx[:n] - row_offset]
 
     def normal(self, xs, rhs, w, n_acc, cap, d, P, with_gram, partial):
         n = int(n_acc)

@@ -381,3 +381,25 @@ def test_fused_target_far_from_the_data(engine):
     o = O.abc(_np(tgt), _np(par).T, _np(ss).T, 0.01, "loclinear")
     np.testing.assert_array_equal(_np(r.idx), o.idx)
     assert r.ds == o.ds and _rel(_np(r.adj_values), o.adj_values) < REL_TOL
+
+
+@pytest.mark.parametrize("n,d,P,tol,method", [(50000, 3, 5, 0.02, "loclinear"), ((1 << 20) + 77, 4, 16, 0.01, "loclinear"),
+                                              ((1 << 20) + 77, 4, 3, 0.003, "rejection")])
+def test_row_major_param_table_gives_the_same_result(engine, n, d, P, tol, method):
+    """`param` as numpy / pandas hand it over (n x P C order, passed as its (P, n) transposed view), on the device and
+    in pinned host memory: same accepted rows, same values as the column-major table (exact and one-pass paths)."""
+    par, ss, tgt = synth.abc_tables(n, d, P, engine.device)
+    ref = engine.abc(tgt, par, ss, tol, method)
+    rm = par.t().contiguous()                              # (n, P) row-major
+    assert rm.t().stride() == (1, P)
+    host = torch.empty((n, P), dtype=torch.float64, pin_memory=True)
+    host.copy_(rm)
+    for table in (rm.t(), host.t()):
+        for _ in range(3):                                 # eager, capture, replay
+            r = engine.abc(tgt, table, ss, tol, method)
+            assert torch.equal(r.idx, ref.idx) and torch.equal(r.unadj_values, ref.unadj_values)
+            assert torch.equal(r.values, ref.values) and torch.equal(r.stats, ref.stats)
+    cols = engine.abc_columns(tgt[:min(d, P)], rm.t()[:min(d, P)], ss[:min(d, P)], tol, "rejection")
+    cref = engine.abc_columns(tgt[:min(d, P)], par[:min(d, P)], ss[:min(d, P)], tol, "rejection")
+    for a, b in zip(cols, cref):
+        assert torch.equal(a.idx, b.idx) and torch.equal(a.unadj_values, b.unadj_values)

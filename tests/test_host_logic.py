@@ -132,3 +132,18 @@ def test_snakemake_range_files_roundtrip(tmp_path):
     assert smc.lmrd4mcsv(str(hard), str(out)) == O.lmrd_calculation(w[0], w[1], hmin, hmax)
     np.testing.assert_array_equal(smc.csv_linenumbers(np.array([0, 5])), [2, 7])
     np.testing.assert_array_equal(smc.csv_linenumbers(np.array([0, 5]), header=False), [1, 6])
+
+
+def test_row_major_param_sequencing_on_the_stage_double():
+    """engine.py routes a (P, n) view with strides (1, P) through gather(param=None) + gather_param_rows."""
+    from abc_dls_b200.engine import AbcEngine
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from cpu_stages import CpuStages
+    eng = AbcEngine(stages=CpuStages())
+    par, ss, tgt = synth.abc_tables(3000, 3, 4, "cpu")
+    rm = par.t().contiguous()
+    a = eng.abc(tgt, par, ss, 0.05, "loclinear")
+    b = eng.abc(tgt, rm.t(), ss, 0.05, "loclinear")
+    assert torch.equal(a.idx, b.idx) and torch.equal(a.adj_values, b.adj_values) and torch.equal(a.stats, b.stats)
+    o = O.abc(tgt.numpy(), par.numpy().T, ss.numpy().T, 0.05, "loclinear")
+    np.testing.assert_array_equal(b.idx.numpy(), o.idx)
