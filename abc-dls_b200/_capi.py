@@ -94,6 +94,9 @@ SIGNATURES = {
     "abcdls_final_pack": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "abcdls_final_small": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
                                   _vp, _vp]),
+    "abcdls_small_supported": (_i32, [_i64, _i64]),
+    "abcdls_small_columns": (_i32, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp,
+                                    _vp]),
     "abcdls_postpr_counts": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp]),
     "abcdls_smc_workspace_bytes": (_sz, [_i64, _i32]),
     "abcdls_smc_oldrange": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _sz, _vp]),

@@ -12,10 +12,15 @@ one strided copy), so a whole cross-validation moves about one table's worth of 
 ascending order, and every validation after the second replays the engine's CUDA graph (same key: same buffers, same
 shapes).  Point estimates stay on the device until the end.
 
+Per-column mode (one parameter, one statistic - how ABC-DLS calls cv4abc for rejection / loclinear, ABC.py:1896-1904)
+on a table that fits one CTA's shared memory does not loop at all: every (tolerance, held-out row) fit is one thread
+block of ``csrc/small.cu`` and the whole cross-validation is ONE launch per tolerance.
+
 Single rank only: the tables of these steps are test-set sized in ABC-DLS (``test_size`` rows).
 """
 from __future__ import annotations
 
+import math
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -100,6 +105,49 @@ class Cv4abcResult:
         return "\n".join(lines)
 
 
+def _small_status(st: int, method: str) -> None:
+    """The R stop() conditions of abc() for a one-CTA fit (same messages as engine.abc)."""
+    from . import _capi
+    if st & _capi.S_NONFINITE:
+        raise AbcError("non-finite values in 'sumstat'/'target' (R's NA-row handling is not implemented)")
+    if st & _capi.S_ZERO_VAR:
+        raise AbcError("Zero variance in the summary statistics.")
+    if st & _capi.S_ZERO_VAR_REGION:
+        msg = "Zero variance in the summary statistics in the selected region."
+        if method != "rejection":
+            raise AbcError(msg + " Try: checking summary statistics, choosing larger tolerance, or rejection method.")
+        print("Warning message:\n" + msg + " Check summary statistics, consider larger tolerance.")
+    if st & _capi.S_SINGULAR:
+        raise AbcError("lsfit: X matrix deemed to be singular (collinear summary statistics in the accepted region)")
+
+
+def small_fits(eng: AbcEngine, par: torch.Tensor, ss: torch.Tensor, col, hold, tol: float, method: str,
+               hcorr: bool = True, target=None) -> Optional[np.ndarray]:
+    """B one-dimensional abc() problems in one launch (csrc/small.cu): problem b uses column col[b] of ``par`` / ``ss``
+    with row hold[b] left out and the held-out statistic as target (hold None: no row removed, target[b] given).
+    Returns (B, 8) = {median, mean, ds, mad, min, max, n_acc, status} or None when the table does not qualify."""
+    k = eng.k
+    N = ss.shape[1]
+    n1 = N - (0 if hold is None else 1)
+    nacc = int(math.ceil(n1 * tol))
+    if not (1 <= nacc <= n1):
+        raise AbcError("'tol' must give 1 <= ceiling(N * tol) <= N")
+    if not (hasattr(k, "small_columns") and ss.stride(1) == 1 and k.small_supported(N, nacc)):
+        return None
+    dev = eng.device
+    col_t = torch.as_tensor(np.asarray(col, dtype=np.int32)).to(dev)
+    hold_t = None if hold is None else torch.as_tensor(np.asarray(hold, dtype=np.int64)).to(dev)
+    tgt_t = None if target is None else target.to(device=dev, dtype=torch.float64).contiguous()
+    out = k.new(col_t.numel(), 8)
+    k.small_columns(ss, par, N, col_t, hold_t, tgt_t, nacc, method == "loclinear", hcorr, out)
+    o = out.cpu().numpy()
+    st = 0
+    for v in np.unique(o[:, 7]):
+        st |= int(v)
+    _small_status(st, method)
+    return o
+
+
 def cv4abc(eng: AbcEngine, par: torch.Tensor, ss: torch.Tensor, nval: int, tols, method: str,
            statistic: str = "median", hcorr: bool = True, cvsamples=None, seed=None, names=None) -> Cv4abcResult:
     """par (P, N), ss (d, N): float64 device tables.  One abc() per (tolerance, held-out row)."""
@@ -109,9 +157,21 @@ def cv4abc(eng: AbcEngine, par: torch.Tensor, ss: torch.Tensor, nval: int, tols,
     P, N = par.shape
     samp = _draw(N, int(nval), seed) if cvsamples is None else np.asarray(cvsamples, dtype=np.int64).reshape(-1)
     tols = np.sort(np.atleast_1d(np.asarray(tols, dtype=np.float64)))
+    names = names or {"parameter.names": [f"P{p + 1}" for p in range(P)]}
+    true = par[:, torch.from_numpy(samp).to(par.device)].t().cpu().numpy()
+    estim: Dict[float, np.ndarray] = {}
+    if P == 1 and ss.shape[0] == 1 and statistic in ("median", "mean") and method in ("rejection", "loclinear"):
+        # per-column mode on a small table: every fit is one thread block, one launch per tolerance
+        for tol in tols:
+            o = small_fits(eng, par, ss, np.zeros(samp.size, dtype=np.int32), samp, float(tol), method, hcorr)
+            if o is None:
+                estim.clear()
+                break
+            estim[float(tol)] = o[:, 0 if statistic == "median" else 1].reshape(-1, 1).copy()
+        if estim:
+            return Cv4abcResult(samp, tols, true, estim, names, statistic)
     loo = LeaveOneOut([par, ss])
     order = np.argsort(samp, kind="stable")            # ascending holes: every row of the buffers moves at most once
-    estim: Dict[float, np.ndarray] = {}
     for tol in tols:
         est = torch.empty((samp.size, P), dtype=torch.float64, device=eng.device)
         for i in order:
@@ -120,9 +180,30 @@ def cv4abc(eng: AbcEngine, par: torch.Tensor, ss: torch.Tensor, nval: int, tols,
             res = eng.abc(ss[:, s], bpar, bss, float(tol), method, hcorr=hcorr)
             est[i] = _summary.point_estimate(res.values, res.weights, res.stats, res.adj_values is not None, statistic)
         estim[float(tol)] = est.cpu().numpy()
-    true = par[:, torch.from_numpy(samp).to(par.device)].t().cpu().numpy()
-    names = names or {"parameter.names": [f"P{p + 1}" for p in range(P)]}
     return Cv4abcResult(samp, tols, true, estim, names, statistic)
+
+
+def cv4abc_columns(eng: AbcEngine, par: torch.Tensor, ss: torch.Tensor, nval: int, tol: float, method: str,
+                   statistic: str = "median", hcorr: bool = True, cvsamples=None, seed=None, names=None):
+    """The whole "Cv error independently" loop of ABC-DLS (ABC.py:1896-1904: one cv4abc per parameter column, column c of
+    ``ss`` against column c of ``par``) as ONE launch of P x nval thread blocks when the table is small; otherwise a loop
+    over cv4abc.  Returns one Cv4abcResult per column (the same held-out rows for every column)."""
+    _engine_single(eng)
+    P, N = par.shape
+    samp = _draw(N, int(nval), seed) if cvsamples is None else np.asarray(cvsamples, dtype=np.int64).reshape(-1)
+    pn = (names or {}).get("parameter.names", [f"P{p + 1}" for p in range(P)])
+    o = None
+    if statistic in ("median", "mean") and method in ("rejection", "loclinear") and ss.shape[0] == P:
+        o = small_fits(eng, par, ss, np.repeat(np.arange(P, dtype=np.int32), samp.size), np.tile(samp, P), float(tol),
+                       method, hcorr)
+    if o is None:
+        return [cv4abc(eng, par[c:c + 1], ss[c:c + 1], nval, tol, method, statistic, hcorr, samp, None,
+                       {"parameter.names": [pn[c]]}) for c in range(P)]
+    est = o[:, 0 if statistic == "median" else 1].reshape(P, samp.size)
+    true = par[:, torch.from_numpy(samp).to(par.device)].cpu().numpy()
+    tols = np.array([float(tol)])
+    return [Cv4abcResult(samp, tols, true[c].reshape(-1, 1), {float(tol): est[c].reshape(-1, 1).copy()},
+                         {"parameter.names": [pn[c]]}, statistic) for c in range(P)]
 
 
 class Cv4postprResult:

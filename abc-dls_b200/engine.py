@@ -627,6 +627,34 @@ class AbcEngine:
         target = target.reshape(-1)
         return [self.abc(target[c:c + 1], par[c:c + 1], ss[c:c + 1], tol, method, hcorr) for c in range(par.shape[0])]
 
+    def abc_columns_summary(self, target, param, sumstat, tol, method, hcorr: bool = True):
+        """Per-column mode when only ``summary(res)`` is kept - ABC-DLS's SMC reads Min and Max of every column
+        (ABC.py:2805-2840): {"min", "max", "median", "mean"} -> (P,) float64 numpy arrays.  On one rank and a table that
+        fits a CTA's shared memory the P problems are ONE launch of csrc/small.cu; otherwise a loop over abc()."""
+        import numpy as np
+        from . import cv as _cv, summary as _summary
+        ss, par = _as_table(sumstat), _as_table(param, row_major_ok=True)
+        target = target.to(device=self.device, dtype=torch.float64).reshape(-1)
+        P = par.shape[0]
+        if ss.shape[0] != P or target.numel() != P:
+            raise AbcError("per-column mode needs one summary statistic and one target value per parameter")
+        if method not in ("rejection", "loclinear"):
+            raise AbcError("Method must be rejection or loclinear (neuralnet / ridge stay with R's nnet)")
+        o = None
+        if self.comm.world == 1 and ss.device == self.device and par.device == self.device:
+            o = _cv.small_fits(self, par, ss, np.arange(P, dtype=np.int32), None, float(tol), method, hcorr, target=target)
+        if o is not None:
+            return {"median": o[:, 0].copy(), "mean": o[:, 1].copy(), "min": o[:, 4].copy(), "max": o[:, 5].copy()}
+        out = {k_: np.empty(P) for k_ in ("median", "mean", "min", "max")}
+        for c, r in enumerate(self.abc_columns(target, par, ss, tol, method, hcorr)):
+            if self.comm.world > 1:
+                raise AbcError("abc_columns_summary over several ranks: use abc_columns and AbcResult.minmax()")
+            w = r.adj_values is not None
+            out["min"][c], out["max"][c] = float(r.stats[0, 0]), float(r.stats[0, 1])
+            out["median"][c] = float(_summary.point_estimate(r.values, r.weights, r.stats, w, "median")[0])
+            out["mean"][c] = float(_summary.point_estimate(r.values, r.weights, r.stats, w, "mean")[0])
+        return out
+
     # ---- postpr() -------------------------------------------------------------------------------
     def postpr(self, target: torch.Tensor, model_id: torch.Tensor, models: List[str], sumstat: torch.Tensor,
                tol: float, method: str = "rejection", keep_dist: bool = False, _level: int = 0) -> PostprResult:

@@ -337,6 +337,15 @@ class CudaStages:
                          self._stream())
         self.launches += 1
 
+    def small_supported(self, n, nacc) -> bool:
+        return bool(self.lib.abcdls_small_supported(int(n), int(nacc)))
+
+    def small_columns(self, ss, par, n, col, hold, target, nacc, loclinear, hcorr, out):
+        """B one-CTA abc() problems with d = P = 1 in ONE launch; ss (cols, n) column-major, par (cols, n) any strides."""
+        self.handle.call("abcdls_small_columns", _p(ss), ss.stride(0), _p(par), par.stride(0), par.stride(1), n, _p(col),
+                         _p(hold), _p(target), col.numel(), nacc, int(loclinear), int(hcorr), _p(out), self._stream())
+        self.launches += 1
+
     def postpr_counts(self, model_id, idx, n_acc, row_offset, cap, K, counts):
         self.handle.call("abcdls_postpr_counts", _p(model_id), _p(idx), _p(n_acc), row_offset, cap, K, _p(counts),
                          self._stream())

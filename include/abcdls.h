@@ -312,6 +312,23 @@ int abcdls_final_small(abcdls_handle_t h, const int* status_dev, const int64_t* 
                        const double* gamma /* NULL: no hcorr */, const double* the_m, const double* sig,
                        const double* pack, const double* sm, int d, int P, double* small_out, void* stream);
 
+/* ---- small tables: one thread block per abc() problem with d = P = 1 (csrc/small.cu) -----------------------------
+ * ABC-DLS's per-column mode (ABC.py:1949-1953, 2805-2809) and cv4abc's leave-one-out loop over it (ABC.py:1900-1902)
+ * are B independent 1-D problems on test-set sized tables (10^4 rows): launch latency, not bandwidth.  Problem b:
+ *   abc(target = hold ? ss[col[b]][hold[b]] : target[b], param = par[col[b]] without row hold[b],
+ *       sumstat = ss[col[b]] without row hold[b], tol -> nacc, method = loclinear ? "loclinear" : "rejection")
+ * runs entirely in one CTA's shared memory; a whole cross-validation is ONE launch.
+ * ss: column-major (ld_ss); par: element (row i, column c) at par[c * par_col_stride + i * par_row_stride] (either
+ * layout); n rows BEFORE the hold-out; hold may be NULL (no row removed; then target[B] is read).
+ * out[b][8] = {median, mean, ds, mad, min, max, n_acc, status (ABCDLS_S_* bits)} of the posterior sample
+ * (summary.abc rows 3, 4, 1, 7: weighted median / mean of adj.values for loclinear, type-7 median / mean of
+ * unadj.values for rejection). */
+int abcdls_small_supported(int64_t n, int64_t nacc);
+int abcdls_small_columns(abcdls_handle_t h, const double* ss, int64_t ld_ss, const double* par, int64_t par_col_stride,
+                         int64_t par_row_stride, int64_t n, const int32_t* col, const int64_t* hold,
+                         const double* target, int B, int64_t nacc, int loclinear, int hcorr, double* out,
+                         void* stream);
+
 /* ---- postpr (rejection): accepted simulations per model ------------------------ */
 int abcdls_postpr_counts(abcdls_handle_t h, const int32_t* model_id, const int64_t* idx,
                          const int64_t* n_acc, int64_t row_offset, int64_t cap, int K, int64_t* counts,

@@ -171,3 +171,73 @@ def test_cv4abc_large_table_replays_the_graph_on_the_fast_path(engine):
     assert engine.path_calls["exact"] == before["exact"]                  # never the small-table path
     want = O.cv4abc(par.cpu().numpy().T, ss.cpu().numpy().T, 4, 0.001, "rejection", cvsamples=samp)
     np.testing.assert_array_equal(got.estim[0.001], want.estim[0.001])
+
+
+# ---- one-CTA-per-fit path (csrc/small.cu): per-column mode on test-set sized tables ------------------------------------
+def _columns(n, P, seed, decimals=None):
+    par, ss, tgt = synth.abc_tables(n, P, P, "cpu")
+    if decimals is not None:                       # exact ties in the statistic and in the distance
+        scale = ss.abs().max(dim=1, keepdim=True).values
+        ss = torch.round(ss / scale * 10 ** decimals) / 10 ** decimals * scale
+    return par, ss, tgt
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,decimals", [(3000, None), (10001, None), (4096, 3), (4096, 2)])
+@pytest.mark.parametrize("method", ["rejection", "loclinear"])
+def test_small_table_cv4abc_is_one_launch_and_matches_the_oracle(engine, n, decimals, method):
+    if decimals == 2 and method == "loclinear":
+        pytest.skip("two decimals leave one or two distinct statistics in the accepted region: lsfit is singular")
+    P, nval, tol = 3, 7, 0.02
+    par, ss, _ = _columns(n, P, 1, decimals)
+    dpar, dss = par.to(engine.device), ss.to(engine.device)
+    samp = np.random.default_rng(n).choice(n, nval, replace=False)
+    samp[0], samp[1] = 0, n - 1
+    for statistic in ("median", "mean"):
+        l0 = engine.k.launches
+        got = CV.cv4abc_columns(engine, dpar, dss, nval, tol, method, statistic=statistic, cvsamples=samp)
+        assert engine.k.launches - l0 == 1                                  # P x nval fits, one launch
+        for c in range(P):
+            want = O.cv4abc(par.numpy()[c], ss.numpy()[c], nval, tol, method, statistic=statistic, cvsamples=samp)
+            scale = np.abs(want.true).max()
+            assert np.max(np.abs(got[c].estim[tol] - want.estim[tol])) <= 1e-9 * scale, (c, statistic)
+            np.testing.assert_array_equal(got[c].true, want.true)
+            one = CV.cv4abc(engine, dpar[c:c + 1], dss[c:c + 1], nval, [tol], method, statistic=statistic, cvsamples=samp)
+            np.testing.assert_array_equal(one.estim[tol], got[c].estim[tol])   # per-column entry point: same kernel
+    # row-major parameter table: same fits
+    rm = dpar.t().contiguous().t()
+    again = CV.cv4abc_columns(engine, rm, dss, nval, tol, method, statistic="mean", cvsamples=samp)
+    for a, b in zip(again, got):
+        np.testing.assert_array_equal(a.estim[tol], b.estim[tol])
+
+
+@pytest.mark.gpu
+def test_small_table_fit_equals_the_streaming_engine_and_reports_r_stops(engine):
+    n, P, tol = 5000, 4, 0.01
+    par, ss, tgt = _columns(n, P, 2)
+    dpar, dss, dtgt = par.to(engine.device), ss.to(engine.device), tgt.to(engine.device)
+    for method in ("rejection", "loclinear"):
+        summ = engine.abc_columns_summary(dtgt, dpar, dss, tol, method)
+        for c, r in enumerate(engine.abc_columns(dtgt, dpar, dss, tol, method)):
+            o = O.abc(tgt.numpy()[c:c + 1], par.numpy()[c], ss.numpy()[c], tol, method)
+            tab = O.summary_abc(o)
+            scale = np.abs(par.numpy()[c]).max()
+            assert abs(summ["min"][c] - tab[0, 0]) <= 1e-9 * scale and abs(summ["max"][c] - tab[6, 0]) <= 1e-9 * scale
+            assert abs(summ["median"][c] - tab[2, 0]) <= 1e-9 * scale and abs(summ["mean"][c] - tab[3, 0]) <= 1e-9 * scale
+            assert abs(summ["min"][c] - float(r.stats[0, 0])) <= 1e-9 * scale
+    flat = dss.clone()
+    flat[1] = 3.0                                                            # a constant statistic: R stops
+    with pytest.raises(CV.AbcError, match="Zero variance in the summary statistics\\."):
+        engine.abc_columns_summary(dtgt, dpar, flat, tol, "rejection")
+    bad = dss.clone()
+    bad[0, 17] = float("nan")
+    with pytest.raises(CV.AbcError, match="non-finite"):
+        engine.abc_columns_summary(dtgt, dpar, bad, tol, "loclinear")
+    region = dss.clone()                                                     # accepted region of column 2 is constant
+    region[2] = torch.where((region[2] - dtgt[2]).abs() < 0.2 * region[2].std(), dtgt[2], region[2])
+    with pytest.raises(CV.AbcError, match="selected region"):
+        engine.abc_columns_summary(dtgt, dpar, region, tol, "loclinear")
+    big = torch.zeros((1, 200000), dtype=torch.float64, device=engine.device).normal_()
+    l0 = engine.k.launches                                                   # too large for one CTA: streaming path
+    engine.abc_columns_summary(big[:, 0], big, big, 0.001, "rejection")
+    assert engine.k.launches - l0 > 1
