@@ -219,6 +219,9 @@ __global__ void __launch_bounds__(kNormThreads) k_normal_partial(const double* _
     const int nA = (M + kBA - 1) / kBA, nB = (Wb + kBB - 1) / kBB;
     const int npairs = nA * nB;
     const int nslots = (npairs + 31) / 32;
+    // <= 16 register blocks (the hcorr refit: no Gram part): the two half-warps take alternate rows instead of leaving
+    // 20 lanes idle - half the instructions per tile
+    const bool split = npairs <= 16;
     // tile columns: 0 = ones, 1..d = xs, M..W-1 = rhs, W = weights, W + 1 = zeros (padding target)
     const int ncols = W + 2;
     double* buf[2] = {smn, smn + (size_t)ncols * kNormPitch};
@@ -246,7 +249,7 @@ __global__ void __launch_bounds__(kNormThreads) k_normal_partial(const double* _
     };
 
     for (int slot = 0; slot < nslots; ++slot) {
-        const int pair = slot * 32 + lane;
+        const int pair = split ? (lane & 15) : slot * 32 + lane;
         const bool on = pair < npairs;
         const int ablk = on ? pair / nB : 0, bblk = on ? pair % nB : 0;
         int ai[kBA], bi[kBB];                                            // tile columns (padding -> the zero column)
@@ -300,8 +303,9 @@ __global__ void __launch_bounds__(kNormThreads) k_normal_partial(const double* _
             }
             const double* __restrict__ T = buf[cur];
             const double* __restrict__ wt = T + (size_t)W * kNormPitch;
+            const int rstart = split ? 2 * wid + (lane >> 4) : wid, rstep = split ? 2 * kNormWarps : kNormWarps;
 #pragma unroll 2
-            for (int rr = wid; rr < kNormRows; rr += kNormWarps) {
+            for (int rr = rstart; rr < kNormRows; rr += rstep) {
                 const double wv = wt[rr];
                 double av[kBA], bv[kBB];
 #pragma unroll
@@ -326,12 +330,15 @@ __global__ void __launch_bounds__(kNormThreads) k_normal_partial(const double* _
         __syncthreads();
         for (int t = threadIdx.x; t < 32 * kBA * kBB; t += kNormThreads) {
             const int ln = t / (kBA * kBB), ij = t % (kBA * kBB);
-            const int pr = slot * 32 + ln;
-            if (pr >= npairs) continue;
+            const int pr = split ? ln : slot * 32 + ln;
+            if (pr >= npairs || (split && ln >= 16)) continue;
             const int a = pr / nB + nA * (ij / kBB), b = b0 + pr % nB + nB * (ij % kBB);
             if (a >= M || b >= W) continue;
             double sum = 0.0;
-            for (int wq = 0; wq < kNormWarps; ++wq) sum += red[((size_t)wq * 32 + ln) * (kBA * kBB) + ij];
+            for (int wq = 0; wq < kNormWarps; ++wq) {
+                sum += red[((size_t)wq * 32 + ln) * (kBA * kBB) + ij];
+                if (split) sum += red[((size_t)wq * 32 + ln + 16) * (kBA * kBB) + ij];
+            }
             const int e = (b < M) ? a * M + b : (with_gram ? M * M : 0) + a * P + (b - M);
             out[e] = sum;
         }

@@ -15,7 +15,7 @@
 
 namespace {
 
-constexpr int kSmT = 1024;        // threads per problem
+constexpr int kSmT = 512;         // threads per problem: 2 CTAs per SM (48 registers, ~92 KB of shared memory each)
 constexpr int kSmBins = 2048;     // 11-bit digits
 
 struct SmallShared {
