@@ -57,6 +57,33 @@ def main():
     np.savez_compressed(os.path.join(HERE, "smc_round.npz"), target=tgt, param=theta, sumstat=ss, tol=0.05,
                         hard_min=hard_min, hard_max=hard_max, post_min=s["post_min"], post_max=s["post_max"],
                         new_min=s["min"], new_max=s["max"], decrease=s["decrease"], lines=s["lines"], lmrd=s["lmrd"])
+    # 5. leave-one-out tools: per-column cv4abc (both methods), cv4postpr, gfit with fixed held-out rows
+    theta, ss, tgt = tables(2500, 2, 2, 404)
+    samp = np.array([0, 17, 1250, 2499, 801, 33])
+    out = {"param": theta, "sumstat": ss, "target": tgt, "cvsamples": samp, "tols": np.array([0.02, 0.05])}
+    for method in ("loclinear", "rejection"):
+        for c in range(2):
+            cv = O.cv4abc(theta[:, c], ss[:, c], samp.size, [0.02, 0.05], method, cvsamples=samp)
+            out[f"{method}_col{c}_estim"] = np.stack([cv.estim[0.02], cv.estim[0.05]])
+            out[f"{method}_col{c}_prederr"] = O.summary_cv4abc(cv)
+    cvj = O.cv4abc(theta, ss, samp.size, [0.05], "rejection", cvsamples=samp)
+    out["rejection_joint_estim"], out["rejection_joint_prederr"] = cvj.estim[0.05], O.summary_cv4abc(cvj)
+    np.savez_compressed(os.path.join(HERE, "cv4abc.npz"), **out)
+    n = 1500
+    logits = rng.normal(size=(n, 3)) + 2.0 * (np.arange(3)[None, :] == (np.arange(n) % 3)[:, None])
+    sm = np.round((np.exp(logits) / np.exp(logits).sum(1, keepdims=True)).astype(np.float32), 5).astype(np.float64)
+    ids = np.arange(n) % 3
+    sp = np.array([0, 300, 3, 1, 601, 1498, 2, 302, 1499])           # 3 per model, models in sorted order
+    sp = np.concatenate([sp[ids[sp] == k] for k in range(3)])
+    cp = O.cv4postpr(np.array(["BNDX", "MNDX", "SNDX"])[ids], sm, 3, [0.05], cvsamples=sp)
+    sc = O.summary_cv4postpr(cp)
+    gs = np.array([5, 77, 1400, 999])
+    gf = O.gfit(np.array([0.2, 0.5, 0.3]), sm, gs.size, 0.05, samples=gs)
+    sg = O.summary_gfit(gf)
+    np.savez_compressed(os.path.join(HERE, "cv4postpr_gfit.npz"), ids=ids, sumstat=sm, cvsamples=sp, tol=0.05,
+                        estim=cp.estim[0.05], conf=sc["conf.matrix"][0.05], probs=sc["probs"][0.05],
+                        gfit_target=np.array([0.2, 0.5, 0.3]), gfit_samples=gs, dist_sim=gf.dist_sim, dist_obs=gf.dist_obs,
+                        pvalue=sg["pvalue"], s_dist_sim=sg["s.dist.sim"])
     print("golden vectors written to", HERE)
 
 

@@ -96,3 +96,53 @@ def test_cuda_reproduces_golden_ties_postpr_smc(engine):
     assert smc.lmrd_calculation(rng, g["hard_min"], g["hard_max"]) == float(g["lmrd"])
     idx = engine.box_filter(par, torch.from_numpy(rng.min), torch.from_numpy(rng.max))
     np.testing.assert_array_equal(idx.cpu().numpy() + 2, g["lines"])
+
+
+# ---- leave-one-out tools -------------------------------------------------------------------------------------------------
+def test_oracle_reproduces_golden_cv():
+    g = _load("cv4abc.npz")
+    for method in ("loclinear", "rejection"):
+        for c in range(2):
+            cv = O.cv4abc(g["param"][:, c], g["sumstat"][:, c], g["cvsamples"].size, g["tols"], method,
+                          cvsamples=g["cvsamples"])
+            np.testing.assert_allclose(np.stack([cv.estim[0.02], cv.estim[0.05]]), g[f"{method}_col{c}_estim"], rtol=1e-12)
+            np.testing.assert_allclose(O.summary_cv4abc(cv), g[f"{method}_col{c}_prederr"], rtol=1e-10)
+    g = _load("cv4postpr_gfit.npz")
+    labels = np.array(["BNDX", "MNDX", "SNDX"])[g["ids"]]
+    cp = O.cv4postpr(labels, g["sumstat"], 3, [float(g["tol"])], cvsamples=g["cvsamples"])
+    np.testing.assert_array_equal(cp.estim[0.05], g["estim"])
+    np.testing.assert_array_equal(O.summary_cv4postpr(cp)["conf.matrix"][0.05], g["conf"])
+    gf = O.gfit(g["gfit_target"], g["sumstat"], g["gfit_samples"].size, float(g["tol"]), samples=g["gfit_samples"])
+    np.testing.assert_allclose(gf.dist_sim, g["dist_sim"], rtol=1e-13)
+    assert O.summary_gfit(gf)["pvalue"] == float(g["pvalue"])
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_golden_cv(engine):
+    from abc_dls_b200 import cv as CV
+    g = _load("cv4abc.npz")
+    dev = engine.device
+    par, ss = _tab(g["param"], dev), _tab(g["sumstat"], dev)
+    scale = np.abs(g["param"]).max(axis=0)
+    for method in ("loclinear", "rejection"):
+        for c in range(2):          # one thread block per fit (csrc/small.cu)
+            cv = CV.cv4abc(engine, par[c:c + 1], ss[c:c + 1], g["cvsamples"].size, g["tols"], method,
+                           cvsamples=g["cvsamples"])
+            got = np.stack([cv.estim[0.02], cv.estim[0.05]])
+            assert np.max(np.abs(got - g[f"{method}_col{c}_estim"])) <= 1e-9 * scale[c]
+            np.testing.assert_allclose(cv.summary(print_=False), g[f"{method}_col{c}_prederr"], rtol=1e-6)
+    cvj = CV.cv4abc(engine, par, ss, g["cvsamples"].size, [0.05], "rejection", cvsamples=g["cvsamples"])   # streaming
+    np.testing.assert_array_equal(cvj.estim[0.05], g["rejection_joint_estim"])
+    g = _load("cv4postpr_gfit.npz")
+    ids = torch.from_numpy(g["ids"].astype(np.int32)).to(dev)
+    ssm = _tab(g["sumstat"], dev)
+    cp = CV.cv4postpr(engine, ids, ["BNDX", "MNDX", "SNDX"], ssm, 3, [float(g["tol"])], cvsamples=g["cvsamples"])
+    np.testing.assert_array_equal(cp.estim[0.05], g["estim"])
+    s = cp.summary(print_=False)
+    np.testing.assert_array_equal(s["conf.matrix"][0.05], g["conf"])
+    np.testing.assert_allclose(s["probs"][0.05], g["probs"], rtol=1e-12)
+    gf = CV.gfit(engine, torch.from_numpy(g["gfit_target"]).to(dev), ssm, g["gfit_samples"].size, float(g["tol"]),
+                 samples=g["gfit_samples"])
+    np.testing.assert_allclose(gf.dist_sim, g["dist_sim"], rtol=1e-12)
+    assert abs(gf.dist_obs - float(g["dist_obs"])) <= 1e-12 * float(g["dist_obs"])
+    assert gf.summary(print_=False)["pvalue"] == float(g["pvalue"])
