@@ -135,17 +135,57 @@ def point_estimate(values: torch.Tensor, weights, stats: torch.Tensor, weighted:
     raise ValueError(statistic)
 
 
+def _sci_parts(x: float, digits: int):
+    """(exponent kp, significant digits nsig <= digits after dropping trailing zeros) of x rounded to `digits`
+    significant digits - R's scientific() in format.c."""
+    if x == 0.0:
+        return 0, 1
+    mant, exp = f"{abs(x):.{digits - 1}e}".split("e")
+    return int(exp), max(1, len(mant.replace(".", "").rstrip("0")))
+
+
+def format_r_column(values, digits: int = 4):
+    """R's formatReal() for one column of a printed numeric matrix: ONE format for the whole column - fixed notation
+    with as many decimals as the element that needs most of them to show `digits` significant digits, or scientific
+    notation when that would be wider.  Returns the list of cell strings (not yet padded)."""
+    vals = [float(v) for v in values]
+    fin = [v for v in vals if np.isfinite(v)]
+    if not fin:
+        return ["NaN" if np.isnan(v) else ("Inf" if v > 0 else "-Inf") for v in vals]
+    parts = [_sci_parts(v, digits) for v in fin]
+    neg = 1 if any(v < 0 for v in fin) else 0
+    rgt = max(max(0, ns - kp - 1) for kp, ns in parts)
+    left = max((kp + 1 if kp >= 0 else 1) + (1 if v < 0 else 0) for v, (kp, ns) in zip(fin, parts))
+    w_fixed = left + rgt + (1 if rgt > 0 else 0)
+    mxe = max(ns for _, ns in parts) - 1
+    wexp = 2 if all(abs(kp) < 100 for kp, _ in parts) else 3
+    w_sci = neg + 1 + (mxe + 1 if mxe > 0 else 0) + 2 + wexp
+    fixed = w_fixed <= w_sci
+    out = []
+    for v in vals:
+        if not np.isfinite(v):
+            out.append("NaN" if np.isnan(v) else ("Inf" if v > 0 else "-Inf"))
+        elif fixed:
+            out.append(f"{v:.{rgt}f}")
+        else:
+            m, e = f"{v:.{mxe}e}".split("e")
+            out.append(f"{m}e{e[0]}{int(e[1:]):0{wexp}d}")
+    return out
+
+
 def summary_text(tab: SummaryTable, n_samples: int, weighted: bool, names=None, digits: int = 4) -> str:
-    """Text from the ``Data:`` line on (what ABC-DLS prints, ABC.py:844-861)."""
+    """Text from the ``Data:`` line on (what ABC-DLS prints, ABC.py:844-861); the table as R's print.table shows it:
+    digits = max(3, getOption("digits") - 3) = 4, one common format per column (format_r_column)."""
     names = names or tab.names or [f"P{p + 1}" for p in range(np.asarray(tab).shape[1])]
     lines = ["Data:", f" abc.out${'adj' if weighted else 'unadj'}.values ({n_samples} posterior samples)"]
     if weighted:
         lines += ["Weights:", " abc.out$weights"]
     lines.append("")
-    cells = [[f"{v:.{digits}g}" for v in row] for row in np.asarray(tab)]
-    widths = [max(len(names[p]), *(len(cells[r][p]) for r in range(7))) for p in range(len(names))]
+    a = np.asarray(tab)
+    cols = [format_r_column(a[:, p], digits) for p in range(len(names))]
+    widths = [max(len(names[p]), *(len(c) for c in cols[p])) for p in range(len(names))]
     lab = max(len(r) for r in ROWS)
     lines.append(" " * lab + " " + " ".join(n.rjust(w) for n, w in zip(names, widths)))
     for r in range(7):
-        lines.append(ROWS[r].ljust(lab) + " " + " ".join(c.rjust(w) for c, w in zip(cells[r], widths)))
+        lines.append(ROWS[r].ljust(lab) + " " + " ".join(cols[p][r].rjust(widths[p]) for p in range(len(names))))
     return "\n".join(lines)

@@ -418,6 +418,38 @@ def summary_abc(res: AbcOracleResult, intvl: float = 0.95) -> np.ndarray:
     return out
 
 
+def r_format_real(x, digits: int = 4) -> List[str]:
+    """R ``formatReal`` as print.default applies it to one column of a numeric matrix (src/main/format.c, restated):
+    per element the decimal exponent e and the number of significant digits sig (<= digits, trailing zeros dropped);
+    fixed notation needs max(sig - e - 1, 0) decimals and max(e + 1, 1) digits before the point; the column is printed in
+    fixed notation with the largest decimal count unless scientific notation is narrower (R_print.scipen = 0)."""
+    x = np.asarray(x, dtype=np.float64)
+    es, sigs = [], []
+    for v in x:
+        if v == 0:
+            es.append(0), sigs.append(1)
+            continue
+        e = int(math.floor(math.log10(abs(v))))
+        m = round(abs(v) / 10.0 ** e, digits - 1)
+        if m >= 10.0:
+            m, e = m / 10.0, e + 1
+        q = int(round(m * 10 ** (digits - 1)))
+        sig = digits
+        while sig > 1 and q % 10 == 0:
+            q //= 10
+            sig -= 1
+        es.append(e), sigs.append(sig)
+    neg = bool((x < 0).any())
+    rgt = max(max(s_ - e - 1, 0) for s_, e in zip(sigs, es))
+    left = max(max(e + 1, 1) + (1 if v < 0 else 0) for v, e in zip(x, es))
+    w_fixed = left + rgt + (1 if rgt else 0)
+    mxe = max(sigs) - 1
+    w_sci = int(neg) + 1 + (mxe + 1 if mxe else 0) + 4
+    if w_fixed <= w_sci:
+        return ["%.*f" % (rgt, v) for v in x]
+    return ["%.*e" % (mxe, v) for v in x]
+
+
 # --------------------------------------------------------------------------------------
 # ABC-DLS SMC range logic (pandas in the reference; numpy here, same arithmetic order)
 # --------------------------------------------------------------------------------------

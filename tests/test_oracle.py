@@ -271,3 +271,23 @@ def test_product_summary_table_matches_the_oracle_including_the_mode_row():
                               weighted=(method == "loclinear"))
         np.testing.assert_allclose(np.asarray(got), want, rtol=1e-9, atol=1e-15)
         assert not np.isnan(np.asarray(got)).any()
+
+
+def test_r_print_format_of_the_summary_table():
+    """print.table / formatReal: one format per column, digits = 4 (what R shows for summary.abc)."""
+    from abc_dls_b200 import summary as S
+    assert O.r_format_real([0.1234567, 12.5, 1000.123]) == ["0.1235", "12.5000", "1000.1230"]
+    assert O.r_format_real([1.234e-4, 150000.0]) == ["1.234e-04", "1.500e+05"]
+    assert O.r_format_real([123456.0, 0.5]) == ["123456.0", "0.5"]
+    assert O.r_format_real([-2.0, 3.14159]) == ["-2.000", "3.142"]
+    assert O.r_format_real([0.0, 10.0]) == ["0", "10"]
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        col = rng.normal(size=7) * 10.0 ** rng.integers(-6, 7)
+        if rng.random() < 0.3:
+            col = np.round(col, int(rng.integers(0, 3)))
+        assert S.format_r_column(col) == O.r_format_real(col), col
+    tab = S.SummaryTable(np.array([[1.0, 0.001], [2.5, 0.002], [3.25, 0.00345], [3.0, 0.004], [2.9, 0.0041],
+                                   [4.0, 0.005], [10.0, 0.0123456]]), ["N_A", "mig"])
+    txt = S.summary_text(tab, 100, True).splitlines()
+    assert txt[0] == "Data:" and txt[-1].split() == ["Max.:", "10.00", "0.01235"]
