@@ -361,7 +361,8 @@ def main():
             ev[2].record()
             vals = (r.adj_values if r.adj_values is not None else r.unadj_values).t()   # (P, n_local_acc), contiguous
             n_loc = vals.shape[1]
-            h_out[:, :n_loc].copy_(vals, non_blocking=True)       # pinned destination: PCIe line rate
+            # pinned AND dense destination: PCIe line rate (a strided pinned view is copied at ~2 GB/s)
+            h_out.view(-1)[: P * n_loc].view(P, n_loc).copy_(vals, non_blocking=True)
             h_stats.copy_(r.stats, non_blocking=True)
             ev[3].record()
             torch.cuda.current_stream(dev).synchronize()
