@@ -241,3 +241,33 @@ def test_small_table_fit_equals_the_streaming_engine_and_reports_r_stops(engine)
     l0 = engine.k.launches                                                   # too large for one CTA: streaming path
     engine.abc_columns_summary(big[:, 0], big, big, 0.001, "rejection")
     assert engine.k.launches - l0 > 1
+
+
+@pytest.mark.gpu
+def test_small_table_edge_cases_match_the_oracle(engine):
+    """MAD == 0 (more than half of a column identical: R leaves it unscaled), nacc = 1, half the table accepted, even
+    and odd row counts, target outside the simulated range."""
+    rng = np.random.default_rng(12)
+    for n in (1001, 1002):
+        x = rng.normal(size=(3, n))
+        x[1, : (6 * n) // 10] = 1.5                                     # column 1: MAD = 0
+        x[2] = np.round(x[2], 1)                                        # column 2: heavy ties
+        y = x + 0.1 * rng.normal(size=(3, n))
+        tgt = np.array([0.3, 1.5001, 9.0])                             # column 2: target far outside
+        dx, dy, dt = (torch.from_numpy(a).to(engine.device) for a in (x, y, tgt))
+        for method in ("rejection", "loclinear"):
+            for tol in (1.0 / n, 0.01, 0.5):
+                if method == "loclinear" and tol * n < 8:
+                    continue                                            # a fit needs a few points
+                cols = [0, 2] if method == "loclinear" else [0, 1, 2]  # loclinear on the 60 % constant column: R stops
+                got = engine.abc_columns_summary(dt[cols], dy[cols], dx[cols], tol, method)
+                for i, c in enumerate(cols):
+                    o = O.abc(tgt[c:c + 1], y[c], x[c], tol, method)
+                    tab = O.summary_abc(o) if o.idx.size > 1 else None
+                    v = o.adj_values if method == "loclinear" else o.unadj_values
+                    scale = max(np.abs(y[c]).max(), np.abs(v).max())    # the far target extrapolates the fit by 1e7
+                    assert abs(got["min"][i] - v.min()) <= 1e-9 * scale and abs(got["max"][i] - v.max()) <= 1e-9 * scale, \
+                        (n, method, tol, c)
+                    if tab is not None:
+                        assert abs(got["median"][i] - tab[2, 0]) <= 1e-9 * scale, (n, method, tol, c)
+                        assert abs(got["mean"][i] - tab[3, 0]) <= 1e-9 * scale, (n, method, tol, c)
