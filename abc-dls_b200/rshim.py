@@ -14,7 +14,6 @@ import numpy as np
 class _R:
     def __init__(self):
         self._sink_file = None
-        self._stdout = None
 
     def options(self, **_kw):
         return None
@@ -23,16 +22,21 @@ class _R:
         return getattr(self, "_" + verb.replace(".", "_"))
 
     def _summary(self, obj, **kw):
+        # R's sink() diverts R's own output only: what summary() prints goes to the sink file (flushed at once - the
+        # reference reads its first line while the sink is still open, ABC.py:1915-1918), Python's prints are untouched
+        if self._sink_file is not None and not self._sink_file.closed:
+            with contextlib.redirect_stdout(self._sink_file):
+                res = obj.summary(**kw)
+            self._sink_file.flush()
+            return res
         return obj.summary(**kw)
 
     def _sink(self, path=None):  # R sink(file) / sink()
-        if path is not None:
-            self._stdout, self._sink_file = sys.stdout, open(path, "w")
-            sys.stdout = self._sink_file
-        elif self._stdout is not None:
-            sys.stdout = self._stdout
+        if self._sink_file is not None:
             self._sink_file.close()
-            self._stdout = self._sink_file = None
+            self._sink_file = None
+        if path is not None:
+            self._sink_file = open(path, "w")
 
     def _pdf(self, *_a, **_k):
         return None

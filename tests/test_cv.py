@@ -102,8 +102,14 @@ def test_rshim_verbs(tmp_path):
     p = tmp_path / "sink.txt"
     r["sink"](str(p))
     x = r["summary"](Obj())
+    assert open(p).readline() == "first line\n"          # readable while the sink is still open (ABC.py:1915-1918)
+    print("python output is not diverted")
     r["sink"]()
-    assert open(p).readline() == "first line\n" and x[0][0] == 0.25
+    assert open(p).read() == "first line\n" and x[0][0] == 0.25
+    r["sink"](str(p))                                      # a second sink() without closing the first, then removal
+    os.remove(p)
+    r["summary"](Obj())
+    r["sink"]()
     assert r["pdf"]("x.pdf") is None and r["dev.off"]() is None and r["plot"](Obj(), ask=False) is None
     np.testing.assert_allclose(r["sapply"](np.array([[1.0, 2.0], [3.0, 2.0]]), "sd"), [np.sqrt(2.0), 0.0])
 

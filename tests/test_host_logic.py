@@ -147,3 +147,21 @@ def test_row_major_param_sequencing_on_the_stage_double():
     assert torch.equal(a.idx, b.idx) and torch.equal(a.adj_values, b.adj_values) and torch.equal(a.stats, b.stats)
     o = O.abc(tgt.numpy(), par.numpy().T, ss.numpy().T, 0.05, "loclinear")
     np.testing.assert_array_equal(b.idx.numpy(), o.idx)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the CUDA arm): one JSON line with the contract
+    keys, the same metric / unit / config as the CUDA arm, timed on a bounded sample."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1", "--cpu-rows", "20000"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "sims/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert "workload" in line["config"] and line["config"]["rows"] == 100000000
