@@ -180,7 +180,7 @@ k_fused_pass(const __grid_constant__ CUtensorMap tmap, long long n, long long nt
              double* __restrict__ candM, long long capM, double* __restrict__ candU, long long capU,
              unsigned long long* __restrict__ cnt, unsigned short* __restrict__ mask16, double* __restrict__ cand_e,
              long long ecap, int* __restrict__ erow, unsigned long long* __restrict__ ealloc, long long tpc,
-             int* status) {
+             int chunkM, int chunkU, int* status) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FusedSmem& sm = *reinterpret_cast<FusedSmem*>(smem_raw);
     double* ring = reinterpret_cast<double*>(smem_raw + kFHeader);
@@ -236,6 +236,8 @@ k_fused_pass(const __grid_constant__ CUtensorMap tmap, long long n, long long nt
     double* __restrict__ gU = candU + (size_t)jc * capU;
     unsigned long long* cntM = &cnt[jc * 2 + 0];
     unsigned long long* cntU = &cnt[jc * 2 + 1];
+    long long posM = 0, endM = 0, posU = 0, endU = 0;   // this warp's reserved chunk of each global list (warp uniform)
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
     unsigned c_neg = 0, c_in = 0;                // per lane: x < c, |x - c| < r1
     unsigned eoff = 0;                           // candidate-row emission: next free slot of this warp's 64-slot chunk
     int eroom = 0;
@@ -259,24 +261,45 @@ k_fused_pass(const __grid_constant__ CUtensorMap tmap, long long n, long long nt
             if (lane >= o) incl += t;
         }
         const int tot = __shfl_sync(0xffffffffu, incl, 31);
-        unsigned long long bM = 0ull, bU = 0ull;
-        if (lane == 0) {
-            if (tot & 0xffff) bM = atomicAdd(cntM, (unsigned long long)(tot & 0xffff));
-            if (tot >> 16) bU = atomicAdd(cntU, (unsigned long long)(tot >> 16));
+        // Space in the global lists comes from chunks this warp reserved earlier (column j of this CTA belongs to this
+        // warp alone): a flush pays the ~1 us round trip of a global atomic only when a chunk runs out.  A flush stalls
+        // its warp, the warp holds its ring stage, and five stages are ~2.5 us of work - with two atomics per flush the
+        // ring kept draining.  What is left of a chunk is padded with NaN, which every reader of the lists skips.
+        const long long nM = tot & 0xffff, nU = tot >> 16;
+        if (nM > endM - posM) {
+            for (long long i = posM + lane; i < endM; i += 32)
+                if (i < capM) gM[i] = qnan;
+            const long long take = nM > chunkM ? nM : chunkM;
+            unsigned long long b = 0ull;
+            if (lane == 0) b = atomicAdd(cntM, (unsigned long long)take);
+            posM = (long long)__shfl_sync(0xffffffffu, b, 0);
+            endM = posM + take;
         }
-        bM = __shfl_sync(0xffffffffu, bM, 0);
-        bU = __shfl_sync(0xffffffffu, bU, 0);
-        long long dM = (long long)bM + ((incl - mine) & 0xffff);
-        long long dU = (long long)bU + ((incl - mine) >> 16);
-        for (int t = 0; t < fill; ++t) {
+        if (nU > endU - posU) {
+            for (long long i = posU + lane; i < endU; i += 32)
+                if (i < capU) gU[i] = qnan;
+            const long long take = nU > chunkU ? nU : chunkU;
+            unsigned long long b = 0ull;
+            if (lane == 0) b = atomicAdd(cntU, (unsigned long long)take);
+            posU = (long long)__shfl_sync(0xffffffffu, b, 0);
+            endU = posU + take;
+        }
+        // branch-free copy-out: one select of the destination per entry, no divergence between the two bands; the
+        // capacity test runs per entry only when this warp's chunk sticks out of a list (which is then a flagged miss)
+        double* pM = gM + posM + ((incl - mine) & 0xffff);
+        double* pU = gU + posU + ((incl - mine) >> 16);
+        posM += nM;
+        posU += nU;
+        const bool roomy = endM <= capM && endU <= capU;
+        for (int t = 0; t < mx; ++t) {
             double v;
             asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(q0 + t * 256));
-            if (fabs(__dsub_rn(v, c)) <= r0) {
-                if (dM < capM) gM[dM] = v;
-                ++dM;
-            } else {
-                if (dU < capU) gU[dU] = v;
-                ++dU;
+            if (t < fill) {
+                const bool isM = fabs(__dsub_rn(v, c)) <= r0;
+                double* dst = isM ? pM : pU;
+                if (roomy || (isM ? (pM - gM) < capM : (pU - gU) < capU)) *dst = v;
+                pM += isM ? 1 : 0;
+                pU += isM ? 0 : 1;
             }
         }
         pq = q0;
@@ -401,6 +424,10 @@ k_fused_pass(const __grid_constant__ CUtensorMap tmap, long long n, long long nt
     }
     if (has_col) {
         flush();
+        for (long long i = posM + lane; i < endM; i += 32)
+            if (i < capM) gM[i] = qnan;
+        for (long long i = posU + lane; i < endU; i += 32)
+            if (i < capU) gU[i] = qnan;
         c_neg = warp_sum(c_neg);
         c_in = warp_sum(c_in);
         if (lane == 0) {
@@ -442,7 +469,7 @@ __global__ void __launch_bounds__(256) k_fused_histM(const double* __restrict__ 
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            if (i0 + u * stride >= nv) continue;
+            if (i0 + u * stride >= nv || xv[u] != xv[u]) continue;      // NaN: padding of a reserved chunk
             atomicAdd(&hist[bin_of(xv[u], lo, scale)], 1u);
             neg += (unsigned)__double2hiint(__dsub_rn(xv[u], c)) >> 31;
         }
@@ -675,11 +702,20 @@ struct FusedWs {
 
 inline long long round_chunk(long long x) { return (x + kFChunk - 1) / kFChunk * kFChunk; }
 
+// entries a warp of the pass reserves at a time in a global candidate list whose expected fill is `expect`
+inline int fused_chunk(long long expect) {
+    long long c = expect / (160 * 16);
+    c = c < 128 ? 128 : (c > 2048 ? 2048 : c);
+    return (int)((c + 31) / 32 * 32);
+}
+
 inline FusedWs carve_fused(void* ws, int64_t n, int d) {
     FusedWs w;
     const int G = sample_ctas(n);
-    w.capM = round_chunk(cap_for(n, 0.03));
-    w.capU = round_chunk(cap_for(n, 0.08));
+    // + room for the NaN padding of the per-warp chunk reservations of the pass (one open chunk per CTA and list, and
+    // what a chunk switch leaves behind)
+    w.capM = round_chunk(cap_for(n, 0.03) + fused_chunk(cap_for(n, 0.03)) * 2 * 160);
+    w.capU = round_chunk(cap_for(n, 0.08) + fused_chunk(cap_for(n, 0.08)) * 2 * 160);
     w.m = carve_mad(ws, d, G, w.capM, w.capU);
     char* p = reinterpret_cast<char*>(ws);
     size_t o = w.m.total;
@@ -807,7 +843,8 @@ int abcdls_fused_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int
     }
     k_fused_pass<<<(unsigned)grid, kFThreads, smem, st>>>(tmap, n, ntiles, d, nstages, w.m.brk, w.par, w.m.counts,
                                                          w.m.candM, w.capM, w.m.candU, w.capU, w.m.cnt, w.mask16, cand_ss,
-                                                         ecap, cand_lrow, w.ealloc, tpc, status_dev);
+                                                         ecap, cand_lrow, w.ealloc, tpc, fused_chunk(cap_for(n, 0.03)),
+                                                         fused_chunk(cap_for(n, 0.08)), status_dev);
     ABCDLS_LAUNCH_CHECK(h);
     {
         long long gx = (w.capM + 256 * 8 - 1) / (256 * 8);

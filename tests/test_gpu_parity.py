@@ -403,3 +403,30 @@ def test_row_major_param_table_gives_the_same_result(engine, n, d, P, tol, metho
     cref = engine.abc_columns(tgt[:min(d, P)], par[:min(d, P)], ss[:min(d, P)], tol, "rejection")
     for a, b in zip(cols, cref):
         assert torch.equal(a.idx, b.idx) and torch.equal(a.unadj_values, b.unadj_values)
+
+
+def test_cfg4_smc_round_per_column_on_a_large_table(engine):
+    """BASELINE cfg4 shape at 2^21 rows per round: 12 parameters, per-column rejection (ABC.py:2805-2840) -> posterior
+    min / max -> updating_newrange + noise_injection_update (decrease .95, increase .01, hard range) -> box filter of
+    the simulated parameters -> lmrd; two rounds, the second on the rows the first one kept."""
+    from abc_dls_b200 import smc
+    n, P, tol = 1 << 21, 12, 0.01
+    par, ss, tgt = synth.abc_tables(n, P, P, engine.device)
+    hard_min, hard_max = _np(par).min(axis=1) - 1.0, _np(par).max(axis=1) + 1.0
+    for rnd in range(2):
+        res = engine.abc_columns(tgt, par, ss, tol, "rejection")
+        pmin = np.array([float(r.minmax()[0][0]) for r in res])
+        pmax = np.array([float(r.minmax()[1][0]) for r in res])
+        omin, omax = engine.oldrange(par)
+        rng = smc.updating_newrange(pmin, pmax, _np(omin), _np(omax), 0.95)
+        rng = smc.noise_injection_update(rng, _np(omin), _np(omax), 0.01, hard_min, hard_max, 0.95)
+        keep = engine.box_filter(par, torch.from_numpy(rng.min), torch.from_numpy(rng.max))
+        want = O.smc_round(_np(tgt), _np(par).T, _np(ss).T, tol, "rejection", _np(par).T, 0.95, 0.01, hard_min, hard_max)
+        np.testing.assert_array_equal(pmin, want["post_min"])
+        np.testing.assert_array_equal(pmax, want["post_max"])
+        np.testing.assert_array_equal(rng.min, want["min"])
+        np.testing.assert_array_equal(rng.max, want["max"])
+        np.testing.assert_array_equal(smc.csv_linenumbers(keep), want["lines"])
+        assert smc.lmrd_calculation(rng, hard_min, hard_max) == want["lmrd"]
+        assert 0 < keep.numel() < par.shape[1]
+        par, ss = par[:, keep].contiguous(), ss[:, keep].contiguous()      # next round: the narrowed table
