@@ -31,8 +31,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "simulations scored/sec (ABC loclinear)"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture at the default
-# workload (profiles/r01_ncu_full_fused_pass.txt); None until a capture of the current kernel is committed
-TRAFFIC = {"k_fused_pass": 12.802646e9 + 0.782786e9, "k_bracket_pass": 12.800307e9 + 0.494554e9, "k_dist_pass": None}
+# workload (profiles/r01_ncu_full_fused_pass_final.txt); None until a capture of the current kernel is committed
+TRAFFIC = {"k_fused_pass": 12.806535e9 + 0.807694e9, "k_bracket_pass": 12.800307e9 + 0.494554e9, "k_dist_pass": None}
 UNIT = "sims/s"
 
 
