@@ -291,3 +291,40 @@ def test_r_print_format_of_the_summary_table():
                                    [4.0, 0.005], [10.0, 0.0123456]]), ["N_A", "mig"])
     txt = S.summary_text(tab, 100, True).splitlines()
     assert txt[0] == "Data:" and txt[-1].split() == ["Max.:", "10.00", "0.01235"]
+
+
+# ---- leave-one-out tools: hand-checkable cases of the restatements -----------------------------------------------------
+def test_cv_summaries_known_answers():
+    cv = O.Cv4abcOracleResult(cvsamples=np.arange(3), tols=np.array([0.1]), true=np.array([[1.0], [2.0], [4.0]]),
+                              estim={0.1: np.array([[1.5], [2.0], [3.0]])})
+    # sum (est - true)^2 = .25 + 0 + 1 = 1.25; var(true) = 7/3 (n - 1 denominator); nval = 3
+    assert abs(O.summary_cv4abc(cv)[0, 0] - 1.25 / (7.0 / 3.0 * 3)) < 1e-15
+    cp = O.Cv4postprOracleResult(cvsamples=np.arange(4), tols=np.array([0.5]), true=np.array(["A", "A", "B", "B"]),
+                                 models=["A", "B"],
+                                 estim={0.5: np.array([[0.9, 0.1], [0.5, 0.5], [0.2, 0.8], [0.7, 0.3]])})
+    s = O.summary_cv4postpr(cp)
+    np.testing.assert_array_equal(s["conf.matrix"][0.5], [[2, 0], [1, 1]])       # the 0.5 / 0.5 tie goes to the first model
+    np.testing.assert_allclose(s["probs"][0.5], [[0.7, 0.3], [0.45, 0.55]])
+    g = O.GfitOracleResult(dist_obs=2.0, dist_sim=np.array([1.0, 3.0, 2.0, 5.0]))
+    sg = O.summary_gfit(g)
+    assert sg["pvalue"] == 0.5 and sg["dist.obs"] == 2.0                          # strictly greater than the observed
+    np.testing.assert_allclose(sg["s.dist.sim"], [1.0, 1.75, 2.5, 2.75, 3.5, 5.0])   # Min 1stQu Median Mean 3rdQu Max
+
+
+def test_leave_one_out_is_abc_on_the_table_without_the_row():
+    """cv4abc / gfit restate a loop of abc() calls: one fit reproduced by hand (row removed, N - 1 rows in the MADs)."""
+    rng = np.random.default_rng(21)
+    par = rng.uniform(0, 10, size=(300, 2))
+    ss = par + rng.normal(size=(300, 2))
+    s = 123
+    keep = np.arange(300) != s
+    direct = O.abc(ss[s], par[keep], ss[keep], 0.1, "loclinear")
+    assert direct.nacc == 30 and direct.idx.size == 30                     # ceiling(299 * 0.1)
+    cv = O.cv4abc(par, ss, 1, 0.1, "loclinear", cvsamples=[s])
+    np.testing.assert_array_equal(cv.estim[0.1][0], O.summary_abc(direct)[2])
+    np.testing.assert_array_equal(cv.true[0], par[s])
+    g = O.gfit(ss[5], ss, 1, 0.1, samples=[s])
+    r = O.abc(ss[s], ss[keep, 0], ss[keep], 0.1, "rejection")
+    assert g.dist_sim[0] == O.r_mean(r.dist[r.region])
+    full = O.abc(ss[5], ss[:, 0], ss, 0.1, "rejection")
+    assert g.dist_obs == O.r_mean(full.dist[full.region]) and full.dist[5] == 0.0   # the target is row 5 itself
