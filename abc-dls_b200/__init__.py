@@ -6,5 +6,5 @@ device tables; everything numeric is CUDA (sm_100a) behind the C ABI in ``includ
 """
 from . import _capi  # noqa: F401  (loading the shared library is deferred to first use)
 
-__all__ = ["rabc", "engine", "smc", "synth", "summary", "rshim", "stages", "comm"]
+__all__ = ["rabc", "engine", "cv", "smc", "synth", "summary", "rshim", "stages", "comm"]
 __version__ = "0.1.0"
