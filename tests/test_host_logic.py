@@ -165,3 +165,55 @@ def test_bench_reference_arm_contract():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     assert "workload" in line["config"] and line["config"]["rows"] == 100000000
+
+
+def _worker_postpr_smc(rank, world, port, N, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from abc_dls_b200.engine import AbcEngine
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from cpu_stages import CpuStages
+    eng = AbcEngine(stages=CpuStages())
+    per = (N + world - 1) // world
+    r0, r1 = rank * per, min(N, (rank + 1) * per)
+    ids, ss, tgt = synth.postpr_tables(N, "cpu")
+    ss = torch.round(ss, decimals=2)                      # coarse grid: many rows tie exactly at ds
+    pp = eng.postpr(tgt, ids[r0:r1].contiguous(), ["BNDX", "MNDX", "SNDX"], ss[:, r0:r1].contiguous(), 0.05)
+    par, _, _ = synth.abc_tables(N, 1, 5, "cpu")
+    mn, mx = eng.oldrange(par[:, r0:r1].contiguous())
+    lo, hi = mn + 0.2 * (mx - mn), mx - 0.1 * (mx - mn)
+    keep = eng.box_filter(par[:, r0:r1].contiguous(), lo, hi)
+    q.put((rank, pp.counts.numpy(), pp.idx.numpy(), pp.ds, mn.numpy(), mx.numpy(), keep.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_postpr_and_smc_passes_sharded_world2_gloo():
+    """postpr (5-decimal softmax: exact ties across the shard boundary, so the cross-rank cap rule decides), oldrange and
+    the box filter over two ranks: global row numbers, global extremes."""
+    N, world = 6001, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + (os.getpid() % 90)
+    procs = [ctx.Process(target=_worker_postpr_smc, args=(r, world, port, N, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ids, ss, tgt = synth.postpr_tables(N, "cpu")
+    ss = torch.round(ss, decimals=2)
+    o = O.postpr(tgt.numpy(), np.array(["BNDX", "MNDX", "SNDX"])[ids.numpy()], ss.numpy().T, 0.05)
+    for t in out:
+        np.testing.assert_array_equal(t[1], o.counts)                       # global counts on every rank
+        assert t[3] == o.ds
+    np.testing.assert_array_equal(np.concatenate([t[2] for t in out]), o.idx)
+    assert (o.dist <= o.ds).sum() > o.nacc                                   # ties at ds: the cap rule was exercised
+    par, _, _ = synth.abc_tables(N, 1, 5, "cpu")
+    p = par.numpy()
+    for t in out:
+        np.testing.assert_array_equal(t[4], p.min(axis=1))
+        np.testing.assert_array_equal(t[5], p.max(axis=1))
+    lo, hi = p.min(axis=1) + 0.2 * (p.max(axis=1) - p.min(axis=1)), p.max(axis=1) - 0.1 * (p.max(axis=1) - p.min(axis=1))
+    np.testing.assert_array_equal(np.concatenate([t[6] for t in out]) + 2, O.narrowing_params(p.T, lo, hi))
