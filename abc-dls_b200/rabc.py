@@ -149,16 +149,22 @@ class PostprFit:
             print(self.summary_text())
         return {"Prob": dict(zip(self.models, pred.tolist())), "BayesF": bf}
 
-    def summary_text(self) -> str:
+    def summary_text(self, digits: int = 4) -> str:
+        """summary.postpr as R prints it: the proportions are one named vector (one common format), the Bayes factors a
+        matrix (one format per column); digits = max(3, getOption("digits") - 3) = 4."""
         pred, bf = self._tables()
-        w = max(max(len(m) for m in self.models), 8)
+        pcell = _summary.format_r_column(pred, digits)
+        w = max(max(len(m) for m in self.models), max(len(c) for c in pcell))
+        bcols = [_summary.format_r_column(bf[:, k], digits) for k in range(len(self.models))]
+        bw = [max(len(self.models[k]), max(len(c) for c in bcols[k])) for k in range(len(self.models))]
+        lab = max(len(m) for m in self.models)
         lines = ["Data:", f" postpr.out$values ({int(self.res.counts.sum())} posterior samples)", "Models a priori:",
                  " " + ", ".join(self.models), "Models a posteriori:", " " + ", ".join(self.models), "",
                  "Proportion of accepted simulations (rejection):",
-                 " ".join(m.rjust(w) for m in self.models), " ".join(f"{p:.4f}".rjust(w) for p in pred), "",
-                 "Bayes factors:", " " * w + " " + " ".join(m.rjust(w) for m in self.models)]
+                 " ".join(m.rjust(w) for m in self.models), " ".join(c.rjust(w) for c in pcell), "",
+                 "Bayes factors:", " " * lab + " " + " ".join(m.rjust(x) for m, x in zip(self.models, bw))]
         for i, m in enumerate(self.models):
-            lines.append(m.ljust(w) + " " + " ".join(f"{v:.4f}".rjust(w) for v in bf[i]))
+            lines.append(m.ljust(lab) + " " + " ".join(bcols[k][i].rjust(bw[k]) for k in range(len(self.models))))
         return "\n".join(lines)
 
 

@@ -217,3 +217,22 @@ def test_postpr_and_smc_passes_sharded_world2_gloo():
         np.testing.assert_array_equal(t[5], p.max(axis=1))
     lo, hi = p.min(axis=1) + 0.2 * (p.max(axis=1) - p.min(axis=1)), p.max(axis=1) - 0.1 * (p.max(axis=1) - p.min(axis=1))
     np.testing.assert_array_equal(np.concatenate([t[6] for t in out]) + 2, O.narrowing_params(p.T, lo, hi))
+
+
+def test_postpr_summary_text_uses_r_formats():
+    from abc_dls_b200 import rabc
+    from abc_dls_b200.engine import PostprResult
+    counts = torch.tensor([40, 187, 74])
+    res = PostprResult(models=["BNDX", "MNDX", "SNDX"], counts=counts, pred=counts.double() / counts.sum(), nacc=301,
+                       n_global=6001, ds=0.67, mad=torch.ones(3), idx=torch.arange(301), ss=torch.zeros(301, 3),
+                       values=torch.zeros(301, dtype=torch.int32))
+    fit = rabc.PostprFit(res)
+    txt = fit.summary_text().splitlines()
+    assert txt[0] == "Data:" and txt[1] == " postpr.out$values (301 posterior samples)"
+    i = txt.index("Proportion of accepted simulations (rejection):")
+    assert txt[i + 1].split() == ["BNDX", "MNDX", "SNDX"] and txt[i + 2].split() == ["0.1329", "0.6213", "0.2458"]
+    j = txt.index("Bayes factors:")
+    assert txt[j + 2].split() == ["BNDX", "1.000", "0.2139", "0.5405"]       # one format per column, 4 significant digits
+    assert txt[j + 3].split() == ["MNDX", "4.675", "1.0000", "2.5270"]
+    s = fit.summary(print_=False)
+    assert abs(s["Prob"]["MNDX"] - 187 / 301) < 1e-15 and s["BayesF"].shape == (3, 3)
