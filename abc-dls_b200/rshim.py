@@ -53,7 +53,19 @@ class _R:
     def _sapply(self, df, fn):
         if fn != "sd":
             raise NotImplementedError(fn)
-        return np.asarray(df).std(axis=0, ddof=1)   # R sd(): n-1 denominator (ABC.py:1778)
+        # R sd() (ABC.py:1778; ABC-DLS tests the result for == 0): n - 1 denominator around R's mean - a long double
+        # sum with one refinement pass -, which is exactly c for a constant column; numpy's pairwise mean is not
+        # (np.std(np.full(1000, 0.1), ddof=1) = 1.4e-17) and would let a constant column through
+        a = np.asarray(df.to_numpy() if hasattr(df, "to_numpy") else df, dtype=np.float64)
+        if a.ndim == 1:
+            a = a[:, None]
+        n = a.shape[0]
+        al = a.astype(np.longdouble)
+        m = al.sum(axis=0) / np.longdouble(n)
+        m = m + (al - m).sum(axis=0) / np.longdouble(n)
+        dev = al - m
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return np.sqrt(((dev * dev).sum(axis=0) / np.longdouble(n - 1))).astype(np.float64)
 
 
 r = _R()

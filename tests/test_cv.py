@@ -112,6 +112,10 @@ def test_rshim_verbs(tmp_path):
     r["sink"]()
     assert r["pdf"]("x.pdf") is None and r["dev.off"]() is None and r["plot"](Obj(), ask=False) is None
     np.testing.assert_allclose(r["sapply"](np.array([[1.0, 2.0], [3.0, 2.0]]), "sd"), [np.sqrt(2.0), 0.0])
+    import pandas as pd
+    const = pd.DataFrame({"a": np.full(1000, 0.1), "b": np.full(1000, 1.0 / 3.0), "c": np.arange(1000.0)})
+    sd = pd.Series(r["sapply"](const, "sd"), index=const.columns)        # ABC.py:1778-1779
+    assert list(sd[sd == 0].index) == ["a", "b"] and abs(sd["c"] - np.arange(1000.0).std(ddof=1)) < 1e-10
 
 
 # ---- the same through the CUDA engine ---------------------------------------------------------------------------------
