@@ -236,3 +236,50 @@ def test_postpr_summary_text_uses_r_formats():
     assert txt[j + 3].split() == ["MNDX", "4.675", "1.0000", "2.5270"]
     s = fit.summary(print_=False)
     assert abs(s["Prob"]["MNDX"] - 187 / 301) < 1e-15 and s["BayesF"].shape == (3, 3)
+
+
+def test_reference_summary_flows_through_the_shim(tmp_path, capsys):
+    """The three ways ABC-DLS reads an abc() result (ABC.py:844-861 r_summary, 2821-2840 per-parameter min / max,
+    2842-2861 all parameters), driven exactly like the reference does - sink to a temp file, summary(), sink() - over
+    the rpy2 stand-ins, with the engine's sequencing running on the numpy stage double."""
+    from abc_dls_b200 import rabc
+    from abc_dls_b200.rshim import r
+    from abc_dls_b200.engine import AbcEngine
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from cpu_stages import CpuStages
+    eng = AbcEngine(stages=CpuStages())
+    par, ss, tgt = synth.abc_tables(4000, 2, 2, "cpu")
+    o = O.abc(tgt.numpy(), par.numpy().T, ss.numpy().T, 0.05, "loclinear")
+    want = O.summary_abc(o)
+    fit = rabc.AbcFit(eng.abc(tgt, par, ss, 0.05, "loclinear"), eng, ["N_A", "T_B"], ["s1", "s2"])
+
+    temp = str(tmp_path / "summary.txt")
+    r.options(width=10000)
+    r["sink"](temp)
+    r["summary"](fit)
+    r["sink"]()
+    lines = open(temp).read().splitlines()
+    k = [i for i, l in enumerate(lines) if l.startswith("Data:")][0]
+    assert lines[k + 1].strip() == "abc.out$adj.values (200 posterior samples)" and lines[k + 2] == "Weights:"
+    body = [l for l in lines if l.startswith("Min.:") or l.startswith("Max.:")]
+    assert len(body) == 2 and len(body[0].split()) == 3
+
+    r["sink"](temp)
+    single_min = r["summary"](fit)[0]
+    r["sink"]()
+    r["sink"](temp)
+    single_max = r["summary"](fit)[6]
+    r["sink"]()
+    assert abs(single_min - want[0, 0]) <= 1e-9 * abs(want[0, 0]) and abs(single_max - want[6, 0]) <= 1e-9 * abs(want[6, 0])
+
+    import pandas
+    r["sink"](temp)
+    min_df = pandas.DataFrame(np.array(r["summary"](fit))).iloc[0, :]
+    r["sink"]()
+    r["sink"](temp)
+    max_df = pandas.DataFrame(np.array(r["summary"](fit))).iloc[-1, :]
+    r["sink"]()
+    np.testing.assert_allclose(min_df.to_numpy(), want[0], rtol=1e-9)
+    np.testing.assert_allclose(max_df.to_numpy(), want[6], rtol=1e-9)
+    np.testing.assert_allclose(np.array(fit.summary(print_=False)), want, rtol=1e-9)
+    assert capsys.readouterr().out == ""                   # everything summary() printed went to the sink
