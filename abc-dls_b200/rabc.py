@@ -25,6 +25,9 @@ from . import summary as _summary
 from . import cv as _cv
 
 _engine: Optional[AbcEngine] = None
+# R draws the held-out rows of cv4abc / cv4postpr / gfit from its session RNG (set.seed); the reference never seeds it.
+# ``default_seed`` plays set.seed's role for callers that cannot pass ``seed=`` (ABC-DLS's unmodified call sites).
+default_seed: Optional[int] = None
 
 
 def engine() -> AbcEngine:
@@ -220,7 +223,8 @@ def cv4abc(param, sumstat, nval, tols, method, statistic: str = "median", hcorr:
     if par.shape[1] != ss.shape[1]:
         raise AbcError("'param' and 'sumstat' must have the same number of rows")
     names = {"parameter.names": _names(param, par.shape[0], "P"), "statistics.names": _names(sumstat, ss.shape[0], "S")}
-    return _cv.cv4abc(eng, par, ss, int(nval), tols, method, statistic, hcorr, cvsamples, seed, names)
+    return _cv.cv4abc(eng, par, ss, int(nval), tols, method, statistic, hcorr, cvsamples,
+                      default_seed if seed is None else seed, names)
 
 
 def cv4postpr(index, sumstat, nval, tols=None, method="rejection", subset=None, kernel: str = "epanechnikov",
@@ -239,7 +243,7 @@ def cv4postpr(index, sumstat, nval, tols=None, method="rejection", subset=None, 
         raise AbcError("'index' must be the same length as the number of rows in 'sumstat'.")
     if len(models) < 2:
         raise AbcError("At least two different models must be given.")
-    return _cv.cv4postpr(eng, ids, models, ss, int(nval), tols, method, cvsamples, seed)
+    return _cv.cv4postpr(eng, ids, models, ss, int(nval), tols, method, cvsamples, default_seed if seed is None else seed)
 
 
 def gfit(target, sumstat, nb_replicate, tol, statistic="mean", subset=None, trace: bool = False, samples=None,
@@ -254,4 +258,4 @@ def gfit(target, sumstat, nb_replicate, tol, statistic="mean", subset=None, trac
     tgt = _to_vec(target, eng.device)
     if tgt.numel() != ss.shape[0]:
         raise AbcError("Number of summary statistics in 'target' has to be the same as in 'sumstat'.")
-    return _cv.gfit(eng, tgt, ss, int(nb_replicate), float(tol), statistic, samples, seed)
+    return _cv.gfit(eng, tgt, ss, int(nb_replicate), float(tol), statistic, samples, default_seed if seed is None else seed)

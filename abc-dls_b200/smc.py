@@ -126,3 +126,99 @@ def csv_linenumbers(rows, header: bool = True) -> np.ndarray:
     row + 2 for a file with a header line (ABC.py:2974-2990), row + 1 without (src/SFS/Class.py:817-818)."""
     rows = np.asarray(rows.cpu() if hasattr(rows, "cpu") else rows, dtype=np.int64)
     return rows + (2 if header else 1)
+
+
+# ---- Narrowed.csv: the simulations that stay inside the new box are reused by the next round ------------------------
+# ABC.py:2948-3014 (narrowing_input / narrowing_params / extracting_by_linenumber, csv WITH a header line) and the
+# Snakemake variant src/SFS/Class.py:799-846 (All.csv WITHOUT a header; remove_repeated_params).  The row filter is the
+# device box filter (csrc/smc.cu:k_box_tiles through engine.box_filter); reading and writing text lines is host I/O.
+def _open_text(path: str):
+    if path.endswith(".gz"):
+        import gzip
+        return gzip.open(path, "rt")
+    return open(path, "r")
+
+
+def extracting_by_linenumber(file: str, linenumbers, outputfile: str = "out.txt") -> str:
+    """ABC.py:2992-3014: copy the lines whose 1-BASED number is in ``linenumbers`` (any order, duplicates ignored),
+    in file order.  A ``.gz`` input is read through gzip instead of the reference's ``zcat > temp.csv``."""
+    want = np.unique(np.asarray(linenumbers, dtype=np.int64).reshape(-1)) - 1
+    want = want[want >= 0]
+    k = 0
+    with _open_text(file) as src, open(outputfile, "w") as out:
+        for lno, ln in enumerate(src):
+            if k >= want.size:
+                break
+            if lno == want[k]:
+                out.write(ln)
+                k += 1
+    return outputfile
+
+
+def _read_params(inputfile: str, paramsnumbers: int, header: bool) -> np.ndarray:
+    import pandas
+    tab = pandas.read_csv(inputfile, usecols=range(paramsnumbers), header=0 if header else None)
+    return np.ascontiguousarray(tab.to_numpy(dtype=np.float64))
+
+
+def _shuffle_lines(src: str, dst: str, seed) -> int:
+    """The reference pipes the extracted lines through its external-memory shuffler (ABC.py:331-364, shuffle.py); the
+    order is random there too, so only the SET of lines is comparable.  ``seed`` makes it reproducible."""
+    with open(src) as fh:
+        lines = fh.readlines()
+    order = np.random.default_rng(seed).permutation(len(lines))
+    with open(dst, "w") as fh:
+        fh.writelines(lines[i] for i in order)
+    return len(lines)
+
+
+def narrowing_input(inputfile: str, new_min, new_max, paramsnumbers: int, folder: str = "", header: bool = True,
+                    engine=None, seed=None, shuffle: bool = True) -> int:
+    """Writes ``folder + 'Narrowed.csv'``: the lines of ``inputfile`` whose first ``paramsnumbers`` columns all lie in
+    [new_min, new_max] (inclusive, like ``Series.between``), shuffled; returns its line count.
+    ``header=True``: ABC.py:2948-2972 (the csv named in the info file; its header line is never copied);
+    ``header=False``: src/SFS/Class.py:799-829 (All.csv).  The filter runs on the device (``engine.box_filter``)."""
+    import os
+    import torch
+    out = folder + "Narrowed.csv"
+    if os.path.getsize(inputfile) == 0:
+        open(out, "w").close()
+        return 0
+    if engine is None:
+        from . import rabc
+        engine = rabc.engine()
+    par = _read_params(inputfile, paramsnumbers, header)
+    tab = torch.from_numpy(par.T.copy()).to(engine.device)            # (P, n) column-major table
+    rows = engine.box_filter(tab, torch.as_tensor(np.asarray(new_min, dtype=np.float64)),
+                             torch.as_tensor(np.asarray(new_max, dtype=np.float64)))
+    tmp = folder + "Narrows.csv"
+    extracting_by_linenumber(inputfile, csv_linenumbers(rows, header=header), tmp)
+    if shuffle:
+        n = _shuffle_lines(tmp, out, seed)
+        os.remove(tmp)
+    else:
+        os.replace(tmp, out)
+        with open(out) as fh:
+            n = sum(1 for _ in fh)
+    return n
+
+
+def narrowing_input_rangefile(paramsnumbers: int, inputfile: str, rangefile: str, folder: str = "", engine=None,
+                              seed=None) -> int:
+    """src/SFS/Class.py:799-829 with its own argument order: the new box comes from a Newrange.csv."""
+    _, lo, hi = read_range_csv(rangefile)
+    return narrowing_input(inputfile, lo, hi, paramsnumbers, folder, header=False, engine=engine, seed=seed)
+
+
+def remove_repeated_params(inputfile: str, paramsnumbers: int, outputfile: str, as_reference: bool = True) -> str:
+    """src/SFS/Class.py:831-846: one line per distinct parameter vector of a header-less All.csv.
+
+    The reference takes the 0-based rows ``params.drop_duplicates().index`` (first occurrence of every vector) and
+    hands them to ``extracting_by_linenumber``, which treats its argument as 1-based line numbers: what it actually
+    writes is the line BEFORE every first occurrence (row r - 1; nothing for r = 0).  ``as_reference=True`` (default)
+    reproduces exactly that file, so a pipeline that swaps engines sees identical bytes; ``as_reference=False`` writes
+    the first occurrences themselves (what the docstring there describes)."""
+    par = _read_params(inputfile, paramsnumbers, header=False)
+    _, first = np.unique(par, axis=0, return_index=True)
+    first = np.sort(first)                                        # drop_duplicates keeps file order
+    return extracting_by_linenumber(inputfile, first if as_reference else first + 1, outputfile)
