@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libabcdls.so")
 # status bits / codes (mirror include/abcdls.h)
 OK, E_INVALID, E_WORKSPACE, E_CUDA, E_NODEVICE = 0, 1, 2, 3, 4
 S_NONFINITE, S_FASTPATH_MISS, S_SINGULAR, S_ZERO_VAR, S_ZERO_VAR_REGION, S_CAPACITY = 1, 2, 4, 8, 16, 32
+S_PEER_TIMEOUT, S_NONFINITE_FIT = 64, 128
 SELECT_PASSES = 6
 SELECT_BINS = 2048
 
@@ -94,10 +95,18 @@ SIGNATURES = {
     "abcdls_final_pack": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "abcdls_final_small": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
                                   _vp, _vp]),
+    "abcdls_tail_supported": (_i32, [_i32, _i32]),
+    "abcdls_tail_workspace_bytes": (_sz, [_vp, _i32, _i32]),
+    "abcdls_tail_gather_fit": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64,
+                                      _i64, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "abcdls_tail_resid_fit": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _sz, _vp, _vp]),
+    "abcdls_tail_adjust_final": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp,
+                                        _vp, _vp, _sz, _vp, _vp, _vp]),
     "abcdls_small_supported": (_i32, [_i64, _i64]),
     "abcdls_small_columns": (_i32, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp,
                                     _vp]),
     "abcdls_postpr_counts": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp]),
+    "abcdls_postpr_final": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp]),
     "abcdls_smc_workspace_bytes": (_sz, [_i64, _i32]),
     "abcdls_smc_oldrange": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _sz, _vp]),
     "abcdls_smc_box_filter": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _sz, _vp,

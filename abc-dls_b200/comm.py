@@ -32,6 +32,7 @@ class Comm:
         # NVLink peer-memory mailboxes (csrc/peer.cu): every small exchange is ONE kernel, no NCCL, graph capturable
         self.peer = None
         self.peer_calls = 0
+        self.fused_calls = 0   # exchanges that ran INSIDE a compute kernel's last block (csrc/tail.cu)
         if (self.world > 1 and device is not None and torch.device(device).type == "cuda"
                 and os.environ.get("ABCDLS_NO_PEER", "0") != "1"):
             self._init_peer()

@@ -4,12 +4,12 @@ set -euo pipefail
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC"
-SRCS="api.cu select.cu dist.cu loclinear.cu smc.cu peer.cu small.cu"
+SRCS="api.cu select.cu dist.cu loclinear.cu tail.cu smc.cu peer.cu small.cu"
 [ -f bracket.cu ] && SRCS="$SRCS bracket.cu"
 OBJS=""
 for s in $SRCS; do
   o="${s%.cu}.o"
-  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ fused.cuh -nt "$o" ] || [ compact.cuh -nt "$o" ] || [ ../../include/abcdls.h -nt "$o" ]; then
+  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ fused.cuh -nt "$o" ] || [ compact.cuh -nt "$o" ] || [ peer.cuh -nt "$o" ] || [ ../../include/abcdls.h -nt "$o" ]; then
     $NVCC $FLAGS ${EXTRA:-} -c "$s" -o "$o" &
   fi
   OBJS="$OBJS $o"

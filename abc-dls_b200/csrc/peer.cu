@@ -14,49 +14,21 @@
 // memory and is advanced by the kernel itself, so the kernels are ordinary graph nodes: a multi-rank call replays as
 // ONE CUDA graph per rank.  Slot reuse is safe with two parities: a rank can only start exchange k+2 after every
 // peer has published k+1, i.e. after every peer has finished reading exchange k.
-#include "common.cuh"
+#include "peer.cuh"
 
 #include <string.h>
 
 namespace {
 
-constexpr int kMaxWorld = 64;
-constexpr int kPeerThreads = 512;
-constexpr int kPeerMaxCtas = 32;
-
-struct PeerDev {
-    unsigned long long* seq;       // exchanges completed by this rank (device memory, advanced by the kernels)
-    unsigned long long* bar;       // arrivals of my CTAs (monotonic)
-    unsigned long long* bar_cum;   // arrivals expected before the current exchange
-    unsigned char* box[kMaxWorld]; // mailboxes of all ranks as mapped in THIS process (box[rank] = mine)
-    size_t slot_bytes;
-    int rank, world;
-};
-
-constexpr size_t kFlagsBytes = (size_t)2 * kMaxWorld * sizeof(unsigned long long);   // 1024
-static_assert(kFlagsBytes % 256 == 0, "data slots start 256-byte aligned");
 inline size_t flags_bytes() { return kFlagsBytes; }
 
-__device__ __forceinline__ unsigned long long* flag_ptr(unsigned char* box, int parity, int src) {
-    return reinterpret_cast<unsigned long long*>(box) + (size_t)parity * kMaxWorld + src;
-}
-__device__ __forceinline__ unsigned char* data_ptr(unsigned char* box, size_t slot_bytes, int parity) {
-    return box + kFlagsBytes + (size_t)parity * slot_bytes;
-}
-
-__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 // all CTAs of this launch have arrived (monotonic counter; *bar_cum = arrivals before this exchange)
 __device__ __forceinline__ void grid_arrive_wait(const PeerDev& P) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence_system();
         atomicAdd(P.bar, 1ull);
-        const unsigned long long want = *P.bar_cum + gridDim.x;
-        while (ld_volatile_u64(P.bar) < want) __nanosleep(20);
+        spin_until_ge(P.bar, *P.bar_cum + gridDim.x, P.err);
     }
     __syncthreads();
 }
@@ -68,10 +40,7 @@ __device__ __forceinline__ void publish_and_wait(const PeerDev& P, unsigned long
         unsigned long long* f = flag_ptr(P.box[threadIdx.x], parity, P.rank);   // my entry in peer threadIdx.x's row
         asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(f), "l"(k) : "memory");
     }
-    if (threadIdx.x < P.world) {
-        const unsigned long long* f = flag_ptr(P.box[P.rank], parity, threadIdx.x);
-        while (ld_volatile_u64(f) < k) __nanosleep(20);
-    }
+    if (threadIdx.x < P.world) spin_until_ge(flag_ptr(P.box[P.rank], parity, threadIdx.x), k, P.err);
     __threadfence_system();
     __syncthreads();
 }
@@ -149,15 +118,6 @@ __global__ void __launch_bounds__(kPeerThreads) k_peer_allgather(PeerDev P, cons
 
 }  // namespace
 
-struct abcdls_peer_s {
-    PeerDev dev;
-    void* mine = nullptr;
-    void* opened[kMaxWorld] = {};
-    unsigned long long* ctl = nullptr;   // seq | bar | bar_cum
-    size_t box_bytes = 0;
-    std::string err;
-};
-
 extern "C" {
 
 size_t abcdls_peer_handle_bytes(void) { return sizeof(cudaIpcMemHandle_t); }
@@ -188,6 +148,7 @@ int abcdls_peer_create(abcdls_peer_t* out, int rank, int world, size_t slot_byte
     p->dev.seq = p->ctl;
     p->dev.bar = p->ctl + 8;
     p->dev.bar_cum = p->ctl + 16;
+    p->dev.err = p->ctl + 24;
     p->dev.slot_bytes = slot_bytes;
     p->dev.rank = rank;
     p->dev.world = world;

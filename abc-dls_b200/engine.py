@@ -97,6 +97,8 @@ class AbcResult:
 
 @dataclass
 class PostprResult:
+    """``ss`` / ``values`` (the accepted rows' statistics and model ids) may be lazy: R's summary.postpr only needs the
+    counts, so the rows are gathered from the caller's tables on first access."""
     models: List[str]
     counts: torch.Tensor           # (K,) int64 accepted simulations per model (global)
     pred: torch.Tensor             # (K,) proportions
@@ -108,6 +110,13 @@ class PostprResult:
     ss: torch.Tensor
     values: torch.Tensor           # (n_local_acc,) int32 model ids of accepted rows, row order
     dist: Optional[torch.Tensor] = None
+
+    def __getattribute__(self, name):
+        v = object.__getattribute__(self, name)
+        if callable(v) and name in ("ss", "values"):
+            v = v()
+            object.__setattr__(self, name, v)
+        return v
 
     def bayes_factors(self) -> torch.Tensor:
         return self.pred[:, None] / self.pred[None, :]
@@ -188,11 +197,12 @@ class AbcEngine:
         self.use_graphs = True      # replay the device work of a repeated call as one CUDA graph
         self.copy_results = True    # results of a replayed graph are copied out of the graph's buffers ...
         self.lazy_results = True    # ... the rarely read ones (ss, residuals, unadj of loclinear, dist) on first access
-        self.max_graphs = 8
+        self.max_graphs = 32        # per-column mode of ABC-DLS makes P (19, 24) calls with distinct tables in a row
         # Gather the parameters of ALL candidates on a second stream during the refinement.  Measured at 1e8 x 16: the
         # scattered reads (1.6x more rows) slow the memory-bound refinement kernels by more than the later gather
         # saves (4.94 -> 5.2 ms per call), so it stays off.
         self.pregather = False
+        self.fused_tail = os.environ.get("ABCDLS_NO_TAIL", "0") != "1"   # csrc/tail.cu instead of the 16-launch tail
         self._side = None
         if os.environ.get("ABCDLS_NO_GRAPH", "0") == "1":
             self.use_graphs = False
@@ -428,28 +438,11 @@ class AbcEngine:
 
         # The device work of one call is a fixed sequence of ~90 launches whose shapes depend only on the key below, so
         # it is captured into a CUDA graph the second time a key is seen and replayed afterwards (one launch per call).
-        o = None
-        key = (ss.data_ptr(), tuple(ss.shape), ss.stride(0), par.data_ptr(), tuple(par.shape), par.stride(0), par.stride(1),
-               par.device.type, float(tol), method, bool(hcorr), bool(keep_dist), int(_level), self.comm.world,
-               pl["n_global"], pl["row_offset"])
-        graphable = (self.use_graphs and self.timers is None and self.device.type == "cuda" and not keep_dist)
-        plan = self._graphs.get(key) if graphable else None
-        if plan is not None:
-            plan["target"].copy_(target)
-            plan["gen"] += 1
-            plan["graph"].replay()
-            self.k.launches += plan["launches"]
-            self._graphs[key] = self._graphs.pop(key)          # LRU order
-            o = plan["out"]
-        elif graphable and self._seen.get(key, 0) >= 1:
-            plan = self._capture(key, target, ss, par, pl, method, hcorr)
-            o = plan["out"]
-        else:
-            if graphable:
-                if len(self._seen) > 64:
-                    self._seen.clear()
-                self._seen[key] = self._seen.get(key, 0) + 1
-            o = self._abc_device(target, ss, par, pl, method, hcorr)
+        key = ("abc", ss.data_ptr(), tuple(ss.shape), ss.stride(0), par.data_ptr(), tuple(par.shape), par.stride(0),
+               par.stride(1), par.device.type, float(tol), method, bool(hcorr), bool(keep_dist), int(_level),
+               self.comm.world, pl["n_global"], pl["row_offset"])
+        o, plan = self._run(key, target, lambda tgt: self._abc_device(tgt, ss, par, pl, method, hcorr),
+                            graphable=not keep_dist)
         from_graph = plan is not None
 
         self.host_enqueue_ms.append((time.perf_counter() - _t0) * 1e3)
@@ -472,8 +465,12 @@ class AbcEngine:
             if method != "rejection":
                 raise AbcError(msg + " Try: checking summary statistics, choosing larger tolerance, or rejection method.")
             warnings.append(msg + " Check summary statistics, consider larger tolerance.")
+        if st & _capi.S_PEER_TIMEOUT:
+            raise RuntimeError("a rank did not take part in an exchange of this call (NVLink mailbox wait timed out)")
         if st & _capi.S_SINGULAR:
             raise AbcError("lsfit: X matrix deemed to be singular (collinear summary statistics in the accepted region)")
+        if st & _capi.S_NONFINITE_FIT:
+            raise AbcError("lsfit: NA/NaN/Inf in 'y' (hcorr: a residual is exactly zero, log(residuals^2) = -Inf)")
         if st & _capi.S_CAPACITY:
             raise AbcError("internal: accepted-row buffer overflow")
 
@@ -513,7 +510,39 @@ class AbcEngine:
             r.bic = nacc * ls + math.log(nacc) * (d + 1) * P
         return r
 
-    def _capture(self, key, target, ss, par, pl, method, hcorr):
+    def _run(self, key, target, fn, graphable=True):
+        """Run the device work ``fn(target) -> dict of result tensors`` of one call: eagerly the first time a key is
+        seen, recorded as a CUDA graph the second time, replayed afterwards (one launch per call; the target is the only
+        input that may change under a key - the tables are pinned by their addresses in the key).  -> (out, plan | None)
+
+        Several ranks: whether to record is decided by the CALL COUNT of the key, which is the same on every rank as
+        long as the ranks make the same calls; table addresses are rank-local, so they are left out of the history
+        (a rank whose allocator returned a different address must not record one call later than its peers: with the
+        NCCL fallback a recording rank would issue its collectives twice)."""
+        graphable = graphable and self.use_graphs and self.timers is None and self.device.type == "cuda"
+        if not graphable:
+            return fn(target), None
+        plan = self._graphs.get(key)
+        if plan is not None:
+            plan["target"].copy_(target)
+            plan["gen"] += 1
+            plan["graph"].replay()
+            self.k.launches += plan["launches"]
+            self._graphs[key] = self._graphs.pop(key)          # LRU order
+            return plan["out"], plan
+        hkey = key if self.comm.world == 1 else tuple(x for i, x in enumerate(key) if i not in self._PTR_SLOTS.get(key[0], ()))
+        seen = self._seen.get(hkey, 0)
+        if seen >= 1 and (self.comm.world == 1 or self.comm.peer is not None):
+            plan = self._capture(key, target, fn)
+            return plan["out"], plan
+        if len(self._seen) > 256:
+            self._seen.clear()
+        self._seen[hkey] = seen + 1
+        return fn(target), None
+
+    _PTR_SLOTS = {"abc": (1, 4), "postpr": (1, 4), "columns": (1, 4)}   # positions of table addresses in the keys
+
+    def _capture(self, key, target, fn):
         """Record the device work of this call as CUDA-graph segments (torch allocates its temporaries and outputs from
         a pool owned by the plan).  The tables are NOT referenced by the plan: the key pins their addresses."""
         while len(self._graphs) >= self.max_graphs:
@@ -527,7 +556,7 @@ class AbcEngine:
             sg.begin()
             self.comm.recorder = sg
             try:
-                out = self._abc_device(tgt, ss, par, pl, method, hcorr)
+                out = fn(tgt)
             finally:
                 self.comm.recorder = None
                 sg.end()
@@ -547,6 +576,35 @@ class AbcEngine:
         status = torch.zeros(1, dtype=torch.int32, device=self.device)
         f = self._front(target, ss, status, pl, par)
         cap, idx, n_acc, ds, mad, dacc = f["cap"], f["idx"], f["n_acc"], f["ds"], f["mad"], f["dacc"]
+
+        # The tail as three launches (two for rejection) with their reductions, NVLink exchanges and solves inside
+        # (csrc/tail.cu); the stage-by-stage sequence below stays for d or P > 32 and for the NCCL fallback.
+        use_tail = (self.fused_tail and hasattr(k, "tail_supported") and k.tail_supported(d, P)
+                    and (self.comm.world == 1 or self.comm.peer is not None) and f["cand_par"] is None)
+        if use_tail:
+            lin = method == "loclinear"
+            y, ss_out = k.new(P, cap), k.new(d, cap)
+            xs = w = adj = res = None
+            if lin:
+                xs, w, adj, res = k.new(d, cap), k.new(cap), k.new(P, cap), k.new(P, cap)
+            ws = k.tail_workspace(d, P)
+            peer = self.comm.peer if self.comm.world > 1 else None
+            with self._t("tail_gather_fit"):
+                k.tail_gather_fit(peer, f["cand_ss"] if f["fused"] else None, f["slot"] if f["fused"] else None,
+                                  f["perm"] if f["fused"] else None, None if f["fused"] else ss, par, dacc, idx, n_acc,
+                                  f["row_offset"], cap, d, P, mad, target, ds, lin, xs, y, ss_out, w, ws, status)
+            if lin and hcorr:
+                with self._t("tail_resid_fit"):
+                    k.tail_resid_fit(peer, xs, y, w, n_acc, cap, d, P, ws, status)
+            small = k.new(k.final_small_len(d, P, lin))
+            with self._t("tail_adjust_final"):
+                k.tail_adjust_final(peer, xs, y, w, n_acc, ds, cap, d, P, lin, hcorr, mad, target, adj, res, ws, small,
+                                    status)
+            if self.comm.world > 1:
+                nx = (2 + int(bool(hcorr))) if lin else 1
+                self.comm.calls += nx
+                self.comm.fused_calls += nx
+            return dict(small=small, idx=idx, y=y, ss_out=ss_out, w=w, dacc=dacc, dist=f["dist"], adj=adj, res=res)
 
         xs, y, ss_out = k.new(d, cap), k.new(P, cap), k.new(d, cap)
         w = k.new(cap)
@@ -620,17 +678,21 @@ class AbcEngine:
         k.final_small(status, n_acc, ds, reg, stats, mad, target, logsig, beta, gamma, the_m, sig, pack, sm, d, P, small)
         return dict(small=small, idx=idx, y=y, ss_out=ss_out, w=w, dacc=dacc, dist=f["dist"], adj=adj, res=res)
 
-    def abc_columns(self, target, param, sumstat, tol, method, hcorr: bool = True) -> List[AbcResult]:
+    def abc_columns(self, target, param, sumstat, tol, method, hcorr: bool = True, shard=None) -> List[AbcResult]:
         """ABC-DLS's per-column mode (ABC.py:1949-1953, 2805-2809): P separate 1-D abc() problems,
         column c of ``sumstat`` against column c of ``param``."""
         ss, par = _as_table(sumstat), _as_table(param, row_major_ok=True)
         target = target.reshape(-1)
-        return [self.abc(target[c:c + 1], par[c:c + 1], ss[c:c + 1], tol, method, hcorr) for c in range(par.shape[0])]
+        return [self.abc(target[c:c + 1], par[c:c + 1], ss[c:c + 1], tol, method, hcorr, shard=shard)
+                for c in range(par.shape[0])]
 
-    def abc_columns_summary(self, target, param, sumstat, tol, method, hcorr: bool = True):
+    def abc_columns_summary(self, target, param, sumstat, tol, method, hcorr: bool = True, shard=None,
+                            want=("min", "max", "median", "mean")):
         """Per-column mode when only ``summary(res)`` is kept - ABC-DLS's SMC reads Min and Max of every column
-        (ABC.py:2805-2840): {"min", "max", "median", "mean"} -> (P,) float64 numpy arrays.  On one rank and a table that
-        fits a CTA's shared memory the P problems are ONE launch of csrc/small.cu; otherwise a loop over abc()."""
+        (ABC.py:2805-2840): {"min", "max", "median", "mean"} -> (P,) float64 numpy arrays (those named in ``want``).
+        One rank and a table that fits a CTA's shared memory: the P problems are ONE launch of csrc/small.cu.  Large
+        tables, any number of ranks: ONE pass over the N x P statistics for all P problems (csrc/columns.cu).
+        Otherwise a loop over abc()."""
         import numpy as np
         from . import cv as _cv, summary as _summary
         ss, par = _as_table(sumstat), _as_table(param, row_major_ok=True)
@@ -644,21 +706,49 @@ class AbcEngine:
         if self.comm.world == 1 and ss.device == self.device and par.device == self.device:
             o = _cv.small_fits(self, par, ss, np.arange(P, dtype=np.int32), None, float(tol), method, hcorr, target=target)
         if o is not None:
-            return {"median": o[:, 0].copy(), "mean": o[:, 1].copy(), "min": o[:, 4].copy(), "max": o[:, 5].copy()}
-        out = {k_: np.empty(P) for k_ in ("median", "mean", "min", "max")}
-        for c, r in enumerate(self.abc_columns(target, par, ss, tol, method, hcorr)):
-            if self.comm.world > 1:
-                raise AbcError("abc_columns_summary over several ranks: use abc_columns and AbcResult.minmax()")
+            full = {"median": o[:, 0].copy(), "mean": o[:, 1].copy(), "min": o[:, 4].copy(), "max": o[:, 5].copy()}
+            return {k_: full[k_] for k_ in want}
+        if hasattr(self, "_columns_streaming"):
+            got = self._columns_streaming(target, par, ss, tol, method, hcorr, shard, want)
+            if got is not None:
+                return got
+        out = {k_: np.empty(P) for k_ in want}
+        for c, r in enumerate(self.abc_columns(target, par, ss, tol, method, hcorr, shard)):
             w = r.adj_values is not None
-            out["min"][c], out["max"][c] = float(r.stats[0, 0]), float(r.stats[0, 1])
-            out["median"][c] = float(_summary.point_estimate(r.values, r.weights, r.stats, w, "median")[0])
-            out["mean"][c] = float(_summary.point_estimate(r.values, r.weights, r.stats, w, "mean")[0])
+            if "min" in out:
+                out["min"][c] = float(r.stats[0, 0])
+            if "max" in out:
+                out["max"][c] = float(r.stats[0, 1])
+            if "mean" in out:       # stats are already global: sum w x / sum w
+                out["mean"][c] = float(r.stats[0, 3] / r.stats[0, 5]) if w else float(r.stats[0, 2] / r.nacc)
+            if "median" in out:
+                vals, wts = r.values, r.weights
+                if self.comm.world > 1:
+                    vals, wts = self.gather_sample(vals, wts)
+                out["median"][c] = float(_summary.point_estimate(vals, wts, r.stats, w, "median")[0])
         return out
+
+    def gather_sample(self, vals: torch.Tensor, w: torch.Tensor):
+        """The posterior sample of ALL ranks (rank order = row order) on every rank: (n_acc, P) values, (n_acc,) weights."""
+        c = self.comm
+        if c.world == 1:
+            return vals, w
+        n_loc = torch.tensor([vals.shape[0]], dtype=torch.int64, device=vals.device)
+        ns = c.allgather(n_loc).view(-1).cpu().tolist()
+        cap = max(max(ns), 1)
+        pv = torch.zeros((cap, vals.shape[1]), dtype=torch.float64, device=vals.device)
+        pw = torch.zeros(cap, dtype=torch.float64, device=vals.device)
+        pv[: vals.shape[0]], pw[: vals.shape[0]] = vals, w
+        gv, gw = c.allgather(pv), c.allgather(pw)
+        return (torch.cat([gv[i, : ns[i]] for i in range(c.world)]), torch.cat([gw[i, : ns[i]] for i in range(c.world)]))
 
     # ---- postpr() -------------------------------------------------------------------------------
     def postpr(self, target: torch.Tensor, model_id: torch.Tensor, models: List[str], sumstat: torch.Tensor,
-               tol: float, method: str = "rejection", keep_dist: bool = False, _level: int = 0) -> PostprResult:
-        """``abc::postpr(method='rejection')``: model_id int32 (n_local,) indexes ``models`` (sorted levels)."""
+               tol: float, method: str = "rejection", keep_dist: bool = False, shard=None,
+               _level: int = 0) -> PostprResult:
+        """``abc::postpr(method='rejection')``: model_id int32 (n_local,) indexes ``models`` (sorted levels, the same
+        list on every rank).  Same footing as abc(): one packed small buffer, the status OR-ed and the counts summed
+        over the ranks on the device, ONE blocking read, replayed as a CUDA graph from the third call on."""
         if method != "rejection":
             raise AbcError("postpr: only method='rejection' is implemented (mnlogistic / neuralnet stay with R's nnet)")
         k = self.k
@@ -673,31 +763,61 @@ class AbcEngine:
         if model_id.numel() != n_local:
             raise AbcError("'index' must be the same length as the number of rows in 'sumstat'.")
         model_id = model_id.to(device=self.device, dtype=torch.int32).contiguous()
-        status = torch.zeros(1, dtype=torch.int32, device=self.device)
-        pl = self._plan(ss, tol, keep_dist, _level)
+        _t0 = time.perf_counter()
+        pl = self._plan(ss, tol, keep_dist, _level, shard)
         self.path_calls[pl["path"]] += 1
-        f = self._front(target, ss, status, pl)
-        f.update(n_global=pl["n_global"], nacc=pl["nacc"], row_offset=pl["row_offset"])
-        cap, idx, n_acc = f["cap"], f["idx"], f["n_acc"]
-        counts = torch.zeros(K, dtype=torch.int64, device=self.device)
-        k.postpr_counts(model_id, idx, n_acc, f["row_offset"], cap, K, counts)
-        self.comm.allreduce_sum(counts)
-        all_mad_zero = (f["mad"] == 0).all()
-        host = torch.cat([status.to(torch.float64), n_acc.to(torch.float64), f["ds"],
-                          all_mad_zero.to(torch.float64).view(1)]).cpu()
-        st, n_loc, ds_h = self.comm.allreduce_or_int(int(host[0])), int(host[1]), float(host[2])
-        if (st & _capi.S_FASTPATH_MISS) and f["fast"]:
+        key = ("postpr", ss.data_ptr(), tuple(ss.shape), ss.stride(0), model_id.data_ptr(), K, float(tol),
+               bool(keep_dist), int(_level), self.comm.world, pl["n_global"], pl["row_offset"])
+        o, plan = self._run(key, target, lambda tgt: self._postpr_device(tgt, ss, model_id, K, pl),
+                            graphable=not keep_dist)
+        self.host_enqueue_ms.append((time.perf_counter() - _t0) * 1e3)
+        small = o["small"].cpu()                      # the one blocking read
+        st, n_loc, ds_h = int(small[0]), int(small[1]), float(small[2])
+        if (st & _capi.S_FASTPATH_MISS) and pl["fast"]:
             self.fast_misses += 1
-            return self.postpr(target, model_id, models, sumstat, tol, method, keep_dist,
-                               _level=1 if f["fused"] else 2)
+            return self.postpr(target, model_id, models, sumstat, tol, method, keep_dist, shard,
+                               _level=1 if pl["fused"] else 2)
+        if st & _capi.S_PEER_TIMEOUT:
+            raise RuntimeError("a rank did not take part in an exchange of this call (NVLink mailbox wait timed out)")
         if st & _capi.S_NONFINITE:
             raise AbcError("non-finite values in 'sumstat'/'target' (R's NA-row handling is not implemented)")
-        if host[3] != 0 and self._zero_variance(ss):
+        if small[3] != 0 and self._zero_variance(ss):
             raise AbcError("Zero variance in the summary statistics.")
-        loc = idx[:n_loc] - f["row_offset"]
+        if st & _capi.S_CAPACITY:
+            raise AbcError("internal: accepted-row buffer overflow")
+        counts = small[8 + d: 8 + d + K].to(torch.int64).to(self.device)
+        idx = o["idx"][:n_loc].clone() if plan is not None else o["idx"][:n_loc]
+        row_offset = pl["row_offset"]
         return PostprResult(models=list(models), counts=counts, pred=counts.to(torch.float64) / counts.sum(),
-                            nacc=f["nacc"], n_global=f["n_global"], ds=ds_h, mad=f["mad"], idx=idx[:n_loc],
-                            ss=ss[:, loc].t(), values=model_id[loc], dist=f["dist"] if keep_dist else None)
+                            nacc=pl["nacc"], n_global=pl["n_global"], ds=ds_h, mad=small[8:8 + d].to(self.device),
+                            idx=idx, ss=lambda: ss[:, idx - row_offset].t(), values=lambda: model_id[idx - row_offset],
+                            dist=o["dist"] if keep_dist else None)
+
+    def _postpr_device(self, target, ss, model_id, K, pl):
+        """All device work of postpr() ending in small = [status, n_acc, ds, every MAD zero, 0 x 4 | mad | counts]."""
+        k = self.k
+        d = ss.shape[0]
+        status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        f = self._front(target, ss, status, pl)
+        counts = torch.zeros(K, dtype=torch.int64, device=self.device)
+        k.postpr_counts(model_id, f["idx"], f["n_acc"], f["row_offset"], f["cap"], K, counts)
+        small = k.new(8 + d + K)
+        if hasattr(k, "postpr_final") and (self.comm.world == 1 or self.comm.peer is not None):
+            k.postpr_final(self.comm.peer if self.comm.world > 1 else None, status, f["n_acc"], f["ds"], f["mad"], d,
+                           counts, K, small)
+            if self.comm.world > 1:
+                self.comm.calls += 1
+                self.comm.fused_calls += 1
+        else:   # NCCL fallback / CPU stage double: the same buffer from framework ops
+            self.comm.allreduce_sum(counts)
+            bits = torch.stack([(status[0] >> b) & 1 for b in range(8)]).to(torch.int64)
+            self.comm.allreduce_max(bits)
+            st = (bits << torch.arange(8, device=bits.device)).sum().to(torch.float64).view(1)
+            small[:8] = torch.cat([st, f["n_acc"].to(torch.float64), f["ds"].view(1),
+                                   (f["mad"] == 0).all().to(torch.float64).view(1), small.new_zeros(4)])
+            small[8:8 + d] = f["mad"]
+            small[8 + d:] = counts.to(torch.float64)
+        return dict(small=small, idx=f["idx"], dist=f["dist"])
 
     # ---- SMC table passes -------------------------------------------------------------------------
     def oldrange(self, param_all: torch.Tensor):
@@ -711,11 +831,12 @@ class AbcEngine:
         self.comm.allreduce_max(mx)
         return mn, mx
 
-    def box_filter(self, param_all: torch.Tensor, lo: torch.Tensor, hi: torch.Tensor) -> torch.Tensor:
-        """Ascending GLOBAL row numbers of this rank's rows with every parameter in [lo, hi] (ABC.py:2974-2990)."""
+    def box_filter(self, param_all: torch.Tensor, lo: torch.Tensor, hi: torch.Tensor, shard=None) -> torch.Tensor:
+        """Ascending GLOBAL row numbers of this rank's rows with every parameter in [lo, hi] (ABC.py:2974-2990).
+        shard = (n_global, row_offset) saves the blocking exchange of the shard sizes."""
         tab = _as_table(param_all)
         P, n = tab.shape
-        _, row_offset, _, _ = self._shard_info(n)
+        row_offset = int(shard[1]) if shard is not None else self._shard_info(n)[1]
         lo = lo.to(device=self.device, dtype=torch.float64).contiguous()
         hi = hi.to(device=self.device, dtype=torch.float64).contiguous()
         idx = self.k.new(n, dtype=torch.int64)

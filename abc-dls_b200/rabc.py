@@ -106,19 +106,7 @@ class AbcFit:
         self.aic, self.bic = res.aic, res.bic
 
     def _global_sample(self):
-        r, c = self.res, self._eng.comm
-        vals, w = r.values, r.weights
-        if c.world > 1:
-            n_loc = torch.tensor([vals.shape[0]], dtype=torch.int64, device=vals.device)
-            ns = c.allgather(n_loc).view(-1).cpu().tolist()
-            cap = max(max(ns), 1)
-            pv = torch.zeros((cap, vals.shape[1]), dtype=torch.float64, device=vals.device)
-            pw = torch.zeros(cap, dtype=torch.float64, device=vals.device)
-            pv[: vals.shape[0]], pw[: vals.shape[0]] = vals, w
-            gv, gw = c.allgather(pv), c.allgather(pw)
-            vals = torch.cat([gv[i, : ns[i]] for i in range(c.world)])
-            w = torch.cat([gw[i, : ns[i]] for i in range(c.world)])
-        return vals, w
+        return self._eng.gather_sample(self.res.values, self.res.weights)
 
     def summary(self, intvl: float = 0.95, print_: bool = True) -> _summary.SummaryTable:
         vals, w = self._global_sample()

@@ -337,6 +337,43 @@ class CudaStages:
                          self._stream())
         self.launches += 1
 
+    # ---- kernel 3, fused: three launches with their reductions, exchanges and solves inside (csrc/tail.cu) --------
+    def tail_supported(self, d, P) -> bool:
+        return bool(self.lib.abcdls_tail_supported(int(d), int(P)))
+
+    def tail_workspace(self, d, P) -> torch.Tensor:
+        key = f"tail{d}x{P}"
+        t = self._ws.get(key)
+        if t is None:
+            nbytes = int(self.lib.abcdls_tail_workspace_bytes(self.handle.h, int(d), int(P)))
+            t = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)     # the ticket counters start at zero
+            self._ws[key] = t
+        return t
+
+    def tail_gather_fit(self, peer, cand_ss, slot, perm, ss, par, dist_acc, idx, n_acc, row_offset, cap, d, P, mad,
+                        target, ds, loclinear, xs, y, ss_out, w, ws, status):
+        """par: (P, n) view - unit stride along rows (column-major table) or strides (1, pitch) (row-major table)."""
+        cm = par.stride(1) == 1
+        self.handle.call("abcdls_tail_gather_fit", peer, _p(cand_ss), cand_ss.stride(0) if cand_ss is not None else 0,
+                         _p(slot), _p(perm), _p(ss), ss.stride(0) if ss is not None else 0,
+                         _p(par) if cm else None, par.stride(0) if cm else 0,
+                         None if cm else _p(par), 0 if cm else par.stride(1),
+                         _p(dist_acc), _p(idx), _p(n_acc), row_offset, cap, d, P, _p(mad), _p(target), _p(ds),
+                         int(loclinear), _p(xs), _p(y), _p(ss_out), _p(w), _p(ws), ws.numel(), _p(status), self._stream())
+        self.launches += 1
+
+    def tail_resid_fit(self, peer, xs, y, w, n_acc, cap, d, P, ws, status):
+        self.handle.call("abcdls_tail_resid_fit", peer, _p(xs), _p(y), _p(w), _p(n_acc), cap, d, P, _p(ws),
+                         ws.numel(), _p(status), self._stream())
+        self.launches += 1
+
+    def tail_adjust_final(self, peer, xs, y, w, n_acc, ds, cap, d, P, loclinear, hcorr, mad, target, adj, res, ws, small,
+                          status):
+        self.handle.call("abcdls_tail_adjust_final", peer, _p(xs), _p(y), _p(w), _p(n_acc), _p(ds), cap, d, P,
+                         int(loclinear), int(hcorr), _p(mad), _p(target), _p(adj), _p(res), _p(ws), ws.numel(), _p(small),
+                         _p(status), self._stream())
+        self.launches += 1
+
     def small_supported(self, n, nacc) -> bool:
         return bool(self.lib.abcdls_small_supported(int(n), int(nacc)))
 
@@ -350,6 +387,11 @@ class CudaStages:
         self.handle.call("abcdls_postpr_counts", _p(model_id), _p(idx), _p(n_acc), row_offset, cap, K, _p(counts),
                          self._stream())
         self.launches += 2
+
+    def postpr_final(self, peer, status, n_acc, ds, mad, d, counts, K, small):
+        self.handle.call("abcdls_postpr_final", peer, _p(status), _p(n_acc), _p(ds), _p(mad), d, _p(counts), K, _p(small),
+                         self._stream())
+        self.launches += 1
 
     # ---- kernel 4 -------------------------------------------------------------------------------
     def smc_workspace(self, n, P):

@@ -49,12 +49,15 @@ extern "C" {
 #define ABCDLS_S_ZERO_VAR 0x8        /* every sumstat column constant (R stop: Zero variance ...) */
 #define ABCDLS_S_ZERO_VAR_REGION 0x10 /* no sumstat column varies inside the accepted region */
 #define ABCDLS_S_CAPACITY 0x20       /* an output buffer was too small */
+#define ABCDLS_S_PEER_TIMEOUT 0x40   /* a peer never published its part of an exchange (csrc/peer.cuh) */
+#define ABCDLS_S_NONFINITE_FIT 0x80  /* hcorr: log(residuals^2) not finite (R: lsfit stops on NA/NaN/Inf in 'y') */
 
 /* selection modes */
 #define ABCDLS_MODE_AUTO 0  /* sampled-bracket fast path, verified; sets FASTPATH_MISS on failure */
 #define ABCDLS_MODE_EXACT 1 /* distribution-independent 6-pass radix select */
 
 typedef struct abcdls_handle_s* abcdls_handle_t;
+typedef struct abcdls_peer_s* abcdls_peer_t; /* NVLink mailbox group, see the end of this file; NULL = one rank */
 
 /* ---- lifetime ---------------------------------------------------------------------------- */
 int abcdls_create(abcdls_handle_t* out, int device);
@@ -312,6 +315,37 @@ int abcdls_final_small(abcdls_handle_t h, const int* status_dev, const int64_t* 
                        const double* gamma /* NULL: no hcorr */, const double* the_m, const double* sig,
                        const double* pack, const double* sm, int d, int P, double* small_out, void* stream);
 
+
+/* ---- kernel 3, fused (csrc/tail.cu): the whole tail of abc() as THREE launches (two for rejection) ---------------
+ * Each launch ends in its own fixed-order reduction, its cross-rank exchange over the NVLink mailboxes of `peer`
+ * (NULL on one rank) and its small solve, all inside the kernel's last thread block:
+ *   gather_fit   : accepted rows -> xs | y | ss_out | w (column-major, leading dimension cap; xs / w only for loclinear)
+ *                  + X'WX | X'WY + unweighted column sums + region min / max  -> [all-reduce] -> Cholesky -> beta
+ *   resid_fit    : (hcorr only) residuals (not materialised) -> X'W log(res^2) -> [all-reduce] -> gamma
+ *                  (R's the_m = colMeans(residuals) comes algebraically from the column sums of gather_fit)
+ *   adjust_final : adj, res, summary statistics, sigma2 -> [ONE min|sum exchange] -> small_out (layout of
+ *                  abcdls_final_small)
+ * Statistics source: the candidate block of the one-pass path (cand_ss + slot [+ perm]) or the table (ss, via idx);
+ * parameters: column-major (param_cm, ld_param) or row-major (param_rm, row_pitch; device or pinned host) - exactly one.
+ * Replaces abcdls_gather* .. abcdls_final_small (16 launches + 3 exchanges) for d, P <= 32.
+ * ws: abcdls_tail_workspace_bytes(h, d, P) bytes, zeroed ONCE by the caller (the kernels leave their counters zeroed). */
+int abcdls_tail_supported(int d, int P);
+size_t abcdls_tail_workspace_bytes(abcdls_handle_t h, int d, int P);
+int abcdls_tail_gather_fit(abcdls_handle_t h, abcdls_peer_t peer, const double* cand_ss, int64_t ld_cand,
+                           const int64_t* slot, const int64_t* perm, const double* ss, int64_t ld_ss,
+                           const double* param_cm, int64_t ld_param, const double* param_rm, int64_t row_pitch,
+                           const double* dist_acc, const int64_t* idx, const int64_t* n_acc, int64_t row_offset,
+                           int64_t cap, int d, int P, const double* mad, const double* target, const double* ds,
+                           int loclinear, double* xs, double* y, double* ss_out, double* w, void* ws, size_t ws_bytes,
+                           int* status_dev, void* stream);
+int abcdls_tail_resid_fit(abcdls_handle_t h, abcdls_peer_t peer, const double* xs, const double* y, const double* w,
+                          const int64_t* n_acc, int64_t cap, int d, int P, void* ws, size_t ws_bytes, int* status_dev,
+                          void* stream);
+int abcdls_tail_adjust_final(abcdls_handle_t h, abcdls_peer_t peer, const double* xs, const double* y, const double* w,
+                             const int64_t* n_acc, const double* ds, int64_t cap, int d, int P, int loclinear,
+                             int hcorr, const double* mad, const double* target, double* adj, double* res, void* ws,
+                             size_t ws_bytes, double* small_out, int* status_dev, void* stream);
+
 /* ---- small tables: one thread block per abc() problem with d = P = 1 (csrc/small.cu) -----------------------------
  * ABC-DLS's per-column mode (ABC.py:1949-1953, 2805-2809) and cv4abc's leave-one-out loop over it (ABC.py:1900-1902)
  * are B independent 1-D problems on test-set sized tables (10^4 rows): launch latency, not bandwidth.  Problem b:
@@ -334,6 +368,12 @@ int abcdls_postpr_counts(abcdls_handle_t h, const int32_t* model_id, const int64
                          const int64_t* n_acc, int64_t row_offset, int64_t cap, int K, int64_t* counts,
                          void* stream);
 
+/* the end of a postpr() call in one block: counts and status of all ranks in ONE exchange (peer; NULL on one rank), then
+ * small_out[8 + d + K] = {status, n_acc, ds, every MAD zero, 0, 0, 0, 0 | mad[d] | counts[K] (global, as doubles)} */
+int abcdls_postpr_final(abcdls_handle_t h, abcdls_peer_t peer, const int* status_dev, const int64_t* n_acc,
+                        const double* ds, const double* mad, int d, const int64_t* counts, int K, double* small_out,
+                        void* stream);
+
 /* ---- kernel 4: SMC ------------------------------------------------------------------------
  * oldrange  = per-column min/max over ALL simulated parameter rows   (ABC.py:2714-2716)
  * box filter = rows with every parameter in [lo, hi] inclusive        (ABC.py:2974-2990)
@@ -354,7 +394,6 @@ int abcdls_smc_box_filter(abcdls_handle_t h, const double* param_all, int64_t n,
  * no NCCL on the data path: the kernels are ordinary graph nodes.  Bootstrap (exchanging the IPC handles) is the
  * caller's job (the Python host uses torch.distributed for it).
  *   create (per rank) -> all-gather the handles by any channel -> connect -> barrier -> exchanges ... -> destroy */
-typedef struct abcdls_peer_s* abcdls_peer_t;
 size_t abcdls_peer_handle_bytes(void);
 int abcdls_peer_create(abcdls_peer_t* out, int rank, int world, size_t slot_bytes, void* handle_out);
 int abcdls_peer_connect(abcdls_peer_t p, const void* all_handles /* world x handle_bytes, rank order */);
