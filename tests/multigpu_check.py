@@ -37,6 +37,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rows", type=int, default=300001)
     ap.add_argument("--big", type=int, default=0, help="also run a fast-path sized table (rows per rank)")
+    ap.add_argument("--calls", type=int, default=3, help="calls per case: the third replays the CUDA graph")
     a = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
@@ -51,7 +52,8 @@ def main():
         per = (N + world - 1) // world
         r0, r1 = min(rank * per, N), min((rank + 1) * per, N)
         par, ss, tgt = synth.abc_tables(r1 - r0, d, P, dev, row_start=r0)
-        res = eng.abc(tgt, par, ss, tol, method)
+        for _ in range(a.calls):        # call 1 eager, call 2 records the CUDA graph, call 3+ replay it (same results)
+            res = eng.abc(tgt, par, ss, tol, method)
         idx = gather_rows(res.idx, world)
         vals = gather_rows(res.values.contiguous(), world)
         if rank == 0:
@@ -64,8 +66,42 @@ def main():
             e2 = float(np.max(np.abs(mn.cpu().numpy() - ref.min(axis=0)) / np.abs(ref).max(axis=0)))
             good = good and err < 1e-9 and e2 < 1e-9
             print(f"{'PASS' if good else 'FAIL'} world={world} N={N} d={d} P={P} tol={tol} {method}: nacc={o.nacc} "
-                  f"max rel err={err:.2e} fast_misses={eng.fast_misses} collectives={eng.comm.calls}", flush=True)
+                  f"max rel err={err:.2e} fast_misses={eng.fast_misses} collectives={eng.comm.calls} "
+                  f"(in compute kernels: {eng.comm.fused_calls}) graphs={len(eng._graphs)}", flush=True)
             ok = ok and good
+    # postpr over the ranks: counts and the accepted set against the single-table oracle (ties by construction)
+    for N in (200_001, a.big * world + 5 if a.big else 0):
+        if not N:
+            continue
+        per = (N + world - 1) // world
+        r0, r1 = min(rank * per, N), min((rank + 1) * per, N)
+        ids, ss, tgt = synth.postpr_tables(r1 - r0, dev, K=3, row_start=r0)
+        for _ in range(a.calls):
+            res = eng.postpr(tgt, ids, ["A", "B", "C"], ss, 0.05)
+        idx = gather_rows(res.idx, world)
+        if rank == 0:
+            fid, fss, ftgt = synth.postpr_tables(N, dev, K=3)
+            o = O.postpr(ftgt.cpu().numpy(), np.array(["A", "B", "C"])[fid.cpu().numpy()], fss.cpu().numpy().T, 0.05)
+            good = (np.array_equal(idx.cpu().numpy(), o.idx) and res.ds == o.ds
+                    and np.array_equal(res.counts.cpu().numpy(), o.counts))
+            print(f"{'PASS' if good else 'FAIL'} world={world} postpr N={N}: counts={res.counts.cpu().tolist()}", flush=True)
+            ok = ok and good
+    # SMC table passes: oldrange and the box filter over the ranks
+    N = 400_003
+    per = (N + world - 1) // world
+    r0, r1 = min(rank * per, N), min((rank + 1) * per, N)
+    par, _, _ = synth.abc_tables(r1 - r0, 4, 4, dev, row_start=r0)
+    mn, mx = eng.oldrange(par)
+    lo, hi = mn + 0.2 * (mx - mn), mx - 0.3 * (mx - mn)
+    keep = gather_rows(eng.box_filter(par, lo, hi), world)
+    if rank == 0:
+        fpar, _, _ = synth.abc_tables(N, 4, 4, dev)
+        f = fpar.cpu().numpy()
+        want = np.flatnonzero(np.all((f >= lo.cpu().numpy()[:, None]) & (f <= hi.cpu().numpy()[:, None]), axis=0))
+        good = (np.array_equal(keep.cpu().numpy(), want) and np.array_equal(mn.cpu().numpy(), f.min(axis=1))
+                and np.array_equal(mx.cpu().numpy(), f.max(axis=1)))
+        print(f"{'PASS' if good else 'FAIL'} world={world} oldrange + box filter N={N}: kept {want.size}", flush=True)
+        ok = ok and good
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
     dist.destroy_process_group()
