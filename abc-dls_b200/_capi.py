@@ -102,6 +102,20 @@ SIGNATURES = {
     "abcdls_tail_resid_fit": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _sz, _vp, _vp]),
     "abcdls_tail_adjust_final": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp,
                                         _vp, _vp, _sz, _vp, _vp, _vp]),
+    "abcdls_columns_supported": (_i32, [_vp, _i64, _i32, _i64]),
+    "abcdls_columns_workspace_bytes": (_sz, [_vp, _i64, _i32, _i64]),
+    "abcdls_columns_sample": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _i64, _i64, _i64, _i32, _vp, _sz, C.POINTER(_vp),
+                                     C.POINTER(_sz), _vp]),
+    "abcdls_columns_pass": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _i64, _i32, _vp, _sz, C.POINTER(_vp), C.POINTER(_sz),
+                                   C.POINTER(_vp), _vp]),
+    "abcdls_columns_refine": (_i32, [_vp, _i64, _i64, _i32, _i64, _i32, _i32, _vp, _vp, _vp, _sz, _vp, _vp, _vp,
+                                     C.POINTER(_vp), C.POINTER(_sz), C.POINTER(_vp), C.POINTER(_sz), _vp]),
+    "abcdls_columns_exact": (_i32, [_vp, _i64, _i32, _i64, _vp, _vp, _vp, _sz, C.POINTER(_vp), C.POINTER(_i64), _vp, _vp,
+                                    _vp]),
+    "abcdls_columns_count": (_i32, [_vp, _i64, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _sz, C.POINTER(_vp), _vp, _vp]),
+    "abcdls_columns_rowkeys": (_i32, [_vp, _i64, _i32, _i64, _vp, _vp, _vp, _sz, C.POINTER(_vp), _vp]),
+    "abcdls_columns_accept": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp,
+                                     _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "abcdls_small_supported": (_i32, [_i64, _i64]),
     "abcdls_small_columns": (_i32, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp,
                                     _vp]),

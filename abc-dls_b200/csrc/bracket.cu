@@ -1583,3 +1583,4 @@ int abcdls_dist_fast_pass(abcdls_handle_t h, const double* ss, int64_t n, int d,
 }  // extern "C"
 
 #include "fused.cuh"
+#include "columns.cuh"

@@ -203,6 +203,7 @@ class AbcEngine:
         # saves (4.94 -> 5.2 ms per call), so it stays off.
         self.pregather = False
         self.fused_tail = os.environ.get("ABCDLS_NO_TAIL", "0") != "1"   # csrc/tail.cu instead of the 16-launch tail
+        self.use_columns = os.environ.get("ABCDLS_NO_COLUMNS", "0") != "1"   # csrc/columns.cuh for per-column summaries
         self._side = None
         if os.environ.get("ABCDLS_NO_GRAPH", "0") == "1":
             self.use_graphs = False
@@ -240,14 +241,15 @@ class AbcEngine:
         ns = [c[0] for c in counts]
         return sum(ns), sum(ns[: self.comm.rank]), ns, all(c[1] for c in counts)
 
-    def _select(self, table: torch.Tensor, n_local: int, center, k0, k1, counts=None) -> torch.Tensor:
+    def _select(self, table: torch.Tensor, n_local: int, center, k0, k1, counts=None, local: bool = False) -> torch.Tensor:
         """Exact global order statistics k0,k1 (0-based) of every row of ``table`` (njobs, n_local); counts (device
-        int64 per job, optional): only the first counts[j] entries of row j exist."""
+        int64 per job, optional): only the first counts[j] entries of row j exist.  local: order statistics of THIS
+        rank's entries (no histogram exchange)."""
         k = self.k
         njobs, ld = table.shape[0], table.stride(0)
         ws = k.select_workspace(njobs)
         k.select_begin(ws, njobs, table, n_local, ld, counts, center, k0, k1)
-        hist = k.select_hist_tensor(ws, njobs) if self.comm.world > 1 else None
+        hist = k.select_hist_tensor(ws, njobs) if (self.comm.world > 1 and not local) else None
         for p in range(_capi.SELECT_PASSES):
             with self._t(f"select_hist[{njobs}x{n_local}]"):
                 k.select_hist(ws, njobs, n_local, p)
@@ -708,10 +710,9 @@ class AbcEngine:
         if o is not None:
             full = {"median": o[:, 0].copy(), "mean": o[:, 1].copy(), "min": o[:, 4].copy(), "max": o[:, 5].copy()}
             return {k_: full[k_] for k_ in want}
-        if hasattr(self, "_columns_streaming"):
-            got = self._columns_streaming(target, par, ss, tol, method, hcorr, shard, want)
-            if got is not None:
-                return got
+        got = self._columns_streaming(target, par, ss, tol, method, hcorr, shard, want)
+        if got is not None:
+            return got
         out = {k_: np.empty(P) for k_ in want}
         for c, r in enumerate(self.abc_columns(target, par, ss, tol, method, hcorr, shard)):
             w = r.adj_values is not None
@@ -726,6 +727,108 @@ class AbcEngine:
                 if self.comm.world > 1:
                     vals, wts = self.gather_sample(vals, wts)
                 out["median"][c] = float(_summary.point_estimate(vals, wts, r.stats, w, "median")[0])
+        return out
+
+    # ---- per-column mode as ONE pass over the N x P statistics (csrc/columns.cuh) ---------------------------------------
+    def _columns_streaming(self, target, par, ss, tol, method, hcorr, shard, want):
+        """All P one-dimensional rejection problems from one read of the statistics table; any number of ranks.
+        None when the table does not qualify or the device flags a bracket miss (the caller then loops over abc())."""
+        import numpy as np
+        from . import summary as _summary
+        k = self.k
+        if method != "rejection" or not hasattr(k, "columns_supported") or not self.use_columns:
+            return None
+        P, n_local = ss.shape
+        ok = (ss.device == self.device and ss.stride(1) == 1 and k.columns_supported(ss, n_local, P, ss.stride(0))
+              and (par.device == self.device or (par.device.type == "cpu" and par.is_pinned()))
+              and (self.comm.world == 1 or self.comm.peer is not None))
+        if shard is not None and self.comm.world > 1:
+            n_global, row_offset = int(shard[0]), int(shard[1])
+            per = -(-n_global // self.comm.world)
+            ok = ok and min(per, n_global - (self.comm.world - 1) * per) >= (1 << 20)
+        else:
+            n_global, row_offset, ns, ok = self._shard_info(n_local, int(ok))
+        if not ok:
+            return None
+        nacc = int(math.ceil(n_global * tol))
+        if not (1 <= nacc <= n_global):
+            raise AbcError("'tol' must give 1 <= ceiling(N * tol) <= N")
+        hint = -(-nacc * n_local // n_global)
+        lists = "median" in want
+        key = ("columns", ss.data_ptr(), tuple(ss.shape), ss.stride(0), par.data_ptr(), par.stride(0), par.stride(1),
+               par.device.type, float(tol), self.comm.world, n_global, row_offset, lists)
+        _t0 = time.perf_counter()
+        o, plan = self._run(key, target, lambda tgt: self._columns_device(tgt, par, ss, n_global, nacc, hint, lists))
+        self.host_enqueue_ms.append((time.perf_counter() - _t0) * 1e3)
+        small = o["small"].cpu()                    # the one blocking read
+        st = int(small[0])
+        if st & _capi.S_PEER_TIMEOUT:
+            raise RuntimeError("a rank did not take part in an exchange of this call (NVLink mailbox wait timed out)")
+        per_col = small[8:].view(P, 8).numpy()
+        if (st & _capi.S_FASTPATH_MISS) or (per_col[:, 1] == 0).any() or (per_col[:, 5] != nacc).any():
+            self.fast_misses += 1                   # a zero MAD needs R's zero-variance checks: the exact path has them
+            return None
+        if st & _capi.S_NONFINITE:
+            raise AbcError("non-finite values in 'sumstat'/'target' (R's NA-row handling is not implemented)")
+        self.path_calls["columns"] = self.path_calls.get("columns", 0) + 1
+        for c in np.flatnonzero(per_col[:, 7] != 0):
+            print("Warning message:\nZero variance in the summary statistics in the selected region. Check summary "
+                  f"statistics, consider larger tolerance. (column {c + 1})")
+        out = {}
+        if "min" in want:
+            out["min"] = per_col[:, 2].copy()
+        if "max" in want:
+            out["max"] = per_col[:, 3].copy()
+        if "mean" in want:
+            out["mean"] = per_col[:, 4] / per_col[:, 5]
+        if lists:
+            cnts = o["acc_cnt"].cpu().tolist()
+            med = np.empty(P)
+            for c in range(P):
+                vals = o["acc_val"][c, : cnts[c]].reshape(-1, 1)
+                vals, _ = self.gather_sample(vals, torch.ones(vals.shape[0], dtype=torch.float64, device=self.device))
+                med[c] = float(_summary.point_estimate(vals, None, None, False, "median")[0])
+            out["median"] = med
+        out["ds"], out["mad"] = per_col[:, 0].copy(), per_col[:, 1].copy()
+        return {k_: out[k_] for k_ in tuple(want) + ("ds", "mad")}
+
+    def _columns_device(self, target, par, ss, n_global, nacc, hint, lists):
+        k = self.k
+        P, n_local = ss.shape
+        comm = self.comm if self.comm.world > 1 else None
+        status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        med, mad = k.new(P), k.new(P)
+        with self._t("columns_front"):
+            ws, dist, cnt = k.columns_front(ss, n_local, n_global, P, ss.stride(0), target, nacc, hint, med, mad, status,
+                                            comm)
+        with self._t("columns_select"):
+            sel = self._select(dist, dist.shape[1], None, nacc - 1, nacc - 1, counts=cnt)      # (P, 2): ds_j twice
+        with self._t("columns_accept"):
+            c2 = k.columns_count(ws, n_local, P, hint, nacc, sel, mad, target, cnt, status)
+            # R's cap rule: the first nacc rows, in row order, of {dist <= ds}; lower ranks hold the lower rows
+            mine = c2.sum(dim=1)
+            before = torch.zeros_like(mine)
+            if comm is not None:
+                before = comm.allgather(mine.contiguous())[: comm.rank].sum(0)
+            quota = torch.minimum((nacc - before).clamp(min=0), mine)
+            keys = k.columns_rowkeys(ws, n_local, P, hint, sel, cnt, dist.shape[1])
+            k0 = (quota - 1).clamp(min=0).contiguous()
+            thr = self._select(keys, keys.shape[1], None, k0, k0, counts=cnt, local=True)          # (P, 2)
+            thr = torch.where((quota > 0)[:, None], thr, torch.full_like(thr, -1.0)).contiguous()
+            small = k.new(8 + 8 * P)
+            acc = None
+            if lists:
+                cap = min(n_local, 2 * hint + 1024)
+                acc = (cap, torch.empty((P, cap), dtype=torch.int32, device=self.device), k.new(P, cap), k.new(P, cap),
+                       torch.zeros(P, dtype=torch.int64, device=self.device))
+            k.columns_accept(self.comm.peer if comm is not None else None, ws, n_local, P, hint, sel, med, mad, cnt,
+                             thr, par, small, status, acc)
+            if comm is not None:
+                self.comm.calls += 1
+                self.comm.fused_calls += 1
+        out = dict(small=small)
+        if lists:
+            out.update(acc_row=acc[1], acc_val=acc[2], acc_dist=acc[3], acc_cnt=acc[4])
         return out
 
     def gather_sample(self, vals: torch.Tensor, w: torch.Tensor):

@@ -159,12 +159,35 @@ class PostprFit:
         return "\n".join(lines)
 
 
+_r_abc = None
+
+
+def _delegate(fn: str, why: str, **kwargs):
+    """Arguments this engine does not cover (R's nnet-based methods ``neuralnet`` / ``ridge`` / ``mnlogistic``,
+    ``transf``, ``subset``, other kernels) go to the R package the reference binds (ABC.py:36), when rpy2 can load it:
+    ``rabc`` then really is a drop-in for the rpy2 handle - the default ``--method`` of two Run_ParamsEstimation
+    sub-commands is ``neuralnet``.  Without R the call stops with the reason."""
+    global _r_abc
+    if _r_abc is None:
+        try:
+            from rpy2.robjects.packages import importr
+            from rpy2.robjects import pandas2ri
+            pandas2ri.activate()
+            _r_abc = importr("abc")
+        except Exception as e:
+            raise AbcError(f"{fn}: {why} is not implemented by the B200 engine and R's abc package could not be loaded "
+                           f"through rpy2 to take the call ({type(e).__name__}: {e})") from e
+    return getattr(_r_abc, fn)(**{k: v for k, v in kwargs.items() if v is not None})
+
+
 def abc(target, param, sumstat, tol, method, hcorr: bool = True, transf: str = "none", subset=None,
-        kernel: str = "epanechnikov", **_ignored) -> AbcFit:
-    if transf != "none" and not (isinstance(transf, (list, tuple)) and all(t == "none" for t in transf)):
-        raise AbcError("only transf='none' is implemented (ABC-DLS never passes transf)")
-    if subset is not None:
-        raise AbcError("'subset' is not implemented")
+        kernel: str = "epanechnikov", **extra) -> AbcFit:
+    plain_transf = transf == "none" or (isinstance(transf, (list, tuple)) and all(t == "none" for t in transf))
+    if method not in ("rejection", "loclinear") or not plain_transf or subset is not None or kernel != "epanechnikov":
+        why = (f"method='{method}'" if method not in ("rejection", "loclinear") else
+               "transf" if not plain_transf else "subset" if subset is not None else f"kernel='{kernel}'")
+        return _delegate("abc", why, target=target, param=param, sumstat=sumstat, tol=tol, method=method, hcorr=hcorr,
+                         transf=transf, subset=subset, kernel=kernel, **extra)
     eng = engine()
     ss = to_table(sumstat, eng.device)
     par = to_table(param, eng.device, row_major_ok=True)
@@ -175,9 +198,10 @@ def abc(target, param, sumstat, tol, method, hcorr: bool = True, transf: str = "
     return AbcFit(res, eng, _names(param, par.shape[0], "P"), _names(sumstat, ss.shape[0], "S"))
 
 
-def postpr(target, index, sumstat, tol, method="rejection", subset=None, **_ignored) -> PostprFit:
-    if subset is not None:
-        raise AbcError("'subset' is not implemented")
+def postpr(target, index, sumstat, tol, method="rejection", subset=None, **extra) -> PostprFit:
+    if method != "rejection" or subset is not None:
+        return _delegate("postpr", f"method='{method}'" if method != "rejection" else "subset", target=target,
+                         index=index, sumstat=sumstat, tol=tol, method=method, subset=subset, **extra)
     eng = engine()
     ss = to_table(sumstat, eng.device)
     tgt = _to_vec(target, eng.device)
@@ -202,10 +226,10 @@ def cv4abc(param, sumstat, nval, tols, method, statistic: str = "median", hcorr:
            **_ignored) -> _cv.Cv4abcResult:
     """``abc::cv4abc`` (leave-one-out prediction error of the point estimate).  ``cvsamples`` (0-based rows) / ``seed``
     are extras: R draws the rows with its own sample() stream, which is not reproduced."""
-    if transf != "none" or subset is not None or kernel != "epanechnikov":
-        raise AbcError("cv4abc: only transf='none', subset=NULL, kernel='epanechnikov' are implemented")
-    if method not in ("rejection", "loclinear"):
-        raise AbcError("Method must be rejection or loclinear (neuralnet / ridge stay with R's nnet)")
+    if transf != "none" or subset is not None or kernel != "epanechnikov" or method not in ("rejection", "loclinear"):
+        return _delegate("cv4abc", f"method='{method}'" if method not in ("rejection", "loclinear") else
+                         "transf / subset / kernel", param=param, sumstat=sumstat, nval=nval, tols=tols, method=method,
+                         statistic=statistic, hcorr=hcorr, transf=transf, subset=subset, kernel=kernel, trace=trace)
     eng = engine()
     ss, par = to_table(sumstat, eng.device), to_table(param, eng.device)
     if par.shape[1] != ss.shape[1]:
@@ -222,8 +246,9 @@ def cv4postpr(index, sumstat, nval, tols=None, method="rejection", subset=None, 
         tols = tol
     if tols is None:
         raise AbcError("'tols' is missing")
-    if subset is not None:
-        raise AbcError("'subset' is not implemented")
+    if subset is not None or method != "rejection":
+        return _delegate("cv4postpr", f"method='{method}'" if method != "rejection" else "subset", index=index,
+                         sumstat=sumstat, nval=nval, tols=tols, method=method, subset=subset, kernel=kernel, trace=trace)
     eng = engine()
     ss = to_table(sumstat, eng.device)
     ids, models = _model_ids(index, eng)

@@ -374,6 +374,68 @@ class CudaStages:
                          _p(status), self._stream())
         self.launches += 1
 
+    # ---- per-column mode as one pass (csrc/columns.cuh) ---------------------------------------------------------------
+    def columns_supported(self, ss, n, P, ld) -> bool:
+        return bool(self.lib.abcdls_columns_supported(_p(ss), n, P, ld))
+
+    def columns_front(self, ss, n, n_global, P, ld, target, nacc, hint, med, mad, status, comm=None):
+        """sample -> pass -> medians / MADs -> exact distances of the T-band members.
+        -> (ws, dist table (P, capT) view, cnt (P,) int64 device tensor)"""
+        world = comm.world if comm is not None else 1
+        ws = self.workspace(f"columns{P}", self.lib.abcdls_columns_workspace_bytes(self.handle.h, n, P, hint))
+        p0, c0, p1, c1, p2 = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t(), C.c_void_p()
+        st = self._stream()
+        self.handle.call("abcdls_columns_sample", _p(ss), n, P, ld, _p(target), nacc, n_global, hint, world, _p(ws),
+                         ws.numel(), C.byref(p0), C.byref(c0), st)
+        if world > 1:
+            comm.allreduce_sum(self._view(ws, p0, c0, torch.float64, 8))
+        with self._timed("k_columns_pass"):
+            self.handle.call("abcdls_columns_pass", _p(ss), n, P, ld, _p(target), hint, world, _p(ws), ws.numel(),
+                             C.byref(p0), C.byref(c0), C.byref(p2), st)
+        if world > 1:
+            comm.allreduce_sum(self._view(ws, p0, c0, torch.int64, 8))
+            comm.allreduce_sum(self._view(ws, p2, C.c_size_t(P), torch.int64, 8))
+        gs = gc = None
+        with self._timed("columns_refine"):
+            for phase in range(4):
+                self.handle.call("abcdls_columns_refine", n, n_global, P, hint, phase, world, _p(gs), _p(gc), _p(ws),
+                                 ws.numel(), _p(med), _p(mad), _p(status), C.byref(p0), C.byref(c0), C.byref(p1),
+                                 C.byref(c1), st)
+                if world > 1:
+                    if phase in (0, 2):
+                        gs = comm.allgather(self._view(ws, p0, c0, torch.float64, 8)).contiguous()
+                        gc = comm.allgather(self._view(ws, p1, c1, torch.int32, 4)).contiguous()
+                    elif phase == 1:
+                        comm.allreduce_sum(self._view(ws, p0, c0, torch.int64, 8))
+        cnt = self.new(P, dtype=torch.int64)
+        cap = C.c_int64()
+        self.handle.call("abcdls_columns_exact", n, P, hint, _p(mad), _p(target), _p(ws), ws.numel(), C.byref(p0),
+                         C.byref(cap), _p(cnt), _p(status), st)
+        dist = self._view(ws, p0, C.c_size_t(P * cap.value), torch.float64, 8).view(P, cap.value)
+        self.launches += 22
+        return ws, dist, cnt
+
+    def columns_count(self, ws, n, P, hint, nacc, sel, mad, target, cnt, status) -> torch.Tensor:
+        p0 = C.c_void_p()
+        self.handle.call("abcdls_columns_count", n, P, hint, nacc, _p(sel), _p(mad), _p(target), _p(cnt), _p(ws),
+                         ws.numel(), C.byref(p0), _p(status), self._stream())
+        self.launches += 1
+        return self._view(ws, p0, C.c_size_t(2 * P), torch.int64, 8).view(P, 2)
+
+    def columns_rowkeys(self, ws, n, P, hint, sel, cnt, cap) -> torch.Tensor:
+        p0 = C.c_void_p()
+        self.handle.call("abcdls_columns_rowkeys", n, P, hint, _p(sel), _p(cnt), _p(ws), ws.numel(), C.byref(p0),
+                         self._stream())
+        self.launches += 1
+        return self._view(ws, p0, C.c_size_t(P * cap), torch.float64, 8).view(P, cap)
+
+    def columns_accept(self, peer, ws, n, P, hint, sel, med, mad, cnt, thr, par, small, status, lists=None):
+        acc_cap, row, val, dst, acnt = (0, None, None, None, None) if lists is None else lists
+        self.handle.call("abcdls_columns_accept", peer, n, P, hint, _p(sel), _p(med), _p(mad), _p(cnt), _p(thr),
+                         _p(par), par.stride(0), par.stride(1), acc_cap, _p(row), _p(val), _p(dst), _p(acnt), _p(ws),
+                         ws.numel(), _p(small), _p(status), self._stream())
+        self.launches += 2
+
     def small_supported(self, n, nacc) -> bool:
         return bool(self.lib.abcdls_small_supported(int(n), int(nacc)))
 

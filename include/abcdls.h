@@ -346,6 +346,42 @@ int abcdls_tail_adjust_final(abcdls_handle_t h, abcdls_peer_t peer, const double
                              int hcorr, const double* mad, const double* target, double* adj, double* res, void* ws,
                              size_t ws_bytes, double* small_out, int* status_dev, void* stream);
 
+/* ---- per-column mode as ONE pass (csrc/columns.cuh): P independent 1-D abc(method = "rejection") problems sharing the
+ * N rows of an N x P statistics table - ABC-DLS's SMC round (ABC.py:2805-2840) and abc_params (1949-1953).
+ * For one statistic the distance is monotone in |x - t_j| on either side of the target, so the tolerance cut is a third
+ * band of the bracket pass (median band, MAD band, T band); exact or ABCDLS_S_FASTPATH_MISS (then: P separate calls).
+ *   sample -> [all-reduce est] -> pass -> [all-reduce counts, tcount] -> refine 0..3 (exchanges as
+ *   abcdls_mad_fast_refine) -> exact -> [abcdls_select_* over (P, cap) with cnt, rank nacc - 1 -> sel] -> count ->
+ *   [all-gather cnt2 -> quota] -> rowkeys -> [abcdls_select_* per rank, rank quota - 1 -> thr] -> accept (its last
+ *   kernel sums / mins the per-column results over the ranks of `peer`).  R's cap rule keeps the FIRST nacc rows of
+ *   {dist <= ds} in row order: the members are unordered, so the cut is a row number found by a second selection.
+ * nacc_local_hint (this rank's expected share of nacc) sizes the member lists; pass the same value to every call. */
+int abcdls_columns_supported(const double* ss, int64_t n, int P, int64_t ld);
+size_t abcdls_columns_workspace_bytes(abcdls_handle_t h, int64_t n, int P, int64_t nacc_local_hint);
+int abcdls_columns_sample(abcdls_handle_t h, const double* ss, int64_t n, int P, int64_t ld, const double* target,
+                          int64_t nacc, int64_t n_global, int64_t nacc_local_hint, int world, void* ws, size_t ws_bytes,
+                          double** est_out, size_t* est_count, void* stream);
+int abcdls_columns_pass(abcdls_handle_t h, const double* ss, int64_t n, int P, int64_t ld, const double* target,
+                        int64_t nacc_local_hint, int world, void* ws, size_t ws_bytes, int64_t** counts_out,
+                        size_t* counts_count, int64_t** tcount_out, void* stream);
+int abcdls_columns_refine(abcdls_handle_t h, int64_t n, int64_t n_global, int P, int64_t nacc_local_hint, int phase,
+                          int world, const double* gath_small, const int32_t* gath_cnt, void* ws, size_t ws_bytes,
+                          double* med, double* mad, int* status_dev, void** x0, size_t* x0_count, void** x1,
+                          size_t* x1_count, void* stream);
+int abcdls_columns_exact(abcdls_handle_t h, int64_t n, int P, int64_t nacc_local_hint, const double* mad,
+                         const double* target, void* ws, size_t ws_bytes, double** dist_out, int64_t* cap_out,
+                         int64_t* cnt_out, int* status_dev, void* stream);
+int abcdls_columns_count(abcdls_handle_t h, int64_t n, int P, int64_t nacc_local_hint, int64_t nacc, const double* sel,
+                         const double* mad, const double* target, const int64_t* cnt, void* ws, size_t ws_bytes,
+                         int64_t** cnt2_out, int* status_dev, void* stream);
+int abcdls_columns_rowkeys(abcdls_handle_t h, int64_t n, int P, int64_t nacc_local_hint, const double* sel,
+                           const int64_t* cnt, void* ws, size_t ws_bytes, double** keys_out, void* stream);
+int abcdls_columns_accept(abcdls_handle_t h, abcdls_peer_t peer, int64_t n, int P, int64_t nacc_local_hint,
+                          const double* sel, const double* med, const double* mad, const int64_t* cnt,
+                          const double* thr, const double* par, int64_t par_col_stride, int64_t par_row_stride,
+                          int64_t acc_cap, int32_t* acc_row, double* acc_val, double* acc_dist, int64_t* acc_cnt,
+                          void* ws, size_t ws_bytes, double* small_out, int* status_dev, void* stream);
+
 /* ---- small tables: one thread block per abc() problem with d = P = 1 (csrc/small.cu) -----------------------------
  * ABC-DLS's per-column mode (ABC.py:1949-1953, 2805-2809) and cv4abc's leave-one-out loop over it (ABC.py:1900-1902)
  * are B independent 1-D problems on test-set sized tables (10^4 rows): launch latency, not bandwidth.  Problem b:

@@ -86,6 +86,30 @@ def main():
                     and np.array_equal(res.counts.cpu().numpy(), o.counts))
             print(f"{'PASS' if good else 'FAIL'} world={world} postpr N={N}: counts={res.counts.cpu().tolist()}", flush=True)
             ok = ok and good
+    # per-column mode as one pass over the sharded table (csrc/columns.cuh), incl. ties that straddle the rank boundary
+    if a.big:
+        N, P = a.big * world + 13, 4
+        per = (N + world - 1) // world
+        r0, r1 = min(rank * per, N), min((rank + 1) * per, N)
+        for coarse in (False, True):
+            par, ss, tgt = synth.abc_tables(r1 - r0, P, P, dev, row_start=r0)
+            if coarse:      # a coarse grid: thousands of equal distances, the cap rule decides by row order across ranks
+                ss = (torch.round(ss / tgt[:, None] * 400.0) * tgt[:, None] / 400.0).to(torch.float32).to(torch.float64)
+            for _ in range(a.calls):
+                got = eng.abc_columns_summary(tgt, par, ss, 0.01, "rejection", shard=(N, r0), want=("min", "max", "mean"))
+            if rank == 0:
+                fpar, fss, ftgt = synth.abc_tables(N, P, P, dev)
+                if coarse:
+                    fss = (torch.round(fss / ftgt[:, None] * 400.0) * ftgt[:, None] / 400.0).to(torch.float32).to(torch.float64)
+                good = eng.path_calls.get("columns", 0) > 0
+                for c in range(P):
+                    o = O.abc(ftgt[c:c + 1].cpu().numpy(), fpar[c].cpu().numpy(), fss[c].cpu().numpy(), 0.01, "rejection")
+                    v = o.unadj_values[:, 0]
+                    good = good and got["min"][c] == v.min() and got["max"][c] == v.max() and got["ds"][c] == o.ds
+                    good = good and abs(got["mean"][c] - v.mean()) <= 1e-12 * abs(v.mean())
+                print(f"{'PASS' if good else 'FAIL'} world={world} per-column one-pass N={N} P={P} coarse={coarse} "
+                      f"columns calls={eng.path_calls.get('columns', 0)} misses={eng.fast_misses}", flush=True)
+                ok = ok and good
     # SMC table passes: oldrange and the box filter over the ranks
     N = 400_003
     per = (N + world - 1) // world

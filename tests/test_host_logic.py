@@ -283,3 +283,29 @@ def test_reference_summary_flows_through_the_shim(tmp_path, capsys):
     np.testing.assert_allclose(max_df.to_numpy(), want[6], rtol=1e-9)
     np.testing.assert_allclose(np.array(fit.summary(print_=False)), want, rtol=1e-9)
     assert capsys.readouterr().out == ""                   # everything summary() printed went to the sink
+
+
+def test_unsupported_methods_are_delegated_to_r_or_stop_with_the_reason():
+    """`rabc` replaces the rpy2 handle wholesale, and 'neuralnet' is the default --method of two
+    Run_ParamsEstimation sub-commands: such calls go to R's abc package through rpy2 when it is there, and stop with a
+    message that says so when it is not (no R in this container)."""
+    from abc_dls_b200 import rabc
+    from abc_dls_b200.engine import AbcError
+    x = np.arange(20.0).reshape(10, 2)
+    for call in (lambda: rabc.abc(target=[1.0, 2.0], param=x, sumstat=x, tol=0.5, method="neuralnet"),
+                 lambda: rabc.abc(target=[1.0, 2.0], param=x, sumstat=x, tol=0.5, method="loclinear", transf="log"),
+                 lambda: rabc.postpr(target=[1.0, 2.0], index=list("ab" * 5), sumstat=x, tol=0.5, method="mnlogistic"),
+                 lambda: rabc.cv4abc(param=x, sumstat=x, nval=2, tols=0.5, method="neuralnet"),
+                 lambda: rabc.cv4postpr(index=list("ab" * 5), sumstat=x, nval=2, tol=0.5, method="neuralnet")):
+        with pytest.raises(AbcError, match="R's abc package could not be loaded through rpy2"):
+            call()
+    # with an R package object in place the call is forwarded untouched
+    class FakeR:
+        def abc(self, **kw):
+            return ("R", sorted(kw))
+    rabc._r_abc = FakeR()
+    try:
+        tag, keys = rabc.abc(target=[1.0], param=x[:, :1], sumstat=x[:, :1], tol=0.5, method="ridge")
+        assert tag == "R" and {"target", "param", "sumstat", "tol", "method"} <= set(keys)
+    finally:
+        rabc._r_abc = None
