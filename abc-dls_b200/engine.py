@@ -708,14 +708,17 @@ class AbcEngine:
         if self.comm.world == 1 and ss.device == self.device and par.device == self.device:
             o = _cv.small_fits(self, par, ss, np.arange(P, dtype=np.int32), None, float(tol), method, hcorr, target=target)
         if o is not None:
-            full = {"median": o[:, 0].copy(), "mean": o[:, 1].copy(), "min": o[:, 4].copy(), "max": o[:, 5].copy()}
-            return {k_: full[k_] for k_ in want}
+            full = {"median": o[:, 0].copy(), "mean": o[:, 1].copy(), "min": o[:, 4].copy(), "max": o[:, 5].copy(),
+                    "ds": o[:, 2].copy(), "mad": o[:, 3].copy()}
+            return {k_: full[k_] for k_ in tuple(want) + ("ds", "mad")}
         got = self._columns_streaming(target, par, ss, tol, method, hcorr, shard, want)
         if got is not None:
             return got
-        out = {k_: np.empty(P) for k_ in want}
-        for c, r in enumerate(self.abc_columns(target, par, ss, tol, method, hcorr, shard)):
+        out = {k_: np.empty(P) for k_ in tuple(want) + ("ds", "mad")}
+        # (no shard= here: a one-column slice of the table need not have the aligned layout that promise is about)
+        for c, r in enumerate(self.abc_columns(target, par, ss, tol, method, hcorr)):
             w = r.adj_values is not None
+            out["ds"][c], out["mad"][c] = r.ds, float(r.mad[0])
             if "min" in out:
                 out["min"][c] = float(r.stats[0, 0])
             if "max" in out:
