@@ -133,6 +133,7 @@ SIGNATURES = {
     "abcdls_peer_slot_bytes": (_sz, [_vp]),
     "abcdls_peer_allreduce": (_i32, [_vp, _vp, _sz, _i32, _i32, _vp]),
     "abcdls_peer_allgather": (_i32, [_vp, _vp, _sz, _vp, _vp]),
+    "abcdls_peer_allgather_ragged": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -116,6 +116,26 @@ class Comm:
             self._do(lambda: dist.all_gather_into_tensor(out.view(-1), src, group=self.group))
         return out
 
+    def allgather_ragged(self, vals: torch.Tensor, cnt: torch.Tensor):
+        """vals (nj * cap,) float64 = nj rows of which only the first cnt[j] (int32) entries exist ->
+        ((world, nj * cap) values, (world, nj) counts).  Over the mailboxes only the existing entries cross NVLink and
+        both arrays travel in ONE exchange; otherwise two plain all-gathers."""
+        nj = cnt.numel()
+        cap = vals.numel() // nj
+        if (self.world > 1 and self.peer is not None and vals.is_cuda and vals.is_contiguous() and cnt.is_contiguous()
+                and (nj + nj * cap) * 8 <= PEER_SLOT_BYTES):
+            gv = torch.empty((self.world, nj * cap), dtype=torch.float64, device=vals.device)
+            gc = torch.empty((self.world, nj), dtype=torch.int32, device=vals.device)
+            rc = self._lib.abcdls_peer_allgather_ragged(self.peer, C.c_void_p(vals.data_ptr()), C.c_void_p(cnt.data_ptr()),
+                                                        nj, cap, C.c_void_p(gv.data_ptr()), C.c_void_p(gc.data_ptr()),
+                                                        self._stream())
+            if rc != 0:
+                raise RuntimeError("abcdls_peer_allgather_ragged failed")
+            self.calls += 1
+            self.peer_calls += 1
+            return gv, gc
+        return self.allgather(vals).contiguous(), self.allgather(cnt).contiguous()
+
     def allgather_ints(self, vals: List[int]) -> List[List[int]]:
         """Host integers from every rank (shapes / row counts); one small collective + a sync."""
         if self.world == 1:

@@ -116,6 +116,38 @@ __global__ void __launch_bounds__(kPeerThreads) k_peer_allgather(PeerDev P, cons
     finish(P, k);
 }
 
+// nj ragged rows per rank: src_vals[nj][cap] of which only the first src_cnt[j] entries of row j exist (the refinement
+// blocks: <= 8192 band values per column, a few hundred in practice).  dst_vals[world][nj][cap] / dst_cnt[world][nj]
+// get every rank's rows, but only the existing entries cross NVLink (the padded block is 1 MB per rank at d = 16).
+// Slot layout: nj counts (8-byte words) | nj x cap values.  CTA b serves the (rank, row) pairs b, b + grid, ...
+__global__ void __launch_bounds__(kPeerThreads) k_peer_allgather_ragged(PeerDev P, const double* __restrict__ src_vals,
+                                                                        const unsigned* __restrict__ src_cnt, int nj,
+                                                                        long long cap, double* __restrict__ dst_vals,
+                                                                        unsigned* __restrict__ dst_cnt) {
+    const unsigned long long k = *P.seq + 1ull;
+    const int parity = (int)(k & 1ull);
+    unsigned long long* mine = reinterpret_cast<unsigned long long*>(data_ptr(P.box[P.rank], P.slot_bytes, parity));
+    double* mine_v = reinterpret_cast<double*>(mine + nj);
+    for (int j = blockIdx.x; j < nj; j += gridDim.x) {
+        long long c = src_cnt[j];
+        if (threadIdx.x == 0) mine[j] = (unsigned long long)c;     // the raw count: an overflowed row must stay visible
+        if (c > cap) c = cap;
+        for (long long i = threadIdx.x; i < c; i += blockDim.x) mine_v[(size_t)j * cap + i] = src_vals[(size_t)j * cap + i];
+    }
+    publish_and_wait(P, k, parity);
+    for (int pair = blockIdx.x; pair < P.world * nj; pair += gridDim.x) {
+        const int r = pair / nj, j = pair - r * nj;
+        const unsigned long long* peer = reinterpret_cast<const unsigned long long*>(data_ptr(P.box[r], P.slot_bytes, parity));
+        long long c = (long long)__ldcv(peer + j);
+        const double* pv = reinterpret_cast<const double*>(peer + nj) + (size_t)j * cap;
+        double* out = dst_vals + ((size_t)r * nj + j) * cap;
+        if (threadIdx.x == 0) dst_cnt[(size_t)r * nj + j] = (unsigned)c;
+        if (c > cap) c = cap;
+        for (long long i = threadIdx.x; i < c; i += blockDim.x) out[i] = __ldcv(pv + i);
+    }
+    finish(P, k);
+}
+
 }  // namespace
 
 extern "C" {
@@ -220,6 +252,19 @@ int abcdls_peer_allgather(abcdls_peer_t p, const void* src, size_t bytes, void* 
     if (bytes == 0) return ABCDLS_OK;
     k_peer_allgather<<<peer_grid(bytes), kPeerThreads, 0, (cudaStream_t)stream>>>(p->dev, (const long long*)src, bytes / 8,
                                                                                   (long long*)dst);
+    return cudaGetLastError() == cudaSuccess ? ABCDLS_OK : ABCDLS_E_CUDA;
+}
+
+// every rank's nj ragged rows (see k_peer_allgather_ragged); (nj + nj * cap) * 8 <= slot bytes
+int abcdls_peer_allgather_ragged(abcdls_peer_t p, const double* src_vals, const uint32_t* src_cnt, int nj, int64_t cap,
+                                 double* dst_vals, uint32_t* dst_cnt, void* stream) {
+    if (!p || !src_vals || !src_cnt || !dst_vals || !dst_cnt || nj < 1 || cap < 1 ||
+        ((size_t)nj + (size_t)nj * cap) * 8 > p->dev.slot_bytes)
+        return ABCDLS_E_INVALID;
+    unsigned g = (unsigned)(p->dev.world * nj);
+    if (g > (unsigned)kPeerMaxCtas) g = kPeerMaxCtas;
+    k_peer_allgather_ragged<<<g, kPeerThreads, 0, (cudaStream_t)stream>>>(p->dev, src_vals, src_cnt, nj, cap, dst_vals,
+                                                                         dst_cnt);
     return cudaGetLastError() == cudaSuccess ? ABCDLS_OK : ABCDLS_E_CUDA;
 }
 

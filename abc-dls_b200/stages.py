@@ -151,8 +151,8 @@ class CudaStages:
                                  C.byref(c1), st)
                 if world > 1:
                     if phase in (0, 2):
-                        gs = comm.allgather(self._view(ws, p0, c0, torch.float64, 8)).contiguous()
-                        gc = comm.allgather(self._view(ws, p1, c1, torch.int32, 4)).contiguous()
+                        gs, gc = comm.allgather_ragged(self._view(ws, p0, c0, torch.float64, 8),
+                                                       self._view(ws, p1, c1, torch.int32, 4))
                     elif phase == 1:
                         comm.allreduce_sum(self._view(ws, p0, c0, torch.int64, 8))
         with self._timed("fused_candidates"):
@@ -222,8 +222,8 @@ class CudaStages:
                              _p(med), _p(mad), _p(status), C.byref(p0), C.byref(c0), C.byref(p1), C.byref(c1),
                              self._stream())
             if phase in (0, 2):
-                gs = comm.allgather(self._view(ws, p0, c0, torch.float64, 8)).contiguous()
-                gc = comm.allgather(self._view(ws, p1, c1, torch.int32, 4)).contiguous()
+                gs, gc = comm.allgather_ragged(self._view(ws, p0, c0, torch.float64, 8),
+                                               self._view(ws, p1, c1, torch.int32, 4))
             elif phase == 1:
                 comm.allreduce_sum(self._view(ws, p0, c0, torch.int64, 8))
         self.launches += 15
@@ -403,8 +403,8 @@ class CudaStages:
                                  C.byref(c1), st)
                 if world > 1:
                     if phase in (0, 2):
-                        gs = comm.allgather(self._view(ws, p0, c0, torch.float64, 8)).contiguous()
-                        gc = comm.allgather(self._view(ws, p1, c1, torch.int32, 4)).contiguous()
+                        gs, gc = comm.allgather_ragged(self._view(ws, p0, c0, torch.float64, 8),
+                                                       self._view(ws, p1, c1, torch.int32, 4))
                     elif phase == 1:
                         comm.allreduce_sum(self._view(ws, p0, c0, torch.int64, 8))
         cnt = self.new(P, dtype=torch.int64)

@@ -440,6 +440,10 @@ size_t abcdls_peer_slot_bytes(abcdls_peer_t p);
 int abcdls_peer_allreduce(abcdls_peer_t p, void* data, size_t count, int dtype, int op, void* stream);
 /* dst[world * bytes] <- every rank's src[bytes] (multiple of 8, <= slot bytes), rank order */
 int abcdls_peer_allgather(abcdls_peer_t p, const void* src, size_t bytes, void* dst, void* stream);
+/* nj ragged rows per rank: src_vals[nj][cap] with src_cnt[j] existing entries in row j -> dst_vals[world][nj][cap],
+ * dst_cnt[world][nj]; only the existing entries cross NVLink.  (nj + nj * cap) * 8 <= slot bytes */
+int abcdls_peer_allgather_ragged(abcdls_peer_t p, const double* src_vals, const uint32_t* src_cnt, int nj, int64_t cap,
+                                 double* dst_vals, uint32_t* dst_cnt, void* stream);
 
 #ifdef __cplusplus
 }

@@ -88,7 +88,7 @@ def main():
             ok = ok and good
     # per-column mode as one pass over the sharded table (csrc/columns.cuh), incl. ties that straddle the rank boundary
     if a.big:
-        N, P = a.big * world + 13, 4
+        N, P = (a.big + 64) * world + 13, 4
         per = (N + world - 1) // world
         r0, r1 = min(rank * per, N), min((rank + 1) * per, N)
         for coarse in (False, True):
