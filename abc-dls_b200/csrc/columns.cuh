@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(256) k_cols_final(PeerDev PD, int world, const
 extern "C" {
 
 int abcdls_columns_supported(const double* ss, int64_t n, int P, int64_t ld) {
-    return ss && n >= (1 << 20) && n < (1ll << 31) && P >= 1 && P <= kMaxD && ld >= n;
+    return ss && n >= (1 << 18) && n < (1ll << 31) && P >= 1 && P <= kMaxD && ld >= n;
 }
 
 size_t abcdls_columns_workspace_bytes(abcdls_handle_t h, int64_t n, int P, int64_t nacc_local_hint) {

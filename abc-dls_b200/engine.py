@@ -273,7 +273,7 @@ class AbcEngine:
         return med, mad
 
     # ---- shared front half: scaling, distance, tolerance cut ----------------------------------
-    FAST_MIN_ROWS = 1 << 20   # below this the 6-pass radix select is launch-bound anyway
+    FAST_MIN_ROWS = 1 << 18   # rows per rank; below this the 6-pass radix select (launch bound, always exact) runs
     use_fused = True          # one-pass front half (csrc/fused.cuh) when the table qualifies
 
     def _plan(self, ss, tol, keep_dist=False, level=0, shard=None):
@@ -748,7 +748,7 @@ class AbcEngine:
         if shard is not None and self.comm.world > 1:
             n_global, row_offset = int(shard[0]), int(shard[1])
             per = -(-n_global // self.comm.world)
-            ok = ok and min(per, n_global - (self.comm.world - 1) * per) >= (1 << 20)
+            ok = ok and min(per, n_global - (self.comm.world - 1) * per) >= self.FAST_MIN_ROWS
         else:
             n_global, row_offset, ns, ok = self._shard_info(n_local, int(ok))
         if not ok:

@@ -41,7 +41,7 @@ def _check(engine, par, ss, tgt, tol, want=("min", "max", "mean", "median")):
 
 
 @pytest.mark.parametrize("n,P,tol,layout", [((1 << 20) + 4097, 5, 0.01, "col"), ((1 << 21) + 1, 3, 0.002, "row"),
-                                            ((1 << 20) + 64, 1, 0.05, "col")])
+                                            ((1 << 20) + 64, 1, 0.05, "col"), ((1 << 18) + 1, 4, 0.01, "row")])
 def test_columns_one_pass_matches_the_oracle(engine, n, P, tol, layout):
     par, ss, tgt = synth.abc_tables(n, P, P, engine.device)
     if layout == "row":
