@@ -28,6 +28,7 @@ class CudaStages:
         self._ws = {}
         self.launches = 0  # kernels enqueued through this object (bench.py reports it)
         self.timer = None  # optional: callable(name) -> context manager recording CUDA events (engine._t)
+        self._side = None  # second stream for work that only needs the pass (candidate-row compaction)
 
     def _timed(self, name):
         import contextlib
@@ -131,18 +132,20 @@ class CudaStages:
                              _p(ws), ws.numel(), _p(status), C.byref(p0), C.byref(c0), st)
         if world > 1:
             comm.allreduce_sum(self._view(ws, p0, c0, torch.int64, 8))
-        # the candidate rows need only the pass: compact them now; their parameters can then be gathered on a second
-        # stream (16 scattered 8-byte reads per row) while this stream refines medians / MADs and selects ds
-        self.handle.call("abcdls_fused_rows", _p(ss), n, d, ld, world, row_offset, cap, _p(cand_row), _p(n_cand), _p(ws),
-                         ws.numel(), _p(status), st)
-        if pregather is not None:
-            par, cand_par, side = pregather
-            main = torch.cuda.current_stream(self.device)
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                self.handle.call("abcdls_gather_rows", _p(par), par.stride(0), par.shape[0], _p(cand_row), _p(n_cand),
-                                 row_offset, cap, _p(cand_par), C.c_void_p(side.cuda_stream))
-            self.launches += 1
+        # the candidate rows need only the pass: compact them on a second stream (three small kernels) while this one
+        # refines medians / MADs; joined before the exact distances.  (NCCL fallback: segments cannot span a fork.)
+        fork = world == 1 or getattr(comm, "peer", None) is not None
+        main = torch.cuda.current_stream(self.device)
+        if fork:
+            if self._side is None:
+                self._side = torch.cuda.Stream(self.device)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                self.handle.call("abcdls_fused_rows", _p(ss), n, d, ld, world, row_offset, cap, _p(cand_row), _p(n_cand),
+                                 _p(ws), ws.numel(), _p(status), C.c_void_p(self._side.cuda_stream))
+        else:
+            self.handle.call("abcdls_fused_rows", _p(ss), n, d, ld, world, row_offset, cap, _p(cand_row), _p(n_cand),
+                             _p(ws), ws.numel(), _p(status), st)
         gs = gc = None
         with self._timed("fused_refine"):
             for phase in range(4):
@@ -155,6 +158,8 @@ class CudaStages:
                                                        self._view(ws, p1, c1, torch.int32, 4))
                     elif phase == 1:
                         comm.allreduce_sum(self._view(ws, p0, c0, torch.int64, 8))
+        if fork:
+            main.wait_stream(self._side)
         with self._timed("fused_candidates"):
             self.handle.call("abcdls_fused_exact", _p(ss), n, d, ld, world, _p(mad), _p(target), cap, _p(cand_dist),
                              _p(cand_ss), _p(cand_lrow), cand_ss.shape[0], _p(perm), _p(ws), ws.numel(), _p(status), st)

@@ -366,6 +366,29 @@ def cv_workload(args):
                                        "sample": f"numpy oracle cv4abc, same table, {P} columns x {cpu_nval} held-out rows"}}))
 
 
+def bind_to_gpu_numa(index: int):
+    """Run this process (and first-touch its pinned host buffers) on the CPUs NVML reports as local to GPU `index`: the
+    eight concurrent H2D copies of an 8-rank end-to-end step then read host memory of their own socket instead of
+    contending for one.  Host-side placement only; returns what was done for the JSON line."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        mask = nv.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        local = {i for i in range(ncpu) if (int(mask[i // 64]) >> (i % 64)) & 1}
+        allowed = os.sched_getaffinity(0)
+        use = sorted(local & allowed)
+        if use and len(use) < len(allowed):
+            os.sched_setaffinity(0, use)
+            return {"bound": True, "cpus": len(use), "of": len(allowed)}
+        return {"bound": False, "cpus": len(use), "of": len(allowed)}
+    except Exception as e:  # pragma: no cover
+        return {"bound": False, "error": type(e).__name__}
+
+
 class Ctx:
     """One process per GPU: rank / world from the launcher, the engine, barrier + device sync, max over ranks."""
 
@@ -377,6 +400,7 @@ class Ctx:
         self.rank = int(os.environ.get("RANK", "0"))
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.numa = bind_to_gpu_numa(self.local_rank) if self.world > 1 else {"bound": False}
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
         if self.world > 1:
@@ -623,7 +647,8 @@ def run_abc(ctx, args, N, with_e2e, with_cpu, flush_small=True):
                "breakdown_ms": dict(zip(("h2d_sumstat", "abc_incl_zero_copy_param_gather", "d2h_results"),
                                         [round(sum(p_[i] for p_ in parts) / len(parts), 3) for i in range(3)])),
                "api": "AbcEngine.abc(target, param, sumstat) on pinned HOST tables: sumstat H2D (PCIe line rate), param "
-                      "gathered zero-copy (accepted rows only) -> posterior sample + summary D2H into pinned buffers"}
+                      "gathered zero-copy (accepted rows only) -> posterior sample + summary D2H into pinned buffers",
+               "host_numa_binding": ctx.numa}
         if not args.no_e2e_f32:
             # The same call when the caller hands over float32 (what ABC-DLS does: Keras predictions, ABC.py:1849; the
             # synthetic values are float32-representable by construction): identical results, half the H2D.
