@@ -12,6 +12,10 @@
 //                           `small` result buffer.
 // The normal equations run on the fp64 tensor-core path (mma.sync m8n8k4: 256 FMAs per issued instruction - at 561
 // FMAs per accepted row the scalar version was issue bound); everything else is plain fp64.
+// Measured dead ends (B200, 1e6 accepted rows, d = P = 16; profiles/r02_notes.md): T1 stays at ~0.30 ms whether it
+// runs as 2 x 256-thread CTAs per SM, as 4 x 128, warp specialised with a double-buffered tile (8 loader + 4 / 8
+// accumulator warps), with DMMA or with register-blocked DFMA - it is bound by the 2e6 RANDOM 128-byte record reads
+// (one DRAM row activation each: the accepted rows are 1 % of the table, and the candidate block is in pass order).
 //
 // Reference semantics: CRAN abc 2.2.1 abc(method = "loclinear" | "rejection") as reached from
 // src/Classes/ABC.py:1950-1953 / 2806-2809; same arithmetic as loclinear.cu (design centred on
@@ -761,14 +765,14 @@ __global__ void __launch_bounds__(kTlThreads, 2) k_tail_adjust_final(TailArgs A,
     __syncthreads();
     const int E = kT3Stat * P;
     double* mypart = A.ws.part + (size_t)blockIdx.x * E;
-    if (tid < E) {
-        const int q = tid % kT3Stat;
-        double acc = segs[tid];
+    for (int e = tid; e < E; e += kTlThreads) {
+        const int q = e % kT3Stat;
+        double acc = segs[e];
         for (int s = 1; s < kTlWarps; ++s) {
-            const double v = segs[(size_t)s * E + tid];
+            const double v = segs[(size_t)s * E + e];
             acc = q == 0 ? fmin(acc, v) : (q == 1 ? fmax(acc, v) : acc + v);
         }
-        mypart[tid] = acc;
+        mypart[e] = acc;
     }
     __syncthreads();
     double* stats = sm;                                      // [P][7] (this rank)
