@@ -116,6 +116,11 @@ SIGNATURES = {
     "abcdls_columns_rowkeys": (_i32, [_vp, _i64, _i32, _i64, _vp, _vp, _vp, _sz, C.POINTER(_vp), _vp]),
     "abcdls_columns_accept": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp,
                                      _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
+    "abcdls_wselect_workspace_bytes": (_sz, [_i32]),
+    "abcdls_wselect": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _sz, _vp]),
+    "abcdls_col_moments": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _vp]),
+    "abcdls_density_workspace_bytes": (_sz, [_i32]),
+    "abcdls_density_mode": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "abcdls_small_supported": (_i32, [_i64, _i64]),
     "abcdls_small_columns": (_i32, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp,
                                     _vp]),

@@ -111,7 +111,7 @@ class AbcFit:
     def summary(self, intvl: float = 0.95, print_: bool = True) -> _summary.SummaryTable:
         vals, w = self._global_sample()
         weighted = self.res.adj_values is not None
-        tab = _summary.summary_table(vals, w, self.res.stats, weighted, intvl, self.names["parameter.names"])
+        tab = _summary.summary_table(vals, w, self.res.stats, weighted, intvl, self.names["parameter.names"], eng=self._eng)
         if print_:
             print(_summary.summary_text(tab, vals.shape[0], weighted))
         return tab

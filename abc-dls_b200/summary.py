@@ -84,8 +84,62 @@ def _density_mode(xs: torch.Tensor, ws, n_grid: int = 512, cut: float = 3.0) -> 
     return xout[torch.argmax(yout)]
 
 
-def summary_table(values: torch.Tensor, weights, stats: torch.Tensor, weighted: bool, intvl: float = 0.95, names=None):
-    """values (n, P) global posterior sample, weights (n,) or None, stats (P, 6) from k_col_stats."""
+def summary_table_device(eng, values: torch.Tensor, weights, stats: torch.Tensor, weighted: bool, intvl: float = 0.95,
+                         names=None):
+    """The same 7 x P table from this repo's kernels only (csrc/summary.cu, csrc/select.cu): no sort of the sample.
+    Percentiles: radix select (type-7 ranks for rejection, weight histograms for loclinear); Mode: bw.nrd0 from the
+    column moments and two selected quartiles, then binning + direct gaussian convolution + argmax on the device."""
+    k = eng.k
+    n, P = values.shape
+    vals = values.t()
+    if vals.stride(1) != 1:
+        vals = vals.contiguous()                                 # (P, n) column-major, as the engine produced it
+    a = (1 - intvl) / 2
+    f64 = torch.float64
+    out = torch.full((7, P), float("nan"), dtype=f64, device=values.device)
+    out[0], out[6] = stats[:, 0], stats[:, 1]
+
+    def q7(p):                                                   # R quantile type 7 from two selected order statistics
+        index = 1 + (n - 1) * p
+        eps4 = 4 * np.finfo(float).eps
+        lo, hi = int(np.floor(index + eps4)), int(np.ceil(index - eps4))
+        h = index - lo
+        r = eng._select(vals, n, None, lo - 1, hi - 1, local=True)
+        xl, xh = r[:, 0], (r[:, 1] if hi != lo else r[:, 0])
+        return xl if h == 0 else torch.where(xl == xh, xl, (1 - h) * xl + h * xh)
+
+    if weighted:
+        out[3] = stats[:, 3] / stats[:, 5]
+        w = weights.contiguous()
+        taus = torch.tensor([a, 0.5, 1 - a], dtype=f64, device=values.device)
+        q = k.wselect(vals, w, n, P, taus)
+        out[1], out[2], out[5] = q[:, 0], q[:, 1], q[:, 2]
+    else:
+        out[3] = stats[:, 2] / n
+        w = None
+        out[1], out[2], out[5] = q7(a), q7(0.5), q7(1 - a)
+    if n >= 2:
+        mv = k.col_moments(vals, n, P)
+        sd = torch.sqrt(mv[:, 1] / (n - 1))
+        iqr = q7(0.75) - q7(0.25)
+        lo_ = torch.minimum(sd, iqr / 1.34)
+        x0 = stats[:, 0]
+        lo_ = torch.where(lo_ == 0, torch.where(sd == 0, torch.where(x0 == 0, torch.ones_like(sd), x0.abs()), sd), lo_)
+        bw = 0.9 * lo_ * n ** (-0.2)                             # bw.nrd0 (of the UNWEIGHTED sample, like R)
+        frm, to = stats[:, 0] - 3.0 * bw, stats[:, 1] + 3.0 * bw
+        lo, up = frm - 4.0 * bw, to + 4.0 * bw
+        out[4] = k.density_mode(vals, w, n, P, lo.contiguous(), up.contiguous(), frm.contiguous(), to.contiguous(),
+                                bw.contiguous(), stats[:, 5].contiguous() if weighted else None)
+    return SummaryTable(out.cpu().numpy(), names)
+
+
+def summary_table(values: torch.Tensor, weights, stats: torch.Tensor, weighted: bool, intvl: float = 0.95, names=None,
+                  eng=None):
+    """values (n, P) global posterior sample, weights (n,) or None, stats (P, 6) from k_col_stats.  With an engine whose
+    stages are the CUDA library the table comes from this repo's kernels (summary_table_device); the framework-op
+    formulation below serves the CPU stage double of the tests."""
+    if eng is not None and values.is_cuda and hasattr(eng.k, "wselect"):
+        return summary_table_device(eng, values, weights, stats, weighted, intvl, names)
     a = (1 - intvl) / 2
     n, P = values.shape
     out = torch.full((7, P), float("nan"), dtype=torch.float64, device=values.device)

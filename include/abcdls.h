@@ -382,6 +382,23 @@ int abcdls_columns_accept(abcdls_handle_t h, abcdls_peer_t peer, int64_t n, int 
                           int64_t acc_cap, int32_t* acc_row, double* acc_val, double* acc_dist, int64_t* acc_cnt,
                           void* ws, size_t ws_bytes, double* small_out, int* status_dev, void* stream);
 
+/* ---- summary.abc rows that need more than a reduction (csrc/summary.cu; SURVEY 8f-2, printed by ABC.py:844-861) -------
+ * wselect: out[p * ntau + t] = weighted order statistic of column p at taus_dev[t] - the smallest x whose cumulated
+ *   weight (ascending x) reaches tau * sum(w): quantreg::rq(x ~ 1, tau, weights = w) of summary.abc.  MSB radix select
+ *   with fixed-point weight histograms: no sort, deterministic.  x column-major (ld), n rows, w >= 0.
+ * col_moments: out[2p] = mean, out[2p + 1] = sum (x - mean)^2 (bw.nrd0's sd).
+ * density_mode: the Mode row - argmax over R's density(x, bw, weights = w / wnorm, from, to, n = 512): linear binning,
+ *   gaussian convolution (direct, = R's FFT circular convolution), approx() onto [from, to].  lo / up = from - 4 bw /
+ *   to + 4 bw.  w may be NULL (equal weights). */
+size_t abcdls_wselect_workspace_bytes(int njobs);
+int abcdls_wselect(abcdls_handle_t h, const double* x, int64_t ld, const double* w, int64_t n, int P,
+                   const double* taus_dev, int ntau, double* out, void* ws, size_t ws_bytes, void* stream);
+int abcdls_col_moments(abcdls_handle_t h, const double* x, int64_t ld, int64_t n, int P, double* out, void* stream);
+size_t abcdls_density_workspace_bytes(int P);
+int abcdls_density_mode(abcdls_handle_t h, const double* x, int64_t ld, const double* w, int64_t n, int P,
+                        const double* lo, const double* up, const double* frm, const double* to, const double* bw,
+                        const double* wnorm, double* mode_out, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- small tables: one thread block per abc() problem with d = P = 1 (csrc/small.cu) -----------------------------
  * ABC-DLS's per-column mode (ABC.py:1949-1953, 2805-2809) and cv4abc's leave-one-out loop over it (ABC.py:1900-1902)
  * are B independent 1-D problems on test-set sized tables (10^4 rows): launch latency, not bandwidth.  Problem b:
