@@ -447,21 +447,21 @@ class CudaStages:
         ntau = taus.numel()
         ws = self.workspace("wselect", self.lib.abcdls_wselect_workspace_bytes(P * ntau))
         out = self.new(P, ntau)
-        self.handle.call("abcdls_wselect", _p(x), x.stride(0), _p(w), n, P, _p(taus), ntau, _p(out), _p(ws), ws.numel(),
+        self.handle.call("abcdls_wselect", _p(x), x.stride(0) if P > 1 else n, _p(w), n, P, _p(taus), ntau, _p(out), _p(ws), ws.numel(),
                          self._stream())
         self.launches += 13
         return out
 
     def col_moments(self, x, n, P) -> torch.Tensor:
         out = self.new(P, 2)
-        self.handle.call("abcdls_col_moments", _p(x), x.stride(0), n, P, _p(out), self._stream())
+        self.handle.call("abcdls_col_moments", _p(x), x.stride(0) if P > 1 else n, n, P, _p(out), self._stream())
         self.launches += 1
         return out
 
     def density_mode(self, x, w, n, P, lo, up, frm, to, bw, wnorm) -> torch.Tensor:
         ws = self.workspace("density", self.lib.abcdls_density_workspace_bytes(P))
         out = self.new(P)
-        self.handle.call("abcdls_density_mode", _p(x), x.stride(0), _p(w), n, P, _p(lo), _p(up), _p(frm), _p(to), _p(bw),
+        self.handle.call("abcdls_density_mode", _p(x), x.stride(0) if P > 1 else n, _p(w), n, P, _p(lo), _p(up), _p(frm), _p(to), _p(bw),
                          _p(wnorm), _p(out), _p(ws), ws.numel(), self._stream())
         self.launches += 2
         return out
