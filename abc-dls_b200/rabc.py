@@ -210,15 +210,36 @@ def postpr(target, index, sumstat, tol, method="rejection", subset=None, **extra
     return PostprFit(res)
 
 
-def _model_ids(index, eng: AbcEngine):
-    """R's factor(index): sorted levels + integer codes."""
+def _model_ids(index, eng: AbcEngine, models=None):
+    """R's factor(index): sorted levels + integer codes.  Several ranks: the level table is the union of every rank's
+    labels (one object all-gather), so the codes mean the same model everywhere and a level that is absent from one
+    shard still has its column in the counts.  ``models`` (explicit level list) skips the discovery."""
+    import torch.distributed as dist
+    multi = eng.comm.world > 1
     if torch.is_tensor(index) and index.dtype in (torch.int32, torch.int64):
-        return index, [str(m) for m in range(int(index.max().item()) + 1)]
-    if eng.comm.world > 1:
-        raise AbcError("postpr over several ranks needs integer model ids shared by all ranks")
+        if models is not None:
+            return index, [str(m) for m in models]
+        kmax = index.max().to(torch.int64).reshape(1).to(eng.device) if index.numel() else \
+            torch.zeros(1, dtype=torch.int64, device=eng.device)
+        if multi:
+            kmax = kmax.clone()
+            eng.comm.allreduce_max(kmax)
+        return index, [str(m) for m in range(int(kmax.item()) + 1)]
     labels = np.asarray(index.to_numpy() if hasattr(index, "to_numpy") else index).astype(str)
-    models, inv = np.unique(labels, return_inverse=True)   # sorted levels, like factor()
-    return torch.from_numpy(inv.astype(np.int32)), models.tolist()
+    if models is None:
+        local = np.unique(labels).tolist()
+        if multi:
+            parts = [None] * eng.comm.world
+            dist.all_gather_object(parts, local, group=eng.comm.group)
+            local = sorted(set().union(*parts))            # sorted by code point (R sorts in the locale's collation)
+        models = local
+    models = [str(m) for m in models]
+    lut = {m: i for i, m in enumerate(models)}
+    try:
+        codes = np.fromiter((lut[x] for x in labels), dtype=np.int32, count=labels.size)
+    except KeyError as e:
+        raise AbcError(f"'index' holds a label that is not among the models: {e}") from None
+    return torch.from_numpy(codes), models
 
 
 def cv4abc(param, sumstat, nval, tols, method, statistic: str = "median", hcorr: bool = True, transf: str = "none",

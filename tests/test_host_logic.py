@@ -183,6 +183,12 @@ def _worker_postpr_smc(rank, world, port, N, q):
     mn, mx = eng.oldrange(par[:, r0:r1].contiguous())
     lo, hi = mn + 0.2 * (mx - mn), mx - 0.1 * (mx - mn)
     keep = eng.box_filter(par[:, r0:r1].contiguous(), lo, hi)
+    # string model labels: the level table is the union over ranks (rank 0 never sees "SNDX", rank 1 never "BNDX")
+    from abc_dls_b200 import rabc
+    codes, levels = rabc._model_ids(np.array([["BNDX", "MNDX"], ["SNDX", "MNDX"]][rank] * 3), eng)
+    assert levels == ["BNDX", "MNDX", "SNDX"] and codes.tolist() == [[0, 1], [2, 1]][rank] * 3
+    _, klev = rabc._model_ids(torch.tensor([0, 1 + rank], dtype=torch.int32), eng)
+    assert klev == ["0", "1", "2"]                       # integer ids: the largest id over ALL ranks sizes the table
     q.put((rank, pp.counts.numpy(), pp.idx.numpy(), pp.ds, mn.numpy(), mx.numpy(), keep.numpy()))
     dist.barrier()
     dist.destroy_process_group()
