@@ -48,12 +48,14 @@ SIGNATURES = {
                                   _vp, _vp, _vp, _vp, _vp]),
     "abcdls_fused_supported": (_i32, [_vp, _i64, _i32, _i64]),
     "abcdls_fused_workspace_bytes": (_sz, [_i64, _i32]),
-    "abcdls_fused_sample_cols": (_i32, [_vp, _vp, _i64, _i32, _i64, _i32, _vp, _sz, C.POINTER(_vp), C.POINTER(_sz),
+    "abcdls_fused_sample_cols": (_i32, [_vp, _vp, _i64, _i32, _i64, _i32, _i32, _vp, _sz, C.POINTER(_vp), C.POINTER(_sz),
                                         _vp]),
-    "abcdls_fused_sample_dist": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _i64, _i64, _i32, _vp, _sz, C.POINTER(_vp),
+    "abcdls_fused_sample_fine": (_i32, [_vp, _vp, _i64, _i32, _i64, _i32, _i32, _vp, _sz, C.POINTER(_vp), C.POINTER(_sz),
+                                        _vp]),
+    "abcdls_fused_sample_dist": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _sz, C.POINTER(_vp),
                                         C.POINTER(_sz), _vp]),
     "abcdls_fused_emit_cap": (_i64, [_i64]),
-    "abcdls_fused_pass": (_i32, [_vp, _vp, _i64, _i32, _i64, _i32, _vp, _vp, _i64, _vp, _sz, _vp, C.POINTER(_vp),
+    "abcdls_fused_pass": (_i32, [_vp, _vp, _i64, _i32, _i64, _i32, _i32, _vp, _vp, _i64, _vp, _sz, _vp, C.POINTER(_vp),
                                  C.POINTER(_sz), _vp]),
     "abcdls_fused_refine": (_i32, [_vp, _vp, _i64, _i64, _i32, _i64, _i32, _i32, _vp, _vp, _vp, _sz, _vp, _vp, _vp,
                                    C.POINTER(_vp), C.POINTER(_sz), C.POINTER(_vp), C.POINTER(_sz), _vp]),

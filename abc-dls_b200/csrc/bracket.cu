@@ -196,8 +196,9 @@ struct ColBrk {
 
 // K1b: average the G local estimates (already summed over ranks when world > 1) -> brackets.  One warp per column:
 // lane l adds estimates l, l + 32, ... in order, then a fixed shuffle tree (deterministic).
+// mean_out (optional): the averaged {m_lo, m_hi, r_lo, r_hi} of every column, for the second-stage sample of fused.cuh.
 __global__ void __launch_bounds__(32) k_make_brackets(const double* __restrict__ est, int G, int d, double inv_world,
-                                                      ColBrk* __restrict__ brk) {
+                                                      ColBrk* __restrict__ brk, double* __restrict__ mean_out = nullptr) {
     const int j = blockIdx.x, lane = threadIdx.x;
     if (j >= d) return;
     double m[4] = {0, 0, 0, 0};
@@ -212,6 +213,8 @@ __global__ void __launch_bounds__(32) k_make_brackets(const double* __restrict__
     }
     if (lane != 0) return;
     // m = {m_lo, m_hi, r_lo, r_hi}
+    if (mean_out)
+        for (int q = 0; q < 4; ++q) mean_out[j * 4 + q] = m[q];
     ColBrk B;
     B.c = 0.5 * m[0] + 0.5 * m[1];
     const double hm = fmax(fmax(m[1] - B.c, B.c - m[0]), 0.0);

@@ -174,6 +174,226 @@ __global__ void k_make_fused_thr(const double* __restrict__ est, int G, double i
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Second-stage column sample: COUNTING instead of sorting.  The sorted first-stage sample (k_sample_cols, now only
+// 8 CTAs per column) locates every bracket to +-5.5 sigma_1; a much larger sample (one 128-byte line of 16
+// consecutive rows out of every 2^shift lines: stratified, one jittered line per stratum, so it streams like a
+// strided read) is then only CLASSIFIED against those windows - three 1024-bin histograms per column (the median
+// window, and |x - c| in the MAD window left / right of the centre c) plus the counts outside them.  From the
+// cumulative counts k_fine_brackets reads new brackets at +-5.5 sigma_2 (bin edges, conservative by one bin), which
+// are sqrt(S2 / S1) times narrower: the pass keeps / writes / the refinement re-reads that much less, and the
+// relative uncertainty eps of the MAD estimates (hence the number of emitted candidate rows) shrinks with it.
+// A wrong bracket can only cost a FASTPATH_MISS: the pass still counts exactly and proves completeness.
+constexpr int kFineNB = 1024;
+constexpr int kFineU32 = 3 * kFineNB + 4;   // per column: M window | left wing | right wing | {below, farL, farR, taken}
+static_assert(kFineU32 % 2 == 0, "two 32-bit counts travel as one int64 of the all-reduce");
+
+__global__ void __launch_bounds__(512) k_sample_fine(const double* __restrict__ ss, long long n, long long ld,
+                                                     const ColBrk* __restrict__ brk, long long L, int shift, int rs,
+                                                     unsigned seed, unsigned* __restrict__ out) {
+    __shared__ unsigned h[3 * kFineNB];
+    __shared__ unsigned cn[4];
+    const int j = blockIdx.y;
+    for (int t = threadIdx.x; t < 3 * kFineNB; t += blockDim.x) h[t] = 0u;
+    if (threadIdx.x < 4) cn[threadIdx.x] = 0u;
+    __syncthreads();
+    const ColBrk B = brk[j];
+    const double c = B.c;
+    // window coordinates as ONE fma each: bin = floor(coordinate); < 0 below the window, >= kFineNB above it.  The
+    // edges k_fine_brackets reasons about are these integer coordinates, so both kernels agree by construction.
+    const double sM = B.r0 > 0.0 ? (double)kFineNB / (2.0 * B.r0) : 0.0, oM = B.r0 * sM;
+    const double sW = B.r2 > B.r1 ? (double)kFineNB / (B.r2 - B.r1) : 0.0, oW = -B.r1 * sW;
+    const double* __restrict__ col = ss + (size_t)j * ld + 2 * (threadIdx.x & 7);   // 8 lanes x 16 bytes = one line
+    const int hw = threadIdx.x >> 3;
+    const long long nhw = (long long)gridDim.x * (blockDim.x >> 3);   // quarter-warps working on this column
+    // a stratum is 2^(shift + rs) lines, of which a run of 2^rs consecutive ones (run-aligned, jittered) is read: the
+    // same sample size as one line in 2^shift, in 2^rs times fewer DRAM pages
+    const unsigned run = 1u << rs, jmask = ((1u << (shift + rs)) - 1u) & ~(run - 1u);
+    const unsigned salt = hash3(seed, (unsigned)j, 0x51u);
+    const unsigned hM = smem_u32(h), hL = hM + kFineNB * 4;
+    unsigned below = 0, far = 0, farneg = 0, taken = 0;
+    for (long long q = (long long)blockIdx.x * (blockDim.x >> 3) + hw; 4 * q < L; q += nhw) {   // L is a multiple of 4
+        double x[8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long s = 4 * q + u, stratum = s >> rs;
+            unsigned hsh = ((unsigned)stratum ^ salt) * 0x9E3779B1u;      // jitter only: a multiplicative hash will do
+            hsh ^= hsh >> 15;
+            hsh *= 0x85EBCA77u;
+            const long long line = (stratum << (shift + rs)) + (long long)(((hsh >> 12) & jmask) + ((unsigned)s & (run - 1u)));
+            const double2 v = ld_stream2(col + line * 16);
+            x[2 * u] = v.x;
+            x[2 * u + 1] = v.y;
+        }
+        taken += 8;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const double sg = __dsub_rn(x[u], c);
+            const int bm = __double2int_rd(fma(sg, sM, oM));
+            const int bw = __double2int_rd(fma(fabs(sg), sW, oW));
+            const unsigned neg = (unsigned)__double2hiint(sg) >> 31;
+            below += (unsigned)bm >> 31;
+            const unsigned isfar = bw >= kFineNB ? 1u : 0u;
+            far += isfar;
+            farneg += isfar & neg;
+            const unsigned inM = (unsigned)bm < (unsigned)kFineNB ? 1u : 0u, inW = (unsigned)bw < (unsigned)kFineNB ? 1u : 0u;
+            asm volatile(
+                "{\n\t"
+                ".reg .pred pm, pw;\n\t"
+                "setp.ne.u32 pm, %0, 0;\n\t"
+                "setp.ne.u32 pw, %1, 0;\n\t"
+                "@pm red.shared.add.u32 [%2], 1;\n\t"
+                "@pw red.shared.add.u32 [%3], 1;\n\t"
+                "}" ::"r"(inM),
+                "r"(inW), "r"(hM + (unsigned)bm * 4u), "r"(hL + ((neg ^ 1u) * kFineNB + (unsigned)bw) * 4u)
+                : "memory");
+        }
+    }
+    below = warp_sum(below);
+    far = warp_sum(far);
+    farneg = warp_sum(farneg);
+    taken = warp_sum(taken);
+    if ((threadIdx.x & 31) == 0) {
+        if (below) atomicAdd(&cn[0], below);
+        if (farneg) atomicAdd(&cn[1], farneg);
+        if (far - farneg) atomicAdd(&cn[2], far - farneg);
+        if (taken) atomicAdd(&cn[3], taken);
+    }
+    __syncthreads();
+    unsigned* __restrict__ o = out + (size_t)j * kFineU32;
+    for (int t = threadIdx.x; t < 3 * kFineNB; t += blockDim.x)
+        if (h[t]) atomicAdd(&o[t], h[t]);
+    if (threadIdx.x < 4 && cn[threadIdx.x]) atomicAdd(&o[3 * kFineNB + threadIdx.x], cn[threadIdx.x]);
+}
+
+// One CTA per column: cumulative counts of the three histograms (summed over ranks) -> refined estimates
+// est[j] = {m_lo, m_hi, r_lo, r_hi} in the layout k_make_brackets / k_make_fused_scale average (with G = 1); est comes
+// in holding the first-stage means and keeps them for a column whose refinement is not usable (degenerate window,
+// a crossing outside the window).  r_lo / r_hi bracket the median of |x - c2| around the NEW centre c2 = (m_lo + m_hi)/2:
+// #(|x - c2| <= r) = S - #(x - c > r + D) - #(c - x > r - D), D = c2 - c, each term bounded from the wing histograms.
+__global__ void __launch_bounds__(256) k_fine_brackets(const unsigned* __restrict__ fine,
+                                                       const ColBrk* __restrict__ brk, double z,
+                                                       double* __restrict__ est) {
+    __shared__ long long cum[kFineNB + 1];     // cum[k]  = # M-window samples in bins < k
+    __shared__ long long suf[2][kFineNB + 1];  // suf[k]  = # samples of that side with radius >= edge k (incl. far)
+    __shared__ long long part[3][8];
+    __shared__ int kres[4];
+    const int j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned* __restrict__ f = fine + (size_t)j * kFineU32;
+    const long long below = f[3 * kFineNB + 0], farL = f[3 * kFineNB + 1], farR = f[3 * kFineNB + 2];
+    const long long S = f[3 * kFineNB + 3];
+    // block scans: thread t owns bins 4t .. 4t+3 of each histogram
+    long long loc[3][4], tot[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        tot[a] = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            loc[a][q] = f[a * kFineNB + 4 * tid + q];
+            tot[a] += loc[a][q];
+        }
+    }
+    long long incl[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        incl[a] = tot[a];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long t = __shfl_up_sync(0xffffffffu, incl[a], o);
+            if (lane >= o) incl[a] += t;
+        }
+        if (lane == 31) part[a][wid] = incl[a];
+    }
+    if (tid < 4) kres[tid] = -1;
+    __syncthreads();
+    long long allw[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        long long before = 0, all = 0;
+        for (int w = 0; w < 8; ++w) {
+            if (w < wid) before += part[a][w];
+            all += part[a][w];
+        }
+        incl[a] += before;
+        allw[a] = all;
+    }
+    {
+        long long e = incl[0] - tot[0];                    // exclusive prefix of the M window
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { cum[4 * tid + q] = e; e += loc[0][q]; }
+        if (tid == 255) cum[kFineNB] = e;
+#pragma unroll
+        for (int a = 1; a < 3; ++a) {
+            long long g = allw[a] - (incl[a] - tot[a]) + (a == 1 ? farL : farR);   // radius >= edge 4 tid
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { suf[a - 1][4 * tid + q] = g; g -= loc[a][q]; }
+            if (tid == 255) suf[a - 1][kFineNB] = g;       // = far
+        }
+    }
+    __syncthreads();
+    const ColBrk B = brk[j];
+    const bool usable = S >= 65536 && B.r0 > 0.0 && B.r2 > B.r1;
+    const double dS = (double)S;
+    const double delta = z * 0.5 / sqrt(fmax(dS, 1.0));
+    const double tlo = (0.5 - delta) * dS, thi = (0.5 + delta) * dS;
+    // median: A(k) = # samples below edge k of the M window
+    int klo = -1, khi = 1 << 30;
+    for (int k = tid; k <= kFineNB; k += 256) {
+        const double A = (double)(below + cum[k]);
+        if (A <= tlo) klo = max(klo, k);
+        if (A >= thi) khi = min(khi, k);
+    }
+    klo = __reduce_max_sync(0xffffffffu, klo);
+    khi = __reduce_min_sync(0xffffffffu, khi);
+    if (lane == 0) {
+        atomicMax(&kres[0], klo);
+        atomicMax(&kres[1], (1 << 30) - khi);
+    }
+    __syncthreads();
+    klo = kres[0];
+    khi = (1 << 30) - kres[1];
+    const bool med_ok = usable && klo >= 0 && khi <= kFineNB && khi > klo;
+    const double wM = 2.0 * B.r0 / kFineNB, wW = (B.r2 - B.r1) / kFineNB;
+    const double m_lo = (B.c - B.r0) + klo * wM, m_hi = (B.c - B.r0) + khi * wM;
+    const double c2 = 0.5 * m_lo + 0.5 * m_hi;
+    const double t = med_ok ? (c2 - B.c) / wW : 0.0;       // centre shift in wing bins
+    int rlo = -1, rhi = 1 << 30;
+    for (int k = tid; k <= kFineNB; k += 256) {
+        // right side: x - c > r_k + D  <=>  wing coordinate > k + t;  left side: c - x > r_k - D  <=>  > k - t
+        long long lb = 0, ub = 0;
+        bool ub_ok = true;
+#pragma unroll
+        for (int sd = 0; sd < 2; ++sd) {
+            const double pos = sd ? (double)k + t : (double)k - t;      // sd 0: left wing, 1: right wing
+            int el = (int)ceil(pos) + 1, eu = (int)floor(pos) - 1;
+            el = el < 0 ? 0 : (el > kFineNB ? kFineNB : el);
+            lb += suf[sd][el];
+            if (eu < 0) ub_ok = false;
+            eu = eu < 0 ? 0 : (eu > kFineNB ? kFineNB : eu);
+            ub += suf[sd][eu];
+        }
+        const double in_up = (double)(S - lb);                         // upper bound of #(|x - c2| <= r_k)
+        const double in_dn = ub_ok ? (double)(S - ub) : -1.0;          // lower bound
+        if (in_up <= tlo) rlo = max(rlo, k);
+        if (in_dn >= thi) rhi = min(rhi, k);
+    }
+    rlo = __reduce_max_sync(0xffffffffu, rlo);
+    rhi = __reduce_min_sync(0xffffffffu, rhi);
+    if (lane == 0) {
+        atomicMax(&kres[2], rlo);
+        atomicMax(&kres[3], (1 << 30) - rhi);
+    }
+    __syncthreads();
+    rlo = kres[2];
+    rhi = (1 << 30) - kres[3];
+    if (tid == 0 && med_ok && rlo >= 0 && rhi <= kFineNB && rhi > rlo) {
+        est[j * 4 + 0] = m_lo;
+        est[j * 4 + 1] = m_hi;
+        est[j * 4 + 2] = B.r1 + rlo * wW;
+        est[j * 4 + 3] = B.r1 + rhi * wW;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kFThreads, 1)
 k_fused_pass(const __grid_constant__ CUtensorMap tmap, long long n, long long ntiles, int d, int nstages,
              const ColBrk* __restrict__ brk, const FusedPar* __restrict__ par, unsigned long long* __restrict__ counts,
@@ -696,6 +916,8 @@ struct FusedWs {
     size_t ds_zero_bytes;
     RefJob* ds_job;
     double* ds_small;              // [kSmallCap + 1]
+    unsigned* fine;                // [d * kFineU32] second-stage sample counts (all-reduced as d * kFineU32 / 2 int64)
+    double* est_fine;              // [d * 4] first-stage means, overwritten by the refined estimates
     size_t total_bytes;
 };
 
@@ -707,6 +929,29 @@ inline int fused_chunk(long long expect) {
     long long c = expect / (160 * 16);
     c = c < 128 ? 128 : (c > 2048 ? 2048 : c);
     return (int)((c + 31) / 32 * 32);
+}
+
+// Second-stage sample: one 128-byte line out of every 2^fine lines of a column (fine = 0: off).  The first stage then
+// only has to locate the windows: 8 CTAs per column instead of up to 64.
+constexpr int kFineG1 = 8;
+inline bool fine_valid(int fine) { return fine == 0 || (fine >= 1 && fine <= 12); }
+inline long long fine_lines(long long n, int fine) { return fine ? ((n >> 4) >> fine) : 0; }
+// consecutive 128-byte lines read per stratum (log2); ABCDLS_FINE_RUN overrides for experiments
+inline int fine_run_shift() {
+    static int rs = -1;
+    if (rs < 0) {
+        const char* e = getenv("ABCDLS_FINE_RUN");
+        int v = e ? atoi(e) : 2;
+        rs = v < 0 ? 0 : (v > 4 ? 4 : v);
+    }
+    return rs;
+}
+// how much narrower than the 64-CTA first-stage brackets the refined ones are (for the chunk reservations of the pass)
+inline double fine_ratio(long long n, int fine, int world) {
+    if (!fine) return 1.0;
+    const double s2 = (double)fine_lines(n, fine) * 16.0 * world;
+    const double r = (kZ * 0.5 / sqrt(s2 > 1.0 ? s2 : 1.0)) * 1.15 / col_delta(n, 1);
+    return r > 1.0 ? 1.0 : r;
 }
 
 inline FusedWs carve_fused(void* ws, int64_t n, int d) {
@@ -737,6 +982,8 @@ inline FusedWs carve_fused(void* ws, int64_t n, int d) {
     w.ds_zero_bytes = o - z0;
     w.ds_job = (RefJob*)take(sizeof(RefJob));
     w.ds_small = (double*)take((size_t)(kSmallCap + 1) * 8);
+    w.fine = (unsigned*)take((size_t)d * kFineU32 * 4);
+    w.est_fine = (double*)take((size_t)d * 4 * 8);
     w.total_bytes = o;
     return w;
 }
@@ -755,6 +1002,12 @@ int abcdls_fused_supported(const double* ss, int64_t n, int d, int64_t ld) {
     return encode_tiled_fn() ? 1 : 0;
 }
 
+inline int fused_G(long long n, int world, int fine) {
+    const int g = sample_ctas_w(n, world);
+    return (fine && g > kFineG1) ? kFineG1 : g;
+}
+
+#define FINE_ARG 0   /* entry points that take `fine` redefine it around their prologue */
 #define FUSED_PROLOGUE(name)                                                                                        \
     ABCDLS_CHECK_ARG(h, h && ss && ws && abcdls_fused_supported(ss, n, d, ld) && world >= 1 && world <= 64, name);   \
     FusedWs w = carve_fused(ws, n, d);                                                                              \
@@ -763,16 +1016,21 @@ int abcdls_fused_supported(const double* ss, int64_t n, int d, int64_t ld) {
         return ABCDLS_E_WORKSPACE;                                                                                  \
     }                                                                                                               \
     cudaStream_t st = (cudaStream_t)stream;                                                                         \
-    const int G = sample_ctas_w(n, world);  /* CTAs per column of the sampling kernels */                           \
+    const int G = fused_G(n, world, FINE_ARG);  /* CTAs per column of the first-stage sampling kernel */            \
     const int G2 = (world > 1 && kFG2 / world < 8) ? 8 : kFG2 / (world > 1 ? world : 1);                            \
     (void)G;                                                                                                        \
     (void)G2
 
 // Stage 1: column samples.  est_out: doubles a multi-rank caller all-reduces (sum) before stage 2.
-int abcdls_fused_sample_cols(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, void* ws,
-                             size_t ws_bytes, double** est_out, size_t* est_count, void* stream) {
+#undef FINE_ARG
+#define FINE_ARG fine
+int abcdls_fused_sample_cols(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, int fine,
+                             void* ws, size_t ws_bytes, double** est_out, size_t* est_count, void* stream) {
     FUSED_PROLOGUE("fused_sample_cols");
-    const double delta = col_delta(n, world);
+    ABCDLS_CHECK_ARG(h, fine_valid(fine), "fused_sample_cols: fine");
+    double delta = kZ * 0.5 / sqrt((double)G * kSample * world);
+    if (delta < 2.0 / kSample) delta = 2.0 / kSample;
+    if (fine) ABCDLS_CUDA(h, cudaMemsetAsync(w.fine, 0, (size_t)d * kFineU32 * 4, st));
     const size_t smem = (size_t)2 * kSample * sizeof(double);
     ABCDLS_ONCE(h, cudaFuncSetAttribute(k_sample_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ABCDLS_CUDA(h, cudaMemsetAsync(w.m.cnt, 0, w.m.zero_bytes, st));
@@ -786,15 +1044,45 @@ int abcdls_fused_sample_cols(abcdls_handle_t h, const double* ss, int64_t n, int
     return ABCDLS_OK;
 }
 
+// Stage 1b (fine > 0 only): first-stage windows from the (reduced) column samples, then the second-stage COUNTING
+// sample (one 128-byte line out of every 2^fine of each column).  cnt_out: int64 words to all-reduce (sum) before
+// stage 2 (pairs of 32-bit counts: the sums stay below 2^32).
+int abcdls_fused_sample_fine(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, int fine,
+                             void* ws, size_t ws_bytes, int64_t** cnt_out, size_t* cnt_count, void* stream) {
+    FUSED_PROLOGUE("fused_sample_fine");
+    ABCDLS_CHECK_ARG(h, fine >= 1 && fine_valid(fine), "fused_sample_fine: fine");
+    k_make_brackets<<<d, 32, 0, st>>>(w.m.est, G, d, 1.0 / world, w.m.brk, w.est_fine);
+    const int rs = fine_run_shift();
+    const int rq = rs > 2 ? rs : 2;
+    const long long L = fine_lines(n, fine) >> rq << rq;    // whole runs, and four lines per half-warp step
+    if (L > 0) {
+        long long gx = (L + 64 * 4 - 1) / (64 * 4);
+        long long mx = (long long)h->sm_count * 2 / d;   // 63 registers x 512 threads: two CTAs per SM, one wave
+        if (mx < 1) mx = 1;
+        if (gx > mx) gx = mx;
+        k_sample_fine<<<dim3((unsigned)gx, d), 512, 0, st>>>(ss, n, ld, w.m.brk, L, fine, rs, 0xF17Eu, w.fine);
+    }
+    ABCDLS_LAUNCH_CHECK(h);
+    if (cnt_out) *cnt_out = reinterpret_cast<int64_t*>(w.fine);
+    if (cnt_count) *cnt_count = (size_t)d * kFineU32 / 2;
+    return ABCDLS_OK;
+}
+
 // Stage 2: brackets + scale estimates from the (reduced) column samples, then the row sample of approximate
 // distances.  est_out: doubles to all-reduce (sum) before stage 3.
 int abcdls_fused_sample_dist(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, const double* target,
-                             int64_t nacc, int64_t n_global, int world, void* ws, size_t ws_bytes, double** est_out,
-                             size_t* est_count, void* stream) {
+                             int64_t nacc, int64_t n_global, int world, int fine, void* ws, size_t ws_bytes,
+                             double** est_out, size_t* est_count, void* stream) {
     FUSED_PROLOGUE("fused_sample_dist");
-    ABCDLS_CHECK_ARG(h, target && nacc >= 1 && n_global >= nacc, "fused_sample_dist: nacc");
-    k_make_brackets<<<d, 32, 0, st>>>(w.m.est, G, d, 1.0 / world, w.m.brk);
-    k_make_fused_scale<<<1, 32, 0, st>>>(w.m.est, G, d, 1.0 / world, target, w.par);
+    ABCDLS_CHECK_ARG(h, target && nacc >= 1 && n_global >= nacc && fine_valid(fine), "fused_sample_dist: nacc");
+    if (fine) {
+        k_fine_brackets<<<d, 256, 0, st>>>(w.fine, w.m.brk, kZ, w.est_fine);
+        k_make_brackets<<<d, 32, 0, st>>>(w.est_fine, 1, d, 1.0, w.m.brk);
+        k_make_fused_scale<<<1, 32, 0, st>>>(w.est_fine, 1, d, 1.0, target, w.par);
+    } else {
+        k_make_brackets<<<d, 32, 0, st>>>(w.m.est, G, d, 1.0 / world, w.m.brk);
+        k_make_fused_scale<<<1, 32, 0, st>>>(w.m.est, G, d, 1.0 / world, target, w.par);
+    }
     const double p = (double)nacc / (double)n_global;
     const double delta = kZ * sqrt(p * (1.0 - p) / ((double)G2 * kSampleQ * world));
     k_sample_qdist<<<G2, 512, (size_t)kSampleQ * sizeof(double), st>>>(ss, n, d, ld, w.par, 0xD157u, p, delta, w.est2);
@@ -807,11 +1095,13 @@ int abcdls_fused_sample_dist(abcdls_handle_t h, const double* ss, int64_t n, int
 // Stage 3: THE table pass.  counts_out: int64 block (counts | band counts | median histogram) to all-reduce (sum).
 int64_t abcdls_fused_emit_cap(int64_t cap) { return cap + (int64_t)160 * kFWarps * kFEChunk; }
 
-int abcdls_fused_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, double* cand_ss,
-                      int32_t* cand_lrow, int64_t ecap, void* ws, size_t ws_bytes, int* status_dev, int64_t** counts_out,
-                      size_t* counts_count, void* stream) {
+int abcdls_fused_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, int fine,
+                      double* cand_ss, int32_t* cand_lrow, int64_t ecap, void* ws, size_t ws_bytes, int* status_dev,
+                      int64_t** counts_out, size_t* counts_count, void* stream) {
     FUSED_PROLOGUE("fused_pass");
-    ABCDLS_CHECK_ARG(h, status_dev && cand_ss && cand_lrow && ecap >= 1 && ecap < (1ll << 31), "fused_pass: args");
+    ABCDLS_CHECK_ARG(h, status_dev && cand_ss && cand_lrow && ecap >= 1 && ecap < (1ll << 31) && fine_valid(fine),
+                     "fused_pass: args");
+    const double narrow = fine_ratio(n, fine, world);   // the refined brackets keep that much less per list
     ABCDLS_CUDA(h, cudaMemsetAsync(cand_lrow, 0xff, (size_t)ecap * 4, st));   // -1 = unused slot
     k_make_fused_thr<<<1, 32, 0, st>>>(w.est2, G2, 1.0 / world, d, w.par);
     const int nstages = fused_stages(d);
@@ -843,8 +1133,9 @@ int abcdls_fused_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int
     }
     k_fused_pass<<<(unsigned)grid, kFThreads, smem, st>>>(tmap, n, ntiles, d, nstages, w.m.brk, w.par, w.m.counts,
                                                          w.m.candM, w.capM, w.m.candU, w.capU, w.m.cnt, w.mask16, cand_ss,
-                                                         ecap, cand_lrow, w.ealloc, tpc, fused_chunk(cap_for(n, 0.03)),
-                                                         fused_chunk(cap_for(n, 0.08)), status_dev);
+                                                         ecap, cand_lrow, w.ealloc, tpc,
+                                                         fused_chunk((long long)(cap_for(n, 0.03) * narrow)),
+                                                         fused_chunk((long long)(cap_for(n, 0.08) * narrow)), status_dev);
     ABCDLS_LAUNCH_CHECK(h);
     {
         long long gx = (w.capM + 256 * 8 - 1) / (256 * 8);
@@ -860,6 +1151,8 @@ int abcdls_fused_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int
     return ABCDLS_OK;
 }
 
+#undef FINE_ARG
+#define FINE_ARG 0
 // Stage 4: median / MAD refinement, phases 0..3 with the same exchanges as abcdls_mad_fast_refine.
 int abcdls_fused_refine(abcdls_handle_t h, const double* ss, int64_t n, int64_t n_global, int d, int64_t ld, int phase,
                         int world, const double* gath_small, const int32_t* gath_cnt, void* ws, size_t ws_bytes,

@@ -275,6 +275,8 @@ class AbcEngine:
     # ---- shared front half: scaling, distance, tolerance cut ----------------------------------
     FAST_MIN_ROWS = 1 << 18   # rows per rank; below this the 6-pass radix select (launch bound, always exact) runs
     use_fused = True          # one-pass front half (csrc/fused.cuh) when the table qualifies
+    FINE_SHIFT = int(os.environ.get("ABCDLS_FINE", "5"))               # second-stage sample: 1 line in 2^5 (0 = off)
+    FINE_MIN_ROWS = int(os.environ.get("ABCDLS_FINE_MIN", str(1 << 23)))
 
     def _plan(self, ss, tol, keep_dist=False, level=0, shard=None):
         """Host-side decisions for one call (the only place that may need a host collective: shard sizes).
@@ -301,7 +303,9 @@ class AbcEngine:
             raise AbcError("'tol' must give 1 <= ceiling(N * tol) <= N")
         fast = level < 2 and min(ns) >= self.FAST_MIN_ROWS   # every rank must take the same path
         fused = fast and all_fuse
-        return dict(n_global=n_global, row_offset=row_offset, nacc=nacc, fast=fast, fused=fused, keep_dist=keep_dist,
+        # second-stage counting sample of the one-pass path (csrc/fused.cuh): from FINE_MIN_ROWS rows on EVERY rank
+        fine = self.FINE_SHIFT if (fused and min(ns) >= self.FINE_MIN_ROWS) else 0
+        return dict(n_global=n_global, row_offset=row_offset, nacc=nacc, fast=fast, fused=fused, keep_dist=keep_dist, fine=fine,
                     path="fused" if fused else ("two_pass" if fast else "exact"))
 
     def _front(self, target, ss, status, pl, par=None):
@@ -345,7 +349,8 @@ class AbcEngine:
                 pre = (par, cand_par, self._side)
             with self._t("fused_front"):
                 k.fused_front(ss, n_local, n_global, d, ss.stride(0), target, nacc, row_offset, ccap, med, mad, cand_row,
-                              cand_dist, cand_ss, cand_lrow, perm, n_cand, status, comm, pregather=pre)
+                              cand_dist, cand_ss, cand_lrow, perm, n_cand, status, comm, pregather=pre,
+                              fine=pl.get("fine", 0))
             with self._t("fused_ds"):
                 ds = k.new(1)
                 k.fused_ds(n_local, d, nacc, ccap, cand_dist, n_cand, ds, status, comm)

@@ -111,7 +111,7 @@ class CudaStages:
         return int(self.lib.abcdls_fused_emit_cap(cap))
 
     def fused_front(self, ss, n, n_global, d, ld, target, nacc, row_offset, cap, med, mad, cand_row, cand_dist, cand_ss,
-                    cand_lrow, perm, n_cand, status, comm=None, pregather=None):
+                    cand_lrow, perm, n_cand, status, comm=None, pregather=None, fine=0):
         """Medians + MADs AND the candidate rows of the tolerance cut from ONE read of the table.  Leaves the exact
         distance of every candidate in cand_dist (row order); the caller selects ds among them (all ranks) and then
         calls fused_check."""
@@ -119,16 +119,24 @@ class CudaStages:
         ws = self.workspace("fused", self.lib.abcdls_fused_workspace_bytes(n, d))
         p0, c0, p1, c1 = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t()
         st = self._stream()
-        self.handle.call("abcdls_fused_sample_cols", _p(ss), n, d, ld, world, _p(ws), ws.numel(), C.byref(p0),
+        self.handle.call("abcdls_fused_sample_cols", _p(ss), n, d, ld, world, fine, _p(ws), ws.numel(), C.byref(p0),
                          C.byref(c0), st)
         if world > 1:
             comm.allreduce_sum(self._view(ws, p0, c0, torch.float64, 8))
-        self.handle.call("abcdls_fused_sample_dist", _p(ss), n, d, ld, _p(target), nacc, n_global, world, _p(ws),
+        if fine:
+            # second-stage counting sample against the first-stage windows (narrower brackets for the pass)
+            with self._timed("k_sample_fine"):
+                self.handle.call("abcdls_fused_sample_fine", _p(ss), n, d, ld, world, fine, _p(ws), ws.numel(),
+                                 C.byref(p0), C.byref(c0), st)
+            if world > 1:
+                comm.allreduce_sum(self._view(ws, p0, c0, torch.int64, 8))
+            self.launches += 3
+        self.handle.call("abcdls_fused_sample_dist", _p(ss), n, d, ld, _p(target), nacc, n_global, world, fine, _p(ws),
                          ws.numel(), C.byref(p0), C.byref(c0), st)
         if world > 1:
             comm.allreduce_sum(self._view(ws, p0, c0, torch.float64, 8))
         with self._timed("k_fused_pass"):
-            self.handle.call("abcdls_fused_pass", _p(ss), n, d, ld, world, _p(cand_ss), _p(cand_lrow), cand_ss.shape[0],
+            self.handle.call("abcdls_fused_pass", _p(ss), n, d, ld, world, fine, _p(cand_ss), _p(cand_lrow), cand_ss.shape[0],
                              _p(ws), ws.numel(), _p(status), C.byref(p0), C.byref(c0), st)
         if world > 1:
             comm.allreduce_sum(self._view(ws, p0, c0, torch.int64, 8))

@@ -179,18 +179,26 @@ int abcdls_dist_fast_refine(abcdls_handle_t h, int64_t n, int64_t nacc, int64_t 
  * Requirements (abcdls_fused_supported): d <= 16, n >= 16384, ld even, 16-byte aligned table. */
 int abcdls_fused_supported(const double* ss, int64_t n, int d, int64_t ld);
 size_t abcdls_fused_workspace_bytes(int64_t n, int d);
-int abcdls_fused_sample_cols(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, void* ws,
-                             size_t ws_bytes, double** est_out, size_t* est_count, void* stream);
+/* `fine` (the same value in sample_cols / sample_fine / sample_dist / pass of one call, and on every rank): 0 = the
+ * sorted first-stage column sample alone brackets median / MAD; s in 1..12 = a second, COUNTING sample of one 128-byte
+ * line (16 consecutive rows) out of every 2^s lines of each column refines those brackets (histograms against the
+ * first-stage windows; narrower by sqrt(S2 / S1): the pass keeps, and the refinement re-reads, that much less):
+ *   sample_cols -> [all-reduce est] -> sample_fine -> [all-reduce cnt (int64)] -> sample_dist -> ...
+ * Worth it from ~8e6 rows per rank (the engine uses s = 5 there). */
+int abcdls_fused_sample_cols(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, int fine,
+                             void* ws, size_t ws_bytes, double** est_out, size_t* est_count, void* stream);
+int abcdls_fused_sample_fine(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, int fine,
+                             void* ws, size_t ws_bytes, int64_t** cnt_out, size_t* cnt_count, void* stream);
 int abcdls_fused_sample_dist(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, const double* target,
-                             int64_t nacc, int64_t n_global, int world, void* ws, size_t ws_bytes, double** est_out,
-                             size_t* est_count, void* stream);
+                             int64_t nacc, int64_t n_global, int world, int fine, void* ws, size_t ws_bytes,
+                             double** est_out, size_t* est_count, void* stream);
 /* the pass also EMITS every marked row (its d statistics + local row number) into the caller's block
  * cand_ss[ecap][16] (row-major) / cand_lrow[ecap] (unordered, 64-slot chunks per warp, -1 = unused slot);
  * ecap = abcdls_fused_emit_cap(cap of the candidate list) */
 int64_t abcdls_fused_emit_cap(int64_t cap);
-int abcdls_fused_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, double* cand_ss,
-                      int32_t* cand_lrow, int64_t ecap, void* ws, size_t ws_bytes, int* status_dev, int64_t** counts_out,
-                      size_t* counts_count, void* stream);
+int abcdls_fused_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, int fine,
+                      double* cand_ss, int32_t* cand_lrow, int64_t ecap, void* ws, size_t ws_bytes, int* status_dev,
+                      int64_t** counts_out, size_t* counts_count, void* stream);
 int abcdls_fused_refine(abcdls_handle_t h, const double* ss, int64_t n, int64_t n_global, int d, int64_t ld, int phase,
                         int world, const double* gath_small, const int32_t* gath_cnt, void* ws, size_t ws_bytes,
                         double* med, double* mad, int* status_dev, void** x0, size_t* x0_count, void** x1,
