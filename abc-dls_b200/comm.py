@@ -58,6 +58,21 @@ class Comm:
             lib.abcdls_peer_destroy(p)
         dist.barrier(group=self.group)
 
+    def trace(self):
+        """(records (n, 4) uint64 ns: entry / published / flags seen / exit of the last exchanges, oldest first) when
+        the mailboxes were created under ABCDLS_PEER_TRACE=1, else None (profiles/tools/peer_timeline.py)."""
+        if self.peer is None:
+            return None
+        import numpy as np
+        buf = np.zeros((4096, 4), dtype=np.uint64)
+        n = C.c_uint64(0)
+        cap = self._lib.abcdls_peer_trace_read(self.peer, buf.ctypes.data_as(C.c_void_p), C.byref(n))
+        if cap == 0:
+            return None
+        k = int(n.value)
+        idx = [(i % cap) for i in range(max(1, k - cap + 1), k + 1)]
+        return buf[idx]
+
     def close(self):
         if self.peer is not None:
             self._lib.abcdls_peer_destroy(self.peer)

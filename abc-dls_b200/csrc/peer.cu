@@ -35,7 +35,9 @@ __device__ __forceinline__ void grid_arrive_wait(const PeerDev& P) {
 
 // publish my contribution (already written to my data slot by all CTAs) and wait for everybody's
 __device__ __forceinline__ void publish_and_wait(const PeerDev& P, unsigned long long k, int parity) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) peer_trace(P, k, 0);
     grid_arrive_wait(P);   // every CTA's part of the slot is written and fenced
+    if (blockIdx.x == 0 && threadIdx.x == 0) peer_trace(P, k, 1);
     if (blockIdx.x == 0 && threadIdx.x < P.world) {
         unsigned long long* f = flag_ptr(P.box[threadIdx.x], parity, P.rank);   // my entry in peer threadIdx.x's row
         asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(f), "l"(k) : "memory");
@@ -43,6 +45,7 @@ __device__ __forceinline__ void publish_and_wait(const PeerDev& P, unsigned long
     if (threadIdx.x < P.world) spin_until_ge(flag_ptr(P.box[P.rank], parity, threadIdx.x), k, P.err);
     __threadfence_system();
     __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) peer_trace(P, k, 2);
 }
 
 __device__ __forceinline__ void finish(const PeerDev& P, unsigned long long k) {
@@ -52,6 +55,7 @@ __device__ __forceinline__ void finish(const PeerDev& P, unsigned long long k) {
         __threadfence();
         const unsigned long long a = atomicAdd(P.bar, 1ull) + 1ull;
         if (a == *P.bar_cum + 2ull * gridDim.x) {
+            peer_trace(P, k, 3);
             *P.bar_cum = a;
             *P.seq = k;
         }
@@ -138,12 +142,16 @@ __global__ void __launch_bounds__(kPeerThreads) k_peer_allgather_ragged(PeerDev 
     for (int pair = blockIdx.x; pair < P.world * nj; pair += gridDim.x) {
         const int r = pair / nj, j = pair - r * nj;
         const unsigned long long* peer = reinterpret_cast<const unsigned long long*>(data_ptr(P.box[r], P.slot_bytes, parity));
-        long long c = (long long)__ldcv(peer + j);
         const double* pv = reinterpret_cast<const double*>(peer + nj) + (size_t)j * cap;
         double* out = dst_vals + ((size_t)r * nj + j) * cap;
+        // the count and the first blockDim.x values travel together: ONE NVLink round trip for a typical row (a few
+        // hundred entries) instead of two dependent ones
+        const double v0 = threadIdx.x < cap ? __ldcv(pv + threadIdx.x) : 0.0;
+        long long c = (long long)__ldcv(peer + j);
         if (threadIdx.x == 0) dst_cnt[(size_t)r * nj + j] = (unsigned)c;
         if (c > cap) c = cap;
-        for (long long i = threadIdx.x; i < c; i += blockDim.x) out[i] = __ldcv(pv + i);
+        if (threadIdx.x < c) out[threadIdx.x] = v0;
+        for (long long i = threadIdx.x + blockDim.x; i < c; i += blockDim.x) out[i] = __ldcv(pv + i);
     }
     finish(P, k);
 }
@@ -181,6 +189,12 @@ int abcdls_peer_create(abcdls_peer_t* out, int rank, int world, size_t slot_byte
     p->dev.bar = p->ctl + 8;
     p->dev.bar_cum = p->ctl + 16;
     p->dev.err = p->ctl + 24;
+    p->dev.trace = nullptr;
+    if (const char* e = getenv("ABCDLS_PEER_TRACE"))
+        if (e[0] == '1' && cudaMalloc((void**)&p->trace, (size_t)kPeerTraceCap * 32) == cudaSuccess) {
+            cudaMemset(p->trace, 0, (size_t)kPeerTraceCap * 32);
+            p->dev.trace = p->trace;
+        }
     p->dev.slot_bytes = slot_bytes;
     p->dev.rank = rank;
     p->dev.world = world;
@@ -219,8 +233,19 @@ int abcdls_peer_destroy(abcdls_peer_t p) {
         if (p->opened[r]) cudaIpcCloseMemHandle(p->opened[r]);
     if (p->mine) cudaFree(p->mine);
     if (p->ctl) cudaFree(p->ctl);
+    if (p->trace) cudaFree(p->trace);
     delete p;
     return ABCDLS_OK;
+}
+
+// ABCDLS_PEER_TRACE=1: copies the timeline (kPeerTraceCap records of 4 x uint64 ns: entry, published, flags seen, exit;
+// record k % cap = exchange k) and the number of exchanges so far to the host.  Returns the record capacity (0: off).
+int abcdls_peer_trace_read(abcdls_peer_t p, uint64_t* out, uint64_t* n_exchanges) {
+    if (!p || !p->trace || !out) return 0;
+    cudaDeviceSynchronize();
+    cudaMemcpy(out, p->trace, (size_t)kPeerTraceCap * 32, cudaMemcpyDeviceToHost);
+    if (n_exchanges) cudaMemcpy(n_exchanges, p->dev.seq, 8, cudaMemcpyDeviceToHost);
+    return kPeerTraceCap;
 }
 
 const char* abcdls_peer_last_error(abcdls_peer_t p) { return p ? p->err.c_str() : "null peer"; }
@@ -261,8 +286,8 @@ int abcdls_peer_allgather_ragged(abcdls_peer_t p, const double* src_vals, const 
     if (!p || !src_vals || !src_cnt || !dst_vals || !dst_cnt || nj < 1 || cap < 1 ||
         ((size_t)nj + (size_t)nj * cap) * 8 > p->dev.slot_bytes)
         return ABCDLS_E_INVALID;
-    unsigned g = (unsigned)(p->dev.world * nj);
-    if (g > (unsigned)kPeerMaxCtas) g = kPeerMaxCtas;
+    unsigned g = (unsigned)(p->dev.world * nj);             // one (rank, row) pair per CTA where the device allows
+    if (g > 128u) g = 128u;
     k_peer_allgather_ragged<<<g, kPeerThreads, 0, (cudaStream_t)stream>>>(p->dev, src_vals, src_cnt, nj, cap, dst_vals,
                                                                          dst_cnt);
     return cudaGetLastError() == cudaSuccess ? ABCDLS_OK : ABCDLS_E_CUDA;

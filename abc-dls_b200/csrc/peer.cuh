@@ -17,6 +17,7 @@ struct PeerDev {
     unsigned long long* bar;       // arrivals of my CTAs (monotonic)
     unsigned long long* bar_cum;   // arrivals expected before the current exchange
     unsigned long long* err;       // sticky: != 0 after a wait timed out
+    unsigned long long* trace;     // NULL, or kPeerTraceCap x 4 timestamps (ABCDLS_PEER_TRACE=1): see peer_trace
     unsigned char* box[kMaxWorld]; // mailboxes of all ranks as mapped in THIS process (box[rank] = mine)
     size_t slot_bytes;
     int rank, world;
@@ -27,9 +28,21 @@ struct abcdls_peer_s {
     void* mine = nullptr;
     void* opened[kMaxWorld] = {};
     unsigned long long* ctl = nullptr;   // seq | bar | bar_cum | err
+    unsigned long long* trace = nullptr;
     size_t box_bytes = 0;
     std::string err;
 };
+
+// Optional timeline of the exchanges (ABCDLS_PEER_TRACE=1): record k % kPeerTraceCap holds %globaltimer at
+// {entry, own contribution published, every peer's flag seen, exit} of exchange k, written by one thread.
+constexpr int kPeerTraceCap = 4096;
+__device__ __forceinline__ void peer_trace(const PeerDev& P, unsigned long long k, int what) {
+    if (P.trace) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        P.trace[(k % kPeerTraceCap) * 4 + what] = t;
+    }
+}
 
 constexpr size_t kFlagsBytes = (size_t)2 * kMaxWorld * sizeof(unsigned long long);   // 1024
 static_assert(kFlagsBytes % 256 == 0, "data slots start 256-byte aligned");
@@ -77,9 +90,11 @@ __device__ __forceinline__ void peer_block_allreduce(const PeerDev& P, double* v
     const int parity = (int)(k & 1ull);
     double* mine = reinterpret_cast<double*>(data_ptr(P.box[P.rank], P.slot_bytes, parity));
     __syncthreads();
+    if (threadIdx.x == 0) peer_trace(P, k, 0);
     for (int i = threadIdx.x; i < count; i += blockDim.x) mine[i] = vec[i];
     __threadfence_system();
     __syncthreads();
+    if (threadIdx.x == 0) peer_trace(P, k, 1);
     if (threadIdx.x < P.world) {
         unsigned long long* f = flag_ptr(P.box[threadIdx.x], parity, P.rank);   // my entry in peer threadIdx.x's row
         asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(f), "l"(k) : "memory");
@@ -87,6 +102,7 @@ __device__ __forceinline__ void peer_block_allreduce(const PeerDev& P, double* v
     }
     __threadfence_system();
     __syncthreads();
+    if (threadIdx.x == 0) peer_trace(P, k, 2);
     for (int i = threadIdx.x; i < count; i += blockDim.x) {
         double acc = 0.0;
         for (int r0 = 0; r0 < P.world; r0 += 8) {
@@ -105,6 +121,9 @@ __device__ __forceinline__ void peer_block_allreduce(const PeerDev& P, double* v
         vec[i] = acc;
     }
     __syncthreads();
-    if (threadIdx.x == 0) *P.seq = k;
+    if (threadIdx.x == 0) {
+        peer_trace(P, k, 3);
+        *P.seq = k;
+    }
     __syncthreads();
 }

@@ -16,6 +16,12 @@
 // runs as 2 x 256-thread CTAs per SM, as 4 x 128, warp specialised with a double-buffered tile (8 loader + 4 / 8
 // accumulator warps), with DMMA or with register-blocked DFMA - it is bound by the 2e6 RANDOM 128-byte record reads
 // (one DRAM row activation each: the accepted rows are 1 % of the table, and the candidate block is in pass order).
+// Round-2 elimination experiment (parts of T1 switched off by a debug mask, 1e6 rows, T1 alone): 303 us in all =
+// ~117 us skeleton (row numbers, Markstein scaling, tile stores, barriers, last-block reduction + Cholesky) + ~64 us
+// record reads (2e6 random lines: ~31 G lines/s) + ~55 us stores (344 MB at the DRAM write rate) + ~62 us DMMA + ~12 us
+// region scan: the parts ADD UP (two CTAs per SM in phase) instead of overlapping.  Prefetching the records one tile
+// ahead with cp.async (thread per record, or 8 lanes per record) and splitting both records between the two half
+// blocks changed the sum by less than 7 %; those variants are not kept.
 //
 // Reference semantics: CRAN abc 2.2.1 abc(method = "loclinear" | "rejection") as reached from
 // src/Classes/ABC.py:1950-1953 / 2806-2809; same arithmetic as loclinear.cu (design centred on
@@ -70,6 +76,22 @@ struct TailArgs {
 
 __device__ __forceinline__ double ldcg_f64(const double* p) { return __ldcg(p); }
 
+// src[0], src[stride], ... src[(cnt - 1) * stride] combined IN ORDER (kd: 0 sum, 1 min, 2 max), eight loads in flight at
+// a time: one L2 round trip per eight partials instead of one per partial.
+__device__ __forceinline__ double ordered_combine(const double* src, size_t stride, int cnt, int kd) {
+    double acc = kd == 0 ? 0.0 : (kd == 1 ? __longlong_as_double(0x7ff0000000000000ll)
+                                          : -__longlong_as_double(0x7ff0000000000000ll));
+    for (int c0 = 0; c0 < cnt; c0 += 8) {
+        double v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = c0 + k < cnt ? ldcg_f64(src + (size_t)(c0 + k) * stride) : 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (c0 + k < cnt) acc = (c0 + k == 0) ? v[k] : (kd == 0 ? acc + v[k] : (kd == 1 ? fmin(acc, v[k]) : fmax(acc, v[k])));
+    }
+    return acc;
+}
+
 // Every CTA has written E doubles to part[blockIdx.x * E ...].  Two-level, fixed-order combine: the last CTA of each
 // group of kTlGroup adds the group's partials in CTA order, the last group to finish adds the group sums in group
 // order (deterministic for a given grid).  Returns true in exactly one CTA, with the result in out[0..E).
@@ -85,16 +107,8 @@ __device__ bool hier_reduce(const double* part, int E, double* gpart, unsigned* 
     __syncthreads();
     if (role == 0) return false;
     __threadfence();
-    for (int e = threadIdx.x; e < E; e += blockDim.x) {
-        const int kd = kind(e);
-        const double* src = part + (size_t)g * kTlGroup * E + e;
-        double acc = ldcg_f64(src);
-        for (int c = 1; c < gsize; ++c) {
-            const double v = ldcg_f64(src + (size_t)c * E);
-            acc = kd == 0 ? acc + v : (kd == 1 ? fmin(acc, v) : fmax(acc, v));
-        }
-        gpart[(size_t)g * E + e] = acc;
-    }
+    for (int e = threadIdx.x; e < E; e += blockDim.x)
+        gpart[(size_t)g * E + e] = ordered_combine(part + (size_t)g * kTlGroup * E + e, E, gsize, kind(e));
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -104,15 +118,7 @@ __device__ bool hier_reduce(const double* part, int E, double* gpart, unsigned* 
     __syncthreads();
     if (role != 2) return false;
     __threadfence();
-    for (int e = threadIdx.x; e < E; e += blockDim.x) {
-        const int kd = kind(e);
-        double acc = ldcg_f64(gpart + e);
-        for (int c = 1; c < ngroups; ++c) {
-            const double v = ldcg_f64(gpart + (size_t)c * E + e);
-            acc = kd == 0 ? acc + v : (kd == 1 ? fmin(acc, v) : fmax(acc, v));
-        }
-        out[e] = acc;
-    }
+    for (int e = threadIdx.x; e < E; e += blockDim.x) out[e] = ordered_combine(gpart + e, E, ngroups, kind(e));
     if (threadIdx.x == 0) tickets[ngroups] = 0u;
     __syncthreads();
     return true;
@@ -132,17 +138,19 @@ __device__ void chol_factor(double* L, int M, double* diag0, int* bad) {
     }
     for (int c = 0; c < M; ++c) {
         __syncthreads();
-        if (threadIdx.x == 0) {
-            double s = L[c * M + c];
-            if (!(s > 1e-13 * diag0[c]) || !(s > 0.0)) {
-                *bad = 1;
-                s = 1.0;
-            }
-            L[c * M + c] = sqrt(s);
+        // every thread takes the pivot itself (no one-thread section, two barriers per column)
+        double s = L[c * M + c];
+        if (!(s > 1e-13 * diag0[c]) || !(s > 0.0)) {
+            if (threadIdx.x == 0) *bad = 1;
+            s = 1.0;
         }
-        __syncthreads();
-        const double lcc = L[c * M + c];
-        for (int r = c + 1 + threadIdx.x; r < M; r += blockDim.x) L[r * M + c] = L[r * M + c] / lcc;
+        const double lcc = sqrt(s);
+        double below = 0.0;
+        const int r1 = c + 1 + threadIdx.x;
+        if (r1 < M) below = L[r1 * M + c] / lcc;                      // M <= 33 <= blockDim.x: one row per thread
+        __syncthreads();                                              // everyone has read the pivot and its column
+        if (threadIdx.x == 0) L[c * M + c] = lcc;
+        if (r1 < M) L[r1 * M + c] = below;
         __syncthreads();
         const int nn = M - c - 1;
         for (int t = threadIdx.x; t < nn * nn; t += blockDim.x) {

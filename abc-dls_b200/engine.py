@@ -304,7 +304,8 @@ class AbcEngine:
         fast = level < 2 and min(ns) >= self.FAST_MIN_ROWS   # every rank must take the same path
         fused = fast and all_fuse
         # second-stage counting sample of the one-pass path (csrc/fused.cuh): from FINE_MIN_ROWS rows on EVERY rank
-        fine = self.FINE_SHIFT if (fused and min(ns) >= self.FINE_MIN_ROWS) else 0
+        fine_min = self.FINE_MIN_ROWS * (2 if self.comm.world > 1 else 1)   # several ranks: one more exchange to pay for
+        fine = self.FINE_SHIFT if (fused and min(ns) >= fine_min) else 0
         return dict(n_global=n_global, row_offset=row_offset, nacc=nacc, fast=fast, fused=fused, keep_dist=keep_dist, fine=fine,
                     path="fused" if fused else ("two_pass" if fast else "exact"))
 

@@ -571,6 +571,12 @@ def run_abc(ctx, args, N, with_e2e, with_cpu, flush_small=True):
         return eng.abc(tgt, par, ss, args.tol, args.method, shard=(N, r0))
 
     ms_step, launches, clocks, res = timed_region(ctx, args, step)
+    if os.environ.get("ABCDLS_PEER_TRACE") == "1" and world > 1:   # timeline of the exchanges of the timed calls
+        tr = eng.comm.trace()
+        if tr is not None:
+            import numpy as np
+            os.makedirs("gpurun_out", exist_ok=True)
+            np.save(f"gpurun_out/peer_trace_r{rank}.npy", tr)
     if flush is not None:   # the flush kernel itself is inside the timed region: measure and subtract it
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ctx.sync()

@@ -459,6 +459,10 @@ size_t abcdls_peer_handle_bytes(void);
 int abcdls_peer_create(abcdls_peer_t* out, int rank, int world, size_t slot_bytes, void* handle_out);
 int abcdls_peer_connect(abcdls_peer_t p, const void* all_handles /* world x handle_bytes, rank order */);
 int abcdls_peer_destroy(abcdls_peer_t p);
+/* profiling aid: with ABCDLS_PEER_TRACE=1 in the environment at abcdls_peer_create, every exchange records four
+ * %globaltimer stamps (entry, own contribution published, every peer's flag seen, exit); out: 4096 x 4 uint64 ns (record
+ * k % 4096 = exchange k), n_exchanges: exchanges completed.  Returns the record capacity, 0 when tracing is off. */
+int abcdls_peer_trace_read(abcdls_peer_t p, uint64_t* out, uint64_t* n_exchanges);
 const char* abcdls_peer_last_error(abcdls_peer_t p);
 size_t abcdls_peer_slot_bytes(abcdls_peer_t p);
 /* in place; dtype 0 = double, 1 = int64; op 0 = sum, 1 = min, 2 = max; count * 8 <= slot bytes */
