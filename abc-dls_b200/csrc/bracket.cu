@@ -158,6 +158,7 @@ __device__ __forceinline__ long long sample_row(unsigned seed, unsigned cta, int
 // K1: per-column sample -> local estimates (m_lo, m_hi, r_lo, r_hi).  grid (G, d), 512 threads.
 __global__ void __launch_bounds__(512) k_sample_cols(const double* __restrict__ ss, long long n, long long ld,
                                                      unsigned seed, double delta, double* __restrict__ est) {
+    pdl_prologue();
     extern __shared__ double sm[];
     double* s = sm;            // kSample
     double* a = sm + kSample;  // kSample
@@ -199,6 +200,7 @@ struct ColBrk {
 // mean_out (optional): the averaged {m_lo, m_hi, r_lo, r_hi} of every column, for the second-stage sample of fused.cuh.
 __global__ void __launch_bounds__(32) k_make_brackets(const double* __restrict__ est, int G, int d, double inv_world,
                                                       ColBrk* __restrict__ brk, double* __restrict__ mean_out = nullptr) {
+    pdl_prologue();
     const int j = blockIdx.x, lane = threadIdx.x;
     if (j >= d) return;
     double m[4] = {0, 0, 0, 0};
@@ -271,6 +273,7 @@ __global__ void __launch_bounds__(kAThreads, 3) k_bracket_pass(const double* __r
                                                                double* __restrict__ candM, long long capM,
                                                                double* __restrict__ candU, long long capU,
                                                                unsigned long long* __restrict__ cnt) {
+    pdl_prologue();
     __shared__ unsigned hist[kNB];
     __shared__ unsigned tot2[2];
     __shared__ double stM[kAThreads / 32][kStageM];
@@ -410,6 +413,7 @@ __device__ __forceinline__ int job_bin(double v, double lo, double scale, int po
 
 // one block per job: locate the bins.  (after the histogram is complete / all-reduced)
 __global__ void __launch_bounds__(256) k_refine_pick(RefJob* jobs, int* status) {
+    pdl_prologue();
     RefJob& J = jobs[blockIdx.x];
     __shared__ long long wsum[9];
     __shared__ int bsel[2];
@@ -469,6 +473,7 @@ __global__ void __launch_bounds__(256) k_refine_pick(RefJob* jobs, int* status) 
 
 // grid (gx, njobs): append the values that fall in bins [bq0, bq1] to J.small
 __global__ void __launch_bounds__(256) k_refine_gather(RefJob* jobs, long long n_max) {
+    pdl_prologue();
     RefJob& J = jobs[blockIdx.y];
     if (!J.valid) return;
     long long n = (long long)*J.src_count;
@@ -510,6 +515,7 @@ __global__ void __launch_bounds__(256) k_refine_gather(RefJob* jobs, long long n
 __global__ void __launch_bounds__(1024) k_refine_final(RefJob* jobs, const double* __restrict__ gsmall,
                                                        const unsigned* __restrict__ gcnt, int world, int nj,
                                                        int* status) {
+    pdl_prologue();
     extern __shared__ double sm[];
     __shared__ unsigned off[65];
     RefJob& J = jobs[blockIdx.x];
@@ -555,6 +561,7 @@ __global__ void __launch_bounds__(1024) k_refine_final(RefJob* jobs, const doubl
 }
 
 __global__ void k_copy_u64(unsigned long long* dst, const unsigned long long* src, int n) {
+    pdl_prologue();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[i];
 }
@@ -566,6 +573,7 @@ __global__ void k_plan_median(RefJob* jobs, int d, const ColBrk* __restrict__ br
                               const double* candM, long long capM, const unsigned long long* cnt,
                               const unsigned long long* gcnt, double* small, unsigned* small_count, long long k0,
                               long long k1, int* status) {
+    pdl_prologue();
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= d) return;
     RefJob J;
@@ -601,6 +609,7 @@ __global__ void k_plan_mad(RefJob* jobs, int d, const ColBrk* __restrict__ brk,
                            const double* candU, long long capU, const unsigned long long* cnt,
                            const unsigned long long* gcnt, double* small, unsigned* small_count, long long k0,
                            long long k1, double* __restrict__ med, double* __restrict__ guard, int* status) {
+    pdl_prologue();
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= d) return;
     const RefJob& Jm = jobs[j];
@@ -644,6 +653,7 @@ __global__ void k_plan_mad(RefJob* jobs, int d, const ColBrk* __restrict__ brk,
 
 // histogram of v = |x - center| (or x) of the candidates of every job.  grid (gx, njobs)
 __global__ void __launch_bounds__(256) k_refine_hist(RefJob* jobs, long long n_max) {
+    pdl_prologue();
     __shared__ unsigned hist[kNB];
     RefJob& J = jobs[blockIdx.y];
     if (!J.valid) return;
@@ -678,6 +688,7 @@ __global__ void __launch_bounds__(256) k_refine_hist(RefJob* jobs, long long n_m
 
 __global__ void k_finish_mad(const RefJob* jobs, int d, const double* __restrict__ guard, double* __restrict__ mad,
                              int* status) {
+    pdl_prologue();
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= d) return;
     const RefJob& J = jobs[d + j];
@@ -720,6 +731,7 @@ __device__ __forceinline__ double scaled_value(double x, const double2 dr) {
 __global__ void __launch_bounds__(512) k_sample_dist(const double* __restrict__ ss, long long n, int d, long long ld,
                                                      const double* __restrict__ mad, const double* __restrict__ target,
                                                      unsigned seed, double p, double delta, double* __restrict__ est) {
+    pdl_prologue();
     extern __shared__ double sm[];
     __shared__ ColScale S;
     load_scale(S, mad, target, d);
@@ -749,6 +761,7 @@ struct DistBrk {
 };
 
 __global__ void k_make_dist_bracket(const double* __restrict__ est, int G, double inv_world, DistBrk* brk) {
+    pdl_prologue();
     if (threadIdx.x || blockIdx.x) return;
     double lo = 0, hi = 0;
     for (int g = 0; g < G; ++g) { lo += est[g * 2]; hi += est[g * 2 + 1]; }
@@ -788,6 +801,7 @@ __global__ void __launch_bounds__(kBThreads) k_dist_pass(const double* __restric
                                                          long long* __restrict__ rec_off,
                                                          int* __restrict__ rec_cnt, int* __restrict__ wtot,
                                                          int* __restrict__ nrec, int* status) {
+    pdl_prologue();
     __shared__ ColScale S;
     __shared__ unsigned hist[kNB];
     __shared__ long long st_row[kBThreads / 32][kStageB];
@@ -970,6 +984,7 @@ __global__ void __launch_bounds__(kTThreads, 2) k_dist_pass_tma(const double* __
                                                                 long long rcap, long long* __restrict__ rec_off,
                                                                 int* __restrict__ rec_cnt, int* __restrict__ wtot,
                                                                 int* __restrict__ nrec, int* status) {
+    pdl_prologue();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TmaSmem& sm = *reinterpret_cast<TmaSmem*>(smem_raw);
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1110,6 +1125,7 @@ __global__ void __launch_bounds__(256) k_order_cands(const long long* __restrict
                                                      const double* __restrict__ dist_in, long long cap,
                                                      long long row_offset, long long* __restrict__ row_out,
                                                      double* __restrict__ dist_out) {
+    pdl_prologue();
     const int lane = threadIdx.x & 31;
     const long long gw = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
     if (gw >= nprod) return;
@@ -1132,6 +1148,7 @@ __global__ void k_plan_ds(RefJob* job, const DistBrk* __restrict__ brk, const un
                           const unsigned long long* __restrict__ gcand_cnt, unsigned long long* hist,
                           const double* cand_dist, long long cap, double* small, unsigned* small_count, long long k,
                           int* status) {
+    pdl_prologue();
     if (threadIdx.x || blockIdx.x) return;
     RefJob J;
     const long long c_lt = (long long)*n_lt, c_all = (long long)*gcand_cnt;   // summed over ranks
@@ -1158,6 +1175,7 @@ __global__ void k_plan_ds(RefJob* job, const DistBrk* __restrict__ brk, const un
 }
 
 __global__ void k_copy_result(const RefJob* job, double* out) {
+    pdl_prologue();
     if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = job->result[0];
 }
 
@@ -1387,29 +1405,29 @@ static int refine_impl(abcdls_handle_t h, const MadWs& w, long long capM, long l
     if (x1) *x1 = nullptr;
     switch (phase) {
         case 0:
-            k_plan_median<<<1, 64, 0, st>>>(w.jobs, d, w.brk, w.counts, w.histM, w.candM, capM, w.cnt, w.gcnt, w.small,
+            launch_pdl(k_plan_median, dim3(1), dim3(64), 0, st, w.jobs, d, w.brk, w.counts, w.histM, w.candM, capM, w.cnt, w.gcnt, w.small,
                                             w.small_count, k0, k1, status_dev);
-            k_refine_pick<<<d, 256, 0, st>>>(w.jobs, status_dev);
-            k_refine_gather<<<dim3(gx_for(capM), d), 256, 0, st>>>(w.jobs, capM);
+            launch_pdl(k_refine_pick, dim3(d), dim3(256), 0, st, w.jobs, status_dev);
+            launch_pdl(k_refine_gather, dim3(dim3(gx_for(capM), d)), dim3(256), 0, st, w.jobs, capM);
             if (x0) { *x0 = w.small; *x0_count = (size_t)d * kSmallCap; }
             if (x1) { *x1 = w.small_count; *x1_count = (size_t)d; }
             break;
         case 1:
-            k_refine_final<<<d, 1024, smem, st>>>(w.jobs, gath_small, gc, gath_small ? world : 1, d, status_dev);
-            k_plan_mad<<<1, 64, 0, st>>>(w.jobs, d, w.brk, w.counts, w.histU, w.candU, capU, w.cnt, w.gcnt, w.small,
+            launch_pdl(k_refine_final, dim3(d), dim3(1024), smem, st, w.jobs, gath_small, gc, gath_small ? world : 1, d, status_dev);
+            launch_pdl(k_plan_mad, dim3(1), dim3(64), 0, st, w.jobs, d, w.brk, w.counts, w.histU, w.candU, capU, w.cnt, w.gcnt, w.small,
                                          w.small_count, k0, k1, med, w.guard, status_dev);
-            k_refine_hist<<<dim3(gx_for(capU), d), 256, 0, st>>>(w.jobs + d, capU);
+            launch_pdl(k_refine_hist, dim3(dim3(gx_for(capU), d)), dim3(256), 0, st, w.jobs + d, capU);
             if (x0) { *x0 = w.histU; *x0_count = w.redB_count; }
             break;
         case 2:
-            k_refine_pick<<<d, 256, 0, st>>>(w.jobs + d, status_dev);
-            k_refine_gather<<<dim3(gx_for(capU), d), 256, 0, st>>>(w.jobs + d, capU);
+            launch_pdl(k_refine_pick, dim3(d), dim3(256), 0, st, w.jobs + d, status_dev);
+            launch_pdl(k_refine_gather, dim3(dim3(gx_for(capU), d)), dim3(256), 0, st, w.jobs + d, capU);
             if (x0) { *x0 = w.small + (size_t)d * kSmallCap; *x0_count = (size_t)d * kSmallCap; }
             if (x1) { *x1 = w.small_count + d; *x1_count = (size_t)d; }
             break;
         default:
-            k_refine_final<<<d, 1024, smem, st>>>(w.jobs + d, gath_small, gc, gath_small ? world : 1, d, status_dev);
-            k_finish_mad<<<1, 64, 0, st>>>(w.jobs, d, w.guard, mad, status_dev);
+            launch_pdl(k_refine_final, dim3(d), dim3(1024), smem, st, w.jobs + d, gath_small, gc, gath_small ? world : 1, d, status_dev);
+            launch_pdl(k_finish_mad, dim3(1), dim3(64), 0, st, w.jobs, d, w.guard, mad, status_dev);
             break;
     }
     ABCDLS_LAUNCH_CHECK(h);

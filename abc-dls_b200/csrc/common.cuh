@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string>
 
 #include "../../include/abcdls.h"
@@ -42,6 +43,38 @@ struct abcdls_handle_s {
     } while (0)
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- programmatic dependent launch -----------------------------------------------------------------------------------
+// A call is a chain of ~45 mostly tiny, dependent kernels; between two of them the GPU idles for the launch latency
+// (~2-3 us in a CUDA graph).  Kernels of the hot path start with pdl_prologue(): "my dependents may be scheduled now"
+// + "wait until everything before me has completed and is visible", and are launched with the programmatic stream
+// serialization attribute, so the NEXT kernel's blocks are already resident (parked at the wait) when this one ends.
+// Launched without the attribute (ABCDLS_NO_PDL=1, or the other paths) both instructions are no-ops.
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+inline bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("ABCDLS_NO_PDL");
+        on = (e && e[0] == '1') ? 0 : 1;
+    }
+    return on != 0;
+}
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // ---- order-preserving 64-bit key of a double -------------------------------------------------
 __device__ __forceinline__ unsigned long long dkey(double x) {

@@ -14,6 +14,7 @@ constexpr int kTile = kTileThreads * kItems;   // 2048 rows per tile
 constexpr int kScanItems = 8;
 __global__ void __launch_bounds__(1024) k_scan_tiles(const int* __restrict__ tile_cnt, long long ntiles,
                                                      long long* __restrict__ tile_off) {
+    pdl_prologue();
     __shared__ long long wsum[33];
     __shared__ long long carry_sh;
     if (threadIdx.x == 0) carry_sh = 0;

@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(kDistThreads) k_scale_dist(const double* __res
                                                              long long ld, const double* __restrict__ mad,
                                                              const double* __restrict__ target,
                                                              double* __restrict__ dist, int* status) {
+    pdl_prologue();
     __shared__ ColScale S;
     load_scale(S, mad, target, d);
     __syncthreads();
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(kTileThreads) k_tile_count_le(const double* __
                                                                 const double* __restrict__ ds_ptr,
                                                                 int* __restrict__ tile_cnt,
                                                                 unsigned long long* total) {
+    pdl_prologue();
     __shared__ int sh[33];
     const double ds = *ds_ptr;
     if (n_dev && *n_dev < n) n = *n_dev;
@@ -143,6 +145,7 @@ __global__ void __launch_bounds__(kTileThreads) k_tile_write_le(const double* __
                                                                 long long* __restrict__ slot_out,
                                                                 const unsigned long long* __restrict__ total,
                                                                 long long* __restrict__ n_out, int* status) {
+    pdl_prologue();
     __shared__ int sh[33];
     const double ds = *ds_ptr;
     long long quota = *quota_ptr;
@@ -229,9 +232,9 @@ int abcdls_count_le(abcdls_handle_t h, const double* dist, int64_t n, const int6
     int* tile_cnt = reinterpret_cast<int*>(p + 256);
     long long* tile_off = reinterpret_cast<long long*>(p + 256 + align_up((size_t)nt * sizeof(int), 256));
     ABCDLS_CUDA(h, cudaMemsetAsync(total, 0, 8, st));
-    k_tile_count_le<<<(unsigned)nt, kTileThreads, 0, st>>>(dist, n, (const long long*)n_dev, ds, tile_cnt, total);
+    launch_pdl(k_tile_count_le, dim3((unsigned)nt), dim3(kTileThreads), 0, st, dist, n, (const long long*)n_dev, ds, tile_cnt, total);
     ABCDLS_LAUNCH_CHECK(h);
-    k_scan_tiles<<<1, 1024, 0, st>>>(tile_cnt, nt, tile_off);
+    launch_pdl(k_scan_tiles, dim3(1), dim3(1024), 0, st, tile_cnt, nt, tile_off);
     ABCDLS_LAUNCH_CHECK(h);
     if (le_count)
         ABCDLS_CUDA(h, cudaMemcpyAsync(le_count, total, 8, cudaMemcpyDeviceToDevice, st));
@@ -252,7 +255,7 @@ int abcdls_accept(abcdls_handle_t h, const double* dist, int64_t n, const int64_
     char* p = reinterpret_cast<char*>(ws);
     unsigned long long* total = reinterpret_cast<unsigned long long*>(p);
     long long* tile_off = reinterpret_cast<long long*>(p + 256 + align_up((size_t)nt * sizeof(int), 256));
-    k_tile_write_le<<<(unsigned)nt, kTileThreads, 0, (cudaStream_t)stream>>>(
+    launch_pdl(k_tile_write_le, dim3((unsigned)nt), dim3(kTileThreads), 0, (cudaStream_t)stream, 
         dist, n, (const long long*)n_dev, (const long long*)src_idx, dist_out, ds, tile_off,
         (const long long*)quota, row_offset, cap, (long long*)idx_out, (long long*)slot_out, total, (long long*)n_out,
         status_dev);

@@ -95,6 +95,7 @@ inline int fused_stages(int d) {
 // scale estimates from the (rank-summed) column sample: est[g][j][{m_lo, m_hi, r_lo, r_hi}]
 __global__ void k_make_fused_scale(const double* __restrict__ est, int G, int d, double inv_world,
                                    const double* __restrict__ target, FusedPar* par) {
+    pdl_prologue();
     const int j = threadIdx.x;   // one warp
     double eps = 0.0;
     bool ok = true;
@@ -133,6 +134,7 @@ __global__ void k_make_fused_scale(const double* __restrict__ est, int G, int d,
 __global__ void __launch_bounds__(512) k_sample_qdist(const double* __restrict__ ss, long long n, int d, long long ld,
                                                       const FusedPar* __restrict__ par, unsigned seed, double p,
                                                       double delta, double* __restrict__ est) {
+    pdl_prologue();
     extern __shared__ double sm[];
     __shared__ double2 sc[kFMaxD];
     if (threadIdx.x < kFMaxD) sc[threadIdx.x] = make_double2(par->tgt[threadIdx.x], par->rho[threadIdx.x]);
@@ -156,6 +158,7 @@ __global__ void __launch_bounds__(512) k_sample_qdist(const double* __restrict__
 }
 
 __global__ void k_make_fused_thr(const double* __restrict__ est, int G, double inv_world, int d, FusedPar* par) {
+    pdl_prologue();
     if (threadIdx.x || blockIdx.x) return;
     double hi = 0.0;
     for (int g = 0; g < G; ++g) hi += est[g];
@@ -190,6 +193,7 @@ static_assert(kFineU32 % 2 == 0, "two 32-bit counts travel as one int64 of the a
 __global__ void __launch_bounds__(512) k_sample_fine(const double* __restrict__ ss, long long n, long long ld,
                                                      const ColBrk* __restrict__ brk, long long L, int shift, int rs,
                                                      unsigned seed, unsigned* __restrict__ out) {
+    pdl_prologue();
     __shared__ unsigned h[3 * kFineNB];
     __shared__ unsigned cn[4];
     const int j = blockIdx.y;
@@ -273,6 +277,7 @@ __global__ void __launch_bounds__(512) k_sample_fine(const double* __restrict__ 
 __global__ void __launch_bounds__(256) k_fine_brackets(const unsigned* __restrict__ fine,
                                                        const ColBrk* __restrict__ brk, double z,
                                                        double* __restrict__ est) {
+    pdl_prologue();
     __shared__ long long cum[kFineNB + 1];     // cum[k]  = # M-window samples in bins < k
     __shared__ long long suf[2][kFineNB + 1];  // suf[k]  = # samples of that side with radius >= edge k (incl. far)
     __shared__ long long part[3][8];
@@ -401,6 +406,7 @@ k_fused_pass(const __grid_constant__ CUtensorMap tmap, long long n, long long nt
              unsigned long long* __restrict__ cnt, unsigned short* __restrict__ mask16, double* __restrict__ cand_e,
              long long ecap, int* __restrict__ erow, unsigned long long* __restrict__ ealloc, long long tpc,
              int chunkM, int chunkU, int* status) {
+    pdl_prologue();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FusedSmem& sm = *reinterpret_cast<FusedSmem*>(smem_raw);
     double* ring = reinterpret_cast<double*>(smem_raw + kFHeader);
@@ -668,6 +674,7 @@ __global__ void __launch_bounds__(256) k_fused_histM(const double* __restrict__ 
                                                      const ColBrk* __restrict__ brk,
                                                      unsigned long long* __restrict__ histM,
                                                      unsigned long long* __restrict__ counts) {
+    pdl_prologue();
     __shared__ unsigned hist[kNB];
     __shared__ unsigned negs;
     const int j = blockIdx.y;
@@ -707,6 +714,7 @@ __global__ void __launch_bounds__(256) k_fused_histM(const double* __restrict__ 
 constexpr int kMWords = 8;   // words per thread
 __global__ void __launch_bounds__(256) k_mask_count(const unsigned* __restrict__ bitmap, long long nwords,
                                                     int* __restrict__ tile_cnt, unsigned long long* total) {
+    pdl_prologue();
     __shared__ int sh[33];
     const long long base = ((long long)blockIdx.x * 256 + threadIdx.x) * kMWords;
     int c = 0;
@@ -727,6 +735,7 @@ __global__ void __launch_bounds__(256) k_mask_write(const unsigned* __restrict__
                                                     int* __restrict__ wprefix,
                                                     const unsigned long long* __restrict__ total,
                                                     long long* __restrict__ n_out, int* status) {
+    pdl_prologue();
     __shared__ int sh[33];
     const long long base = ((long long)blockIdx.x * 256 + threadIdx.x) * kMWords;
     unsigned wv[kMWords];
@@ -767,6 +776,7 @@ __global__ void __launch_bounds__(256) k_cand_exact(const double* __restrict__ c
                                                     const unsigned* __restrict__ bitmap, const int* __restrict__ wprefix,
                                                     long long cap, double* __restrict__ cand_dist,
                                                     long long* __restrict__ perm, int* status) {
+    pdl_prologue();
     __shared__ ColScale S;
     load_scale(S, mad, target, d);
     __syncthreads();
@@ -808,6 +818,7 @@ __global__ void __launch_bounds__(256) k_cand_exact(const double* __restrict__ c
 __global__ void k_plan_ds_fused(RefJob* job, const FusedPar* __restrict__ par, const long long* n_cand,
                                 const double* cand_dist, long long cap, unsigned long long* hist, double* small,
                                 unsigned* small_count, long long k, int d, int* status) {
+    pdl_prologue();
     if (threadIdx.x || blockIdx.x) return;
     RefJob J;
     const bool ok = par->ok != 0 && par->thr > 0.0;
@@ -838,12 +849,14 @@ __global__ void k_plan_ds_fused(RefJob* job, const FusedPar* __restrict__ par, c
 
 // the exchange block of a rank: kSmallCap gathered values followed by their count (as a double)
 __global__ void k_ds_pack(const RefJob* job) {
+    pdl_prologue();
     if (threadIdx.x == 0 && blockIdx.x == 0) job->small[kSmallCap] = (double)*job->small_count;
 }
 
 // blocks[world][kSmallCap + 1] (or the job's own block when world == 1): sort, read the rank -> ds
 __global__ void __launch_bounds__(1024) k_ds_final(RefJob* job, const double* __restrict__ blocks, int world,
                                                    double* __restrict__ ds_out, int* status) {
+    pdl_prologue();
     extern __shared__ double sm[];
     __shared__ unsigned off[65];
     RefJob& J = *job;
@@ -887,6 +900,7 @@ __global__ void __launch_bounds__(1024) k_ds_final(RefJob* job, const double* __
 // the completeness proof (header comment, item 4)
 __global__ void k_fused_check(const FusedPar* __restrict__ par, const double* __restrict__ mad, int d,
                               const double* __restrict__ ds_ptr, int* status) {
+    pdl_prologue();
     if (threadIdx.x || blockIdx.x) return;
     const double eps = par->eps, eta = par->eta, thr = par->thr, ds = *ds_ptr;
     bool ok = par->ok != 0 && thr > 0.0;
@@ -1037,7 +1051,7 @@ int abcdls_fused_sample_cols(abcdls_handle_t h, const double* ss, int64_t n, int
     ABCDLS_CUDA(h, cudaMemsetAsync(w.total, 0, 8, st));
     ABCDLS_CUDA(h, cudaMemsetAsync(w.ealloc, 0, 8, st));
     ABCDLS_CUDA(h, cudaMemsetAsync(w.ds_hist, 0, w.ds_zero_bytes, st));
-    k_sample_cols<<<dim3(G, d), 512, smem, st>>>(ss, n, ld, 0x5EEDu, delta, w.m.est);
+    launch_pdl(k_sample_cols, dim3(dim3(G, d)), dim3(512), smem, st, ss, n, ld, 0x5EEDu, delta, w.m.est);
     ABCDLS_LAUNCH_CHECK(h);
     if (est_out) *est_out = w.m.est;
     if (est_count) *est_count = (size_t)G * d * 4;
@@ -1051,7 +1065,7 @@ int abcdls_fused_sample_fine(abcdls_handle_t h, const double* ss, int64_t n, int
                              void* ws, size_t ws_bytes, int64_t** cnt_out, size_t* cnt_count, void* stream) {
     FUSED_PROLOGUE("fused_sample_fine");
     ABCDLS_CHECK_ARG(h, fine >= 1 && fine_valid(fine), "fused_sample_fine: fine");
-    k_make_brackets<<<d, 32, 0, st>>>(w.m.est, G, d, 1.0 / world, w.m.brk, w.est_fine);
+    launch_pdl(k_make_brackets, dim3(d), dim3(32), 0, st, w.m.est, G, d, 1.0 / world, w.m.brk, w.est_fine);
     const int rs = fine_run_shift();
     const int rq = rs > 2 ? rs : 2;
     const long long L = fine_lines(n, fine) >> rq << rq;    // whole runs, and four lines per half-warp step
@@ -1060,7 +1074,7 @@ int abcdls_fused_sample_fine(abcdls_handle_t h, const double* ss, int64_t n, int
         long long mx = (long long)h->sm_count * 2 / d;   // 63 registers x 512 threads: two CTAs per SM, one wave
         if (mx < 1) mx = 1;
         if (gx > mx) gx = mx;
-        k_sample_fine<<<dim3((unsigned)gx, d), 512, 0, st>>>(ss, n, ld, w.m.brk, L, fine, rs, 0xF17Eu, w.fine);
+        launch_pdl(k_sample_fine, dim3(dim3((unsigned)gx, d)), dim3(512), 0, st, ss, n, ld, w.m.brk, L, fine, rs, 0xF17Eu, w.fine);
     }
     ABCDLS_LAUNCH_CHECK(h);
     if (cnt_out) *cnt_out = reinterpret_cast<int64_t*>(w.fine);
@@ -1076,16 +1090,16 @@ int abcdls_fused_sample_dist(abcdls_handle_t h, const double* ss, int64_t n, int
     FUSED_PROLOGUE("fused_sample_dist");
     ABCDLS_CHECK_ARG(h, target && nacc >= 1 && n_global >= nacc && fine_valid(fine), "fused_sample_dist: nacc");
     if (fine) {
-        k_fine_brackets<<<d, 256, 0, st>>>(w.fine, w.m.brk, kZ, w.est_fine);
-        k_make_brackets<<<d, 32, 0, st>>>(w.est_fine, 1, d, 1.0, w.m.brk);
-        k_make_fused_scale<<<1, 32, 0, st>>>(w.est_fine, 1, d, 1.0, target, w.par);
+        launch_pdl(k_fine_brackets, dim3(d), dim3(256), 0, st, w.fine, w.m.brk, kZ, w.est_fine);
+        launch_pdl(k_make_brackets, dim3(d), dim3(32), 0, st, w.est_fine, 1, d, 1.0, w.m.brk, nullptr);
+        launch_pdl(k_make_fused_scale, dim3(1), dim3(32), 0, st, w.est_fine, 1, d, 1.0, target, w.par);
     } else {
-        k_make_brackets<<<d, 32, 0, st>>>(w.m.est, G, d, 1.0 / world, w.m.brk);
-        k_make_fused_scale<<<1, 32, 0, st>>>(w.m.est, G, d, 1.0 / world, target, w.par);
+        launch_pdl(k_make_brackets, dim3(d), dim3(32), 0, st, w.m.est, G, d, 1.0 / world, w.m.brk, nullptr);
+        launch_pdl(k_make_fused_scale, dim3(1), dim3(32), 0, st, w.m.est, G, d, 1.0 / world, target, w.par);
     }
     const double p = (double)nacc / (double)n_global;
     const double delta = kZ * sqrt(p * (1.0 - p) / ((double)G2 * kSampleQ * world));
-    k_sample_qdist<<<G2, 512, (size_t)kSampleQ * sizeof(double), st>>>(ss, n, d, ld, w.par, 0xD157u, p, delta, w.est2);
+    launch_pdl(k_sample_qdist, dim3(G2), dim3(512), (size_t)kSampleQ * sizeof(double), st, ss, n, d, ld, w.par, 0xD157u, p, delta, w.est2);
     ABCDLS_LAUNCH_CHECK(h);
     if (est_out) *est_out = w.est2;
     if (est_count) *est_count = (size_t)G2;
@@ -1103,7 +1117,7 @@ int abcdls_fused_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int
                      "fused_pass: args");
     const double narrow = fine_ratio(n, fine, world);   // the refined brackets keep that much less per list
     ABCDLS_CUDA(h, cudaMemsetAsync(cand_lrow, 0xff, (size_t)ecap * 4, st));   // -1 = unused slot
-    k_make_fused_thr<<<1, 32, 0, st>>>(w.est2, G2, 1.0 / world, d, w.par);
+    launch_pdl(k_make_fused_thr, dim3(1), dim3(32), 0, st, w.est2, G2, 1.0 / world, d, w.par);
     const int nstages = fused_stages(d);
     const size_t smem = kFHeader + (size_t)nstages * d * kFRows * 8 + kFQBytes;
     ABCDLS_ONCE(h, cudaFuncSetAttribute(k_fused_pass, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1131,7 +1145,7 @@ int abcdls_fused_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int
             return ABCDLS_E_CUDA;
         }
     }
-    k_fused_pass<<<(unsigned)grid, kFThreads, smem, st>>>(tmap, n, ntiles, d, nstages, w.m.brk, w.par, w.m.counts,
+    launch_pdl(k_fused_pass, dim3((unsigned)grid), dim3(kFThreads), smem, st, tmap, n, ntiles, d, nstages, w.m.brk, w.par, w.m.counts,
                                                          w.m.candM, w.capM, w.m.candU, w.capU, w.m.cnt, w.mask16, cand_ss,
                                                          ecap, cand_lrow, w.ealloc, tpc,
                                                          fused_chunk((long long)(cap_for(n, 0.03) * narrow)),
@@ -1142,8 +1156,8 @@ int abcdls_fused_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int
         long long mx = (long long)h->sm_count * 8 / d;
         if (mx < 1) mx = 1;
         if (gx > mx) gx = mx;
-        k_fused_histM<<<dim3((unsigned)gx, d), 256, 0, st>>>(w.m.candM, w.capM, w.m.cnt, w.m.brk, w.m.histM, w.m.counts);
-        k_copy_u64<<<1, 128, 0, st>>>(w.m.gcnt, w.m.cnt, 2 * d);
+        launch_pdl(k_fused_histM, dim3(dim3((unsigned)gx, d)), dim3(256), 0, st, w.m.candM, w.capM, w.m.cnt, w.m.brk, w.m.histM, w.m.counts);
+        launch_pdl(k_copy_u64, dim3(1), dim3(128), 0, st, w.m.gcnt, w.m.cnt, 2 * d);
         ABCDLS_LAUNCH_CHECK(h);
     }
     if (counts_out) *counts_out = reinterpret_cast<int64_t*>(w.m.counts);
@@ -1176,9 +1190,9 @@ int abcdls_fused_rows(abcdls_handle_t h, const double* ss, int64_t n, int d, int
     const long long nwords = ntiles * (kFRows / 32);
     const long long nblk = (nwords + 256 * kMWords - 1) / (256 * kMWords);
     const unsigned* bitmap = reinterpret_cast<const unsigned*>(w.mask16);
-    k_mask_count<<<(unsigned)nblk, 256, 0, st>>>(bitmap, nwords, w.tile_cnt, w.total);
-    k_scan_tiles<<<1, 1024, 0, st>>>(w.tile_cnt, nblk, w.tile_off);
-    k_mask_write<<<(unsigned)nblk, 256, 0, st>>>(bitmap, nwords, w.tile_off, row_offset, cap, (long long*)cand_row,
+    launch_pdl(k_mask_count, dim3((unsigned)nblk), dim3(256), 0, st, bitmap, nwords, w.tile_cnt, w.total);
+    launch_pdl(k_scan_tiles, dim3(1), dim3(1024), 0, st, w.tile_cnt, nblk, w.tile_off);
+    launch_pdl(k_mask_write, dim3((unsigned)nblk), dim3(256), 0, st, bitmap, nwords, w.tile_off, row_offset, cap, (long long*)cand_row,
                                                  w.wprefix, w.total, (long long*)n_cand, status_dev);
     ABCDLS_LAUNCH_CHECK(h);
     return ABCDLS_OK;
@@ -1197,7 +1211,7 @@ int abcdls_fused_exact(abcdls_handle_t h, const double* ss, int64_t n, int d, in
     const unsigned* bitmap = reinterpret_cast<const unsigned*>(w.mask16);
     long long g = (ecap + 255) / 256;
     if (g > (long long)h->sm_count * 16) g = (long long)h->sm_count * 16;
-    k_cand_exact<<<(unsigned)g, 256, 0, st>>>(cand_ss, ecap, cand_lrow, w.ealloc, d, mad, target, bitmap, w.wprefix, cap,
+    launch_pdl(k_cand_exact, dim3((unsigned)g), dim3(256), 0, st, cand_ss, ecap, cand_lrow, w.ealloc, d, mad, target, bitmap, w.wprefix, cap,
                                               cand_dist, (long long*)perm, status_dev);
     ABCDLS_LAUNCH_CHECK(h);
     return ABCDLS_OK;
@@ -1234,19 +1248,19 @@ int abcdls_fused_ds(abcdls_handle_t h, int64_t n, int d, int phase, int world, c
     if (gg > (long long)h->sm_count * 4) gg = (long long)h->sm_count * 4;
     if (x0) *x0 = nullptr;
     if (phase == 0) {
-        k_plan_ds_fused<<<1, 32, 0, st>>>(w.ds_job, w.par, (const long long*)n_cand, cand_dist, cap, w.ds_hist, w.ds_small,
+        launch_pdl(k_plan_ds_fused, dim3(1), dim3(32), 0, st, w.ds_job, w.par, (const long long*)n_cand, cand_dist, cap, w.ds_hist, w.ds_small,
                                           w.ds_small_count, nacc - 1, d, status_dev);
-        k_refine_hist<<<dim3((unsigned)gg, 1), 256, 0, st>>>(w.ds_job, cap);
+        launch_pdl(k_refine_hist, dim3(dim3((unsigned)gg, 1)), dim3(256), 0, st, w.ds_job, cap);
         if (x0) { *x0 = w.ds_hist; *x0_count = (size_t)kNB; }
     } else if (phase == 1) {
-        k_refine_pick<<<1, 256, 0, st>>>(w.ds_job, status_dev);
-        k_refine_gather<<<dim3((unsigned)gg, 1), 256, 0, st>>>(w.ds_job, cap);
-        k_ds_pack<<<1, 32, 0, st>>>(w.ds_job);
+        launch_pdl(k_refine_pick, dim3(1), dim3(256), 0, st, w.ds_job, status_dev);
+        launch_pdl(k_refine_gather, dim3(dim3((unsigned)gg, 1)), dim3(256), 0, st, w.ds_job, cap);
+        launch_pdl(k_ds_pack, dim3(1), dim3(32), 0, st, w.ds_job);
         if (x0) { *x0 = w.ds_small; *x0_count = (size_t)kSmallCap + 1; }
     } else {
         const size_t smem = (size_t)kSmallCap * sizeof(double);
         ABCDLS_ONCE(h, cudaFuncSetAttribute(k_ds_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_ds_final<<<1, 1024, smem, st>>>(w.ds_job, gath, gath ? world : 1, ds_out, status_dev);
+        launch_pdl(k_ds_final, dim3(1), dim3(1024), smem, st, w.ds_job, gath, gath ? world : 1, ds_out, status_dev);
     }
     ABCDLS_LAUNCH_CHECK(h);
     return ABCDLS_OK;
@@ -1261,7 +1275,7 @@ int abcdls_fused_check(abcdls_handle_t h, int64_t n, int d, const double* mad, c
         h->err = "fused workspace too small";
         return ABCDLS_E_WORKSPACE;
     }
-    k_fused_check<<<1, 32, 0, (cudaStream_t)stream>>>(w.par, mad, d, ds, status_dev);
+    launch_pdl(k_fused_check, dim3(1), dim3(32), 0, (cudaStream_t)stream, w.par, mad, d, ds, status_dev);
     ABCDLS_LAUNCH_CHECK(h);
     return ABCDLS_OK;
 }

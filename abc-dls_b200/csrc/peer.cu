@@ -68,6 +68,7 @@ __device__ __forceinline__ void finish(const PeerDev& P, unsigned long long k) {
 // exchange costs ONE NVLink round trip, not world - 1.
 template <typename T>
 __global__ void __launch_bounds__(kPeerThreads) k_peer_allreduce(PeerDev P, T* __restrict__ data, size_t count, int op) {
+    pdl_prologue();
     const unsigned long long k = *P.seq + 1ull;
     const int parity = (int)(k & 1ull);
     T* mine = reinterpret_cast<T*>(data_ptr(P.box[P.rank], P.slot_bytes, parity));
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(kPeerThreads) k_peer_allreduce(PeerDev P, T* _
 // dst[r * words .. ) = contribution of rank r (8-byte words)
 __global__ void __launch_bounds__(kPeerThreads) k_peer_allgather(PeerDev P, const long long* __restrict__ src, size_t words,
                                                                  long long* __restrict__ dst) {
+    pdl_prologue();
     const unsigned long long k = *P.seq + 1ull;
     const int parity = (int)(k & 1ull);
     long long* mine = reinterpret_cast<long long*>(data_ptr(P.box[P.rank], P.slot_bytes, parity));
@@ -128,6 +130,7 @@ __global__ void __launch_bounds__(kPeerThreads) k_peer_allgather_ragged(PeerDev 
                                                                         const unsigned* __restrict__ src_cnt, int nj,
                                                                         long long cap, double* __restrict__ dst_vals,
                                                                         unsigned* __restrict__ dst_cnt) {
+    pdl_prologue();
     const unsigned long long k = *P.seq + 1ull;
     const int parity = (int)(k & 1ull);
     unsigned long long* mine = reinterpret_cast<unsigned long long*>(data_ptr(P.box[P.rank], P.slot_bytes, parity));
@@ -265,9 +268,9 @@ int abcdls_peer_allreduce(abcdls_peer_t p, void* data, size_t count, int dtype, 
     if (count == 0) return ABCDLS_OK;
     const unsigned g = peer_grid(count * 8);
     if (dtype == 0)
-        k_peer_allreduce<double><<<g, kPeerThreads, 0, (cudaStream_t)stream>>>(p->dev, (double*)data, count, op);
+        launch_pdl(k_peer_allreduce<double>, dim3(g), dim3(kPeerThreads), 0, (cudaStream_t)stream, p->dev, (double*)data, count, op);
     else
-        k_peer_allreduce<long long><<<g, kPeerThreads, 0, (cudaStream_t)stream>>>(p->dev, (long long*)data, count, op);
+        launch_pdl(k_peer_allreduce<long long>, dim3(g), dim3(kPeerThreads), 0, (cudaStream_t)stream, p->dev, (long long*)data, count, op);
     return cudaGetLastError() == cudaSuccess ? ABCDLS_OK : ABCDLS_E_CUDA;
 }
 
@@ -275,7 +278,7 @@ int abcdls_peer_allreduce(abcdls_peer_t p, void* data, size_t count, int dtype, 
 int abcdls_peer_allgather(abcdls_peer_t p, const void* src, size_t bytes, void* dst, void* stream) {
     if (!p || !src || !dst || (bytes & 7) || bytes > p->dev.slot_bytes) return ABCDLS_E_INVALID;
     if (bytes == 0) return ABCDLS_OK;
-    k_peer_allgather<<<peer_grid(bytes), kPeerThreads, 0, (cudaStream_t)stream>>>(p->dev, (const long long*)src, bytes / 8,
+    launch_pdl(k_peer_allgather, dim3(peer_grid(bytes)), dim3(kPeerThreads), 0, (cudaStream_t)stream, p->dev, (const long long*)src, bytes / 8,
                                                                                   (long long*)dst);
     return cudaGetLastError() == cudaSuccess ? ABCDLS_OK : ABCDLS_E_CUDA;
 }
@@ -288,7 +291,7 @@ int abcdls_peer_allgather_ragged(abcdls_peer_t p, const double* src_vals, const 
         return ABCDLS_E_INVALID;
     unsigned g = (unsigned)(p->dev.world * nj);             // one (rank, row) pair per CTA where the device allows
     if (g > 128u) g = 128u;
-    k_peer_allgather_ragged<<<g, kPeerThreads, 0, (cudaStream_t)stream>>>(p->dev, src_vals, src_cnt, nj, cap, dst_vals,
+    launch_pdl(k_peer_allgather_ragged, dim3(g), dim3(kPeerThreads), 0, (cudaStream_t)stream, p->dev, src_vals, src_cnt, nj, cap, dst_vals,
                                                                          dst_cnt);
     return cudaGetLastError() == cudaSuccess ? ABCDLS_OK : ABCDLS_E_CUDA;
 }

@@ -303,6 +303,7 @@ __device__ __forceinline__ double scaled_by(double x, double div, double rcp) {
 // for the tensor-core accumulation.  The row numbers of the NEXT tile are fetched while this one accumulates.
 template <int NA>
 __global__ void __launch_bounds__(kTlThreads, 2) k_tail_gather_fit(TailArgs A, PeerDev PD) {
+    pdl_prologue();
     extern __shared__ __align__(16) double sm[];
     const int d = A.d, P = A.P, M = d + 1, W = M + P, lin = A.lin;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -560,6 +561,7 @@ __device__ __forceinline__ double the_m_of(const double* usum, const double* sbe
 // computes the residuals of parameters {4k + 2h, 4k + 2h + 1}; the tile [ones | xs | log res^2 | w] feeds the DMMA.
 template <int DC>
 __global__ void __launch_bounds__(kTlThreads, DC > 16 ? 1 : 2) k_tail_resid_fit(TailArgs A, PeerDev PD) {
+    pdl_prologue();
     extern __shared__ __align__(16) double sm[];
     const int d = A.d, P = A.P, M = d + 1, W = M + P, Pp = (P + 3) & ~3;
     const int tid = threadIdx.x;
@@ -656,6 +658,7 @@ __global__ void __launch_bounds__(kTlThreads, DC > 16 ? 1 : 2) k_tail_resid_fit(
 constexpr int kT3Stat = 7;   // min, max, sum x, sum w x, sum w x^2, sum w, sum w res^2 (uncorrected residual: sigma2)
 template <int DC>
 __global__ void __launch_bounds__(kTlThreads, 2) k_tail_adjust_final(TailArgs A, PeerDev PD) {
+    pdl_prologue();
     extern __shared__ __align__(16) double sm[];
     const int d = A.d, P = A.P, M = d + 1, Pp = (P + 3) & ~3;
     constexpr bool lin = DC > 0;
@@ -881,6 +884,7 @@ __global__ void __launch_bounds__(256) k_postpr_final(PeerDev PD, int world, con
                                                       const double* __restrict__ mad, int d,
                                                       const long long* __restrict__ counts, int K,
                                                       double* __restrict__ small) {
+    pdl_prologue();
     extern __shared__ double vec[];   // [8 status bits (negated: min) | K counts (sum)]
     const int tid = threadIdx.x;
     int st = *status;
@@ -910,6 +914,29 @@ __global__ void __launch_bounds__(256) k_postpr_final(PeerDev PD, int world, con
         small[2] = *ds;
         small[3] = (double)allzero;
         small[4] = small[5] = small[6] = small[7] = 0.0;
+    }
+}
+
+// What a caller normally reads from a result (small buffer, accepted rows, weights, posterior sample) leaves the
+// buffers of the replayed CUDA graph in ONE launch: up to four 2-D segments (rows x cols, source pitch ld) are
+// packed back to back into a freshly allocated block.  (Four framework clone calls cost ~35 us of host time per
+// call - the GPU idles meanwhile, because the next call cannot be enqueued before this one's results are safe.)
+struct CopySegs {
+    const double* src[4];
+    long long ld[4], rows[4], cols[4], off[4];
+    int n;
+};
+constexpr int kCopyChunk = 4096;
+__global__ void __launch_bounds__(256) k_copy_out(CopySegs S, double* __restrict__ dst) {
+    const int sgi = blockIdx.y;
+    if (sgi >= S.n) return;
+    const long long cols = S.cols[sgi], nch = (cols + kCopyChunk - 1) / kCopyChunk;
+    for (long long b = blockIdx.x; b < S.rows[sgi] * nch; b += gridDim.x) {
+        const long long r = b / nch, c0 = (b - r * nch) * kCopyChunk;
+        const double* __restrict__ src = S.src[sgi] + r * S.ld[sgi];
+        double* __restrict__ out = dst + S.off[sgi] + r * cols;
+        const long long c1 = min(cols, c0 + (long long)kCopyChunk);
+        for (long long c = c0 + threadIdx.x; c < c1; c += blockDim.x) out[c] = src[c];
     }
 }
 
@@ -1028,13 +1055,13 @@ int abcdls_tail_gather_fit(abcdls_handle_t h, abcdls_peer_t peer, const double* 
     cudaStream_t st = (cudaStream_t)stream;                                 // intercept + d slopes + the unweighted ones row
     if (rowsA <= 8) {
         if (int rc = ensure_smem(h, k_tail_gather_fit<1>, smem, &have[0])) return rc;
-        k_tail_gather_fit<1><<<grid, kTlThreads, smem, st>>>(A, PD);
+        launch_pdl(k_tail_gather_fit<1>, dim3(grid), dim3(kTlThreads), smem, st, A, PD);
     } else if (rowsA <= 24) {
         if (int rc = ensure_smem(h, k_tail_gather_fit<3>, smem, &have[1])) return rc;
-        k_tail_gather_fit<3><<<grid, kTlThreads, smem, st>>>(A, PD);
+        launch_pdl(k_tail_gather_fit<3>, dim3(grid), dim3(kTlThreads), smem, st, A, PD);
     } else {
         if (int rc = ensure_smem(h, k_tail_gather_fit<5>, smem, &have[2])) return rc;
-        k_tail_gather_fit<5><<<grid, kTlThreads, smem, st>>>(A, PD);
+        launch_pdl(k_tail_gather_fit<5>, dim3(grid), dim3(kTlThreads), smem, st, A, PD);
     }
     ABCDLS_LAUNCH_CHECK(h);
     return ABCDLS_OK;
@@ -1064,19 +1091,19 @@ int abcdls_tail_resid_fit(abcdls_handle_t h, abcdls_peer_t peer, const double* x
     switch (dc_index(d)) {
         case 0:
             if (int rc = ensure_smem(h, k_tail_resid_fit<2>, smem, &have[0])) return rc;
-            k_tail_resid_fit<2><<<grid, kTlThreads, smem, st>>>(A, PD);
+            launch_pdl(k_tail_resid_fit<2>, dim3(grid), dim3(kTlThreads), smem, st, A, PD);
             break;
         case 1:
             if (int rc = ensure_smem(h, k_tail_resid_fit<8>, smem, &have[1])) return rc;
-            k_tail_resid_fit<8><<<grid, kTlThreads, smem, st>>>(A, PD);
+            launch_pdl(k_tail_resid_fit<8>, dim3(grid), dim3(kTlThreads), smem, st, A, PD);
             break;
         case 2:
             if (int rc = ensure_smem(h, k_tail_resid_fit<16>, smem, &have[2])) return rc;
-            k_tail_resid_fit<16><<<grid, kTlThreads, smem, st>>>(A, PD);
+            launch_pdl(k_tail_resid_fit<16>, dim3(grid), dim3(kTlThreads), smem, st, A, PD);
             break;
         default:
             if (int rc = ensure_smem(h, k_tail_resid_fit<32>, smem, &have[3])) return rc;
-            k_tail_resid_fit<32><<<grid, kTlThreads, smem, st>>>(A, PD);
+            launch_pdl(k_tail_resid_fit<32>, dim3(grid), dim3(kTlThreads), smem, st, A, PD);
             break;
     }
     ABCDLS_LAUNCH_CHECK(h);
@@ -1111,25 +1138,52 @@ int abcdls_tail_adjust_final(abcdls_handle_t h, abcdls_peer_t peer, const double
     switch (loclinear ? dc_index(d) : 4) {
         case 0:
             if (int rc = ensure_smem(h, k_tail_adjust_final<2>, smem, &have[0])) return rc;
-            k_tail_adjust_final<2><<<grid, kTlThreads, smem, st>>>(A, PD);
+            launch_pdl(k_tail_adjust_final<2>, dim3(grid), dim3(kTlThreads), smem, st, A, PD);
             break;
         case 1:
             if (int rc = ensure_smem(h, k_tail_adjust_final<8>, smem, &have[1])) return rc;
-            k_tail_adjust_final<8><<<grid, kTlThreads, smem, st>>>(A, PD);
+            launch_pdl(k_tail_adjust_final<8>, dim3(grid), dim3(kTlThreads), smem, st, A, PD);
             break;
         case 2:
             if (int rc = ensure_smem(h, k_tail_adjust_final<16>, smem, &have[2])) return rc;
-            k_tail_adjust_final<16><<<grid, kTlThreads, smem, st>>>(A, PD);
+            launch_pdl(k_tail_adjust_final<16>, dim3(grid), dim3(kTlThreads), smem, st, A, PD);
             break;
         case 3:
             if (int rc = ensure_smem(h, k_tail_adjust_final<32>, smem, &have[3])) return rc;
-            k_tail_adjust_final<32><<<grid, kTlThreads, smem, st>>>(A, PD);
+            launch_pdl(k_tail_adjust_final<32>, dim3(grid), dim3(kTlThreads), smem, st, A, PD);
             break;
         default:
             if (int rc = ensure_smem(h, k_tail_adjust_final<0>, smem, &have[4])) return rc;
-            k_tail_adjust_final<0><<<grid, kTlThreads, smem, st>>>(A, PD);
+            launch_pdl(k_tail_adjust_final<0>, dim3(grid), dim3(kTlThreads), smem, st, A, PD);
             break;
     }
+    ABCDLS_LAUNCH_CHECK(h);
+    return ABCDLS_OK;
+}
+
+// nseg <= 4 segments; segment i = rows[i] x cols[i] 8-byte elements read with pitch ld[i] from src[i], written densely
+// (row after row) to dst, segment after segment.
+int abcdls_copy_out(abcdls_handle_t h, int nseg, const void* const* src, const int64_t* ld, const int64_t* rows,
+                    const int64_t* cols, void* dst, void* stream) {
+    ABCDLS_CHECK_ARG(h, h && src && ld && rows && cols && dst && nseg >= 1 && nseg <= 4, "copy_out");
+    CopySegs S = {};
+    S.n = nseg;
+    long long off = 0, most = 1;
+    for (int i = 0; i < nseg; ++i) {
+        ABCDLS_CHECK_ARG(h, (src[i] || rows[i] * cols[i] == 0) && rows[i] >= 0 && cols[i] >= 0 && ld[i] >= cols[i], "copy_out: segment");
+        S.src[i] = reinterpret_cast<const double*>(src[i]);
+        S.ld[i] = ld[i];
+        S.rows[i] = rows[i];
+        S.cols[i] = cols[i];
+        S.off[i] = off;
+        off += rows[i] * cols[i];
+        const long long blocks = rows[i] * ((cols[i] + kCopyChunk - 1) / kCopyChunk);
+        if (blocks > most) most = blocks;
+    }
+    if (off == 0) return ABCDLS_OK;
+    const long long mx = (long long)h->sm_count * 8;
+    k_copy_out<<<dim3((unsigned)(most > mx ? mx : most), (unsigned)nseg), 256, 0, (cudaStream_t)stream>>>(
+        S, reinterpret_cast<double*>(dst));
     ABCDLS_LAUNCH_CHECK(h);
     return ABCDLS_OK;
 }
@@ -1141,7 +1195,7 @@ int abcdls_postpr_final(abcdls_handle_t h, abcdls_peer_t peer, const int* status
     ABCDLS_CHECK_ARG(h, d >= 1 && d <= 64 && K >= 1 && K <= 4096, "postpr_final: shape");
     PeerDev PD = {};
     if (peer) PD = peer->dev;
-    k_postpr_final<<<1, 256, (size_t)(8 + K) * sizeof(double), (cudaStream_t)stream>>>(
+    launch_pdl(k_postpr_final, dim3(1), dim3(256), (size_t)(8 + K) * sizeof(double), (cudaStream_t)stream, 
         PD, peer ? peer->dev.world : 1, status_dev, (const long long*)n_acc, ds, mad, d, (const long long*)counts, K,
         small_out);
     ABCDLS_LAUNCH_CHECK(h);

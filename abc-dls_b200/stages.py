@@ -375,6 +375,26 @@ class CudaStages:
                          int(loclinear), _p(xs), _p(y), _p(ss_out), _p(w), _p(ws), ws.numel(), _p(status), self._stream())
         self.launches += 1
 
+    def copy_out(self, segs, memo=None):
+        """segs: up to four (tensor2d_or_1d, rows, cols) with unit stride along cols -> ONE dense float64 block holding
+        the segments back to back (int64 data travels as raw 8-byte words), in one launch; returns the block.
+        memo (a dict that lives as long as the source buffers, e.g. the graph plan): keeps the marshalled arguments."""
+        shape = tuple((r, c) for _, r, c in segs)
+        co = memo.get("copy_out") if memo is not None else None
+        if co is None or co[0] != shape:
+            n = len(segs)
+            src = (C.c_void_p * n)(*[t.data_ptr() for t, _, _ in segs])
+            ld = (C.c_int64 * n)(*[(t.stride(0) if t.dim() == 2 else max(c, 1)) for t, _, c in segs])
+            rows = (C.c_int64 * n)(*[r for _, r, _ in segs])
+            cols = (C.c_int64 * n)(*[c for _, _, c in segs])
+            co = (shape, n, src, ld, rows, cols, sum(r * c for r, c in shape))
+            if memo is not None:
+                memo["copy_out"] = co
+        _, n, src, ld, rows, cols, total = co
+        out = torch.empty(total, dtype=torch.float64, device=self.device)
+        self.handle.call("abcdls_copy_out", n, src, ld, rows, cols, _p(out), self._stream())
+        return out
+
     def tail_resid_fit(self, peer, xs, y, w, n_acc, cap, d, P, ws, status):
         self.handle.call("abcdls_tail_resid_fit", peer, _p(xs), _p(y), _p(w), _p(n_acc), cap, d, P, _p(ws),
                          ws.numel(), _p(status), self._stream())

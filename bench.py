@@ -475,11 +475,16 @@ def timed_region(ctx, args, step):
     res = None
     with sampler as clocks:
         ctx.sync()
+        if hasattr(ctx.eng, "host_profile"):
+            ctx.eng.host_profile = {k_: 0 for k_ in ctx.eng.host_profile}
+            ctx.eng._t_last_return = None
         ev0.record()
         for _ in range(args.steps):
             res = step()
         ev1.record()
         ctx.sync()
+        if hasattr(ctx.eng, "host_profile"):
+            ctx.host_profile_timed = dict(ctx.eng.host_profile)
     ms = ctx.allmax(ev0.elapsed_time(ev1)) / args.steps
     return ms, ctx.eng.k.launches - l0, clocks.summary(), res
 
@@ -533,7 +538,10 @@ def streaming_roofline(kern, d, n_local, bytes_per_sim, N, ms_step, world):
 def engine_facts(ctx):
     eng = ctx.eng
     host_ms = eng.host_enqueue_ms[-8:]
+    hp = dict(getattr(ctx, "host_profile_timed", None) or eng.host_profile)   # of the timed calls
+    nc = max(1, hp.pop("calls"))
     return {"fast_path_misses": eng.fast_misses, "host_enqueue_ms": round(sum(host_ms) / max(1, len(host_ms)), 3),
+            "host_profile_us": {k_: round(v_ / nc, 1) for k_, v_ in hp.items()},
             "cuda_graph": bool(eng._graphs), "front_half": dict(eng.path_calls),
             "collectives": {"total": eng.comm.calls, "nvlink_mailbox_kernels": eng.comm.peer_calls,
                             "fused_into_compute_kernels": eng.comm.fused_calls,

@@ -429,6 +429,10 @@ int abcdls_postpr_counts(abcdls_handle_t h, const int32_t* model_id, const int64
                          const int64_t* n_acc, int64_t row_offset, int64_t cap, int K, int64_t* counts,
                          void* stream);
 
+/* Results out of the buffers of a replayed CUDA graph in ONE launch: up to 4 segments (rows[i] x cols[i] 8-byte
+ * elements, source pitch ld[i]) are packed densely, one after the other, into dst. */
+int abcdls_copy_out(abcdls_handle_t h, int nseg, const void* const* src, const int64_t* ld, const int64_t* rows,
+                    const int64_t* cols, void* dst, void* stream);
 /* the end of a postpr() call in one block: counts and status of all ranks in ONE exchange (peer; NULL on one rank), then
  * small_out[8 + d + K] = {status, n_acc, ds, every MAD zero, 0, 0, 0, 0 | mad[d] | counts[K] (global, as doubles)} */
 int abcdls_postpr_final(abcdls_handle_t h, abcdls_peer_t peer, const int* status_dev, const int64_t* n_acc,
