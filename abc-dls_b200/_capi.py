@@ -55,6 +55,7 @@ SIGNATURES = {
     "abcdls_fused_sample_dist": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _sz, C.POINTER(_vp),
                                         C.POINTER(_sz), _vp]),
     "abcdls_fused_emit_cap": (_i64, [_i64]),
+    "abcdls_fused_emit_pitch": (_i32, [_i32]),
     "abcdls_fused_pass": (_i32, [_vp, _vp, _i64, _i32, _i64, _i32, _i32, _vp, _vp, _i64, _vp, _sz, _vp, C.POINTER(_vp),
                                  C.POINTER(_sz), _vp]),
     "abcdls_fused_refine": (_i32, [_vp, _vp, _i64, _i64, _i32, _i64, _i32, _i32, _vp, _vp, _vp, _sz, _vp, _vp, _vp,

@@ -9,7 +9,7 @@ SRCS="api.cu select.cu dist.cu loclinear.cu tail.cu summary.cu smc.cu peer.cu sm
 OBJS=""
 for s in $SRCS; do
   o="${s%.cu}.o"
-  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ fused.cuh -nt "$o" ] || [ compact.cuh -nt "$o" ] || [ peer.cuh -nt "$o" ] || [ columns.cuh -nt "$o" ] || [ ../../include/abcdls.h -nt "$o" ]; then
+  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ fused.cuh -nt "$o" ] || [ fused_wide.cuh -nt "$o" ] || [ compact.cuh -nt "$o" ] || [ peer.cuh -nt "$o" ] || [ columns.cuh -nt "$o" ] || [ ../../include/abcdls.h -nt "$o" ]; then
     $NVCC $FLAGS ${EXTRA:-} -c "$s" -o "$o" &
   fi
   OBJS="$OBJS $o"

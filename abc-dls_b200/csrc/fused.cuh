@@ -56,7 +56,10 @@ __device__ __forceinline__ void tma_tile_g2s(void* dst_smem, const CUtensorMap* 
 }
 
 constexpr int kFRows = 256;
-constexpr int kFMaxD = 16;
+constexpr int kFNarrowD = 16;    // k_fused_pass: 256-row tiles, one column per consumer warp, 16-double candidate records
+constexpr int kFMaxD = 32;       // k_fused_pass_wide (fused_wide.cuh): 128-row tiles, two columns per warp, 32-double records
+inline int fused_tile_rows(int d) { return d > kFNarrowD ? 128 : kFRows; }
+inline int fused_emit_pitch(int d) { return d > kFNarrowD ? 32 : kFNarrowD; }
 constexpr int kFWarps = 16;
 constexpr int kFConsumers = kFWarps * 32;
 constexpr int kFThreads = kFConsumers + 32;
@@ -88,7 +91,7 @@ struct FusedSmem {
 static_assert(sizeof(FusedSmem) <= kFHeader, "header");
 
 inline int fused_stages(int d) {
-    int s = kFRingBytes / (d * kFRows * 8);
+    int s = kFRingBytes / (d * fused_tile_rows(d) * 8);
     return s > kFMaxStages ? kFMaxStages : s;
 }
 
@@ -562,7 +565,7 @@ k_fused_pass(const __grid_constant__ CUtensorMap tmap, long long n, long long nt
                 : "+r"(pq)                                                                           \
                 : "r"((unsigned)cand), "d"(xv));                                                     \
         }
-        if (d == kFMaxD) {
+        if (d == kFNarrowD) {
             // every warp owns a column: ONE straight-line block, so that the classification chains and the distance
             // FMAs of the tile overlap in the pipeline
             if (__any_sync(0xffffffffu, pq > qlim)) flush();
@@ -628,7 +631,7 @@ k_fused_pass(const __grid_constant__ CUtensorMap tmap, long long n, long long nt
                 if ((long long)slot < ecap) {
                     // row-major block: 128 bytes per candidate; this lane writes columns [8 half, 8 half + 8)
                     if (half == 0) erow[slot] = (int)(tile * kFRows + row);
-                    double* dst = cand_e + (size_t)slot * kFMaxD + 8 * half;
+                    double* dst = cand_e + (size_t)slot * kFNarrowD + 8 * half;
                     const double* src = stage + (size_t)(8 * half) * kFRows + row;
 #pragma unroll
                     for (int q2 = 0; q2 < 4; ++q2) {
@@ -664,6 +667,8 @@ k_fused_pass(const __grid_constant__ CUtensorMap tmap, long long n, long long nt
     }
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(status, ABCDLS_S_NONFINITE);
 }
+
+#include "fused_wide.cuh"
 
 // Fine histogram of the M band of every column from its (dense) candidates, after the pass: the pass itself stays
 // free of the binning arithmetic and of 16M global reductions.  Also turns counts[4j] from "x < c" into "strictly
@@ -771,7 +776,7 @@ __global__ void __launch_bounds__(256) k_mask_write(const unsigned* __restrict__
 // (prefix of its word + bits below it), where the distance and the slot number are scattered to.
 __global__ void __launch_bounds__(256) k_cand_exact(const double* __restrict__ cand_e, long long ecap,
                                                     const int* __restrict__ erow,
-                                                    const unsigned long long* __restrict__ ealloc, int d,
+                                                    const unsigned long long* __restrict__ ealloc, int d, int pitch,
                                                     const double* __restrict__ mad, const double* __restrict__ target,
                                                     const unsigned* __restrict__ bitmap, const int* __restrict__ wprefix,
                                                     long long cap, double* __restrict__ cand_dist,
@@ -789,7 +794,7 @@ __global__ void __launch_bounds__(256) k_cand_exact(const double* __restrict__ c
         const int r = erow[sl];
         if (r < 0) continue;   // unused tail of a chunk
         double s0 = 0.0;
-        const double* __restrict__ rowp = cand_e + (size_t)sl * kFMaxD;
+        const double* __restrict__ rowp = cand_e + (size_t)sl * pitch;
         for (int j = 0; j < d; j += 2) {
             const double2 v = *reinterpret_cast<const double2*>(rowp + j);
             const double a = __dsub_rn(scaled_value(v.x, S.dr[j]), S.tgt[j]);
@@ -979,13 +984,14 @@ inline FusedWs carve_fused(void* ws, int64_t n, int d) {
     char* p = reinterpret_cast<char*>(ws);
     size_t o = w.m.total;
     auto take = [&](size_t bytes) { size_t a = o; o += align_up(bytes, 256); return p ? p + a : (char*)nullptr; };
-    const long long ntiles = (n + kFRows - 1) / kFRows;
-    const long long nwords = ntiles * (kFRows / 32);
+    const int trows = fused_tile_rows(d);
+    const long long ntiles = (n + trows - 1) / trows;
+    const long long nwords = ntiles * (trows / 32);
     const long long nblk = (nwords + 256 * kMWords - 1) / (256 * kMWords);
     w.par = (FusedPar*)take(sizeof(FusedPar));
     w.est2 = (double*)take((size_t)kFG2 * 8);
     w.total = (unsigned long long*)take(8);
-    w.mask16 = (unsigned short*)take((size_t)ntiles * kFWarps * 2 + 64);
+    w.mask16 = (unsigned short*)take((size_t)nwords * 4 + 64);   // one bit per row of every (padded) tile
     w.tile_cnt = (int*)take((size_t)nblk * 4);
     w.tile_off = (long long*)take((size_t)nblk * 8);
     w.wprefix = (int*)take((size_t)nwords * 4);
@@ -1108,6 +1114,8 @@ int abcdls_fused_sample_dist(abcdls_handle_t h, const double* ss, int64_t n, int
 
 // Stage 3: THE table pass.  counts_out: int64 block (counts | band counts | median histogram) to all-reduce (sum).
 int64_t abcdls_fused_emit_cap(int64_t cap) { return cap + (int64_t)160 * kFWarps * kFEChunk; }
+// doubles per emitted candidate record (the row pitch of cand_ss): 16 for d <= 16, 32 for d <= 32
+int abcdls_fused_emit_pitch(int d) { return fused_emit_pitch(d); }
 
 int abcdls_fused_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, int fine,
                       double* cand_ss, int32_t* cand_lrow, int64_t ecap, void* ws, size_t ws_bytes, int* status_dev,
@@ -1119,10 +1127,14 @@ int abcdls_fused_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int
     ABCDLS_CUDA(h, cudaMemsetAsync(cand_lrow, 0xff, (size_t)ecap * 4, st));   // -1 = unused slot
     launch_pdl(k_make_fused_thr, dim3(1), dim3(32), 0, st, w.est2, G2, 1.0 / world, d, w.par);
     const int nstages = fused_stages(d);
-    const size_t smem = kFHeader + (size_t)nstages * d * kFRows * 8 + kFQBytes;
+    const int trows = fused_tile_rows(d);
+    const bool wide = d > kFNarrowD;
+    const size_t smem = kFHeader + (size_t)nstages * d * trows * 8 + kFQBytes;
     ABCDLS_ONCE(h, cudaFuncSetAttribute(k_fused_pass, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         kFHeader + kFRingBytes + kFQBytes));
-    const long long ntiles = (n + kFRows - 1) / kFRows;
+    ABCDLS_ONCE(h, cudaFuncSetAttribute(k_fused_pass_wide, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kFHeader + kFRingBytes + kFQBytes));
+    const long long ntiles = (n + trows - 1) / trows;
     long long grid = h->sm_count;
     if (grid > ntiles) grid = ntiles;
     const long long tpc = (ntiles + grid - 1) / grid;
@@ -1135,7 +1147,7 @@ int abcdls_fused_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int
     {
         const cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)d};
         const cuuint64_t gstr[1] = {(cuuint64_t)ld * 8};
-        const cuuint32_t box[2] = {(cuuint32_t)kFRows, (cuuint32_t)d};
+        const cuuint32_t box[2] = {(cuuint32_t)trows, (cuuint32_t)d};
         const cuuint32_t estr[2] = {1, 1};
         const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ss), gdim, gstr, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -1145,11 +1157,16 @@ int abcdls_fused_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int
             return ABCDLS_E_CUDA;
         }
     }
-    launch_pdl(k_fused_pass, dim3((unsigned)grid), dim3(kFThreads), smem, st, tmap, n, ntiles, d, nstages, w.m.brk, w.par, w.m.counts,
-                                                         w.m.candM, w.capM, w.m.candU, w.capU, w.m.cnt, w.mask16, cand_ss,
-                                                         ecap, cand_lrow, w.ealloc, tpc,
-                                                         fused_chunk((long long)(cap_for(n, 0.03) * narrow)),
-                                                         fused_chunk((long long)(cap_for(n, 0.08) * narrow)), status_dev);
+    const int chM = fused_chunk((long long)(cap_for(n, 0.03) * narrow)), chU = fused_chunk((long long)(cap_for(n, 0.08) * narrow));
+    if (wide)
+        launch_pdl(k_fused_pass_wide, dim3((unsigned)grid), dim3(kFThreads), smem, st, tmap, n, ntiles, d, nstages, w.m.brk,
+                   w.par, w.m.counts, w.m.candM, w.capM, w.m.candU, w.capU, w.m.cnt,
+                   reinterpret_cast<unsigned char*>(w.mask16), cand_ss, ecap, cand_lrow, w.ealloc, tpc, chM, chU,
+                   status_dev);
+    else
+        launch_pdl(k_fused_pass, dim3((unsigned)grid), dim3(kFThreads), smem, st, tmap, n, ntiles, d, nstages, w.m.brk,
+                   w.par, w.m.counts, w.m.candM, w.capM, w.m.candU, w.capU, w.m.cnt, w.mask16, cand_ss, ecap, cand_lrow,
+                   w.ealloc, tpc, chM, chU, status_dev);
     ABCDLS_LAUNCH_CHECK(h);
     {
         long long gx = (w.capM + 256 * 8 - 1) / (256 * 8);
@@ -1186,8 +1203,9 @@ int abcdls_fused_rows(abcdls_handle_t h, const double* ss, int64_t n, int d, int
                       void* stream) {
     FUSED_PROLOGUE("fused_rows");
     ABCDLS_CHECK_ARG(h, cand_row && n_cand && status_dev && cap >= 1, "fused_rows");
-    const long long ntiles = (n + kFRows - 1) / kFRows;
-    const long long nwords = ntiles * (kFRows / 32);
+    const int trows = fused_tile_rows(d);
+    const long long ntiles = (n + trows - 1) / trows;
+    const long long nwords = ntiles * (trows / 32);
     const long long nblk = (nwords + 256 * kMWords - 1) / (256 * kMWords);
     const unsigned* bitmap = reinterpret_cast<const unsigned*>(w.mask16);
     launch_pdl(k_mask_count, dim3((unsigned)nblk), dim3(256), 0, st, bitmap, nwords, w.tile_cnt, w.total);
@@ -1211,7 +1229,7 @@ int abcdls_fused_exact(abcdls_handle_t h, const double* ss, int64_t n, int d, in
     const unsigned* bitmap = reinterpret_cast<const unsigned*>(w.mask16);
     long long g = (ecap + 255) / 256;
     if (g > (long long)h->sm_count * 16) g = (long long)h->sm_count * 16;
-    launch_pdl(k_cand_exact, dim3((unsigned)g), dim3(256), 0, st, cand_ss, ecap, cand_lrow, w.ealloc, d, mad, target, bitmap, w.wprefix, cap,
+    launch_pdl(k_cand_exact, dim3((unsigned)g), dim3(256), 0, st, cand_ss, ecap, cand_lrow, w.ealloc, d, fused_emit_pitch(d), mad, target, bitmap, w.wprefix, cap,
                                               cand_dist, (long long*)perm, status_dev);
     ABCDLS_LAUNCH_CHECK(h);
     return ABCDLS_OK;

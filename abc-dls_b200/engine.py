@@ -125,7 +125,10 @@ class PostprResult:
 
     def __getattribute__(self, name):
         v = object.__getattribute__(self, name)
-        if callable(v) and name in ("ss", "values"):
+        if isinstance(v, _Lazy):
+            v = v.resolve()
+            object.__setattr__(self, name, v)
+        elif callable(v) and name in ("ss", "values"):
             v = v()
             object.__setattr__(self, name, v)
         return v
@@ -223,6 +226,7 @@ class AbcEngine:
         self.host_profile = dict(calls=0, enqueue_us=0.0, wait_us=0.0, result_us=0.0, between_calls_us=0.0)
         self._t_last_return = None
         self._last_call = None
+        self._last_postpr = None
         if hasattr(stages, "timer"):
             stages.timer = self._t
 
@@ -289,7 +293,7 @@ class AbcEngine:
 
     # ---- shared front half: scaling, distance, tolerance cut ----------------------------------
     FAST_MIN_ROWS = 1 << 18   # rows per rank; below this the 6-pass radix select (launch bound, always exact) runs
-    use_fused = True          # one-pass front half (csrc/fused.cuh) when the table qualifies
+    use_fused = os.environ.get("ABCDLS_NO_FUSED", "0") != "1"   # one-pass front half (csrc/fused.cuh) when the table qualifies
     FINE_SHIFT = int(os.environ.get("ABCDLS_FINE", "5"))               # second-stage sample: 1 line in 2^5 (0 = off)
     FINE_MIN_ROWS = int(os.environ.get("ABCDLS_FINE_MIN", str(1 << 23)))
 
@@ -309,7 +313,7 @@ class AbcEngine:
             if ns[self.comm.rank] != n_local or row_offset != self.comm.rank * per:
                 raise AbcError("shard=(n_global, row_offset) does not describe the standard contiguous split")
             all_fuse = can_fuse
-            if (self.use_fused and level == 0 and not keep_dist and min(ns) >= 16384 and d <= 16 and not can_fuse):
+            if (self.use_fused and level == 0 and not keep_dist and min(ns) >= 16384 and d <= 32 and not can_fuse):
                 raise AbcError("shard= promises the same 16-byte aligned, even-pitch table layout on every rank")
         else:
             n_global, row_offset, ns, all_fuse = self._shard_info(n_local, int(can_fuse))
@@ -350,7 +354,7 @@ class AbcEngine:
             dist = None
             cand_row, cand_dist = k.new(ccap, dtype=torch.int64), k.new(ccap)
             ecap = k.fused_emit_cap(ccap)                     # the pass emits candidate rows in 64-slot chunks per warp
-            cand_ss = k.new(ecap, 16)                         # row-major: 16 doubles per emitted row
+            cand_ss = k.new(ecap, k.fused_emit_pitch(d))      # row-major: 16 (d <= 16) or 32 doubles per emitted row
             cand_lrow = k.new(ecap, dtype=torch.int32)
             perm = k.new(ccap, dtype=torch.int64)
             slot = k.new(cap, dtype=torch.int64)
@@ -947,26 +951,41 @@ class AbcEngine:
         if method != "rejection":
             raise AbcError("postpr: only method='rejection' is implemented (mnlogistic / neuralnet stay with R's nnet)")
         k = self.k
-        ss = _as_table(sumstat)
-        target = target.to(device=self.device, dtype=torch.float64).reshape(-1).contiguous()
-        d, n_local = ss.shape
-        K = len(models)
-        if K < 2:
-            raise AbcError("At least two different models must be given.")
-        if target.numel() != d:
-            raise AbcError("Number of summary statistics in 'target' has to be the same as in 'sumstat'.")
-        if model_id.numel() != n_local:
-            raise AbcError("'index' must be the same length as the number of rows in 'sumstat'.")
-        model_id = model_id.to(device=self.device, dtype=torch.int32).contiguous()
         _t0 = time.perf_counter()
-        pl = self._plan(ss, tol, keep_dist, _level, shard)
+        if not (target.dtype == torch.float64 and target.device == self.device and target.dim() == 1
+                and target.is_contiguous()):
+            target = target.to(device=self.device, dtype=torch.float64).reshape(-1).contiguous()
+        K = len(models)
+        # same memo as abc(): a repeated call on the same table objects skips validation, plan and key
+        sig = (id(sumstat), id(model_id), sumstat.data_ptr(), model_id.data_ptr(), tuple(sumstat.shape), sumstat.stride(),
+               K, float(tol), bool(keep_dist), int(_level), None if shard is None else (int(shard[0]), int(shard[1])))
+        memo = self._last_postpr
+        if memo is not None and memo[0] == sig and memo[1]() is sumstat and memo[2]() is model_id:
+            ss = sumstat
+            _, _, _, d, n_local, pl, key = memo
+            if target.numel() != d:
+                raise AbcError("Number of summary statistics in 'target' has to be the same as in 'sumstat'.")
+        else:
+            ss = _as_table(sumstat)
+            d, n_local = ss.shape
+            if K < 2:
+                raise AbcError("At least two different models must be given.")
+            if target.numel() != d:
+                raise AbcError("Number of summary statistics in 'target' has to be the same as in 'sumstat'.")
+            if model_id.numel() != n_local:
+                raise AbcError("'index' must be the same length as the number of rows in 'sumstat'.")
+            mid0 = model_id
+            model_id = model_id.to(device=self.device, dtype=torch.int32).contiguous()
+            pl = self._plan(ss, tol, keep_dist, _level, shard)
+            key = ("postpr", ss.data_ptr(), tuple(ss.shape), ss.stride(0), model_id.data_ptr(), K, float(tol),
+                   bool(keep_dist), int(_level), self.comm.world, pl["n_global"], pl["row_offset"])
+            self._last_postpr = ((sig, weakref.ref(sumstat), weakref.ref(mid0), d, n_local, pl, key)
+                                 if (ss is sumstat and model_id is mid0 and ss.device == self.device) else None)
         self.path_calls[pl["path"]] += 1
-        key = ("postpr", ss.data_ptr(), tuple(ss.shape), ss.stride(0), model_id.data_ptr(), K, float(tol),
-               bool(keep_dist), int(_level), self.comm.world, pl["n_global"], pl["row_offset"])
         o, plan = self._run(key, target, lambda tgt: self._postpr_device(tgt, ss, model_id, K, pl),
                             graphable=not keep_dist)
         self.host_enqueue_ms.append((time.perf_counter() - _t0) * 1e3)
-        small = o["small"].cpu()                      # the one blocking read
+        small = o["small"].cpu().tolist()             # the one blocking read
         st, n_loc, ds_h = int(small[0]), int(small[1]), float(small[2])
         if (st & _capi.S_FASTPATH_MISS) and pl["fast"]:
             self.fast_misses += 1
@@ -980,11 +999,16 @@ class AbcEngine:
             raise AbcError("Zero variance in the summary statistics.")
         if st & _capi.S_CAPACITY:
             raise AbcError("internal: accepted-row buffer overflow")
-        counts = small[8 + d: 8 + d + K].to(torch.int64).to(self.device)
+        # counts / proportions / MADs come from the host copy of the small buffer, built on first access (the host time
+        # spent here delays the next call); the accepted rows are copied out of the graph's buffers now
+        dev, cnt_h, mad_h = self.device, [int(c) for c in small[8 + d: 8 + d + K]], small[8:8 + d]
+        tot = float(sum(cnt_h))
         idx = o["idx"][:n_loc].clone() if plan is not None else o["idx"][:n_loc]
         row_offset = pl["row_offset"]
-        return PostprResult(models=list(models), counts=counts, pred=counts.to(torch.float64) / counts.sum(),
-                            nacc=pl["nacc"], n_global=pl["n_global"], ds=ds_h, mad=small[8:8 + d].to(self.device),
+        return PostprResult(models=list(models), counts=_Lazy(lambda: torch.tensor(cnt_h, dtype=torch.int64, device=dev)),
+                            pred=_Lazy(lambda: torch.tensor([c / tot for c in cnt_h], dtype=torch.float64, device=dev)),
+                            nacc=pl["nacc"], n_global=pl["n_global"], ds=ds_h,
+                            mad=_Lazy(lambda: torch.tensor(mad_h, dtype=torch.float64, device=dev)),
                             idx=idx, ss=lambda: ss[:, idx - row_offset].t(), values=lambda: model_id[idx - row_offset],
                             dist=o["dist"] if keep_dist else None)
 

@@ -110,6 +110,9 @@ class CudaStages:
     def fused_emit_cap(self, cap) -> int:
         return int(self.lib.abcdls_fused_emit_cap(cap))
 
+    def fused_emit_pitch(self, d) -> int:
+        return int(self.lib.abcdls_fused_emit_pitch(int(d)))
+
     def fused_front(self, ss, n, n_global, d, ld, target, nacc, row_offset, cap, med, mad, cand_row, cand_dist, cand_ss,
                     cand_lrow, perm, n_cand, status, comm=None, pregather=None, fine=0):
         """Medians + MADs AND the candidate rows of the tolerance cut from ONE read of the table.  Leaves the exact

@@ -176,7 +176,8 @@ int abcdls_dist_fast_refine(abcdls_handle_t h, int64_t n, int64_t nacc, int64_t 
  *   sample_cols -> [all-reduce est] -> sample_dist -> [all-reduce est] -> pass -> [all-reduce counts]
  *   -> refine phases 0..3 (exchanges as abcdls_mad_fast_refine) -> candidates -> [select ds among the
  *   candidates of all ranks: abcdls_select_*] -> check -> abcdls_count_le / abcdls_accept on the candidate list.
- * Requirements (abcdls_fused_supported): d <= 16, n >= 16384, ld even, 16-byte aligned table. */
+ * Requirements (abcdls_fused_supported): d <= 32 (d <= 16: 256-row tiles, one column per consumer warp; 17..32:
+ * 128-row tiles, two columns per warp, csrc/fused_wide.cuh), n >= 16384, ld even, 16-byte aligned table. */
 int abcdls_fused_supported(const double* ss, int64_t n, int d, int64_t ld);
 size_t abcdls_fused_workspace_bytes(int64_t n, int d);
 /* `fine` (the same value in sample_cols / sample_fine / sample_dist / pass of one call, and on every rank): 0 = the
@@ -193,9 +194,10 @@ int abcdls_fused_sample_dist(abcdls_handle_t h, const double* ss, int64_t n, int
                              int64_t nacc, int64_t n_global, int world, int fine, void* ws, size_t ws_bytes,
                              double** est_out, size_t* est_count, void* stream);
 /* the pass also EMITS every marked row (its d statistics + local row number) into the caller's block
- * cand_ss[ecap][16] (row-major) / cand_lrow[ecap] (unordered, 64-slot chunks per warp, -1 = unused slot);
+ * cand_ss[ecap][abcdls_fused_emit_pitch(d)] (row-major) / cand_lrow[ecap] (unordered, 64-slot chunks per warp, -1 = unused slot);
  * ecap = abcdls_fused_emit_cap(cap of the candidate list) */
 int64_t abcdls_fused_emit_cap(int64_t cap);
+int abcdls_fused_emit_pitch(int d);   /* doubles per emitted record = row pitch of cand_ss: 16 (d <= 16) or 32 (d <= 32) */
 int abcdls_fused_pass(abcdls_handle_t h, const double* ss, int64_t n, int d, int64_t ld, int world, int fine,
                       double* cand_ss, int32_t* cand_lrow, int64_t ecap, void* ws, size_t ws_bytes, int* status_dev,
                       int64_t** counts_out, size_t* counts_count, void* stream);

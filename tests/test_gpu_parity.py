@@ -441,3 +441,20 @@ def test_fused_one_pass_on_tables_just_above_the_threshold(engine, n, d, P, tol)
     of the BASELINE cfg5 sweep among them)."""
     par, ss, tgt = synth.abc_tables(n, d, P, engine.device)
     _check_fused(engine, par, ss, tgt, tol, "loclinear" if d > 1 else "rejection")
+
+
+# ---- 16 < d <= 32: 128-row tiles, two columns per consumer warp (csrc/fused_wide.cuh) -----------------------------------
+@pytest.mark.parametrize("n,d,P", [((1 << 20) + 130, 17, 5), ((1 << 20) + 64, 19, 19), ((1 << 21) + 8, 24, 24),
+                                   (1 << 20, 32, 32), ((1 << 20) + 254, 31, 3)])
+def test_fused_one_pass_wide_tables(engine, n, d, P):
+    """The reference's models have 19 and 24 parameters (tests/Model.info): a joint call then has 19 / 24 statistics
+    and must still take ONE table read."""
+    par, ss, tgt = synth.abc_tables(n, d, P, engine.device)
+    _check_fused(engine, par, ss, tgt, 0.01, "loclinear")
+
+
+def test_fused_wide_with_the_second_stage_sample_and_ties(engine):
+    n = (1 << 23) + 512                                             # fine sample on (engine.FINE_MIN_ROWS)
+    par, ss, tgt = synth.abc_tables(n, 24, 4, engine.device)
+    ss[3] = torch.round(ss[3], decimals=2)                          # one coarse column: ties inside the bands
+    _check_fused(engine, par, ss, tgt, 0.002, "rejection")
