@@ -1094,7 +1094,12 @@ int abcdls_fused_sample_dist(abcdls_handle_t h, const double* ss, int64_t n, int
                              int64_t nacc, int64_t n_global, int world, int fine, void* ws, size_t ws_bytes,
                              double** est_out, size_t* est_count, void* stream) {
     FUSED_PROLOGUE("fused_sample_dist");
-    ABCDLS_CHECK_ARG(h, target && nacc >= 1 && n_global >= nacc && fine_valid(fine), "fused_sample_dist: nacc");
+    if (!(target && nacc >= 1 && n_global >= nacc && fine_valid(fine))) {
+        h->err = "invalid argument: fused_sample_dist: target " + std::string(target ? "ok" : "NULL") + ", nacc " +
+                 std::to_string((long long)nacc) + ", n_global " + std::to_string((long long)n_global) + ", fine " +
+                 std::to_string(fine);
+        return ABCDLS_E_INVALID;
+    }
     if (fine) {
         launch_pdl(k_fine_brackets, dim3(d), dim3(256), 0, st, w.fine, w.m.brk, kZ, w.est_fine);
         launch_pdl(k_make_brackets, dim3(d), dim3(32), 0, st, w.est_fine, 1, d, 1.0, w.m.brk, nullptr);

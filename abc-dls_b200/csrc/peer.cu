@@ -28,7 +28,7 @@ __device__ __forceinline__ void grid_arrive_wait(const PeerDev& P) {
     if (threadIdx.x == 0) {
         __threadfence_system();
         atomicAdd(P.bar, 1ull);
-        spin_until_ge(P.bar, *P.bar_cum + gridDim.x, P.err);
+        spin_until_ge(P.bar, *P.bar_cum + gridDim.x, P.err, P.spin_ns);
     }
     __syncthreads();
 }
@@ -42,7 +42,7 @@ __device__ __forceinline__ void publish_and_wait(const PeerDev& P, unsigned long
         unsigned long long* f = flag_ptr(P.box[threadIdx.x], parity, P.rank);   // my entry in peer threadIdx.x's row
         asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(f), "l"(k) : "memory");
     }
-    if (threadIdx.x < P.world) spin_until_ge(flag_ptr(P.box[P.rank], parity, threadIdx.x), k, P.err);
+    if (threadIdx.x < P.world) spin_until_ge(flag_ptr(P.box[P.rank], parity, threadIdx.x), k, P.err, P.spin_ns);
     __threadfence_system();
     __syncthreads();
     if (blockIdx.x == 0 && threadIdx.x == 0) peer_trace(P, k, 2);
@@ -192,6 +192,11 @@ int abcdls_peer_create(abcdls_peer_t* out, int rank, int world, size_t slot_byte
     p->dev.bar = p->ctl + 8;
     p->dev.bar_cum = p->ctl + 16;
     p->dev.err = p->ctl + 24;
+    p->dev.spin_ns = kPeerSpinNsDefault;
+    if (const char* e = getenv("ABCDLS_PEER_TIMEOUT_S")) {
+        const double sec = atof(e);
+        if (sec > 0.0) p->dev.spin_ns = (unsigned long long)(sec * 1e9);
+    }
     p->dev.trace = nullptr;
     if (const char* e = getenv("ABCDLS_PEER_TRACE"))
         if (e[0] == '1' && cudaMalloc((void**)&p->trace, (size_t)kPeerTraceCap * 32) == cudaSuccess) {

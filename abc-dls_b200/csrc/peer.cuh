@@ -8,15 +8,18 @@ constexpr int kMaxWorld = 64;
 constexpr int kPeerThreads = 512;
 constexpr int kPeerMaxCtas = 32;
 // A peer that never publishes (crashed rank, a rank that raised before enqueueing its half of the call) must not hang
-// this GPU inside a kernel that cannot be cancelled: every wait gives up after kPeerSpinNs and raises the sticky error
-// word, which the end-of-call kernel turns into ABCDLS_S_PEER_TIMEOUT.
-constexpr unsigned long long kPeerSpinNs = 4000000000ull;   // 4 s
+// this GPU inside a kernel that cannot be cancelled: every wait gives up after PeerDev::spin_ns and raises the sticky
+// error word, which the end-of-call kernel turns into ABCDLS_S_PEER_TIMEOUT.  Default 60 s (ABCDLS_PEER_TIMEOUT_S at
+// abcdls_peer_create): a rank may legitimately be seconds late (host work between calls - the 4 s of the first version
+// fired in the 8-GPU parity test while rank 0 was still computing the previous case's CPU oracle).
+constexpr unsigned long long kPeerSpinNsDefault = 60000000000ull;
 
 struct PeerDev {
     unsigned long long* seq;       // exchanges completed by this rank (device memory, advanced by the kernels)
     unsigned long long* bar;       // arrivals of my CTAs (monotonic)
     unsigned long long* bar_cum;   // arrivals expected before the current exchange
     unsigned long long* err;       // sticky: != 0 after a wait timed out
+    unsigned long long spin_ns;    // budget of every wait
     unsigned long long* trace;     // NULL, or kPeerTraceCap x 4 timestamps (ABCDLS_PEER_TRACE=1): see peer_trace
     unsigned char* box[kMaxWorld]; // mailboxes of all ranks as mapped in THIS process (box[rank] = mine)
     size_t slot_bytes;
@@ -65,7 +68,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
 }
 // spin until *p >= want; false (and the sticky error word set) when the budget runs out
 __device__ __forceinline__ bool spin_until_ge(const unsigned long long* p, unsigned long long want,
-                                              unsigned long long* err) {
+                                              unsigned long long* err, unsigned long long budget_ns) {
     if (ld_volatile_u64(p) >= want) return true;
     const unsigned long long t0 = global_ns();
     for (;;) {
@@ -74,7 +77,7 @@ __device__ __forceinline__ bool spin_until_ge(const unsigned long long* p, unsig
             __nanosleep(20);
         }
         if (ld_volatile_u64(err) != 0ull) return false;          // somebody already gave up: do not wait 4 s each
-        if (global_ns() - t0 > kPeerSpinNs) {
+        if (global_ns() - t0 > budget_ns) {
             atomicExch(err, 1ull);
             return false;
         }
@@ -98,7 +101,7 @@ __device__ __forceinline__ void peer_block_allreduce(const PeerDev& P, double* v
     if (threadIdx.x < P.world) {
         unsigned long long* f = flag_ptr(P.box[threadIdx.x], parity, P.rank);   // my entry in peer threadIdx.x's row
         asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(f), "l"(k) : "memory");
-        spin_until_ge(flag_ptr(P.box[P.rank], parity, threadIdx.x), k, P.err);
+        spin_until_ge(flag_ptr(P.box[P.rank], parity, threadIdx.x), k, P.err, P.spin_ns);
     }
     __threadfence_system();
     __syncthreads();

@@ -38,8 +38,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "simulations scored/sec (ABC loclinear)"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture at the default
-# workload (profiles/r01_ncu_full_fused_pass_final.txt); None until a capture of the current kernel is committed
-TRAFFIC = {"k_fused_pass": 12.806535e9 + 0.807694e9, "k_bracket_pass": 12.800307e9 + 0.494554e9, "k_dist_pass": None}
+# workload (k_fused_pass: profiles/r02_ncu_full_pass_and_fine_sample.txt; k_bracket_pass: profiles/r01_*); None until a capture of the current kernel is committed
+TRAFFIC = {"k_fused_pass": 12.814157e9 + 0.376328e9, "k_bracket_pass": 12.800307e9 + 0.494554e9, "k_dist_pass": None}
 UNIT = "sims/s"
 PRESETS = {"cfg5": dict(rows=1e8, stats=16, params=16, tol=0.01),
            "cfg3": dict(rows=1e7, stats=10, params=10, tol=0.001)}

@@ -49,6 +49,7 @@ def main():
     if a.big:
         cases += [(a.big * world, 16, 16, 0.01, "loclinear"), (a.big * world + 77, 3, 3, 0.002, "rejection")]
     for (N, d, P, tol, method) in cases:
+        dist.barrier()      # rank 0 may still be busy with the previous case's CPU oracle: enter the exchanges together
         per = (N + world - 1) // world
         r0, r1 = min(rank * per, N), min((rank + 1) * per, N)
         par, ss, tgt = synth.abc_tables(r1 - r0, d, P, dev, row_start=r0)
@@ -73,6 +74,7 @@ def main():
     for N in (200_001, a.big * world + 5 if a.big else 0):
         if not N:
             continue
+        dist.barrier()
         per = (N + world - 1) // world
         r0, r1 = min(rank * per, N), min((rank + 1) * per, N)
         ids, ss, tgt = synth.postpr_tables(r1 - r0, dev, K=3, row_start=r0)
@@ -92,6 +94,7 @@ def main():
         per = (N + world - 1) // world
         r0, r1 = min(rank * per, N), min((rank + 1) * per, N)
         for coarse in (False, True):
+            dist.barrier()
             par, ss, tgt = synth.abc_tables(r1 - r0, P, P, dev, row_start=r0)
             if coarse:      # a coarse grid: thousands of equal distances, the cap rule decides by row order across ranks
                 ss = (torch.round(ss / tgt[:, None] * 400.0) * tgt[:, None] / 400.0).to(torch.float32).to(torch.float64)
@@ -111,6 +114,7 @@ def main():
                       f"columns calls={eng.path_calls.get('columns', 0)} misses={eng.fast_misses}", flush=True)
                 ok = ok and good
     # SMC table passes: oldrange and the box filter over the ranks
+    dist.barrier()
     N = 400_003
     per = (N + world - 1) // world
     r0, r1 = min(rank * per, N), min((rank + 1) * per, N)

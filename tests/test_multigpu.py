@@ -25,14 +25,17 @@ def _run(world, env_extra, port, extra=()):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["mailbox", "nccl_fallback"])
+@pytest.mark.parametrize("mode", ["mailbox", "mailbox_fine", "nccl_fallback"])
 def test_sharded_parity_over_all_visible_gpus(mode):
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
     world = 8 if n >= 8 else (4 if n >= 4 else 2)
-    env = {} if mode == "mailbox" else {"ABCDLS_NO_PEER": "1"}
-    lines = _run(world, env, 29541 if mode == "mailbox" else 29542, ("--big", str(1 << 20)))
+    # mailbox_fine: the second-stage counting sample (one more exchange: the window histograms) switched on at this
+    # size (by default it starts at 2^24 rows per rank when there are several ranks)
+    env = {"mailbox": {}, "mailbox_fine": {"ABCDLS_FINE_MIN": str(1 << 18)}, "nccl_fallback": {"ABCDLS_NO_PEER": "1"}}[mode]
+    port = {"mailbox": 29541, "mailbox_fine": 29543, "nccl_fallback": 29542}[mode]
+    lines = _run(world, env, port, ("--big", str(1 << 20)))
     assert len(lines) >= 8
-    if mode == "mailbox":
+    if mode != "nccl_fallback":
         assert any("graphs=" in l and not l.rstrip().endswith("graphs=0") for l in lines)
