@@ -315,3 +315,51 @@ def test_unsupported_methods_are_delegated_to_r_or_stop_with_the_reason():
         assert tag == "R" and {"target", "param", "sumstat", "tol", "method"} <= set(keys)
     finally:
         rabc._r_abc = None
+
+
+def test_repeated_call_memo_is_safe():
+    """abc() / postpr() reuse the validated views, the plan and the key of the previous call when they are made on the
+    very same table objects (engine._last_call: weak references).  The memo must never serve another table, a changed
+    target must be honoured, and the engine must not keep the caller's tables alive."""
+    import gc
+    import weakref
+    from abc_dls_b200.engine import AbcEngine
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from cpu_stages import CpuStages
+    eng = AbcEngine(stages=CpuStages())
+    par, ss, tgt = synth.abc_tables(5000, 3, 2, "cpu")
+    a = eng.abc(tgt, par, ss, 0.02, "loclinear")
+    assert eng._last_call is not None                                   # the second call will take the memo
+    b = eng.abc(tgt, par, ss, 0.02, "loclinear")
+    o = O.abc(tgt.numpy(), par.numpy().T, ss.numpy().T, 0.02, "loclinear")
+    for r in (a, b):
+        np.testing.assert_array_equal(r.idx.numpy(), o.idx)
+        assert r.ds == o.ds
+    tgt2 = tgt * 1.01                                                   # another target, same tables: memo + new result
+    c = eng.abc(tgt2, par, ss, 0.02, "loclinear")
+    o2 = O.abc(tgt2.numpy(), par.numpy().T, ss.numpy().T, 0.02, "loclinear")
+    np.testing.assert_array_equal(c.idx.numpy(), o2.idx)
+    assert c.ds == o2.ds and c.ds != a.ds
+    c2 = eng.abc(tgt2, par, ss, 0.05, "rejection")                      # other tol / method: not the memoised plan
+    assert c2.nacc == 250 and c2.adj_values is None
+    with pytest.raises(Exception, match="Number of summary statistics"):
+        eng.abc(tgt[:2], par, ss, 0.05, "rejection")                    # validation that depends on the target stays
+    # other tables of the same shape (possibly at a recycled address / id): the memo must not serve them
+    par3, ss3, tgt3 = synth.abc_tables(5000, 3, 2, "cpu", row_start=5000)
+    d3 = eng.abc(tgt3, par3, ss3, 0.05, "rejection")
+    o3 = O.abc(tgt3.numpy(), par3.numpy().T, ss3.numpy().T, 0.05, "rejection")
+    np.testing.assert_array_equal(d3.idx.numpy(), o3.idx)
+    # the engine holds weak references only
+    w = weakref.ref(ss3)
+    del ss3, d3
+    gc.collect()
+    assert w() is None, "the engine keeps the caller's table alive"
+    # postpr: same rules
+    ids, pss, ptgt = synth.postpr_tables(4000, "cpu")
+    p1 = eng.postpr(ptgt, ids, ["A", "B", "C"], pss, 0.05)
+    p2 = eng.postpr(ptgt, ids, ["A", "B", "C"], pss, 0.05)
+    po = O.postpr(ptgt.numpy(), np.array(["A", "B", "C"])[ids.numpy()], pss.numpy().T, 0.05)
+    for r in (p1, p2):
+        np.testing.assert_array_equal(r.counts.numpy(), po.counts)
+        np.testing.assert_array_equal(r.idx.numpy(), po.idx)
+        assert abs(float(r.pred.sum()) - 1.0) < 1e-15 and r.mad.shape == (3,)
