@@ -614,12 +614,10 @@ class AbcEngine:
             return fn(target), None
         plan = self._graphs.get(key)
         if plan is not None:
-            # the target is the only input that may change under a key: copy it unless it is provably the tensor (same
-            # storage - kept alive by the reference held here - and same version counter) of the previous replay
-            ref = plan.get("tgt_ref")
-            if ref is None or ref.data_ptr() != target.data_ptr() or ref._version != target._version:
-                plan["target"].copy_(target)
-                plan["tgt_ref"] = target
+            # the target is the only input that may change under a key.  It is copied on every replay: skipping the copy
+            # for "the same tensor, same version counter" (-8 us) would silently serve a stale target whenever the caller
+            # fills that tensor through a raw pointer (dlpack, cupy, an own kernel), which torch's counter does not see
+            plan["target"].copy_(target)
             plan["gen"] += 1
             plan["graph"].replay()
             self.k.launches += plan["launches"]
