@@ -139,6 +139,10 @@ SIGNATURES = {
     "abcdls_peer_destroy": (_i32, [_vp]),
     "abcdls_peer_trace_read": (_i32, [_vp, _vp, _vp]),
     "abcdls_copy_out": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "abcdls_abc_single_workspace_bytes": (_sz, [_vp, _i64, _i32, _i32, _f64]),
+    "abcdls_abc_single_nacc": (_i64, [_i64, _f64]),
+    "abcdls_abc_single": (_i32, [_vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _f64, _i32, _i32, _vp, _vp,
+                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "abcdls_peer_last_error": (C.c_char_p, [_vp]),
     "abcdls_peer_slot_bytes": (_sz, [_vp]),
     "abcdls_peer_allreduce": (_i32, [_vp, _vp, _sz, _i32, _i32, _vp]),

@@ -4,7 +4,7 @@ set -euo pipefail
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC"
-SRCS="api.cu select.cu dist.cu loclinear.cu tail.cu summary.cu smc.cu peer.cu small.cu"
+SRCS="api.cu select.cu dist.cu loclinear.cu tail.cu summary.cu smc.cu peer.cu small.cu single.cu"
 [ -f bracket.cu ] && SRCS="$SRCS bracket.cu"
 OBJS=""
 for s in $SRCS; do

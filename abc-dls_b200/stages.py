@@ -398,6 +398,30 @@ class CudaStages:
         self.handle.call("abcdls_copy_out", n, src, ld, rows, cols, _p(out), self._stream())
         return out
 
+    def abc_single(self, target, param, sumstat, tol, method, hcorr=True):
+        """The call-level C entry point (csrc/single.cu: abc() on one GPU as ONE C call, one-pass path only) - what a
+        non-Python host binds instead of mirroring engine.py.  Returns the raw output blocks (leading dimension cap)
+        and the packed small buffer; nothing is synchronised.  The engine itself keeps sequencing the stages (it needs
+        the exchanges of several ranks, the fallback ladder and CUDA graphs in between)."""
+        d, n = sumstat.shape
+        P = param.shape[0]
+        lin = method == "loclinear"
+        nacc = int(self.lib.abcdls_abc_single_nacc(n, float(tol)))
+        cap = min(nacc, n)
+        ws = self.workspace("single", int(self.lib.abcdls_abc_single_workspace_bytes(self.handle.h, n, d, P, float(tol))))
+        idx, dacc = self.new(cap, dtype=torch.int64), self.new(cap)
+        y, ss_out = self.new(P, cap), self.new(d, cap)
+        xs = w = adj = res = None
+        if lin:
+            xs, w, adj, res = self.new(d, cap), self.new(cap), self.new(P, cap), self.new(P, cap)
+        small = self.new(self.final_small_len(d, P, lin))
+        cm = param.stride(1) == 1
+        self.handle.call("abcdls_abc_single", _p(target), _p(param) if cm else None, param.stride(0) if cm else 0,
+                         None if cm else _p(param), 0 if cm else param.stride(1), _p(sumstat), sumstat.stride(0), n, d, P,
+                         float(tol), int(lin), int(bool(hcorr)), _p(idx), _p(dacc), _p(y), _p(ss_out), _p(xs), _p(w),
+                         _p(adj), _p(res), _p(small), _p(ws), ws.numel(), self._stream())
+        return dict(nacc=nacc, cap=cap, idx=idx, dist=dacc, y=y, ss_out=ss_out, xs=xs, w=w, adj=adj, res=res, small=small)
+
     def tail_resid_fit(self, peer, xs, y, w, n_acc, cap, d, P, ws, status):
         self.handle.call("abcdls_tail_resid_fit", peer, _p(xs), _p(y), _p(w), _p(n_acc), cap, d, P, _p(ws),
                          ws.numel(), _p(status), self._stream())

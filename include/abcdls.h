@@ -431,6 +431,26 @@ int abcdls_postpr_counts(abcdls_handle_t h, const int32_t* model_id, const int64
                          const int64_t* n_acc, int64_t row_offset, int64_t cap, int K, int64_t* counts,
                          void* stream);
 
+/* ---- call level (csrc/single.cu): abc(target, param, sumstat, tol, method) on ONE GPU as ONE call ---------------------
+ * What the reference binds through rpy2 - abc.abc(target=, param=, sumstat=, tol=, method=) at
+ * /root/reference/src/Classes/ABC.py:1950-1953, 1964, 2806-2809 - for hosts that do not want to mirror the stage
+ * sequencing of engine.py / stages.py.  Sequences the stage-level entry points of the one-pass path (world = 1) on
+ * `stream`; nothing synchronises.  The table must satisfy abcdls_fused_supported (else ABCDLS_E_INVALID: use the stages).
+ *   nacc = abcdls_abc_single_nacc(n, tol) = ceiling(n tol); cap = min(nacc, n) is the leading dimension of the outputs:
+ *   idx_out[cap] ascending accepted rows, dist_out[cap], y[P][cap] accepted parameters (unadj.values), ss_out[d][cap],
+ *   and for loclinear xs[d][cap] (scaled, centred statistics), w[cap], adj[P][cap] (adj.values), res[P][cap];
+ *   small_out[abcdls_final_small_doubles(d, P, loclinear)]: {status, n_acc, ds, ...} | mad | stats | sigma2 | pred | coef.
+ * param: exactly one of param_cm (column-major P x n, leading dimension ld_param) / param_rm (row-major n x P records,
+ * row_pitch doubles apart; may be pinned host memory).  Data-dependent outcomes come back as status bits in small_out[0];
+ * ABCDLS_S_FASTPATH_MISS means "not proven complete on this path: rerun through abcdls_mad_fast_* / abcdls_select_*". */
+size_t abcdls_abc_single_workspace_bytes(abcdls_handle_t h, int64_t n, int d, int P, double tol);
+int64_t abcdls_abc_single_nacc(int64_t n, double tol);
+int abcdls_abc_single(abcdls_handle_t h, const double* target, const double* param_cm, int64_t ld_param,
+                      const double* param_rm, int64_t row_pitch, const double* sumstat, int64_t ld, int64_t n, int d,
+                      int P, double tol, int loclinear, int hcorr, int64_t* idx_out, double* dist_out, double* y,
+                      double* ss_out, double* xs, double* w, double* adj, double* res, double* small_out, void* ws,
+                      size_t ws_bytes, void* stream);
+
 /* Results out of the buffers of a replayed CUDA graph in ONE launch: up to 4 segments (rows[i] x cols[i] 8-byte
  * elements, source pitch ld[i]) are packed densely, one after the other, into dst. */
 int abcdls_copy_out(abcdls_handle_t h, int nseg, const void* const* src, const int64_t* ld, const int64_t* rows,
