@@ -455,7 +455,10 @@ class AbcEngine:
         sig = (id(sumstat), id(param), sumstat.data_ptr(), param.data_ptr(), tuple(sumstat.shape), tuple(param.shape),
                sumstat.stride(), param.stride(), float(tol), method, bool(hcorr), bool(keep_dist), int(_level),
                None if shard is None else (int(shard[0]), int(shard[1])))
-        memo = self._last_call
+        # Several ranks without `shard=`: _plan runs a collective (shard sizes), which every rank must enter or none -
+        # a memo hit on one rank only would hang the others, so the memo is used only where _plan is local.
+        local_plan = self.comm.world == 1 or shard is not None
+        memo = self._last_call if local_plan else None
         if memo is not None and memo[0] == sig and memo[1]() is sumstat and memo[2]() is param:
             ss, par = sumstat, param
             _, _, _, d, n_local, P, pl, key = memo
@@ -957,7 +960,7 @@ class AbcEngine:
         # same memo as abc(): a repeated call on the same table objects skips validation, plan and key
         sig = (id(sumstat), id(model_id), sumstat.data_ptr(), model_id.data_ptr(), tuple(sumstat.shape), sumstat.stride(),
                K, float(tol), bool(keep_dist), int(_level), None if shard is None else (int(shard[0]), int(shard[1])))
-        memo = self._last_postpr
+        memo = self._last_postpr if (self.comm.world == 1 or shard is not None) else None   # see abc()
         if memo is not None and memo[0] == sig and memo[1]() is sumstat and memo[2]() is model_id:
             ss = sumstat
             _, _, _, d, n_local, pl, key = memo
