@@ -95,7 +95,7 @@ class CudaStages:
     def count_le(self, dist, n, n_dev, ds, le_count, ws):
         self.handle.call("abcdls_count_le", _p(dist), n, _p(n_dev), _p(ds), _p(le_count), _p(ws), ws.numel(),
                          self._stream())
-        self.launches += 4
+        self.launches += 2        # k_tile_count_le, k_scan_tiles
 
     def accept(self, dist, n, n_dev, src_idx, ds, quota, row_offset, cap, idx, dist_out, n_out, ws, status,
                slot_out=None):
@@ -174,7 +174,7 @@ class CudaStages:
         with self._timed("fused_candidates"):
             self.handle.call("abcdls_fused_exact", _p(ss), n, d, ld, world, _p(mad), _p(target), cap, _p(cand_dist),
                              _p(cand_ss), _p(cand_lrow), cand_ss.shape[0], _p(perm), _p(ws), ws.numel(), _p(status), st)
-        self.launches += 24
+        self.launches += 22       # the kernels of profiles/r02_launches_1e8_final.txt up to k_cand_exact (+ 3 above with `fine`)
 
     def fused_ds(self, n, d, nacc, cap, cand_dist, n_cand, ds, status, comm=None):
         """Exact ds = nacc-th smallest candidate distance over all ranks (3 small kernels-stages, 2 exchanges)."""
@@ -189,7 +189,7 @@ class CudaStages:
                 comm.allreduce_sum(self._view(ws, p0, c0, torch.int64, 8))
             elif world > 1 and phase == 1:
                 gath = comm.allgather(self._view(ws, p0, c0, torch.float64, 8)).contiguous()
-        self.launches += 7
+        self.launches += 6        # plan, hist, pick, gather, pack, final
 
     def fused_check(self, n, d, mad, ds, status):
         ws = self._ws["fused"]
@@ -396,6 +396,7 @@ class CudaStages:
         _, n, src, ld, rows, cols, total = co
         out = torch.empty(total, dtype=torch.float64, device=self.device)
         self.handle.call("abcdls_copy_out", n, src, ld, rows, cols, _p(out), self._stream())
+        self.launches += 1
         return out
 
     def abc_single(self, target, param, sumstat, tol, method, hcorr=True):
